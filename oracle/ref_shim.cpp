@@ -1,0 +1,426 @@
+// TEST INFRASTRUCTURE ONLY -- never linked, imported or executed by the product path.
+//
+// ref_shim.cpp: a flat extern "C" window onto the UNMODIFIED reference sources
+// (/root/reference/deepgroebner/{polynomials,ideals,buchberger}.cpp), compiled where they
+// lie by oracle/Makefile into oracle/_ref/libdgref.so.  Nothing from the reference is copied:
+// this file only #includes its headers and calls its public functions/classes.
+//
+// Used (a) to pin oracle/bb_oracle.c (the plain-C restatement) and the CUDA path bit-exactly,
+// (b) to generate tests/golden/*.json (tests/golden/make_golden.py), and
+// (c) as the `--impl reference` / cpu_baseline arm of bench.py (kind "reference").
+//
+// Wire format shared with bb_oracle.c ("flat polys"): a polynomial list is
+//   lens[npoly]            number of terms of each polynomial
+//   terms[sum(lens) * 9]   per term: coefficient in [0,P) followed by the 8 exponents
+// Pairs are int pairs (i, j) flattened.
+
+#include <algorithm>
+#include <array>
+#include <chrono>
+#include <cstring>
+#include <functional>
+#include <map>
+#include <memory>
+#include <optional>
+#include <random>
+#include <sstream>
+#include <string>
+#include <thread>
+#include <tuple>
+#include <vector>
+
+// The C++ env cannot be handed an explicit ideal (ideal_gen is private, buchberger.h:200).
+// Open the access specifiers for the reference headers only (std headers are already in).
+#define private public
+#define protected public
+#include "polynomials.h"
+#include "ideals.h"
+#include "buchberger.h"
+#undef private
+#undef protected
+
+namespace {
+
+constexpr int W = 9;  // ints per term on the wire
+
+Polynomial poly_from(const int* t, int n) {
+  if (n == 0) return Polynomial{};
+  std::vector<Term> tv;
+  for (int i = 0; i < n; i++) {
+    std::array<int, N> e{};
+    for (int k = 0; k < N; k++) e[k] = t[i * W + 1 + k];
+    tv.push_back(Term{Coefficient(t[i * W]), Monomial(e)});
+  }
+  return Polynomial(tv);
+}
+
+std::vector<Polynomial> polys_from(const int* terms, const int* lens, int npoly) {
+  std::vector<Polynomial> F;
+  int off = 0;
+  for (int p = 0; p < npoly; p++) {
+    F.push_back(poly_from(terms + off * W, lens[p]));
+    off += lens[p];
+  }
+  return F;
+}
+
+int coef_int(Coefficient c) { return c.c; }
+
+// returns number of terms, or -(needed) if cap too small
+int poly_to(const Polynomial& f, int* out, int cap_terms) {
+  int n = f.terms.size();
+  if (n > cap_terms) return -n;
+  for (int i = 0; i < n; i++) {
+    out[i * W] = coef_int(f.terms[i].coeff);
+    for (int k = 0; k < N; k++) out[i * W + 1 + k] = f.terms[i].monom[k];
+  }
+  return n;
+}
+
+// returns npoly or negative on overflow
+int polys_to(const std::vector<Polynomial>& F, int* terms, int cap_terms, int* lens, int cap_polys) {
+  if ((int)F.size() > cap_polys) return -1;
+  int off = 0;
+  for (size_t p = 0; p < F.size(); p++) {
+    int n = poly_to(F[p], terms + off * W, cap_terms - off);
+    if (n < 0) return -1;
+    lens[p] = n;
+    off += n;
+  }
+  return F.size();
+}
+
+EliminationType elim_of(int e) {
+  return e == 0 ? EliminationType::GebauerMoeller : (e == 1 ? EliminationType::LCM : EliminationType::None);
+}
+RewardType rew_of(int r) { return r == 0 ? RewardType::Additions : RewardType::Reductions; }
+SelectionType sel_of(int s) { return static_cast<SelectionType>(s); }  // First,Degree,Normal,Sugar,Random,Last,Codegree,Strange,Spice
+
+// Row index the reference's comparator (buchberger.cpp:160-241) would pick via std::min_element.
+int select_row(const std::vector<Polynomial>& G, const std::vector<SPair>& P, int selection) {
+  std::function<bool(const SPair&, const SPair&)> select;
+  switch (selection) {
+    case 0:
+      select = [](const SPair& p1, const SPair& p2) { return std::tie(p1.j, p1.i) < std::tie(p2.j, p2.i); };
+      break;
+    case 1:
+      select = [&G](const SPair& p1, const SPair& p2) {
+        int d1 = lcm(G[p1.i].LM(), G[p1.j].LM()).deg();
+        int d2 = lcm(G[p2.i].LM(), G[p2.j].LM()).deg();
+        return std::tie(d1, p1.j, p1.i) < std::tie(d2, p2.j, p2.i);
+      };
+      break;
+    case 2:
+      select = [&G](const SPair& p1, const SPair& p2) {
+        Monomial m1 = lcm(G[p1.i].LM(), G[p1.j].LM());
+        Monomial m2 = lcm(G[p2.i].LM(), G[p2.j].LM());
+        return std::tie(m1, p1.j, p1.i) < std::tie(m2, p2.j, p2.i);
+      };
+      break;
+    case 3:
+      select = [&G](const SPair& p1, const SPair& p2) {
+        Monomial m1 = lcm(G[p1.i].LM(), G[p1.j].LM());
+        Monomial m2 = lcm(G[p2.i].LM(), G[p2.j].LM());
+        int s1 = std::max(G[p1.i].sugar() + (m1 / G[p1.i].LM()).deg(), G[p1.j].sugar() + (m1 / G[p1.j].LM()).deg());
+        int s2 = std::max(G[p2.i].sugar() + (m2 / G[p2.i].LM()).deg(), G[p2.j].sugar() + (m2 / G[p2.j].LM()).deg());
+        return std::tie(s1, m1, p1.j, p1.i) < std::tie(s2, m2, p2.j, p2.i);
+      };
+      break;
+    default:
+      return -1;
+  }
+  return std::min_element(P.begin(), P.end(), select) - P.begin();
+}
+
+struct RefEnv {
+  BuchbergerEnv env;
+  RefEnv(const char* dist, int elim, int rew, bool si, bool sr) : env(dist, elim_of(elim), rew_of(rew), si, sr) {}
+};
+
+}  // namespace
+
+extern "C" {
+
+int ref_prime() { return P; }
+int ref_nslots() { return N; }
+
+// ---- L0: field + monomials (polynomials.cpp) ----
+int ref_coef_div(int a, int b) { return coef_int(Coefficient(a) / Coefficient(b)); }
+int ref_coef_mul(int a, int b) { return coef_int(Coefficient(a) * Coefficient(b)); }
+int ref_coef_add(int a, int b) { return coef_int(Coefficient(a) + Coefficient(b)); }
+int ref_coef_sub(int a, int b) { return coef_int(Coefficient(a) - Coefficient(b)); }
+int ref_coef_norm(int a) { return coef_int(Coefficient(a)); }
+
+int ref_mono_cmp(const int* e1, const int* e2) {
+  std::array<int, N> a{}, b{};
+  for (int k = 0; k < N; k++) { a[k] = e1[k]; b[k] = e2[k]; }
+  Monomial m1(a), m2(b);
+  return (m1 > m2) ? 1 : ((m2 > m1) ? -1 : 0);
+}
+int ref_mono_divisible(const int* e1, const int* e2) {
+  std::array<int, N> a{}, b{};
+  for (int k = 0; k < N; k++) { a[k] = e1[k]; b[k] = e2[k]; }
+  return is_divisible(Monomial(a), Monomial(b)) ? 1 : 0;
+}
+void ref_mono_lcm(const int* e1, const int* e2, int* out) {
+  std::array<int, N> a{}, b{};
+  for (int k = 0; k < N; k++) { a[k] = e1[k]; b[k] = e2[k]; }
+  Monomial m = lcm(Monomial(a), Monomial(b));
+  for (int k = 0; k < N; k++) out[k] = m[k];
+}
+
+// normalises a term list the way the Polynomial ctor does (sort only; polynomials.cpp:139-145)
+int ref_poly_make(const int* t, int n, int* out, int cap) { return poly_to(poly_from(t, n), out, cap); }
+int ref_poly_add(const int* f, int nf, const int* g, int ng, int* out, int cap) {
+  return poly_to(poly_from(f, nf) + poly_from(g, ng), out, cap);
+}
+int ref_poly_sub(const int* f, int nf, const int* g, int ng, int* out, int cap) {
+  return poly_to(poly_from(f, nf) - poly_from(g, ng), out, cap);
+}
+int ref_poly_mul(const int* f, int nf, const int* g, int ng, int* out, int cap) {
+  return poly_to(poly_from(f, nf) * poly_from(g, ng), out, cap);
+}
+int ref_term_mul(const int* t, const int* f, int nf, int* out, int cap) {
+  std::array<int, N> e{};
+  for (int k = 0; k < N; k++) e[k] = t[1 + k];
+  Term tt{Coefficient(t[0]), Monomial(e)};
+  return poly_to(tt * poly_from(f, nf), out, cap);
+}
+int ref_parse_polynomial(const char* s, int* out, int cap) { return poly_to(parse_polynomial(std::string(s)), out, cap); }
+
+// ---- L1: spoly / reduce / update / minimalize / interreduce (buchberger.cpp:18-122) ----
+int ref_spoly(const int* f, int nf, const int* g, int ng, int* out, int cap) {
+  return poly_to(spoly(poly_from(f, nf), poly_from(g, ng)), out, cap);
+}
+
+int ref_reduce(const int* g, int ng, const int* Fterms, const int* Flens, int nF, int* out, int cap, int* steps) {
+  auto [r, st] = reduce(poly_from(g, ng), polys_from(Fterms, Flens, nF));
+  *steps = st.steps;
+  return poly_to(r, out, cap);
+}
+
+// pairs: in/out, capacity cap_pairs; returns new number of pairs (G is NOT returned: it is G + [f])
+int ref_update(const int* Gterms, const int* Glens, int nG, int* pairs, int nP, int cap_pairs, const int* f, int nf,
+               int elimination) {
+  std::vector<Polynomial> G = polys_from(Gterms, Glens, nG);
+  std::vector<SPair> P;
+  for (int i = 0; i < nP; i++) P.push_back(SPair{pairs[2 * i], pairs[2 * i + 1]});
+  update(G, P, poly_from(f, nf), elim_of(elimination));
+  if ((int)P.size() > cap_pairs) return -1;
+  for (size_t i = 0; i < P.size(); i++) { pairs[2 * i] = P[i].i; pairs[2 * i + 1] = P[i].j; }
+  return P.size();
+}
+
+int ref_minimalize(const int* Gterms, const int* Glens, int nG, int* oterms, int cap_terms, int* olens, int cap_polys) {
+  return polys_to(minimalize(polys_from(Gterms, Glens, nG)), oterms, cap_terms, olens, cap_polys);
+}
+int ref_interreduce(const int* Gterms, const int* Glens, int nG, int* oterms, int cap_terms, int* olens, int cap_polys) {
+  return polys_to(interreduce(polys_from(Gterms, Glens, nG)), oterms, cap_terms, olens, cap_polys);
+}
+
+// full buchberger(F, ...) (buchberger.cpp:125-140); stats[5] = zero, nonzero, additions, total_reward, discounted_return
+int ref_buchberger(const int* Fterms, const int* Flens, int nF, int selection, int elimination, int rewards,
+                   int sort_input, int sort_reducers, double gamma, int seed, int* oterms, int cap_terms, int* olens,
+                   int cap_polys, double* stats) {
+  auto [G, st] = buchberger(polys_from(Fterms, Flens, nF), sel_of(selection), elim_of(elimination), rew_of(rewards),
+                            sort_input != 0, sort_reducers != 0, gamma, std::optional<int>(seed));
+  stats[0] = st.zero_reductions; stats[1] = st.nonzero_reductions; stats[2] = st.polynomial_additions;
+  stats[3] = st.total_reward; stats[4] = st.discounted_return;
+  return polys_to(G, oterms, cap_terms, olens, cap_polys);
+}
+
+// ---- L0': generators (ideals.cpp) ----
+void* ref_gen_create(const char* dist) {
+  try { return parse_ideal_dist(std::string(dist)).release(); } catch (...) { return nullptr; }
+}
+void ref_gen_destroy(void* g) { delete static_cast<IdealGenerator*>(g); }
+void ref_gen_seed(void* g, int seed) { static_cast<IdealGenerator*>(g)->seed(seed); }
+int ref_gen_nvars(void* g) { return static_cast<IdealGenerator*>(g)->nvars(); }
+int ref_gen_next(void* g, int* oterms, int cap_terms, int* olens, int cap_polys) {
+  try {
+    return polys_to(static_cast<IdealGenerator*>(g)->next(), oterms, cap_terms, olens, cap_polys);
+  } catch (...) { return -2; }
+}
+int ref_basis(int n, int d, int* out, int cap) {
+  auto B = basis(n, d);
+  if ((int)B.size() > cap) return -(int)B.size();
+  for (size_t i = 0; i < B.size(); i++) for (int k = 0; k < N; k++) out[i * N + k] = B[i][k];
+  return B.size();
+}
+int ref_degree_distribution(int n, int d, int dist, int constants, double* out, int cap) {
+  auto dd = degree_distribution(n, d, static_cast<DistributionType>(dist), constants != 0);
+  auto p = dd.probabilities();
+  if ((int)p.size() > cap) return -1;
+  for (size_t i = 0; i < p.size(); i++) out[i] = p[i];
+  return p.size();
+}
+int ref_cyclic(int n, int* oterms, int cap_terms, int* olens, int cap_polys) {
+  return polys_to(cyclic(n), oterms, cap_terms, olens, cap_polys);
+}
+
+// ---- L2: BuchbergerEnv (buchberger.cpp:269-351) ----
+void* ref_env_create(const char* dist, int elimination, int rewards, int sort_input, int sort_reducers) {
+  try { return new RefEnv(dist, elimination, rewards, sort_input != 0, sort_reducers != 0); } catch (...) { return nullptr; }
+}
+void ref_env_destroy(void* h) { delete static_cast<RefEnv*>(h); }
+void ref_env_seed(void* h, int seed) { static_cast<RefEnv*>(h)->env.seed(seed); }
+// analogue of passing FixedIdealGenerator(F) to the Python env (buchberger.py:389-394)
+void ref_env_set_ideal(void* h, const int* terms, const int* lens, int npoly) {
+  static_cast<RefEnv*>(h)->env.ideal_gen = std::make_unique<FixedIdealGenerator>(polys_from(terms, lens, npoly));
+}
+int ref_env_nvars(void* h) { return static_cast<RefEnv*>(h)->env.nvars(); }
+void ref_env_reset(void* h) { static_cast<RefEnv*>(h)->env.reset(); }
+double ref_env_step(void* h, int i, int j) { return static_cast<RefEnv*>(h)->env.step(SPair{i, j}); }
+int ref_env_npairs(void* h) { return static_cast<RefEnv*>(h)->env.P.size(); }
+int ref_env_nbasis(void* h) { return static_cast<RefEnv*>(h)->env.G.size(); }
+int ref_env_nterms(void* h) {
+  int n = 0;
+  for (const auto& g : static_cast<RefEnv*>(h)->env.G) n += g.size();
+  return n;
+}
+int ref_env_pairs(void* h, int* pairs, int cap) {
+  auto& P = static_cast<RefEnv*>(h)->env.P;
+  if ((int)P.size() > cap) return -1;
+  for (size_t i = 0; i < P.size(); i++) { pairs[2 * i] = P[i].i; pairs[2 * i + 1] = P[i].j; }
+  return P.size();
+}
+int ref_env_basis(void* h, int* oterms, int cap_terms, int* olens, int cap_polys) {
+  return polys_to(static_cast<RefEnv*>(h)->env.G, oterms, cap_terms, olens, cap_polys);
+}
+int ref_env_reducers(void* h, int* oterms, int cap_terms, int* olens, int cap_polys) {
+  return polys_to(static_cast<RefEnv*>(h)->env.G_, oterms, cap_terms, olens, cap_polys);
+}
+double ref_env_value(void* h, const char* strategy, double gamma) {
+  return static_cast<RefEnv*>(h)->env.value(std::string(strategy), gamma);
+}
+int ref_env_select(void* h, int selection) {
+  auto& e = static_cast<RefEnv*>(h)->env;
+  return select_row(e.G, e.P, selection);
+}
+int ref_env_final_gb(void* h, int* oterms, int cap_terms, int* olens, int cap_polys) {
+  return polys_to(interreduce(minimalize(static_cast<RefEnv*>(h)->env.G)), oterms, cap_terms, olens, cap_polys);
+}
+
+// Run one episode from the env's CURRENT state (after reset) to completion.
+//   selection >= 0 : on-the-fly First/Degree/Normal/Sugar row choice (comparators of buchberger.cpp:160-241)
+//   selection <  0 : replay `actions` (row indices into P, as LeadMonomialsEnv::step(int) takes them)
+// trace rows: (i, j, additions = -reward under Additions, |P| after, |G| after); returns number of steps or -1.
+int ref_env_run(void* h, int selection, const int* actions, int nactions, int* trace, int cap_steps) {
+  auto& e = static_cast<RefEnv*>(h)->env;
+  int t = 0;
+  while (!e.P.empty()) {
+    int row;
+    if (selection >= 0) row = select_row(e.G, e.P, selection);
+    else { if (t >= nactions) break; row = actions[t]; }
+    if (row < 0 || row >= (int)e.P.size()) return -2;
+    SPair p = e.P[row];
+    double reward = e.step(p);
+    if (t >= cap_steps) return -1;
+    trace[5 * t + 0] = p.i; trace[5 * t + 1] = p.j; trace[5 * t + 2] = (int)(-reward);
+    trace[5 * t + 3] = e.P.size(); trace[5 * t + 4] = e.G.size();
+    t++;
+  }
+  return t;
+}
+
+// ---- L2: LeadMonomialsEnv (buchberger.cpp:373-408) exactly as wrapped.pyx drives it ----
+void* ref_lm_create(const char* dist, int sort_input, int sort_reducers, int k) {
+  try { return new LeadMonomialsEnv(dist, sort_input != 0, sort_reducers != 0, k); } catch (...) { return nullptr; }
+}
+void ref_lm_destroy(void* h) { delete static_cast<LeadMonomialsEnv*>(h); }
+void ref_lm_seed(void* h, int seed) { static_cast<LeadMonomialsEnv*>(h)->seed(seed); }
+void ref_lm_set_ideal(void* h, const int* terms, const int* lens, int npoly, int nvars) {
+  auto* e = static_cast<LeadMonomialsEnv*>(h);
+  e->env.ideal_gen = std::make_unique<FixedIdealGenerator>(polys_from(terms, lens, npoly));
+  if (nvars > 0) { e->n = nvars; e->cols = 2 * nvars * e->k; }  // quirk Q1: stock nvars() is off by one
+}
+void ref_lm_reset(void* h) { static_cast<LeadMonomialsEnv*>(h)->reset(); }
+double ref_lm_step(void* h, int action) { return static_cast<LeadMonomialsEnv*>(h)->step(action); }
+int ref_lm_cols(void* h) { return static_cast<LeadMonomialsEnv*>(h)->cols; }
+int ref_lm_state(void* h, int* out, int cap) {
+  auto& s = static_cast<LeadMonomialsEnv*>(h)->state;
+  if ((int)s.size() > cap) return -(int)s.size();
+  std::copy(s.begin(), s.end(), out);
+  return s.size();
+}
+double ref_lm_value(void* h, const char* strategy, double gamma) {
+  return static_cast<LeadMonomialsEnv*>(h)->value(std::string(strategy), gamma);
+}
+
+// ---- CPU baseline drivers (timed inside, multi-threaded: one independent env per thread) ----
+//
+// Workload "episodes to completion under a built-in selection": per episode e in [seed0, seed0+count):
+//   env.seed(e); env.reset(); then select/step until P is empty (the env API the GPU path replaces).
+// out[0]=env steps, out[1]=polynomial additions, out[2]=seconds (wall, max over threads is the caller's wall).
+// with_matrix != 0 steps LeadMonomialsEnv(k) instead (state matrix rebuilt per step, as wrapped.pyx sees it)
+// and picks the action from the matrix-free comparator on the inner env.
+void ref_bench_selection(const char* dist, int selection, int seed0, int count, int nthreads, int with_matrix, int k,
+                         double* out) {
+  std::vector<long long> steps(nthreads, 0), adds(nthreads, 0);
+  auto t0 = std::chrono::steady_clock::now();
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthreads; t++) {
+    th.emplace_back([&, t]() {
+      if (with_matrix) {
+        LeadMonomialsEnv env{dist, false, true, k};
+        for (int e = seed0 + t; e < seed0 + count; e += nthreads) {
+          env.seed(e);
+          env.reset();
+          while (!env.env.P.empty()) {
+            int row = select_row(env.env.G, env.env.P, selection);
+            double r = env.step(row);
+            steps[t]++; adds[t] += (long long)(-r);
+          }
+        }
+      } else {
+        BuchbergerEnv env{dist};
+        for (int e = seed0 + t; e < seed0 + count; e += nthreads) {
+          env.seed(e);
+          env.reset();
+          while (!env.P.empty()) {
+            int row = select_row(env.G, env.P, selection);
+            double r = env.step(env.P[row]);
+            steps[t]++; adds[t] += (long long)(-r);
+          }
+        }
+      }
+    });
+  }
+  for (auto& x : th) x.join();
+  auto t1 = std::chrono::steady_clock::now();
+  long long S = 0, A = 0;
+  for (int t = 0; t < nthreads; t++) { S += steps[t]; A += adds[t]; }
+  out[0] = (double)S; out[1] = (double)A; out[2] = std::chrono::duration<double>(t1 - t0).count();
+}
+
+// Mirror of scripts/random_episodes.cpp:13-29 (uniform-random actions on LeadMonomialsEnv(dist,false,true,2)),
+// one env per thread, env seeded seed0+t, harness RNG minstd_rand0 default-seeded like the script.
+void ref_bench_random(const char* dist, int seed0, int episodes, int nthreads, double* out) {
+  std::vector<long long> steps(nthreads, 0);
+  std::vector<double> ret(nthreads, 0.0);
+  auto t0 = std::chrono::steady_clock::now();
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthreads; t++) {
+    th.emplace_back([&, t]() {
+      LeadMonomialsEnv env{dist, false, true, 2};
+      env.seed(seed0 + t);
+      std::default_random_engine rng;
+      for (int e = t; e < episodes; e += nthreads) {
+        env.reset();
+        while (env.state.size() != 0) {
+          std::uniform_int_distribution<int> ud{0, static_cast<int>(env.state.size() / env.cols) - 1};
+          int action = ud(rng);
+          ret[t] += env.step(action);
+          steps[t]++;
+        }
+      }
+    });
+  }
+  for (auto& x : th) x.join();
+  auto t1 = std::chrono::steady_clock::now();
+  long long S = 0; double R = 0;
+  for (int t = 0; t < nthreads; t++) { S += steps[t]; R += ret[t]; }
+  out[0] = (double)S; out[1] = -R; out[2] = std::chrono::duration<double>(t1 - t0).count();
+}
+
+}  // extern "C"
