@@ -1,0 +1,334 @@
+"""Vectorised Buchberger environments on B200: the reference's gym-style API over libbbenv.so.
+
+Mirrors ``deepgroebner.buchberger.BuchbergerEnv`` / ``LeadMonomialsEnv`` (buchberger.py:243-394, 448-542) and the
+Cython ``CLeadMonomialsEnv`` (wrapped.pyx:11-38): same constructor keywords, same ``reset()`` / ``step()`` /
+``seed()`` contract, same observation matrix, action index and reward semantics -- for ``num_envs`` independent
+episodes at once.  With ``num_envs=1`` the return values have the reference's shapes (a ``[len(P), 2nk]`` int32
+matrix, a float reward, a bool done).  PyTorch only carries device memory and the CUDA stream; every
+environment operation is a hand-written CUDA kernel behind the C-ABI in include/bbenv.h.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from .ideals import BinomialSpec, FixedIdealGenerator, parse_ideal_dist
+
+# arena capacities per environment: (max_basis, max_pairs, max_terms, max_poly_terms)
+CAPACITY_PRESETS = {
+    "binomial": dict(max_basis=512, max_pairs=1024, max_terms=1536, max_poly_terms=64),
+    "general": dict(max_basis=2048, max_pairs=8192, max_terms=1 << 18, max_poly_terms=4096),
+}
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class BuchbergerEngine:
+    """Owns one bb_handle (one GPU).  The two environment classes below are thin views over it."""
+
+    def __init__(self, ideal_dist="3-20-10-uniform", elimination="gebauermoeller", rewards="additions",
+                 sort_input=False, sort_reducers=True, k=1, num_envs=1, device="cuda:0", prime=32003,
+                 capacity=None, **caps):
+        self.lib = _lib.load()
+        if not torch.cuda.is_available():
+            raise _lib.BBError("no CUDA device: deepgroebner_b200 has no CPU fallback")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise ValueError("device must be a CUDA device")
+        self.spec = ideal_dist if isinstance(ideal_dist, (BinomialSpec, FixedIdealGenerator)) \
+            else parse_ideal_dist(ideal_dist, prime)
+        self.n = self.spec.n if isinstance(self.spec, BinomialSpec) else self.spec.nvars()
+        self.k, self.num_envs, self.prime = int(k), int(num_envs), int(prime)
+        self.elimination, self.rewards = elimination, rewards
+        preset = dict(CAPACITY_PRESETS[capacity or ("binomial" if isinstance(self.spec, BinomialSpec) else "general")])
+        preset.update(caps)
+        if isinstance(self.spec, BinomialSpec):
+            max_gens, max_gen_terms = self.spec.s, 2 * self.spec.s
+        else:
+            max_gens = len(self.spec.F)
+            max_gen_terms = sum(len(f) for f in self.spec.F)
+        cfg = _lib.BBConfig(
+            abi_version=_lib.BB_ABI_VERSION, device=self.device.index or 0, nvars=self.n, k=self.k, prime=self.prime,
+            elimination=_lib.ELIMINATION[elimination], rewards=_lib.REWARDS[rewards], sort_input=int(sort_input),
+            sort_reducers=int(sort_reducers), num_envs=self.num_envs, max_gens=max(max_gens, 1),
+            max_gen_terms=max(max_gen_terms, 1), **preset)
+        self.caps = preset
+        h = C.c_void_p()
+        rc = self.lib.bb_create(C.byref(cfg), C.byref(h))
+        if rc < 0:
+            raise _lib.BBError("bb_create failed (%d): %s" % (rc, self.lib.bb_last_error(None).decode()))
+        self.h = h
+        self.cols = self.lib.bb_cols(self.h)
+        self.sm_count = self.lib.bb_sm_count(self.h)
+        if isinstance(self.spec, BinomialSpec):
+            s = self.spec
+            self._ck(self.lib.bb_set_distribution(self.h, s.d, s.s, _lib.DISTRIBUTION[s.dist], int(s.constants),
+                                                  int(s.homogeneous), int(s.pure)), "bb_set_distribution")
+        else:
+            self.set_ideals([self.spec.F] * self.num_envs)
+
+    def __del__(self):
+        h = getattr(self, "h", None)
+        if h:
+            self.lib.bb_destroy(h)
+            self.h = None
+
+    def _ck(self, rc, what):
+        return _lib.check(self.lib, self.h, rc, what)
+
+    # ---- inputs
+    def seed(self, seed=None):
+        """seed(int): environment e gets stream seed + e (num_envs=1: exactly BuchbergerEnv.seed);
+        seed(sequence): explicit per-environment seeds."""
+        if seed is None:
+            return
+        if np.ndim(seed) == 0:
+            self._ck(self.lib.bb_seed(self.h, None, int(seed)), "bb_seed")
+        else:
+            a = np.ascontiguousarray(seed, dtype=np.int32)
+            assert a.shape == (self.num_envs,)
+            self._ck(self.lib.bb_seed(self.h, a.ctypes.data_as(C.POINTER(C.c_int32)), 0), "bb_seed")
+
+    def set_ideals(self, ideals, env_ids=None):
+        """ideals: list (one per environment) of lists of polynomials [(coef, exps), ...]."""
+        n = self.n
+        ideal_off, poly_off, exps, coefs = [0], [0], [], []
+        for F in ideals:
+            for f in F:
+                for c, e in f:
+                    e = tuple(e)[:n] + (0,) * max(0, n - len(e))
+                    exps.extend(int(x) for x in e)
+                    coefs.append(int(c))
+                poly_off.append(len(coefs))
+            ideal_off.append(len(poly_off) - 1)
+        ip = C.POINTER(C.c_int32)
+        a_io, a_po = np.asarray(ideal_off, np.int32), np.asarray(poly_off, np.int32)
+        a_e, a_c = np.asarray(exps, np.int32), np.asarray(coefs, np.int32)
+        ids = None if env_ids is None else np.ascontiguousarray(env_ids, np.int32)
+        self._ck(self.lib.bb_set_ideals(self.h, None if ids is None else ids.ctypes.data_as(ip), len(ideals),
+                                        a_io.ctypes.data_as(ip), a_po.ctypes.data_as(ip), a_e.ctypes.data_as(ip),
+                                        a_c.ctypes.data_as(ip)), "bb_set_ideals")
+
+    # ---- the step path (all device-side, asynchronous on the current torch stream)
+    def reset(self, mask=None):
+        with torch.cuda.device(self.device):
+            if mask is not None:
+                mask = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            self._ck(self.lib.bb_reset(self.h, _ptr(mask), _stream()), "bb_reset")
+
+    def step(self, actions, reward=None, done=None):
+        with torch.cuda.device(self.device):
+            actions = torch.as_tensor(actions, device=self.device).to(torch.int32).contiguous().view(-1)
+            assert actions.numel() == self.num_envs
+            if reward is None:
+                reward = torch.empty(self.num_envs, dtype=torch.float64, device=self.device)
+            if done is None:
+                done = torch.empty(self.num_envs, dtype=torch.uint8, device=self.device)
+            self._ck(self.lib.bb_step(self.h, _ptr(actions), _ptr(reward), _ptr(done), _stream()), "bb_step")
+        return reward, done
+
+    def select(self, strategy="degree", out=None):
+        with torch.cuda.device(self.device):
+            if out is None:
+                out = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
+            self._ck(self.lib.bb_select(self.h, _lib.SELECTION[strategy], _ptr(out), _stream()), "bb_select")
+        return out
+
+    def lengths(self):
+        with torch.cuda.device(self.device):
+            out = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
+            self._ck(self.lib.bb_observe(self.h, None, _ptr(out), 0, _stream()), "bb_observe")
+        return out
+
+    def observe(self, pmax, obs=None, lengths=None):
+        with torch.cuda.device(self.device):
+            if obs is None:
+                obs = torch.empty((self.num_envs, pmax, self.cols), dtype=torch.int32, device=self.device)
+            if lengths is None:
+                lengths = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
+            self._ck(self.lib.bb_observe(self.h, _ptr(obs), _ptr(lengths), int(pmax), _stream()), "bb_observe")
+        return obs, lengths
+
+    def pairs(self, pmax):
+        with torch.cuda.device(self.device):
+            out = torch.empty((self.num_envs, pmax, 2), dtype=torch.int32, device=self.device)
+            lengths = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
+            self._ck(self.lib.bb_pairs(self.h, _ptr(out), _ptr(lengths), int(pmax), _stream()), "bb_pairs")
+        return out, lengths
+
+    def status(self):
+        with torch.cuda.device(self.device):
+            out = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
+            self._ck(self.lib.bb_status(self.h, _ptr(out), _stream()), "bb_status")
+        return out
+
+    def stats(self):
+        """Running per-environment episode records as a numpy structured array (synchronises)."""
+        with torch.cuda.device(self.device):
+            buf = torch.empty(self.num_envs * C.sizeof(_lib.BBEpisodeStats), dtype=torch.uint8, device=self.device)
+            self._ck(self.lib.bb_stats(self.h, _ptr(buf), _stream()), "bb_stats")
+            return buf.cpu().numpy().view(np.dtype(_lib.STATS_DTYPE))
+
+    # ---- whole episodes
+    def run_episodes(self, strategy="degree", episodes=None, seed_base=0, seeds=None, max_steps=0, gamma=0.99,
+                     compute_gb=False, trace_episodes=0, trace_cap=0, to_host=True):
+        """Runs `episodes` episodes to completion with on-device selection (bb_run).  Returns (stats, trace):
+        stats is a structured array of bb_episode_stats (numpy if to_host else a uint8 cuda tensor), trace an
+        int32 [trace_episodes, trace_cap, 4] array of (i, j, additions, |P| after), -1 padded."""
+        episodes = self.num_envs if episodes is None else int(episodes)
+        with torch.cuda.device(self.device):
+            buf = torch.empty(max(episodes, 1) * C.sizeof(_lib.BBEpisodeStats), dtype=torch.uint8, device=self.device)
+            trace = None
+            if trace_episodes > 0 and trace_cap > 0:
+                trace = torch.full((trace_episodes, trace_cap, 4), -1, dtype=torch.int32, device=self.device)
+            d_seeds = None
+            if seeds is not None:
+                d_seeds = torch.as_tensor(np.ascontiguousarray(seeds, np.int32), device=self.device)
+                assert d_seeds.numel() == episodes
+            self._ck(self.lib.bb_run(self.h, _lib.SELECTION[strategy], episodes, int(seed_base), _ptr(d_seeds),
+                                     int(max_steps), float(gamma), int(bool(compute_gb)), _ptr(buf), _ptr(trace),
+                                     int(trace_episodes), int(trace_cap), _stream()), "bb_run")
+            if not to_host:
+                return buf, trace
+            stats = buf.cpu().numpy().view(np.dtype(_lib.STATS_DTYPE))[:episodes]
+            return stats, (trace.cpu().numpy() if trace is not None else None)
+
+    # ---- host views
+    def _polys_out(self, fn, env, what):
+        cap_p, cap_t = self.caps["max_basis"], self.caps["max_terms"]
+        lens = np.zeros(cap_p, np.int32)
+        exps = np.zeros(cap_t * self.n, np.int32)
+        coefs = np.zeros(cap_t, np.int32)
+        nt = C.c_int(0)
+        ip = C.POINTER(C.c_int32)
+        with torch.cuda.device(self.device):
+            torch.cuda.current_stream().synchronize()
+            np_ = self._ck(fn(self.h, int(env), lens.ctypes.data_as(ip), cap_p, exps.ctypes.data_as(ip),
+                              coefs.ctypes.data_as(ip), cap_t, C.byref(nt)), what)
+        out, t = [], 0
+        E = exps.reshape(-1, self.n)
+        for q in range(np_):
+            out.append([(int(coefs[t + r]), tuple(int(x) for x in E[t + r])) for r in range(lens[q])])
+            t += int(lens[q])
+        return out
+
+    def basis(self, env=0):
+        """G of one environment in insertion order: [[(coef, exps), ...], ...] (BuchbergerEnv.G)."""
+        return self._polys_out(self.lib.bb_download_basis, env, "bb_download_basis")
+
+    def final_gb(self, env=0):
+        """interreduce(minimalize(G)) computed on device (buchberger.cpp:102-122, 265)."""
+        return self._polys_out(self.lib.bb_final_gb, env, "bb_final_gb")
+
+    def counters(self, reset=False):
+        c = _lib.BBCounters()
+        self._ck(self.lib.bb_counters_read(self.h, C.byref(c), int(reset)), "bb_counters_read")
+        return c.as_dict()
+
+
+class LeadMonomialsEnv:
+    """A BuchbergerEnv whose state is the matrix of the pairs' lead monomials (buchberger.py:448-542).
+
+    Extra keywords over the reference: ``num_envs`` (N independent episodes), ``device``, ``pmax`` (row capacity
+    of the batched observation; default max_pairs).  Returns for N == 1 match the reference exactly; for N > 1:
+    ``reset() -> (obs[N, pmax, 2nk] int32 padded with -1, lengths[N])``,
+    ``step(actions[N]) -> ((obs, lengths), reward[N] float64, done[N] bool, {})``.
+    """
+
+    def __init__(self, ideal_dist="3-20-10-uniform", elimination="gebauermoeller", rewards="additions",
+                 sort_input=False, sort_reducers=True, k=1, dtype=np.int32, num_envs=1, device="cuda:0", pmax=None,
+                 **engine_kwargs):
+        self.engine = BuchbergerEngine(ideal_dist, elimination, rewards, sort_input, sort_reducers, k, num_envs,
+                                       device, **engine_kwargs)
+        self.k, self.dtype, self.num_envs = k, dtype, num_envs
+        self.pmax = int(pmax) if pmax else self.engine.caps["max_pairs"]
+
+    def seed(self, seed=None):
+        self.engine.seed(seed)
+
+    def _state(self):
+        if self.num_envs == 1:
+            n = int(self.engine.lengths().item())
+            obs, _ = self.engine.observe(max(n, 1))
+            return obs[0, :n].cpu().numpy().astype(self.dtype)
+        return self.engine.observe(self.pmax)
+
+    def reset(self):
+        self.engine.reset()
+        return self._state()
+
+    def step(self, action):
+        reward, done = self.engine.step(action)
+        state = self._state()
+        if self.num_envs == 1:
+            return state, float(reward.item()), bool(done.item()), {}
+        return state, reward, done.bool(), {}
+
+    def value(self, strategy="degree", gamma=0.99):
+        raise NotImplementedError("value() from a live state needs slot forking (SURVEY 8(f) row 2); "
+                                  "use BuchbergerEngine.run_episodes for whole-episode rollouts")
+
+
+class BuchbergerEnv:
+    """Buchberger's algorithm as an environment (buchberger.py:243-394): state (G, P), action a pair (i, j).
+
+    For N == 1 ``reset()`` returns ``(G, P)`` with G a list of polynomials ``[(coef, exps), ...]`` (downloaded
+    from the device) and P a list of pairs; for N > 1 the state is ``(pairs[N, pmax, 2], lengths[N])`` and G is
+    available per environment through ``basis(env)``.  Coefficients are those of the reference's C++ env (basis
+    elements are not made monic)."""
+
+    def __init__(self, ideal_dist="3-20-10-uniform", elimination="gebauermoeller", rewards="additions",
+                 sort_input=False, sort_reducers=True, num_envs=1, device="cuda:0", pmax=None, **engine_kwargs):
+        self.engine = BuchbergerEngine(ideal_dist, elimination, rewards, sort_input, sort_reducers, 1, num_envs,
+                                       device, **engine_kwargs)
+        self.num_envs = num_envs
+        self.pmax = int(pmax) if pmax else self.engine.caps["max_pairs"]
+
+    def seed(self, seed=None):
+        self.engine.seed(seed)
+
+    def basis(self, env=0):
+        return self.engine.basis(env)
+
+    def _state(self):
+        if self.num_envs == 1:
+            n = int(self.engine.lengths().item())
+            pairs, _ = self.engine.pairs(max(n, 1))
+            P = [tuple(int(x) for x in row) for row in pairs[0, :n].cpu().numpy()]
+            return self.engine.basis(0), P
+        return self.engine.pairs(self.pmax)
+
+    def reset(self):
+        self.engine.reset()
+        return self._state()
+
+    def step(self, action):
+        """action: a pair (i, j) (N == 1) or an int tensor [N, 2]."""
+        pairs, lengths = self.engine.pairs(self.pmax)
+        a = torch.as_tensor(action, device=pairs.device).to(torch.int32).view(self.num_envs, 1, 2)
+        hit = (pairs == a).all(-1)
+        rows = torch.where(hit.any(1), hit.int().argmax(1), torch.full_like(lengths, -1)).to(torch.int32)
+        if self.num_envs == 1 and int(rows.item()) < 0:
+            raise ValueError("pair %r is not in the pair set" % (tuple(action),))
+        reward, done = self.engine.step(rows)
+        state = self._state()
+        if self.num_envs == 1:
+            return state, float(reward.item()), bool(done.item()), {}
+        return state, reward, done.bool(), {}
+
+
+class BuchbergerAgent:
+    """First / Degree / Normal selection computed on device (buchberger.py:397-439, buchberger.cpp:165-186)."""
+
+    def __init__(self, selection="normal"):
+        self.strategy = selection
+
+    def act(self, env):
+        return env.engine.select(self.strategy)

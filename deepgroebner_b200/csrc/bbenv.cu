@@ -1,0 +1,638 @@
+// bbenv.cu -- kernels and the extern "C" ABI (include/bbenv.h) of libbbenv.so.  sm_100a only.
+//
+// Kernels (one warp per environment slot, 8 warps per CTA):
+//   k_reset    BuchbergerEnv::reset          buchberger.cpp:299-315  (+ on-device ideal generator, ideals.cpp:168-201)
+//   k_step     LeadMonomialsEnv::step(int)   buchberger.cpp:398-408 -> :318-329 (spoly, reduce, update, insert)
+//   k_select   First/Degree/Normal           buchberger.cpp:165-186
+//   k_observe  state matrix                  buchberger.cpp:354-370, 402-406
+//   k_run      persistent: episodes pulled from a queue and run to completion with on-device selection
+//              (the loop of buchberger(), buchberger.cpp:243-263); finished slots refill at once.
+//   k_final_gb interreduce(minimalize(G))    buchberger.cpp:102-122
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bb_device.cuh"
+
+#define BB_WARPS 8
+#define BB_THREADS (BB_WARPS * 32)
+
+// ------------------------------------------------------------------------------------------------ counters
+__device__ __forceinline__ void counters_flush(const BBParams& P, const WarpCounters& ct, unsigned long long* sh) {
+  // warp -> CTA (shared atomics) -> one global atomic per CTA and counter
+  if (threadIdx.x < CT_COUNT) sh[threadIdx.x] = 0ull;
+  __syncthreads();
+  if (bb_lane() == 0) {
+#pragma unroll
+    for (int i = 0; i < CT_COUNT; i++)
+      if (ct.v[i]) atomicAdd(&sh[i], ct.v[i]);
+  }
+  __syncthreads();
+  if (threadIdx.x < CT_COUNT && sh[threadIdx.x]) atomicAdd(&P.counters[threadIdx.x], sh[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------------ kernels
+__global__ void __launch_bounds__(BB_THREADS) k_seed(BBParams P, const int* seeds, int base) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < P.num_envs) P.st[e].rng = rng_seed(seeds ? seeds[e] : base + e);
+}
+
+__global__ void __launch_bounds__(BB_THREADS) k_reset(BBParams P, const uint8_t* mask) {
+  __shared__ unsigned long long sh[CT_COUNT];
+  const int slot = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
+  WarpCounters ct; ct.clear();
+  if (slot < P.num_envs && (!mask || mask[slot])) {
+    Env e; env_bind(P, slot, e);
+    BBEnvState& S = P.st[slot];
+    unsigned long long rng = S.rng;
+    int rerolls = 0;
+    warp_reset(P, slot, slot, e, rng, rerolls, ct);
+    if (bb_lane() == 0) {
+      S.rng = rng; S.rerolls = rerolls;
+      S.steps = 0; S.adds = 0; S.zero = 0; S.nonzero = 0; S.truncated = 0;
+      S.trace_hash = 0; S.disc_return = 0.0; S.discount = 1.0;
+    }
+    env_store(P, slot, e);
+  }
+  counters_flush(P, ct, sh);
+}
+
+__global__ void __launch_bounds__(BB_THREADS) k_step(BBParams P, const int* __restrict__ actions,
+                                                     double* __restrict__ reward, uint8_t* __restrict__ done) {
+  __shared__ unsigned long long sh[CT_COUNT];
+  const int slot = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
+  WarpCounters ct; ct.clear();
+  if (slot < P.num_envs) {
+    Env e; env_load(P, slot, e);
+    double r = 0.0;
+    if (e.status == BB_STATUS_RUNNING) {
+      int pi, pj;
+      int adds = warp_step(P, e, actions[slot], &pi, &pj, ct);
+      if (pi >= 0) {
+        r = (P.rewards == BB_REWARD_ADDITIONS) ? -(double)adds : -1.0;
+        if (bb_lane() == 0) {
+          BBEnvState& S = P.st[slot];
+          S.trace_hash += trace_hash_item(pi, pj, adds, S.steps);
+          S.steps += 1; S.adds += adds;
+          if (e.nG > S.nG) S.nonzero += 1; else S.zero += 1;
+        }
+      }
+      env_store(P, slot, e);
+    }
+    if (bb_lane() == 0) {
+      if (reward) reward[slot] = r;
+      if (done) done[slot] = (e.status != BB_STATUS_RUNNING) ? 1 : 0;
+    }
+  }
+  counters_flush(P, ct, sh);
+}
+
+__global__ void __launch_bounds__(BB_THREADS) k_select(BBParams P, int strategy, int* __restrict__ actions) {
+  const int slot = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
+  if (slot >= P.num_envs) return;
+  Env e; env_load(P, slot, e);
+  int a = (e.status == BB_STATUS_RUNNING) ? warp_select(P, e, strategy) : 0;
+  if (bb_lane() == 0) actions[slot] = a;
+}
+
+__global__ void __launch_bounds__(BB_THREADS) k_observe(BBParams P, int32_t* __restrict__ obs,
+                                                        int32_t* __restrict__ lengths, int pmax) {
+  __shared__ unsigned long long sh[CT_COUNT];
+  const int slot = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
+  WarpCounters ct; ct.clear();
+  if (slot < P.num_envs) {
+    Env e; env_load(P, slot, e);
+    if (obs) warp_observe(P, e, obs + (size_t)slot * pmax * P.cols, pmax, ct);
+    if (lengths && bb_lane() == 0) lengths[slot] = e.nP;
+  }
+  counters_flush(P, ct, sh);
+}
+
+__global__ void __launch_bounds__(BB_THREADS) k_pairs(BBParams P, int32_t* __restrict__ out,
+                                                      int32_t* __restrict__ lengths, int pmax) {
+  const int slot = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
+  if (slot >= P.num_envs) return;
+  Env e; env_load(P, slot, e);
+  int32_t* o = out + (size_t)slot * pmax * 2;
+  for (int r = bb_lane(); r < pmax; r += 32) {
+    int i = -1, j = -1;
+    if (r < e.nP) { uint32_t pr = e.pairs[r]; i = pr & 0xffffu; j = pr >> 16; }
+    o[2 * r] = i; o[2 * r + 1] = j;
+  }
+  if (lengths && bb_lane() == 0) lengths[slot] = e.nP;
+}
+
+__global__ void __launch_bounds__(BB_THREADS) k_status(BBParams P, int32_t* status, bb_episode_stats* stats) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= P.num_envs) return;
+  const BBEnvState& S = P.st[e];
+  if (status) status[e] = S.status;
+  if (stats) {
+    bb_episode_stats o;
+    memset(&o, 0, sizeof o);
+    o.steps = S.steps; o.additions = S.adds; o.zero_reductions = S.zero; o.nonzero_reductions = S.nonzero;
+    o.nbasis = S.nG; o.nterms = S.nT; o.status = S.status; o.rerolls = S.rerolls;
+    o.trace_hash = S.trace_hash; o.discounted_return = S.disc_return;
+    stats[e] = o;
+  }
+}
+
+__global__ void __launch_bounds__(32) k_final_gb(BBParams P, int slot, int* ok_out) {
+  WarpCounters ct; ct.clear();
+  Env e; env_load(P, slot, e);
+  bool ok = warp_final_gb(P, slot, e, ct);
+  if (bb_guard_tripped(P.L, e.guard)) ok = false;
+  if (bb_lane() == 0) *ok_out = ok ? 1 : 0;
+}
+
+// Persistent episode runner.  Each warp owns slot = its global warp index and loops: pop an episode, reset from
+// that episode's stream, select/step until P is empty (or max_steps), write the episode record, repeat.
+__global__ void __launch_bounds__(BB_THREADS) k_run(BBParams P, int strategy, int episodes, int seed_base,
+                                                    const int* __restrict__ seeds, int max_steps, double gamma,
+                                                    int compute_gb, bb_episode_stats* __restrict__ out,
+                                                    int32_t* __restrict__ trace, int trace_eps, int trace_cap,
+                                                    int* queue) {
+  __shared__ unsigned long long sh[CT_COUNT];
+  const int slot = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
+  const int lane = bb_lane();
+  WarpCounters ct; ct.clear();
+  if (slot < P.num_envs) {
+    Env e; env_bind(P, slot, e);
+    e.nG = e.nP = e.nT = 0; e.status = BB_STATUS_EMPTY;
+    const int nstaged = P.num_envs;
+    int last_steps = 0, last_adds = 0, last_zero = 0, last_nonzero = 0, last_rerolls = 0;
+    unsigned long long last_hash = 0; double last_ret = 0.0;
+    for (;;) {
+      int ep = 0;
+      if (lane == 0) ep = atomicAdd(queue, 1);
+      ep = __shfl_sync(BB_FULL, ep, 0);
+      if (ep >= episodes) break;
+      unsigned long long rng = rng_seed(seeds ? seeds[ep] : seed_base + ep);
+      int rerolls = 0;
+      // fixed ideals: episode ep replays the ideal staged for slot (ep mod N), read in place (staging is immutable)
+      warp_reset(P, slot, ep % nstaged, e, rng, rerolls, ct);
+      int steps = 0, adds = 0, zero = 0, nonzero = 0;
+      unsigned long long th = 0;
+      double ret = 0.0, disc = 1.0;
+      while (e.status == BB_STATUS_RUNNING && (max_steps == 0 || steps < max_steps)) {
+        const int row = warp_select(P, e, strategy);
+        const int g0 = e.nG;
+        int pi, pj;
+        const int a = warp_step(P, e, row, &pi, &pj, ct);
+        th += trace_hash_item(pi, pj, a, steps);
+        const double r = (P.rewards == BB_REWARD_ADDITIONS) ? -(double)a : -1.0;
+        ret += disc * r; disc *= gamma;
+        if (trace && ep < trace_eps && steps < trace_cap && lane == 0)
+          reinterpret_cast<int4*>(trace)[(size_t)ep * trace_cap + steps] = make_int4(pi, pj, a, e.nP);
+        steps++; adds += a;
+        if (e.nG > g0) nonzero++; else zero++;
+      }
+      ct.v[CT_EPISODES]++;
+      const unsigned long long bh = warp_terms_hash(P.L, e.tkey, e.tcoef, e.nT, nullptr, e.pmeta, e.nG);
+      unsigned long long gh = 0; int gp = 0, gt = 0;
+      if (compute_gb && e.status == BB_STATUS_DONE) {
+        if (warp_final_gb(P, slot, e, ct) && !bb_guard_tripped(P.L, e.guard)) {
+          gp = P.gcount[2 * slot]; gt = P.gcount[2 * slot + 1];
+          gh = warp_terms_hash(P.L, P.gkey + (size_t)slot * P.max_terms, P.gcoef + (size_t)slot * P.max_terms, gt,
+                               P.glen + (size_t)slot * P.max_basis, nullptr, gp);
+        } else {
+          e.status = BB_STATUS_OVERFLOW_SCRATCH;
+        }
+      }
+      if (lane == 0) {
+        bb_episode_stats o;
+        o.steps = steps; o.additions = adds; o.zero_reductions = zero; o.nonzero_reductions = nonzero;
+        o.nbasis = e.nG; o.nterms = e.nT; o.status = e.status; o.rerolls = rerolls;
+        o.trace_hash = th; o.basis_hash = bh; o.gb_hash = gh; o.gb_polys = gp; o.gb_terms = gt;
+        o.discounted_return = ret;
+        out[ep] = o;
+      }
+      last_steps = steps; last_adds = adds; last_zero = zero; last_nonzero = nonzero; last_rerolls = rerolls;
+      last_hash = th; last_ret = ret;
+    }
+    env_store(P, slot, e);
+    if (lane == 0) {
+      BBEnvState& S = P.st[slot];
+      S.steps = last_steps; S.adds = last_adds; S.zero = last_zero; S.nonzero = last_nonzero;
+      S.rerolls = last_rerolls; S.trace_hash = last_hash; S.disc_return = last_ret;
+    }
+  }
+  counters_flush(P, ct, sh);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct bb_handle {
+  bb_config cfg;
+  BBParams P;
+  int sm_count;
+  std::vector<void*> allocs;
+  std::string err;
+  int* d_queue;
+  int* d_ok;
+  // host mirrors of the distribution tables
+  std::vector<double> cp;
+};
+
+static thread_local std::string g_create_err;
+
+static int fail(bb_handle* h, const std::string& msg, int code = -1) {
+  if (h) h->err = msg; else g_create_err = msg;
+  return code;
+}
+#define CK(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t _e = (call);                                                                          \
+    if (_e != cudaSuccess)                                                                            \
+      return fail(h, std::string(#call) + ": " + cudaGetErrorString(_e), -2);                         \
+  } while (0)
+
+template <class T>
+static cudaError_t dev_alloc(bb_handle* h, T** p, size_t count) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, count * sizeof(T) + 16);
+  if (e != cudaSuccess) return e;
+  h->allocs.push_back(q);
+  *p = (T*)q;
+  return cudaMemset(q, 0, count * sizeof(T) + 16);
+}
+
+static inline int grid_for_warps(int nwarps) { return (nwarps + BB_WARPS - 1) / BB_WARPS; }
+
+extern "C" {
+
+int bb_abi_version(void) { return BB_ABI_VERSION; }
+
+const char* bb_last_error(const bb_handle* h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+int bb_cols(const bb_handle* h) { return h->P.cols; }
+int bb_num_envs(const bb_handle* h) { return h->P.num_envs; }
+int bb_sm_count(const bb_handle* h) { return h->sm_count; }
+uint64_t bb_hash_item(uint64_t x, uint64_t pos) { return bb_hash_item_impl(x, pos); }
+
+void bb_destroy(bb_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->cfg.device);
+  for (void* p : h->allocs) cudaFree(p);
+  delete h;
+}
+
+int bb_create(const bb_config* cfg, bb_handle** out) {
+  bb_handle* h = nullptr;
+  if (!cfg || !out) return fail(h, "bb_create: null argument");
+  if (cfg->abi_version != BB_ABI_VERSION) return fail(h, "bb_create: ABI version mismatch");
+  if (cfg->nvars < 1 || cfg->nvars > 8) return fail(h, "bb_create: nvars must be in 1..8");
+  if (cfg->prime < 3 || cfg->prime > 65535) return fail(h, "bb_create: prime must be in 3..65535");
+  for (int q = 2; q * q <= cfg->prime; q++)
+    if (cfg->prime % q == 0) return fail(h, "bb_create: prime is not prime");
+  if (cfg->k < 1) return fail(h, "bb_create: k must be >= 1");
+  if (cfg->num_envs < 1) return fail(h, "bb_create: num_envs must be >= 1");
+  if (cfg->max_basis < 2 || cfg->max_basis > 65535) return fail(h, "bb_create: max_basis must be in 2..65535");
+  if (cfg->max_pairs < 1 || cfg->max_pairs > 65536) return fail(h, "bb_create: max_pairs must be in 1..65536");
+  if (cfg->max_terms < 2 || cfg->max_poly_terms < 1 || cfg->max_gens < 1 || cfg->max_gen_terms < 1)
+    return fail(h, "bb_create: capacities must be positive");
+  if (cfg->max_gens > cfg->max_basis) return fail(h, "bb_create: max_gens exceeds max_basis");
+  if ((unsigned)cfg->elimination > 2u || (unsigned)cfg->rewards > 1u) return fail(h, "bb_create: bad enum value");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(h, "bb_create: no CUDA device available (this library has no CPU fallback)", -3);
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(h, "bb_create: bad device ordinal");
+  h = new bb_handle();
+  h->cfg = *cfg;
+  h->d_queue = nullptr; h->d_ok = nullptr;
+  auto bail = [&](int code) { g_create_err = h->err; bb_destroy(h); return code; };
+#define CKC(call)                                                                                     \
+  do {                                                                                                \
+    cudaError_t _e = (call);                                                                          \
+    if (_e != cudaSuccess) { h->err = std::string(#call) + ": " + cudaGetErrorString(_e); return bail(-2); } \
+  } while (0)
+  CKC(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CKC(cudaGetDeviceProperties(&prop, cfg->device));
+  h->sm_count = prop.multiProcessorCount;
+  BBParams& P = h->P;
+  memset(&P, 0, sizeof P);
+  P.L = bb_make_layout(cfg->nvars, (uint32_t)cfg->prime);
+  P.num_envs = cfg->num_envs; P.k = cfg->k; P.cols = 2 * cfg->nvars * cfg->k;
+  P.elimination = cfg->elimination; P.rewards = cfg->rewards;
+  P.sort_input = cfg->sort_input ? 1 : 0; P.sort_reducers = cfg->sort_reducers ? 1 : 0;
+  P.max_basis = cfg->max_basis; P.max_pairs = cfg->max_pairs; P.max_terms = cfg->max_terms;
+  P.max_poly_terms = cfg->max_poly_terms; P.max_gens = cfg->max_gens; P.max_gen_terms = cfg->max_gen_terms;
+  const size_t N = (size_t)cfg->num_envs;
+  CKC(dev_alloc(h, &P.tkey, N * P.max_terms));
+  CKC(dev_alloc(h, &P.tcoef, N * P.max_terms));
+  CKC(dev_alloc(h, &P.pmeta, N * P.max_basis));
+  CKC(dev_alloc(h, &P.lm, N * P.max_basis));
+  CKC(dev_alloc(h, &P.invlc, N * P.max_basis));
+  CKC(dev_alloc(h, &P.rlm, N * P.max_basis));
+  CKC(dev_alloc(h, &P.ridx, N * P.max_basis));
+  CKC(dev_alloc(h, &P.pairs, N * P.max_pairs));
+  CKC(dev_alloc(h, &P.hkey, N * 2 * P.max_poly_terms));
+  CKC(dev_alloc(h, &P.hcoef, N * 2 * P.max_poly_terms));
+  CKC(dev_alloc(h, &P.lscr, N * P.max_basis));
+  CKC(dev_alloc(h, &P.st, N));
+  CKC(dev_alloc(h, &P.in_key, N * P.max_gen_terms));
+  CKC(dev_alloc(h, &P.in_coef, N * P.max_gen_terms));
+  CKC(dev_alloc(h, &P.in_off, N * (P.max_gens + 1)));
+  CKC(dev_alloc(h, &P.in_np, N));
+  CKC(dev_alloc(h, &P.gkey, N * P.max_terms));
+  CKC(dev_alloc(h, &P.gcoef, N * P.max_terms));
+  CKC(dev_alloc(h, &P.glen, N * P.max_basis));
+  CKC(dev_alloc(h, &P.gcount, N * 2));
+  CKC(dev_alloc(h, &P.grlm, N * P.max_basis));
+  CKC(dev_alloc(h, &P.gridx, N * P.max_basis));
+  CKC(dev_alloc(h, &P.gflag, N * P.max_basis));
+  CKC(dev_alloc(h, &P.counters, (size_t)CT_COUNT));
+  CKC(dev_alloc(h, &h->d_queue, (size_t)4));
+  CKC(dev_alloc(h, &h->d_ok, (size_t)4));
+  k_seed<<<(cfg->num_envs + BB_THREADS - 1) / BB_THREADS, BB_THREADS>>>(P, nullptr, 0);
+  CKC(cudaGetLastError());
+  CKC(cudaDeviceSynchronize());
+#undef CKC
+  *out = h;
+  return 0;
+}
+
+// binomial(n,k) as ideals.cpp:67-72 computes it
+static long long binom(int n, int k) {
+  if (k < 0 || k > n) return 0;
+  long long r = 1;
+  for (int i = 1; i <= k; i++) r = r * (n - k + i) / i;
+  return r;
+}
+// basis(n,d) order (ideals.cpp:39-64: permutations of d stars then n-1 bars == lex-descending exponent vectors)
+static void basis_rec(const BBLayout& L, int n, int var, int left, int* e, std::vector<uint64_t>& out) {
+  if (var == n - 1) { e[var] = left; out.push_back(bb_pack(L, e)); return; }
+  for (int x = left; x >= 0; x--) { e[var] = x; basis_rec(L, n, var + 1, left - x, e, out); }
+}
+
+int bb_set_distribution(bb_handle* h, int d, int s, int dist, int constants, int homogeneous, int pure) {
+  if (!h) return -1;
+  BBParams& P = h->P;
+  if (d < 0 || s < 1) return fail(h, "bb_set_distribution: need d >= 0 and s >= 1");
+  if (s > P.max_gens || 2 * s > P.max_gen_terms) return fail(h, "bb_set_distribution: s exceeds max_gens/max_gen_terms");
+  if ((unsigned)dist > 2u) return fail(h, "bb_set_distribution: bad dist");
+  if ((unsigned)d > P.L.emax || (unsigned)d > P.L.dmax) return fail(h, "bb_set_distribution: degree does not fit the packed layout");
+  CK(cudaSetDevice(h->cfg.device));
+  const int n = P.L.n;
+  // degree_distribution counts (ideals.cpp:75-100)
+  std::vector<double> prob;
+  prob.push_back(constants ? 1.0 : 0.0);
+  if (dist == BB_DIST_UNIFORM) for (int i = 1; i <= d; i++) prob.push_back((double)binom(n + i - 1, n - 1));
+  else if (dist == BB_DIST_WEIGHTED) for (int i = 0; i < d; i++) prob.push_back(1.0);
+  else { for (int i = 0; i < d - 1; i++) prob.push_back(0.0); if (d >= 1) prob.push_back(1.0); }
+  // std::discrete_distribution::param_type::_M_initialize (bits/random.tcc:2657-2678)
+  std::vector<double> cp;
+  if (prob.size() >= 2) {
+    double sum = 0.0;
+    for (double x : prob) sum += x;
+    if (!(sum > 0.0)) return fail(h, "bb_set_distribution: empty degree distribution");
+    for (double& x : prob) x /= sum;
+    double acc = 0.0;
+    for (size_t i = 0; i < prob.size(); i++) { acc = (i == 0) ? prob[0] : acc + prob[i]; cp.push_back(acc); }
+    cp.back() = 1.0;
+  }
+  h->cp = cp;
+  std::vector<uint64_t> basis; std::vector<int> off;
+  for (int deg = 0; deg <= d; deg++) {
+    off.push_back((int)basis.size());
+    int e[8] = {0};
+    basis_rec(P.L, n, 0, deg, e, basis);
+  }
+  off.push_back((int)basis.size());
+  double* d_cp = nullptr; uint64_t* d_basis = nullptr; int* d_off = nullptr;
+  CK(dev_alloc(h, &d_cp, cp.size() + 1));
+  CK(dev_alloc(h, &d_basis, basis.size() + 1));
+  CK(dev_alloc(h, &d_off, off.size()));
+  if (!cp.empty()) CK(cudaMemcpy(d_cp, cp.data(), cp.size() * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_basis, basis.data(), basis.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(d_off, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice));
+  P.dist.enabled = 1; P.dist.d = d; P.dist.s = s; P.dist.homogeneous = homogeneous ? 1 : 0; P.dist.pure = pure ? 1 : 0;
+  P.dist.ncp = (int)cp.size(); P.dist.cp = d_cp; P.dist.basis = d_basis; P.dist.basis_off = d_off;
+  return 0;
+}
+
+int bb_seed(bb_handle* h, const int32_t* seeds, int base) {
+  if (!h) return -1;
+  CK(cudaSetDevice(h->cfg.device));
+  int* d_seeds = nullptr;
+  if (seeds) {
+    CK(cudaMalloc(&d_seeds, sizeof(int) * (size_t)h->P.num_envs));
+    CK(cudaMemcpy(d_seeds, seeds, sizeof(int) * (size_t)h->P.num_envs, cudaMemcpyHostToDevice));
+  }
+  k_seed<<<(h->P.num_envs + BB_THREADS - 1) / BB_THREADS, BB_THREADS>>>(h->P, d_seeds, base);
+  cudaError_t e1 = cudaGetLastError(), e2 = cudaDeviceSynchronize();
+  if (d_seeds) cudaFree(d_seeds);
+  CK(e1); CK(e2);
+  return 0;
+}
+
+int bb_set_ideals(bb_handle* h, const int32_t* env_ids, int count, const int32_t* ideal_offsets,
+                  const int32_t* poly_offsets, const int32_t* exps, const int32_t* coefs) {
+  if (!h) return -1;
+  BBParams& P = h->P;
+  if (count < 0 || !ideal_offsets || !poly_offsets || !exps || !coefs) return fail(h, "bb_set_ideals: null argument");
+  CK(cudaSetDevice(h->cfg.device));
+  const int n = P.L.n;
+  std::vector<uint64_t> keys((size_t)P.max_gen_terms);
+  std::vector<uint32_t> cf((size_t)P.max_gen_terms);
+  std::vector<int> off((size_t)P.max_gens + 1);
+  for (int c = 0; c < count; c++) {
+    const int env = env_ids ? env_ids[c] : c;
+    if (env < 0 || env >= P.num_envs) return fail(h, "bb_set_ideals: environment index out of range");
+    const int p0 = ideal_offsets[c], p1 = ideal_offsets[c + 1];
+    const int np = p1 - p0;
+    if (np < 1 || np > P.max_gens) return fail(h, "bb_set_ideals: number of generators outside 1..max_gens");
+    int nt = 0;
+    off[0] = 0;
+    for (int q = 0; q < np; q++) {
+      const int t0 = poly_offsets[p0 + q], t1 = poly_offsets[p0 + q + 1];
+      const int len = t1 - t0;
+      if (len < 1) return fail(h, "bb_set_ideals: the zero polynomial is not a valid generator");
+      if (nt + len > P.max_gen_terms) return fail(h, "bb_set_ideals: ideal exceeds max_gen_terms");
+      std::vector<std::pair<uint64_t, uint32_t>> terms;
+      for (int t = t0; t < t1; t++) {
+        uint32_t deg = 0;
+        for (int v = 0; v < n; v++) {
+          int x = exps[(size_t)t * n + v];
+          if (x < 0 || (uint32_t)x > P.L.emax) return fail(h, "bb_set_ideals: exponent does not fit the packed layout");
+          deg += (uint32_t)x;
+        }
+        if (deg > P.L.dmax) return fail(h, "bb_set_ideals: degree does not fit the packed layout");
+        long long cc = coefs[t] % (long long)P.L.p;
+        if (cc < 0) cc += P.L.p;
+        if (cc == 0) return fail(h, "bb_set_ideals: zero coefficient");
+        terms.push_back({bb_pack(P.L, exps + (size_t)t * n), (uint32_t)cc});
+      }
+      std::stable_sort(terms.begin(), terms.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
+      for (size_t t = 1; t < terms.size(); t++)
+        if (terms[t].first == terms[t - 1].first) return fail(h, "bb_set_ideals: repeated monomial in a generator");
+      for (auto& tm : terms) { keys[nt] = tm.first; cf[nt] = tm.second; nt++; }
+      off[q + 1] = nt;
+    }
+    CK(cudaMemcpy(P.in_key + (size_t)env * P.max_gen_terms, keys.data(), sizeof(uint64_t) * nt, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(P.in_coef + (size_t)env * P.max_gen_terms, cf.data(), sizeof(uint32_t) * nt, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(P.in_off + (size_t)env * (P.max_gens + 1), off.data(), sizeof(int) * (np + 1), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(P.in_np + env, &np, sizeof(int), cudaMemcpyHostToDevice));
+  }
+  P.dist.enabled = 0;
+  return 0;
+}
+
+int bb_reset(bb_handle* h, const uint8_t* mask_dev, void* stream) {
+  if (!h) return -1;
+  CK(cudaSetDevice(h->cfg.device));
+  k_reset<<<grid_for_warps(h->P.num_envs), BB_THREADS, 0, (cudaStream_t)stream>>>(h->P, mask_dev);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int bb_step(bb_handle* h, const int32_t* actions_dev, double* reward_dev, uint8_t* done_dev, void* stream) {
+  if (!h) return -1;
+  if (!actions_dev) return fail(h, "bb_step: null actions");
+  CK(cudaSetDevice(h->cfg.device));
+  k_step<<<grid_for_warps(h->P.num_envs), BB_THREADS, 0, (cudaStream_t)stream>>>(h->P, actions_dev, reward_dev, done_dev);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int bb_select(bb_handle* h, int strategy, int32_t* actions_dev, void* stream) {
+  if (!h) return -1;
+  if ((unsigned)strategy > 2u || !actions_dev) return fail(h, "bb_select: bad argument");
+  CK(cudaSetDevice(h->cfg.device));
+  k_select<<<grid_for_warps(h->P.num_envs), BB_THREADS, 0, (cudaStream_t)stream>>>(h->P, strategy, actions_dev);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int bb_observe(bb_handle* h, int32_t* obs_dev, int32_t* lengths_dev, int pmax, void* stream) {
+  if (!h) return -1;
+  if (pmax < 0 || (obs_dev && pmax == 0)) return fail(h, "bb_observe: bad pmax");
+  CK(cudaSetDevice(h->cfg.device));
+  k_observe<<<grid_for_warps(h->P.num_envs), BB_THREADS, 0, (cudaStream_t)stream>>>(h->P, obs_dev, lengths_dev, pmax);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int bb_pairs(bb_handle* h, int32_t* pairs_dev, int32_t* lengths_dev, int pmax, void* stream) {
+  if (!h) return -1;
+  if (!pairs_dev || pmax < 1) return fail(h, "bb_pairs: bad argument");
+  CK(cudaSetDevice(h->cfg.device));
+  k_pairs<<<grid_for_warps(h->P.num_envs), BB_THREADS, 0, (cudaStream_t)stream>>>(h->P, pairs_dev, lengths_dev, pmax);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int bb_status(bb_handle* h, int32_t* status_dev, void* stream) {
+  if (!h) return -1;
+  CK(cudaSetDevice(h->cfg.device));
+  k_status<<<(h->P.num_envs + BB_THREADS - 1) / BB_THREADS, BB_THREADS, 0, (cudaStream_t)stream>>>(h->P, status_dev, nullptr);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int bb_stats(bb_handle* h, bb_episode_stats* stats_dev, void* stream) {
+  if (!h) return -1;
+  CK(cudaSetDevice(h->cfg.device));
+  k_status<<<(h->P.num_envs + BB_THREADS - 1) / BB_THREADS, BB_THREADS, 0, (cudaStream_t)stream>>>(h->P, nullptr, stats_dev);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int bb_run(bb_handle* h, int strategy, int episodes, int seed_base, const int32_t* seeds_dev, int max_steps,
+           double gamma, int compute_gb, bb_episode_stats* stats_dev, int32_t* trace_dev, int trace_episodes,
+           int trace_cap, void* stream) {
+  if (!h) return -1;
+  if ((unsigned)strategy > 2u || episodes < 0 || !stats_dev) return fail(h, "bb_run: bad argument");
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int), s));
+  int workers = h->P.num_envs < episodes ? h->P.num_envs : episodes;
+  if (workers < 1) return 0;
+  k_run<<<grid_for_warps(workers), BB_THREADS, 0, s>>>(h->P, strategy, episodes, seed_base, seeds_dev, max_steps, gamma,
+                                                      compute_gb, stats_dev, trace_dev, trace_dev ? trace_episodes : 0,
+                                                      trace_cap, h->d_queue);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+static int unpack_polys(bb_handle* h, const std::vector<uint64_t>& keys, const std::vector<uint32_t>& cf,
+                        const std::vector<int>& plen, int32_t* lens, int cap_polys, int32_t* exps, int32_t* coefs,
+                        int cap_terms, int* nterms_out) {
+  const BBLayout& L = h->P.L;
+  int np = (int)plen.size(), nt = 0;
+  for (int q = 0; q < np; q++) nt += plen[q];
+  if (nterms_out) *nterms_out = nt;
+  if (np > cap_polys || nt > cap_terms) return fail(h, "output buffers too small", -4);
+  for (int q = 0; q < np; q++) lens[q] = plen[q];
+  for (int t = 0; t < nt; t++) {
+    coefs[t] = (int32_t)cf[t];
+    for (int v = 0; v < L.n; v++) exps[(size_t)t * L.n + v] = (int32_t)bb_exp(L, keys[t], v);
+  }
+  return np;
+}
+
+int bb_download_basis(bb_handle* h, int env, int32_t* lens, int cap_polys, int32_t* exps, int32_t* coefs,
+                      int cap_terms, int* nterms_out) {
+  if (!h) return -1;
+  BBParams& P = h->P;
+  if (env < 0 || env >= P.num_envs) return fail(h, "bb_download_basis: environment index out of range");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaDeviceSynchronize());
+  BBEnvState S;
+  CK(cudaMemcpy(&S, P.st + env, sizeof S, cudaMemcpyDeviceToHost));
+  std::vector<uint2> meta((size_t)std::max(S.nG, 1));
+  std::vector<uint64_t> keys((size_t)std::max(S.nT, 1));
+  std::vector<uint32_t> cf((size_t)std::max(S.nT, 1));
+  if (S.nG) CK(cudaMemcpy(meta.data(), P.pmeta + (size_t)env * P.max_basis, sizeof(uint2) * S.nG, cudaMemcpyDeviceToHost));
+  if (S.nT) {
+    CK(cudaMemcpy(keys.data(), P.tkey + (size_t)env * P.max_terms, sizeof(uint64_t) * S.nT, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(cf.data(), P.tcoef + (size_t)env * P.max_terms, sizeof(uint32_t) * S.nT, cudaMemcpyDeviceToHost));
+  }
+  // polynomials are stored back to back in insertion order
+  std::vector<int> plen;
+  for (int q = 0; q < S.nG; q++) plen.push_back((int)meta[q].y);
+  return unpack_polys(h, keys, cf, plen, lens, cap_polys, exps, coefs, cap_terms, nterms_out);
+}
+
+int bb_final_gb(bb_handle* h, int env, int32_t* lens, int cap_polys, int32_t* exps, int32_t* coefs, int cap_terms,
+                int* nterms_out) {
+  if (!h) return -1;
+  BBParams& P = h->P;
+  if (env < 0 || env >= P.num_envs) return fail(h, "bb_final_gb: environment index out of range");
+  CK(cudaSetDevice(h->cfg.device));
+  k_final_gb<<<1, 32>>>(P, env, h->d_ok);
+  CK(cudaGetLastError());
+  CK(cudaDeviceSynchronize());
+  int ok = 0, cnt[2] = {0, 0};
+  CK(cudaMemcpy(&ok, h->d_ok, sizeof(int), cudaMemcpyDeviceToHost));
+  if (!ok) return fail(h, "bb_final_gb: arena overflow while interreducing", -5);
+  CK(cudaMemcpy(cnt, P.gcount + 2 * (size_t)env, sizeof cnt, cudaMemcpyDeviceToHost));
+  std::vector<int> plen((size_t)cnt[0]);
+  std::vector<uint64_t> keys((size_t)std::max(cnt[1], 1));
+  std::vector<uint32_t> cf((size_t)std::max(cnt[1], 1));
+  if (cnt[0]) CK(cudaMemcpy(plen.data(), P.glen + (size_t)env * P.max_basis, sizeof(int) * cnt[0], cudaMemcpyDeviceToHost));
+  if (cnt[1]) {
+    CK(cudaMemcpy(keys.data(), P.gkey + (size_t)env * P.max_terms, sizeof(uint64_t) * cnt[1], cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(cf.data(), P.gcoef + (size_t)env * P.max_terms, sizeof(uint32_t) * cnt[1], cudaMemcpyDeviceToHost));
+  }
+  return unpack_polys(h, keys, cf, plen, lens, cap_polys, exps, coefs, cap_terms, nterms_out);
+}
+
+int bb_counters_read(bb_handle* h, bb_counters* out, int reset) {
+  if (!h || !out) return -1;
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaDeviceSynchronize());
+  unsigned long long v[CT_COUNT];
+  CK(cudaMemcpy(v, h->P.counters, sizeof v, cudaMemcpyDeviceToHost));
+  out->env_steps = v[CT_STEPS]; out->additions = v[CT_ADDS]; out->terms_read = v[CT_TREAD];
+  out->terms_written = v[CT_TWRITE]; out->lms_scanned = v[CT_LMS]; out->term_moves = v[CT_MOVES];
+  out->update_basis = v[CT_UPB]; out->update_pairs = v[CT_UPP]; out->obs_rows = v[CT_OBS];
+  out->nonzero_reductions = v[CT_NONZERO]; out->zero_reductions = v[CT_ZERO]; out->episodes = v[CT_EPISODES];
+  if (reset) CK(cudaMemset(h->P.counters, 0, sizeof v));
+  return 0;
+}
+
+}  // extern "C"

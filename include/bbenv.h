@@ -1,0 +1,196 @@
+/*
+ * bbenv.h -- C-ABI of libbbenv.so, the B200-native (sm_100a) batched Buchberger environment.
+ *
+ * This is the drop-in boundary for the reference's native environment, i.e. what the reference's
+ * Cython binding (deepgroebner/buchberger.pxd:8-18, deepgroebner/wrapped.pyx:11-38) binds today:
+ *
+ *   reference (one episode, host)                           this library (N episodes, device)
+ *   ------------------------------------------------------  -----------------------------------------
+ *   LeadMonomialsEnv(string,bint,bint,int) pxd:11           bb_create(cfg)  (+ bb_set_distribution)
+ *   ~LeadMonomialsEnv                                       bb_destroy
+ *   void seed(int)                       pxd:15             bb_seed
+ *   void reset()                         pxd:13             bb_reset / bb_set_ideals
+ *   double step(int)                     pxd:14             bb_step
+ *   vector[int] state, int cols          pxd:17-18          bb_observe, bb_cols
+ *   double value(string,double)          pxd:16             bb_run (First/Degree/Normal rollouts to completion)
+ *   LeadMonomialsEnv(const&)  (copy())   pxd:12             (next round: slot copy)
+ *   BuchbergerEnv::G, ::P   buchberger.h:195-196            bb_download_basis, bb_pairs
+ *   buchberger(...) -> interreduce(minimalize(G))           bb_final_gb
+ *       buchberger.cpp:265
+ *
+ * Conventions: plain pointers and sizes only (no torch types).  Every entry point returns 0 on success and a
+ * negative code otherwise; bb_last_error() gives the message.  Pointers named *_dev are DEVICE pointers in the
+ * handle's device; all others are HOST pointers.  Work is enqueued on `stream` (a cudaStream_t passed as
+ * void*; NULL = the legacy default stream); calls taking host output pointers synchronise that stream.
+ * A handle is single-owner and not thread-safe (the reference env has no threading either).  Per-environment
+ * faults (bad action, arena / exponent overflow) never abort: they set that environment's status word
+ * (BB_STATUS_*), the environment stops stepping and reports done.
+ */
+#ifndef BBENV_H
+#define BBENV_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BB_ABI_VERSION 1
+
+/* EliminationType, buchberger.h:58 */
+enum { BB_ELIM_GEBAUERMOELLER = 0, BB_ELIM_LCM = 1, BB_ELIM_NONE = 2 };
+/* RewardType, buchberger.h:93 */
+enum { BB_REWARD_ADDITIONS = 0, BB_REWARD_REDUCTIONS = 1 };
+/* SelectionType, buchberger.h:111 (the deterministic ones that need no per-polynomial sugar) */
+enum { BB_SELECT_FIRST = 0, BB_SELECT_DEGREE = 1, BB_SELECT_NORMAL = 2 };
+/* DistributionType, ideals.h:40 */
+enum { BB_DIST_UNIFORM = 0, BB_DIST_WEIGHTED = 1, BB_DIST_MAXIMUM = 2 };
+
+/* per-environment status word */
+enum {
+  BB_STATUS_EMPTY = 0,     /* slot holds no episode */
+  BB_STATUS_RUNNING = 1,   /* pair set non-empty */
+  BB_STATUS_DONE = 2,      /* pair set empty: episode finished */
+  BB_STATUS_BAD_ACTION = 3,/* action index outside [0, |P|)  (UB in the reference, buchberger.cpp:399) */
+  BB_STATUS_OVERFLOW_BASIS = 4,
+  BB_STATUS_OVERFLOW_PAIRS = 5,
+  BB_STATUS_OVERFLOW_TERMS = 6,
+  BB_STATUS_OVERFLOW_EXPONENT = 7, /* a packed exponent/degree field would wrap: never silently wrong */
+  BB_STATUS_OVERFLOW_SCRATCH = 8
+};
+
+typedef struct bb_config {
+  int abi_version;    /* BB_ABI_VERSION */
+  int device;         /* CUDA device ordinal */
+  int nvars;          /* n, 1..8 (polynomials.h:29 fixes 8 exponent slots) */
+  int k;              /* lead monomials shown per polynomial (buchberger.h:224-231); cols = 2*n*k */
+  int prime;          /* field characteristic, 2 < p < 65536 (reference: 32003, polynomials.h:10) */
+  int elimination;    /* BB_ELIM_* */
+  int rewards;        /* BB_REWARD_* */
+  int sort_input;     /* buchberger.cpp:301-302 */
+  int sort_reducers;  /* buchberger.cpp:308-311, 323-326 */
+  int num_envs;       /* N environment slots */
+  int max_basis;      /* capacity |G| per env  (<= 65535) */
+  int max_pairs;      /* capacity |P| per env */
+  int max_terms;      /* capacity of the term arena per env (sum of |g| over G) */
+  int max_poly_terms; /* capacity of the dividend scratch (longest intermediate polynomial) */
+  int max_gens;       /* capacity of generators per input ideal */
+  int max_gen_terms;  /* capacity of terms per input ideal */
+} bb_config;
+
+typedef struct bb_handle bb_handle;
+
+/* Work/traffic counters accumulated by the kernels (SURVEY 8(d) algorithmic-bytes model). */
+typedef struct bb_counters {
+  unsigned long long env_steps;        /* step() transitions executed */
+  unsigned long long additions;        /* polynomial additions as the reward counts them (1 per spoly + 1 per reduction) */
+  unsigned long long terms_read;       /* |h_in| + |f| (+|g|) over all additions */
+  unsigned long long terms_written;    /* |h_out| over all additions */
+  unsigned long long lms_scanned;      /* reducer lead monomials examined by divisor searches */
+  unsigned long long term_moves;       /* lead terms moved to the remainder */
+  unsigned long long update_basis;     /* sum of m over update() calls */
+  unsigned long long update_pairs;     /* |P| before + |P_new| over update() calls */
+  unsigned long long obs_rows;         /* observation rows written */
+  unsigned long long nonzero_reductions;
+  unsigned long long zero_reductions;
+  unsigned long long episodes;         /* episodes finished */
+} bb_counters;
+
+/* Per-episode record written by bb_run / kept per slot (BuchbergerStats, buchberger.h:99-105, plus checksums). */
+typedef struct bb_episode_stats {
+  int32_t steps;               /* episode length */
+  int32_t additions;           /* polynomial_additions  (= -total_reward under Additions) */
+  int32_t zero_reductions;
+  int32_t nonzero_reductions;
+  int32_t nbasis;              /* |G| at the end */
+  int32_t nterms;              /* sum of |g| at the end */
+  int32_t status;              /* BB_STATUS_* */
+  int32_t rerolls;             /* ideals skipped by reset() because P came out empty (buchberger.cpp:313-314) */
+  uint64_t trace_hash;         /* checksum of the (i, j, additions) sequence, see "checksums" below */
+  uint64_t basis_hash;         /* checksum of the final basis G (all terms, in insertion order) */
+  uint64_t gb_hash;            /* checksum of interreduce(minimalize(G)) when bb_run(compute_gb=1), else 0 */
+  int32_t gb_polys, gb_terms;  /* its size */
+  double discounted_return;    /* sum gamma^t * reward_t (buchberger.cpp:250-251) */
+} bb_episode_stats;
+
+int bb_abi_version(void);
+
+/* ---- lifetime */
+int bb_create(const bb_config* cfg, bb_handle** out);
+void bb_destroy(bb_handle* h);
+const char* bb_last_error(const bb_handle* h); /* h may be NULL: last error of bb_create */
+int bb_cols(const bb_handle* h);               /* 2*n*k, LeadMonomialsEnv::cols */
+int bb_num_envs(const bb_handle* h);
+int bb_sm_count(const bb_handle* h);
+
+/* ---- input ideals
+ * bb_set_distribution: the analogue of parse_ideal_dist("n-d-s-{uniform,weighted,maximum}[-consts][-homog][-pure]")
+ * (ideals.cpp:103-143) for RandomBinomialIdealGenerator; n must equal cfg.nvars.  Ideals are then drawn ON DEVICE by
+ * bb_reset from per-environment minstd_rand0 streams that reproduce libstdc++'s distributions bit-for-bit.
+ * bb_seed: stream[e] <- seeds[e] for every environment (BuchbergerEnv::seed, buchberger.h:189); seeds == NULL
+ * seeds environment e with base + e. */
+int bb_set_distribution(bb_handle* h, int d, int s, int dist, int constants, int homogeneous, int pure);
+int bb_seed(bb_handle* h, const int32_t* seeds, int base);
+
+/* bb_set_ideals: explicit ideals, the analogue of FixedIdealGenerator (ideals.h:116-138; buchberger.py:389-394).
+ *   count          number of ideals; ideal c goes to environment env_ids[c] (env_ids == NULL: environment c)
+ *   ideal_offsets  [count+1]   polynomial index range of each ideal
+ *   poly_offsets   [npolys+1]  term index range of each polynomial
+ *   exps           [nterms*n]  exponent vectors;  coefs [nterms] in [0,p).  Terms of a polynomial may come in any
+ *                  order (they are sorted like the Polynomial ctor, polynomials.cpp:139-145) but must be distinct.
+ * The ideals are staged; bb_reset loads them (every reset of that environment replays the same ideal). */
+int bb_set_ideals(bb_handle* h, const int32_t* env_ids, int count, const int32_t* ideal_offsets,
+                  const int32_t* poly_offsets, const int32_t* exps, const int32_t* coefs);
+
+/* ---- the environment (BuchbergerEnv::reset/step, buchberger.cpp:299-329)
+ * bb_reset: mask_dev (uint8[N], NULL = all) selects the environments to reset. */
+int bb_reset(bb_handle* h, const uint8_t* mask_dev, void* stream);
+/* bb_step: actions_dev int32[N] row indices into each environment's pair list (LeadMonomialsEnv::step(int),
+ * buchberger.cpp:398-408).  reward_dev double[N] (-(1+steps) or -1), done_dev uint8[N] (|P| == 0).  Environments
+ * that are not RUNNING are skipped (reward 0, done 1). */
+int bb_step(bb_handle* h, const int32_t* actions_dev, double* reward_dev, uint8_t* done_dev, void* stream);
+/* bb_select: built-in pair selection (buchberger.cpp:165-186; ties -> first in P): actions_dev int32[N]. */
+int bb_select(bb_handle* h, int strategy, int32_t* actions_dev, void* stream);
+/* bb_observe: obs_dev int32[N, pmax, cols] padded with -1 (pg.py:217-226), lengths_dev int32[N] = |P|
+ * (lead_monomials_vector rows, buchberger.cpp:354-370, 402-406).  Rows beyond pmax are dropped (lengths keeps |P|). */
+int bb_observe(bb_handle* h, int32_t* obs_dev, int32_t* lengths_dev, int pmax, void* stream);
+/* bb_pairs: pairs_dev int32[N, pmax, 2] = (i, j), padded with -1; lengths_dev int32[N]. */
+int bb_pairs(bb_handle* h, int32_t* pairs_dev, int32_t* lengths_dev, int pmax, void* stream);
+/* bb_status / bb_stats: status_dev int32[N]; stats_dev bb_episode_stats[N] (running totals of the current episode) */
+int bb_status(bb_handle* h, int32_t* status_dev, void* stream);
+int bb_stats(bb_handle* h, bb_episode_stats* stats_dev, void* stream);
+
+/* ---- whole episodes on device (the loop of buchberger(), buchberger.cpp:243-263, per environment)
+ * bb_run: runs `episodes` episodes to completion with on-device selection.  The handle's N slots act as workers that
+ * pull episode e = 0..episodes-1 from a queue (finished slots are refilled at once, so warps stay full); episode e
+ * draws its ideal from stream seed = seed_base + e (or seeds_dev[e]) when a distribution is set, or replays staged
+ * ideal (e mod staged count).  stats_dev bb_episode_stats[episodes].  trace_dev (optional) int32[trace_episodes,
+ * trace_cap, 4] = (i, j, additions, |P| after) for the first trace_episodes episodes, -1 padded.
+ * max_steps truncates an episode (0 = unlimited); gamma feeds discounted_return. */
+int bb_run(bb_handle* h, int strategy, int episodes, int seed_base, const int32_t* seeds_dev, int max_steps,
+           double gamma, int compute_gb, bb_episode_stats* stats_dev, int32_t* trace_dev, int trace_episodes,
+           int trace_cap, void* stream);
+
+/* ---- host views (synchronising)
+ * bb_download_basis: basis G of environment env in insertion order: lens[npoly], exps[nterms*n], coefs[nterms].
+ * Returns the number of polynomials, or <0; *nterms_out receives the number of terms. */
+int bb_download_basis(bb_handle* h, int env, int32_t* lens, int cap_polys, int32_t* exps, int32_t* coefs,
+                      int cap_terms, int* nterms_out);
+/* bb_final_gb: interreduce(minimalize(G)) (buchberger.cpp:102-122, 265) of environment env computed ON DEVICE,
+ * ascending lead monomial, monic.  Same output convention as bb_download_basis. */
+int bb_final_gb(bb_handle* h, int env, int32_t* lens, int cap_polys, int32_t* exps, int32_t* coefs, int cap_terms,
+                int* nterms_out);
+int bb_counters_read(bb_handle* h, bb_counters* out, int reset);
+
+/* ---- checksums (so a host-side checker can recompute them from an oracle's episode)
+ * item(x, pos) = splitmix64_finalizer(x + 0x9E3779B97F4A7C15 * (pos + 1));  all sums are mod 2^64.
+ *   trace_hash = sum over steps t of item(i | j<<16 | additions<<32, t)
+ *   basis_hash / gb_hash = sum over terms t (flattened over the polynomial list, in order) of
+ *        item(coef, 3t) + item(e0 | e1<<16 | e2<<32 | e3<<48, 3t+1) + item(e4 | e5<<16 | e6<<32 | e7<<48, 3t+2)
+ *      + sum over polynomials q of splitmix64_finalizer(len_q + 0xD1B54A32D192ED03 * (q + 1)) */
+uint64_t bb_hash_item(uint64_t x, uint64_t pos);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BBENV_H */
