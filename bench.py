@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s of the batched Buchberger environment on B200 (BASELINE.json metric), beside the
+reference's own CPU environment.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            this repo's CUDA path
+  python bench.py --impl reference [--steps K] [--warmup W]      the unmodified reference on the host cores
+
+Workload (BASELINE.json configs[1]): 3-20-10-weighted, 16384 episodes per GPU run to completion under Degree
+selection; episode e draws its ideal from the reference generator stream seed(e).  One bench "step" = one pass of
+the hot path over that batch = one launch of the persistent episode kernel (reset + select + spoly + reduce +
+update for every step of every episode).  `value` = env steps / device time with the inputs (seeds) resident in
+HBM; `e2e` = the same through BuchbergerEngine.run_episodes with HOST buffers (pinned seeds H2D, episode records
+D2H, inside the timed region).  The oracle / reference is only ever used here as the cpu_baseline leg, the
+`--impl reference` arm and a post-run spot check -- never inside a timed GPU region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DIST = "3-20-10-weighted"
+STRATEGY = "degree"
+EPISODES = 16384
+METRIC = "env_steps_per_sec"
+UNIT = "env-steps/s"
+
+
+def algorithmic_bytes(c):
+    """12 B per term read/written by an addition, 8 B per reducer lead monomial examined,
+    24 B per lead term moved to the remainder, 8 B per basis / pair entry touched by update()."""
+    return (12 * (c["terms_read"] + c["terms_written"]) + 8 * c["lms_scanned"] + 24 * c["term_moves"]
+            + 8 * (c["update_basis"] + c["update_pairs"]))
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of k_run from the committed ncu --set full capture, if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        try:
+            return json.load(open(p)).get("k_run_dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.unlink(self.f.name)
+        except OSError:
+            pass
+        if sm:
+            sm.sort()
+            out.update(sm_mhz=sm[len(sm) // 2], sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def load_cpu_oracle():
+    from oracle import oracle as O
+    if O.have_ref():
+        return O.load_ref(), "reference"
+    return O.load_port(), "port"
+
+
+def cpu_sample(orc, kind, seconds, threads):
+    """Times the reference env (reset + Degree select + step to completion) on `threads` host threads over a
+    bounded sample of the SAME workload (episodes seed 0..count-1), sized for about `seconds` of wall time."""
+    if kind != "reference":
+        threads = 1  # the C restatement is single-threaded
+    probe = orc.bench_selection(DIST, STRATEGY, 0, 64 * threads, nthreads=threads)
+    rate = probe["steps"] / max(probe["seconds"], 1e-9)
+    steps_per_ep = probe["steps"] / (64.0 * threads)
+    count = int(min(EPISODES, max(64 * threads, seconds * rate / steps_per_ep)))
+    if count > EPISODES // 2:
+        count = EPISODES  # the whole workload fits the budget: no sampling at all
+    r = orc.bench_selection(DIST, STRATEGY, 0, count, nthreads=threads)
+    return r, count, threads
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    orc, kind = load_cpu_oracle()
+    threads = host_threads()
+    # each step = the first `count` episodes of the workload, sized for ~4 s per step
+    probe, count, threads = cpu_sample(orc, kind, 4.0, threads)
+    for _ in range(args.warmup):
+        orc.bench_selection(DIST, STRATEGY, 0, max(count // 8, threads), nthreads=threads)
+    steps = adds = 0
+    secs = 0.0
+    for _ in range(args.steps):
+        r = orc.bench_selection(DIST, STRATEGY, 0, count, nthreads=threads)
+        steps += r["steps"]; adds += r["additions"]; secs += r["seconds"]
+    value = steps / secs
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1000.0 * secs / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32 (GF(32003) coefficients, int exponent vectors)",
+        "data": "synthetic (reference RandomBinomialIdealGenerator, env seed e for episode e)",
+        "config": {"workload": "%s, %s selection, episodes to completion; bounded sample: episodes 0..%d of %d per step"
+                               % (DIST, STRATEGY, count - 1, EPISODES), "episodes_per_step": count,
+                   "host_threads": threads},
+        "additions_per_sec": adds / secs,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
+                         "sample": "%d episodes (seeds 0..%d) x %d steps, one BuchbergerEnv per thread, "
+                                   "env.seed(e); reset(); Degree select + step until P empty" % (count, count - 1, args.steps)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def gpu_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from deepgroebner_b200 import _lib
+    from deepgroebner_b200.buchberger import BuchbergerEngine, resident_envs
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+
+    slots = args.slots or resident_envs(local)
+    eng = BuchbergerEngine(DIST, num_envs=slots, device="cuda:%d" % local)
+    seed_base = rank * EPISODES  # weak scaling: every rank runs its own 16384 episodes, disjoint seeds
+    seeds_host = torch.arange(seed_base, seed_base + EPISODES, dtype=torch.int32).pin_memory()
+    seeds_dev = seeds_host.to(dev)
+    stats_bytes = EPISODES * 72
+    stats_dev = torch.empty(stats_bytes, dtype=torch.uint8, device=dev)
+    stats_host = torch.empty(stats_bytes, dtype=torch.uint8).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    import ctypes as C
+    lib = eng.lib
+
+    def launch(gb):
+        rc = lib.bb_run(eng.h, _lib.SELECTION[STRATEGY], EPISODES, 0, C.c_void_p(seeds_dev.data_ptr()), 0, 0.99, gb,
+                        C.c_void_p(stats_dev.data_ptr()), None, 0, 0,
+                        C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        if rc < 0:
+            raise RuntimeError(lib.bb_last_error(eng.h))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(max(args.warmup, 3)):
+        flush.fill_(1)
+        launch(0)
+    torch.cuda.synchronize()
+    eng.counters(reset=True)
+
+    # ---- device-timed region: K launches, L2 flushed between them (flush outside the event pairs)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    wall0 = time.perf_counter()
+    for a, b in ev:
+        flush.fill_(1)
+        a.record()
+        launch(0)
+        b.record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if sampler else None
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    counters = eng.counters(reset=True)
+    stats = stats_dev.cpu().numpy().view(np.dtype(_lib.STATS_DTYPE))
+    assert (stats["status"] == 2).all(), "not every episode finished"
+    steps_per_launch = int(stats["steps"].sum())
+    adds_per_launch = int(stats["additions"].sum())
+    assert counters["env_steps"] == steps_per_launch * args.steps
+
+    # ---- end-to-end through the public API with host buffers
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        seeds_dev.copy_(seeds_host, non_blocking=True)
+        launch(0)
+        stats_host.copy_(stats_dev, non_blocking=True)
+        torch.cuda.synchronize()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    t = torch.tensor([dev_ms, e2e_s * 1000.0], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(steps_per_launch), float(adds_per_launch)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    dev_ms_max, e2e_ms_max = float(t[0]), float(t[1])
+    total_steps, total_adds = float(tot[0]), float(tot[1])
+
+    if rank == 0:
+        # spot check (outside every timed region): a sample of the timed output against the CPU oracle
+        orc, kind = load_cpu_oracle()
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from hashing import trace_hash
+        env = orc.env(DIST)
+        for e in range(0, EPISODES, 1024):
+            env.seed(e)
+            env.reset()
+            tr = env.run(selection=STRATEGY)
+            assert stats["steps"][e] == len(tr) and int(stats["trace_hash"][e]) == trace_hash(tr), \
+                "GPU episode %d differs from the %s oracle" % (e, kind)
+
+        peak, peak_src = measured_peak()
+        abytes = algorithmic_bytes(counters) / args.steps
+        launch_s = dev_ms / 1000.0 / args.steps
+        achieved = abytes / launch_s / 1e9
+        value = total_steps * args.steps / (dev_ms_max / 1000.0)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64 packed monomials + u32 GF(32003) coefficients (integer)",
+            "data": "synthetic (on-device restatement of the reference RandomBinomialIdealGenerator; episode e = stream seed e)",
+            "config": {"workload": "%s, %d episodes per GPU to completion, %s selection (BASELINE configs[1])"
+                                   % (DIST, EPISODES, STRATEGY),
+                       "episodes_per_gpu": EPISODES, "env_steps_per_launch": steps_per_launch, "slots": slots,
+                       "parallelism": "episodes sharded across GPUs, no collective on the step path",
+                       "l2": "256 MiB flush write between timed launches"},
+            "additions_per_sec": total_adds * args.steps / (dev_ms_max / 1000.0),
+            "spair_reductions_per_sec": value,
+            "gpu_launches": args.steps,
+            "wall_s_timed_region": wall,
+            "clocks": clocks,
+            "e2e": {"value": total_steps * args.steps / (e2e_ms_max / 1000.0), "unit": UNIT,
+                    "h2d_bytes_per_step": EPISODES * 4, "d2h_bytes_per_step": stats_bytes},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "k_run",
+                         "algorithmic_bytes_per_launch": abytes,
+                         "note": "latency/integer bound at binomial sizes (working set lives in L1/L2); see DESIGN.md"},
+            "counters_per_launch": {k: v / args.steps for k, v in counters.items()},
+        }
+        if world == 1 and not args.no_cpu:
+            threads = host_threads()
+            r, count, threads = cpu_sample(orc, kind, args.cpu_seconds, threads)
+            line["cpu_baseline"] = {
+                "value": r["steps"] / r["seconds"], "unit": UNIT, "cores": threads, "kind": kind,
+                "sample": "%d episodes (seeds 0..%d) of the same workload, one reference BuchbergerEnv per host "
+                          "thread, %.1f s" % (count, count - 1, r["seconds"])}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--slots", type=int, default=0, help="environment slots (0 = one resident wave)")
+    ap.add_argument("--cpu-seconds", type=float, default=10.0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

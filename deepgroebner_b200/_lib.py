@@ -50,7 +50,7 @@ STATS_DTYPE = [("steps", "<i4"), ("additions", "<i4"), ("zero_reductions", "<i4"
                ("discounted_return", "<f8")]
 
 EXPORTS = [
-    "bb_abi_version", "bb_create", "bb_destroy", "bb_last_error", "bb_cols", "bb_num_envs", "bb_sm_count",
+    "bb_abi_version", "bb_resident_envs", "bb_create", "bb_destroy", "bb_last_error", "bb_cols", "bb_num_envs", "bb_sm_count",
     "bb_set_distribution", "bb_seed", "bb_set_ideals", "bb_reset", "bb_step", "bb_select", "bb_observe", "bb_pairs",
     "bb_status", "bb_stats", "bb_run", "bb_download_basis", "bb_final_gb", "bb_counters_read", "bb_hash_item",
 ]
@@ -82,6 +82,8 @@ def load():
     for n in ("bb_cols", "bb_num_envs", "bb_sm_count"):
         getattr(lib, n).restype = i
         getattr(lib, n).argtypes = [vp]
+    lib.bb_resident_envs.restype = i
+    lib.bb_resident_envs.argtypes = [i]
     lib.bb_set_distribution.restype = i
     lib.bb_set_distribution.argtypes = [vp, i, i, i, i, i, i]
     lib.bb_seed.restype = i

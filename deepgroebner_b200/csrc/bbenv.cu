@@ -272,6 +272,14 @@ int bb_num_envs(const bb_handle* h) { return h->P.num_envs; }
 int bb_sm_count(const bb_handle* h) { return h->sm_count; }
 uint64_t bb_hash_item(uint64_t x, uint64_t pos) { return bb_hash_item_impl(x, pos); }
 
+int bb_resident_envs(int device) {
+  int sms = 0, blocks = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
+  if (cudaSetDevice(device) != cudaSuccess) return -1;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_run, BB_THREADS, 0) != cudaSuccess) return -1;
+  return sms * blocks * BB_WARPS;
+}
+
 void bb_destroy(bb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
