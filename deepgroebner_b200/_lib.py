@@ -83,7 +83,7 @@ def load():
         getattr(lib, n).restype = i
         getattr(lib, n).argtypes = [vp]
     lib.bb_resident_envs.restype = i
-    lib.bb_resident_envs.argtypes = [i]
+    lib.bb_resident_envs.argtypes = [i, i]
     lib.bb_set_distribution.restype = i
     lib.bb_set_distribution.argtypes = [vp, i, i, i, i, i, i]
     lib.bb_seed.restype = i

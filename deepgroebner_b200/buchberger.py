@@ -30,10 +30,10 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
-def resident_envs(device=0):
+def resident_envs(device=0, nvars=3):
     """Slots of the persistent episode runner that are co-resident on the device (one wave of bb_run)."""
     lib = _lib.load()
-    n = lib.bb_resident_envs(int(device))
+    n = lib.bb_resident_envs(int(device), int(nvars))
     if n <= 0:
         raise _lib.BBError("bb_resident_envs failed: no CUDA device (no CPU fallback)")
     return n

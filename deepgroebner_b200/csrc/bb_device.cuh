@@ -1,8 +1,20 @@
-// bb_device.cuh -- warp-per-environment Buchberger step for sm_100a.
+// bb_device.cuh -- warp-per-environment Buchberger step for sm_100a (v2: compact hot loop).
 //
-// One warp owns one environment slot.  All scalars of the slot (|G|, |P|, arena cursor, ...) are warp-uniform
-// register values; all per-slot arrays live in the slot's HBM arena (L1/L2 resident in practice) and are
-// accessed lane-strided, i.e. coalesced.  There is no block-level synchronisation on the step path.
+// One warp owns one environment slot.  All scalars of the slot (|G|, |P|, arena cursor, the dividend's first two
+// terms, ...) are warp-uniform register values; all per-slot arrays live in ONE contiguous arena per slot in HBM
+// (L1/L2 resident in practice) and are accessed lane-strided, i.e. coalesced.  No block-level synchronisation on
+// the step path.
+//
+// What v1's profile (profiles/r01_v1_*) showed and what this file does about it:
+//   * 52 % of stall samples were instruction fetch (10.7 K SASS instructions, every helper inlined 2-3 times)
+//     -> the layout is a compile-time template parameter (KL<NV>), cold paths (reset + generator, final GB, hashes,
+//        the general merge) are __noinline__ single copies that talk to the caller through the slot's state record,
+//        and the hot loop is select -> erase -> spoly -> reduce -> add_basis only.
+//   * 1743 warp instructions per env-step -> polynomials with <= 2 terms (every polynomial of a binomial ideal)
+//     never touch the merge: the dividend's first two terms live in registers, each basis element has a 32-byte
+//     head record (lead monomial, 1/LC, second term) fetched with two 128-bit loads, and every pair caches the
+//     key of its lcm so selection and the Gebauer-Moeller sweep read one coalesced array.
+//   * 124 registers -> counters are 7 x u32 spilled to shared memory per episode, slot pointers are one base.
 //
 // Reference semantics followed (deepgroebner/buchberger.cpp, polynomials.cpp) are cited at each function.
 #pragma once
@@ -27,6 +39,16 @@ struct __align__(16) BBEnvState {  // one per slot, 96 bytes
   unsigned long long pad2[2];
 };
 
+// Head record of a basis element: everything a 2-term polynomial needs, and the arena range of the full term list.
+struct __align__(32) GHead {
+  uint64_t lm;     // lead monomial key
+  uint64_t k1;     // second term's key (undefined when len == 1)
+  uint32_t invlc;  // 1 / lead coefficient
+  uint32_t c1;     // second term's coefficient (0 when len == 1)
+  uint32_t off;    // first term's index in the slot's term arena
+  uint32_t len;    // number of terms
+};
+
 struct BBDist {           // RandomBinomialIdealGenerator parameters (ideals.cpp:157-201)
   int enabled, d, s, homogeneous, pure, ncp;
   const double* cp;       // [d+1] cumulative degree probabilities (libstdc++ discrete_distribution::_M_cp)
@@ -35,17 +57,24 @@ struct BBDist {           // RandomBinomialIdealGenerator parameters (ideals.cpp
 };
 
 struct BBParams {
-  BBLayout L;
+  BBField F;
+  int nvars;
   int num_envs, k, cols, elimination, rewards, sort_input, sort_reducers;
   int max_basis, max_pairs, max_terms, max_poly_terms, max_gens, max_gen_terms;
-  // per-slot arenas, each [num_envs][cap]
-  uint64_t* tkey; uint32_t* tcoef;      // term arena: packed monomial, coefficient
-  uint2* pmeta;                         // per basis polynomial: (offset, length) into the term arena
-  uint64_t* lm; uint32_t* invlc;        // lead monomial key and 1/LC by basis index
-  uint64_t* rlm; uint32_t* ridx;        // reducer list G_ in scan order: lead monomial key, basis index
-  uint32_t* pairs;                      // pair list P in order: (j << 16) | i
-  uint64_t* hkey; uint32_t* hcoef;      // dividend ping-pong scratch [num_envs][2][max_poly_terms]
-  uint64_t* lscr;                       // [num_envs][max_basis] lcm scratch for update / order scratch
+  // one contiguous arena per slot: base = arena + slot * slot_stride; byte offsets of the arrays inside it
+  unsigned char* arena;
+  unsigned long long slot_stride;
+  unsigned o_ghead;   // GHead   [max_basis]          by basis index
+  unsigned o_lm;      // u64     [max_basis]          lead monomial key by basis index
+  unsigned o_rlm;     // u64     [max_basis]          reducer list G_ in scan order: lead monomial key
+  unsigned o_lscr;    // u64     [max_basis]          update() scratch: lcm(LM_i, LM f) exponents | coprime << 63
+  unsigned o_plcm;    // u64     [max_pairs]          key of lcm(LM_i, LM_j) of each pair, in P order
+  unsigned o_tkey;    // u64     [max_terms]          term arena: packed monomials
+  unsigned o_hkey;    // u64     [2][max_poly_terms]  dividend ping-pong scratch
+  unsigned o_ridx;    // u32     [max_basis]          reducer list: basis index
+  unsigned o_pairs;   // u32     [max_pairs]          pair list P in order: (j << 16) | i
+  unsigned o_tcoef;   // u32     [max_terms]          term arena: coefficients
+  unsigned o_hcoef;   // u32     [2][max_poly_terms]
   BBEnvState* st;
   // staged input ideals, one per slot
   uint64_t* in_key; uint32_t* in_coef;  // [num_envs][max_gen_terms], each polynomial sorted descending
@@ -63,21 +92,30 @@ struct BBParams {
 enum { CT_STEPS = 0, CT_ADDS, CT_TREAD, CT_TWRITE, CT_LMS, CT_MOVES, CT_UPB, CT_UPP, CT_OBS, CT_NONZERO, CT_ZERO,
        CT_EPISODES, CT_COUNT };
 
-struct WarpCounters {
-  unsigned long long v[CT_COUNT];
-  __device__ __forceinline__ void clear() {
-#pragma unroll
-    for (int i = 0; i < CT_COUNT; i++) v[i] = 0;
+// Per-warp traffic counters of the step path (warp-uniform u32 registers; spilled to the warp's u64 row in shared
+// memory at least once per episode, so they cannot wrap).  Step / addition / episode counts are added to the row by
+// the kernels directly.
+struct Ctr {
+  uint32_t tread, twrite, lms, moves, upb, upp, obs;
+  __device__ __forceinline__ void clear() { tread = twrite = lms = moves = upb = upp = obs = 0; }
+  __device__ __forceinline__ void spill(unsigned long long* row) {  // row: this warp's CT_COUNT accumulators
+    if ((threadIdx.x & 31) == 0) {
+      row[CT_TREAD] += tread; row[CT_TWRITE] += twrite; row[CT_LMS] += lms; row[CT_MOVES] += moves;
+      row[CT_UPB] += upb; row[CT_UPP] += upp; row[CT_OBS] += obs;
+    }
+    clear();
   }
 };
 
 // Warp-uniform view of one slot.
 struct Env {
-  uint64_t* tkey; uint32_t* tcoef; uint2* pmeta; uint64_t* lm; uint32_t* invlc; uint64_t* rlm; uint32_t* ridx;
-  uint32_t* pairs; uint64_t* hkey; uint32_t* hcoef; uint64_t* lscr;
+  unsigned char* base;
   int nG, nP, nT, status;
   uint64_t guard;  // OR of every produced monomial key: any guard bit set => exponent/degree overflow
 };
+
+#define ENV_PTR(T, e, P, off) (reinterpret_cast<T*>((e).base + (P).off))
+#define SLOT_PTR(T, P, slot, off) (reinterpret_cast<T*>((P).arena + (size_t)(slot) * (P).slot_stride + (P).off))
 
 __device__ __forceinline__ int bb_lane() { return threadIdx.x & 31; }
 __device__ __forceinline__ uint32_t bb_lt_mask() { return (1u << bb_lane()) - 1u; }
@@ -100,31 +138,21 @@ __host__ __device__ __forceinline__ uint64_t bb_hash_item_impl(uint64_t x, uint6
   return z;
 }
 
-// e.guard is accumulated per lane; the overflow decision must be warp-uniform
-__device__ __forceinline__ bool bb_guard_tripped(const BBLayout& L, uint64_t guard) {
-  return __any_sync(BB_FULL, (guard & L.g_all) != 0ull);
-}
-
-__device__ __forceinline__ void env_bind(const BBParams& P, int slot, Env& e) {
-  size_t s = (size_t)slot;
-  e.tkey = P.tkey + s * P.max_terms;   e.tcoef = P.tcoef + s * P.max_terms;
-  e.pmeta = P.pmeta + s * P.max_basis; e.lm = P.lm + s * P.max_basis; e.invlc = P.invlc + s * P.max_basis;
-  e.rlm = P.rlm + s * P.max_basis;     e.ridx = P.ridx + s * P.max_basis;
-  e.pairs = P.pairs + s * P.max_pairs;
-  e.hkey = P.hkey + s * 2 * P.max_poly_terms; e.hcoef = P.hcoef + s * 2 * P.max_poly_terms;
-  e.lscr = P.lscr + s * P.max_basis;
+__device__ __forceinline__ void env_load(const BBParams& P, int slot, Env& e) {
+  e.base = P.arena + (size_t)slot * P.slot_stride;
+  const int4 s = *reinterpret_cast<const int4*>(&P.st[slot]);
+  e.nG = s.x; e.nP = s.y; e.nT = s.z; e.status = s.w;
   e.guard = 0;
 }
-__device__ __forceinline__ void env_load(const BBParams& P, int slot, Env& e) {
-  env_bind(P, slot, e);
-  const BBEnvState& s = P.st[slot];
-  e.nG = s.nG; e.nP = s.nP; e.nT = s.nT; e.status = s.status;
-}
 __device__ __forceinline__ void env_store(const BBParams& P, int slot, const Env& e) {
-  if (bb_lane() == 0) {
-    BBEnvState& s = P.st[slot];
-    s.nG = e.nG; s.nP = e.nP; s.nT = e.nT; s.status = e.status;
-  }
+  if (bb_lane() == 0) *reinterpret_cast<int4*>(&P.st[slot]) = make_int4(e.nG, e.nP, e.nT, e.status);
+}
+__device__ __forceinline__ GHead load_head(const GHead* g) {
+  const uint4 a = reinterpret_cast<const uint4*>(g)[0], b = reinterpret_cast<const uint4*>(g)[1];
+  GHead h;
+  h.lm = ((uint64_t)a.y << 32) | a.x; h.k1 = ((uint64_t)a.w << 32) | a.z;
+  h.invlc = b.x; h.c1 = b.y; h.off = b.z; h.len = b.w;
+  return h;
 }
 
 // ---------------------------------------------------------------------------------------------------- merge
@@ -133,36 +161,33 @@ __device__ __forceinline__ void env_store(const BBParams& P, int slot, const Env
 // Cancelled terms are dropped.  Warp-cooperative merge path: every round each lane holds one element of each
 // 32-wide window, finds its merged rank by a shuffle binary search in the other window, equal monomials are
 // paired (A carries the sum, B retires), and the survivors are scattered in rank order.
-// Returns the number of output terms, or -1 if `cap` would be exceeded.
-__device__ __forceinline__ int warp_merge(const BBLayout& L, const uint64_t* __restrict__ Ak,
-                                          const uint32_t* __restrict__ Ac, int nA, uint32_t cA, uint64_t adjA,
-                                          const uint64_t* __restrict__ Bk, const uint32_t* __restrict__ Bc, int nB,
-                                          uint32_t cB, uint64_t adjB, uint64_t* __restrict__ Ok,
-                                          uint32_t* __restrict__ Oc, int cap, uint64_t& guard) {
+// Returns the number of output terms, -1 if `cap` would be exceeded, -3 if a produced key has a guard bit set.
+// One out-of-line copy: polynomials with more than two terms are the only callers.
+template <int NV>
+__device__ __noinline__ int warp_merge(BBField F, const uint64_t* __restrict__ Ak, const uint32_t* __restrict__ Ac, int nA,
+                                       uint32_t cA, uint64_t adjA, const uint64_t* __restrict__ Bk,
+                                       const uint32_t* __restrict__ Bc, int nB, uint32_t cB, uint64_t adjB,
+                                       uint64_t* __restrict__ Ok, uint32_t* __restrict__ Oc, int cap) {
+  typedef KL<NV> K;
   const int lane = bb_lane();
   int ia = 0, ib = 0, no = 0;
-  if (nA + nB > 0 && nB == 0) {  // scaled copy
-    if (nA > cap) return -1;
-    for (int t = lane; t < nA; t += 32) {
-      uint64_t k = Ak[t] + adjA; guard |= k;
-      Ok[t] = k; Oc[t] = (cA == 1u) ? Ac[t] : bb_mulmod(L, Ac[t], cA);
+  uint64_t guard = 0;
+  if (nB == 0 || nA == 0) {  // scaled copy
+    const uint64_t* Sk = nB == 0 ? Ak : Bk; const uint32_t* Sc = nB == 0 ? Ac : Bc;
+    const int nS = nB == 0 ? nA : nB; const uint32_t cS = nB == 0 ? cA : cB; const uint64_t adjS = nB == 0 ? adjA : adjB;
+    if (nS > cap) return -1;
+    for (int t = lane; t < nS; t += 32) {
+      uint64_t k = Sk[t] + adjS; guard |= k;
+      Ok[t] = k; Oc[t] = (cS == 1u) ? Sc[t] : bbf_mulmod(F, Sc[t], cS);
     }
-    return nA;
-  }
-  if (nA == 0) {
-    if (nB > cap) return -1;
-    for (int t = lane; t < nB; t += 32) {
-      uint64_t k = Bk[t] + adjB; guard |= k;
-      Ok[t] = k; Oc[t] = (cB == 1u) ? Bc[t] : bb_mulmod(L, Bc[t], cB);
-    }
-    return nB;
+    return __any_sync(BB_FULL, (guard & K::g_all) != 0ull) ? -3 : nS;
   }
   while (ia < nA || ib < nB) {
     uint64_t ak = ~0ull, bk = ~0ull;
     uint32_t ac = 0, bc = 0;
     const bool va = ia + lane < nA, vb = ib + lane < nB;
-    if (va) { ak = Ak[ia + lane] + adjA; guard |= ak; ac = (cA == 1u) ? Ac[ia + lane] : bb_mulmod(L, Ac[ia + lane], cA); }
-    if (vb) { bk = Bk[ib + lane] + adjB; guard |= bk; bc = (cB == 1u) ? Bc[ib + lane] : bb_mulmod(L, Bc[ib + lane], cB); }
+    if (va) { ak = Ak[ia + lane] + adjA; guard |= ak; ac = (cA == 1u) ? Ac[ia + lane] : bbf_mulmod(F, Ac[ia + lane], cA); }
+    if (vb) { bk = Bk[ib + lane] + adjB; guard |= bk; bc = (cB == 1u) ? Bc[ib + lane] : bbf_mulmod(F, Bc[ib + lane], cB); }
     // rank of my A element: lane + #{b < a};  of my B element: lane + #{a <= b}  (A first on ties)
     int ca = 0, cb = 0;
 #pragma unroll
@@ -187,7 +212,7 @@ __device__ __forceinline__ int warp_merge(const BBLayout& L, const uint64_t* __r
     const bool emitA = va && ra < 32 && !(partA && ra == 31);
     const bool emitB = vb && rb < 32;
     uint32_t oc = ac;
-    if (partA) oc = bb_addmod(L, ac, pBc);
+    if (partA) oc = bbf_addmod(F, ac, pBc);
     const bool liveA = emitA && oc != 0u;
     const bool liveB = emitB && !partB;
     uint32_t mine = (liveA ? (1u << ra) : 0u) | (liveB ? (1u << rb) : 0u);
@@ -198,58 +223,126 @@ __device__ __forceinline__ int warp_merge(const BBLayout& L, const uint64_t* __r
     if (liveB) { int pos = no + __popc(live & ((1u << rb) - 1u)); Ok[pos] = bk; Oc[pos] = bc; }
     no += nlive;
     const int da = __popc(__ballot_sync(BB_FULL, emitA)), db = __popc(__ballot_sync(BB_FULL, emitB));
-    if (da + db == 0) return -1;  // only reachable with unsorted (overflowed) keys
+    if (da + db == 0) return -3;  // only reachable with unsorted (overflowed) keys
     ia += da; ib += db;
   }
-  return no;
+  __syncwarp();
+  return __any_sync(BB_FULL, (guard & K::g_all) != 0ull) ? -3 : no;
+}
+
+// The dividend h.  Its first two terms are always warp-uniform registers.  `mem` says whether the full list also sits
+// in the slot's ping-pong scratch at half `buf`, offset `pos` (always true when n > 2).
+struct Dividend {
+  uint64_t k0, k1;
+  uint32_t c0, c1;
+  int n, buf, pos;
+  bool mem;
+};
+
+// a + b for lists of at most one term each, entirely in (uniform) registers
+__device__ __forceinline__ void tiny_merge(const BBField& F, bool hasA, uint64_t ka, uint32_t ca, bool hasB, uint64_t kb,
+                                           uint32_t cb, Dividend& o) {
+  o.mem = false;
+  if (hasA && hasB) {
+    if (ka == kb) {
+      const uint32_t c = bbf_addmod(F, ca, cb);
+      o.n = c ? 1 : 0; o.k0 = ka; o.c0 = c;
+    } else {
+      const bool af = ka < kb;
+      o.k0 = af ? ka : kb; o.c0 = af ? ca : cb;
+      o.k1 = af ? kb : ka; o.c1 = af ? cb : ca;
+      o.n = 2;
+    }
+  } else if (hasA) { o.k0 = ka; o.c0 = ca; o.n = 1; }
+  else if (hasB) { o.k0 = kb; o.c0 = cb; o.n = 1; }
+  else o.n = 0;
+}
+
+// h <- the n-term list a general merge left at the start of scratch half `buf`
+__device__ __forceinline__ void dividend_from_scratch(const BBParams& P, const Env& e, Dividend& h, int n, int buf) {
+  const uint64_t* hk = ENV_PTR(uint64_t, e, P, o_hkey) + (size_t)buf * P.max_poly_terms;
+  const uint32_t* hc = ENV_PTR(uint32_t, e, P, o_hcoef) + (size_t)buf * P.max_poly_terms;
+  h.n = n; h.buf = buf; h.pos = 0; h.mem = true;
+  if (n > 0) { h.k0 = hk[0]; h.c0 = hc[0]; }
+  if (n > 1) { h.k1 = hk[1]; h.c1 = hc[1]; }
 }
 
 // ---------------------------------------------------------------------------------------------------- reduce
-// Division algorithm of buchberger.cpp:24-49 on the dividend h = (hk, hc, n) (ascending keys).
-// Reducers are scanned IN ORDER (rlm[0..nR)), the first whose lead monomial divides LM(h) is used
-// (h <- h - (LT h / LT f) f, steps++); otherwise LT(h) moves to the remainder.  The remainder is written
-// to (rk, rc) [cap rcap]; returns its length or -1 (scratch overflow) / -2 (remainder overflow) /
-// -3 (exponent overflow detected).
-// hbuf_id: which half of the ping-pong scratch h currently lives in (0/1), or -1 if h lives elsewhere.
-__device__ __forceinline__ int warp_reduce(const BBParams& P, Env& e, const uint64_t* hk, const uint32_t* hc, int n,
-                                           int hbuf_id, const uint64_t* rlm, const uint32_t* ridx, int nR,
-                                           uint64_t* rk, uint32_t* rc, int rcap, int& steps, WarpCounters& ct) {
-  const BBLayout& L = P.L;
+// Division algorithm of buchberger.cpp:24-49 on the dividend h.  Reducers are scanned IN ORDER (rlm[0..nR)), the
+// first whose lead monomial divides LM(h) is used (h <- h - (LT h / LT f) f, steps++); otherwise LT(h) moves to the
+// remainder, which is written to (rk, rc) [cap rcap].  Returns its length or -1 (scratch overflow) / -2 (remainder
+// overflow) / -3 (exponent overflow detected).  (r0k,r0c,r1k,r1c) receive the remainder's first two terms.
+// `sorted`: the reducer list is ascending in lead monomial, so the scan may stop at the first reducer whose lead
+// monomial exceeds LM(h) (it and everything after it cannot divide); the count of examined lead monomials that
+// feeds the traffic model stays the reference's (found + 1, or all of them).
+template <int NV>
+__device__ __forceinline__ int warp_reduce(const BBParams& P, Env& e, Dividend& h, const uint64_t* __restrict__ rlm,
+                                           const uint32_t* __restrict__ ridx, int nR, bool sorted,
+                                           uint64_t* __restrict__ rk, uint32_t* __restrict__ rc, int rcap, int& steps,
+                                           uint64_t& r0k, uint32_t& r0c, uint64_t& r1k, uint32_t& r1c, Ctr& ct) {
+  typedef KL<NV> K;
+  const BBField F = P.F;
   const int lane = bb_lane();
+  const GHead* gh = ENV_PTR(GHead, e, P, o_ghead);
   int rlen = 0;
   steps = 0;
-  while (n > 0) {
-    const uint64_t lead = hk[0];
+  while (h.n > 0) {
+    const uint64_t lead = h.k0;
     int found = -1;
     for (int base = 0; base < nR; base += 32) {
-      int r = base + lane;
-      bool ok = r < nR && bb_divides(L, rlm[r], lead);
-      uint32_t b = __ballot_sync(BB_FULL, ok);
+      const int r = base + lane;
+      const uint64_t rl = r < nR ? rlm[r] : ~0ull;
+      const uint32_t b = __ballot_sync(BB_FULL, r < nR && K::divides(rl, lead));
       if (b) { found = base + __ffs(b) - 1; break; }
+      if (sorted && __any_sync(BB_FULL, rl < lead)) break;  // larger lead monomials from here on
     }
-    ct.v[CT_LMS] += (found >= 0) ? (found + 1) : nR;
+    ct.lms += (found >= 0) ? (found + 1) : nR;
     if (found >= 0) {
-      const int gi = ridx[found];
-      const uint2 meta = e.pmeta[gi];
-      const uint32_t c = bb_mulmod(L, hc[0], e.invlc[gi]);
-      const uint64_t adj = lead - rlm[found];  // key(LM h / LM f) - bias
-      const int ob = (hbuf_id == 0) ? 1 : 0;
-      uint64_t* ok_ = e.hkey + (size_t)ob * P.max_poly_terms;
-      uint32_t* oc_ = e.hcoef + (size_t)ob * P.max_poly_terms;
-      int n2 = warp_merge(L, hk + 1, hc + 1, n - 1, 1u, 0ull, e.tkey + meta.x + 1, e.tcoef + meta.x + 1,
-                          (int)meta.y - 1, bb_negmod(L, c), adj, ok_, oc_, P.max_poly_terms, e.guard);
-      if (n2 < 0) return -1;
-      if (bb_guard_tripped(L, e.guard)) return -3;  // garbage keys could otherwise keep the loop alive
-      ct.v[CT_TREAD] += (unsigned)(n + (int)meta.y);
-      ct.v[CT_TWRITE] += (unsigned)n2;
-      __syncwarp();
-      hk = ok_; hc = oc_; n = n2; hbuf_id = ob;
+      const GHead f = load_head(gh + ridx[found]);
+      const uint32_t c = bbf_mulmod(F, h.c0, f.invlc);
+      const uint32_t nc = F.p - c;              // c != 0
+      const uint64_t adj = lead - f.lm;         // key(LM h / LM f) - bias
+      ct.tread += (unsigned)h.n + f.len;
+      if (h.n <= 2 && f.len <= 2) {
+        const uint64_t kb = f.k1 + adj;
+        const bool hasB = f.len == 2;
+        if (hasB) e.guard |= kb;
+        tiny_merge(F, h.n == 2, h.k1, h.c1, hasB, kb, bbf_mulmod(F, f.c1, nc), h);
+        if (e.guard & K::g_all) return -3;  // garbage keys could otherwise keep the loop alive
+      } else {
+        uint64_t* hk = ENV_PTR(uint64_t, e, P, o_hkey);
+        uint32_t* hc = ENV_PTR(uint32_t, e, P, o_hcoef);
+        if (!h.mem) {  // the register-resident dividend (n <= 2) goes to scratch half 0; only its tail is read
+          h.buf = 0; h.pos = 0; h.mem = true;
+          if (lane == 0 && h.n == 2) { hk[1] = h.k1; hc[1] = h.c1; }
+          __syncwarp();
+        }
+        const int ob = h.buf ^ 1;
+        const size_t ho = (size_t)h.buf * P.max_poly_terms + h.pos, oo = (size_t)ob * P.max_poly_terms;
+        const uint64_t* tk = ENV_PTR(uint64_t, e, P, o_tkey);
+        const uint32_t* tc = ENV_PTR(uint32_t, e, P, o_tcoef);
+        const int n2 = warp_merge<NV>(F, hk + ho + 1, hc + ho + 1, h.n - 1, 1u, 0ull, tk + f.off + 1, tc + f.off + 1,
+                                      (int)f.len - 1, nc, adj, hk + oo, hc + oo, P.max_poly_terms);
+        if (n2 < 0) return n2;
+        dividend_from_scratch(P, e, h, n2, ob);
+      }
+      ct.twrite += (unsigned)h.n;
       steps++;
     } else {
       if (rlen >= rcap) return -2;
-      if (lane == 0) { rk[rlen] = lead; rc[rlen] = hc[0]; }
-      rlen++; hk++; hc++; n--;
-      ct.v[CT_MOVES]++;
+      if (lane == 0) { rk[rlen] = lead; rc[rlen] = h.c0; }
+      if (rlen == 0) { r0k = lead; r0c = h.c0; }
+      if (rlen == 1) { r1k = lead; r1c = h.c0; }
+      rlen++;
+      ct.moves++;
+      h.n--; h.k0 = h.k1; h.c0 = h.c1;  // drop the lead term
+      if (h.mem) {
+        h.pos++;
+        if (h.n > 1) {
+          const size_t o = (size_t)h.buf * P.max_poly_terms + h.pos + 1;
+          h.k1 = ENV_PTR(uint64_t, e, P, o_hkey)[o]; h.c1 = ENV_PTR(uint32_t, e, P, o_hcoef)[o];
+        }
+      }
     }
   }
   __syncwarp();
@@ -257,122 +350,134 @@ __device__ __forceinline__ int warp_reduce(const BBParams& P, Env& e, const uint
 }
 
 // ---------------------------------------------------------------------------------------------------- update
-// update(G, P, f, elimination), buchberger.cpp:52-99, for the new basis element with index m = e.nG whose lead
-// monomial key is fk (the element itself must already be in the arena; e.nG is NOT incremented here).
+// Registers the polynomial stored at arena[off, off+len) (first two terms given in registers) as basis element
+// m and runs update(G, P, f, elimination), buchberger.cpp:52-99, then the reducer-list insertion
+// (upper_bound by lead monomial when sort_reducers: after every element whose lead monomial is <= the new one,
+// buchberger.cpp:308-311 / 323-326).
 // GebauerMoeller: (1) old (i,j) dropped iff LM f | lcm_ij and lcm_ij != lcm_if and lcm_ij != lcm_jf  (:63-70);
 // (2-4) with L_i = lcm(LM_i, LM f):  (i,m) is emitted iff no L_j strictly divides L_i, no j < i has L_j == L_i,
 // and no j with L_j == L_i is coprime to f.  This is exactly what the reference's ascending std::map sweep with
 // the "not divisible by a previously kept lcm" filter, v[0] representative and none_of(coprime) test produces
 // (:72-85): a kept lcm is a divisibility-minimal distinct lcm, and divisors always precede in grevlex order.
 // (5) new pairs in ascending i (:86), appended after the survivors (:91-92).
-// Returns false on pair-list overflow.
-__device__ __forceinline__ bool warp_update(const BBParams& P, Env& e, uint64_t fk, WarpCounters& ct) {
-  const BBLayout& L = P.L;
+// Every pair carries the key of its lcm (plcm), so step (1) and the selection strategies read one array.
+// One out-of-line copy shared by step and reset.  Returns (emitted << 32) | new |P|, or -1 on pair-list overflow /
+// -2 when the basis is full; the caller bumps nG and nT.
+template <int NV>
+__device__ __noinline__ long long warp_add_basis(const BBParams& P, unsigned char* base, int m, int nP, int off, int len,
+                                                 uint64_t fk, uint32_t lc, uint64_t k1, uint32_t c1) {
+  typedef KL<NV> K;
   const int lane = bb_lane();
-  const int m = e.nG;
   const uint32_t ltm = bb_lt_mask();
-  ct.v[CT_UPB] += (unsigned)m;
-  ct.v[CT_UPP] += (unsigned)e.nP;
+  if (m >= P.max_basis) return -2;
+  uint64_t* lm = reinterpret_cast<uint64_t*>(base + P.o_lm);
+  uint64_t* lscr = reinterpret_cast<uint64_t*>(base + P.o_lscr);
+  uint64_t* plcm = reinterpret_cast<uint64_t*>(base + P.o_plcm);
+  uint32_t* pairs = reinterpret_cast<uint32_t*>(base + P.o_pairs);
+  int emitted = 0;
   if (P.elimination == BB_ELIM_GEBAUERMOELLER) {
-    const uint64_t fe = fk & L.ex_mask;
+    // L_i for every basis element (also the scratch the old-pair filter gathers from)
+    for (int i = lane; i < m; i += 32) {
+      const uint64_t li = lm[i];
+      lscr[i] = K::lcm_exps(li, fk) | (K::coprime(li, fk) ? (1ull << 63) : 0ull);
+    }
+    __syncwarp();
+    const uint64_t fe = fk & K::ex_mask;
     int w = 0;
-    for (int base = 0; base < e.nP; base += 32) {
-      int idx = base + lane;
-      bool valid = idx < e.nP;
-      uint32_t pr = valid ? e.pairs[idx] : 0u;
+    for (int b0 = 0; b0 < nP; b0 += 32) {
+      const int idx = b0 + lane;
+      const bool valid = idx < nP;
+      uint32_t pr = 0u; uint64_t pl = 0ull;
       bool keep = false;
       if (valid) {
-        uint64_t li = e.lm[pr & 0xffffu], lj = e.lm[pr >> 16];
-        uint64_t l = bb_lcm_exps(L, li, lj);
-        bool drop = bb_divides(L, fe, l) && l != bb_lcm_exps(L, li, fk) && l != bb_lcm_exps(L, lj, fk);
+        pr = pairs[idx]; pl = plcm[idx];
+        const uint64_t l = pl & K::ex_mask;
+        const bool drop = K::divides(fe, l) && l != (lscr[pr & 0xffffu] & K::ex_mask) && l != (lscr[pr >> 16] & K::ex_mask);
         keep = !drop;
       }
-      uint32_t km = __ballot_sync(BB_FULL, keep);
-      if (keep) e.pairs[w + __popc(km & ltm)] = pr;  // w + rank <= idx: never overtakes an unread entry of a later chunk
+      const uint32_t km = __ballot_sync(BB_FULL, keep);
+      if (keep) {  // w + rank <= idx: never overtakes an unread entry of a later chunk
+        const int pos = w + __popc(km & ltm);
+        pairs[pos] = pr; plcm[pos] = pl;
+      }
       w += __popc(km);
       __syncwarp();
     }
-    e.nP = w;
-    for (int i = lane; i < m; i += 32) {
-      uint64_t li = e.lm[i];
-      e.lscr[i] = bb_lcm_exps(L, li, fk) | (bb_coprime(L, li, fk) ? (1ull << 63) : 0ull);
-    }
-    __syncwarp();
-    for (int base = 0; base < m; base += 32) {
-      int i = base + lane;
-      bool valid = i < m;
-      uint64_t Li = valid ? (e.lscr[i] & L.ex_mask) : 0ull;
-      bool bad = false;
+    nP = w;
+    for (int b0 = 0; b0 < m; b0 += 32) {
+      const int i = b0 + lane;
+      const bool valid = i < m;
+      const uint64_t Li = valid ? (lscr[i] & K::ex_mask) : 0ull;
+      const uint64_t LiG = Li | K::ge_mask;
+      bool bad = !valid;
+#pragma unroll 4
       for (int j = 0; j < m; j++) {
-        uint64_t Lj = e.lscr[j];
-        uint64_t ej = Lj & L.ex_mask;
-        if (ej == Li) bad |= (j < i) || (Lj >> 63);
-        else bad |= bb_divides(L, ej, Li);
+        const uint64_t Lj = lscr[j];
+        const uint64_t ej = Lj & K::ex_mask;
+        const bool div = ((LiG - ej) & K::ge_mask) == K::ge_mask;
+        const bool eq = ej == Li;
+        bad |= div && (!eq || j < i || (long long)Lj < 0);
       }
-      bool keep = valid && !bad;
-      uint32_t km = __ballot_sync(BB_FULL, keep);
-      int cnt = __popc(km);
-      if (e.nP + cnt > P.max_pairs) return false;
-      if (keep) e.pairs[e.nP + __popc(km & ltm)] = ((uint32_t)m << 16) | (uint32_t)i;
-      e.nP += cnt;
-      ct.v[CT_UPP] += (unsigned)cnt;
+      const bool keep = !bad;
+      const uint32_t km = __ballot_sync(BB_FULL, keep);
+      const int cnt = __popc(km);
+      if (nP + cnt > P.max_pairs) return -1;
+      if (keep) {
+        const int pos = nP + __popc(km & ltm);
+        pairs[pos] = ((uint32_t)m << 16) | (uint32_t)i;
+        plcm[pos] = K::key_from_exps(Li);
+      }
+      nP += cnt; emitted += cnt;
     }
   } else {
-    for (int base = 0; base < m; base += 32) {
-      int i = base + lane;
+    for (int b0 = 0; b0 < m; b0 += 32) {
+      const int i = b0 + lane;
       bool keep = i < m;
-      if (keep && P.elimination == BB_ELIM_LCM) keep = !bb_coprime(L, e.lm[i], fk);  // :58-62
-      uint32_t km = __ballot_sync(BB_FULL, keep);
-      int cnt = __popc(km);
-      if (e.nP + cnt > P.max_pairs) return false;
-      if (keep) e.pairs[e.nP + __popc(km & ltm)] = ((uint32_t)m << 16) | (uint32_t)i;
-      e.nP += cnt;
-      ct.v[CT_UPP] += (unsigned)cnt;
+      const uint64_t li = keep ? lm[i] : 0ull;
+      if (keep && P.elimination == BB_ELIM_LCM) keep = !K::coprime(li, fk);  // :58-62
+      const uint32_t km = __ballot_sync(BB_FULL, keep);
+      const int cnt = __popc(km);
+      if (nP + cnt > P.max_pairs) return -1;
+      if (keep) {
+        const int pos = nP + __popc(km & ltm);
+        pairs[pos] = ((uint32_t)m << 16) | (uint32_t)i;
+        plcm[pos] = K::key_from_exps(K::lcm_exps(li, fk));
+      }
+      nP += cnt; emitted += cnt;
     }
   }
-  __syncwarp();
-  return true;
-}
-
-// Registers the polynomial stored at arena[off, off+len) as basis element m = e.nG: lead data, pair update,
-// reducer-list insertion (upper_bound by lead monomial when sort_reducers: after every element whose lead
-// monomial is <= the new one, buchberger.cpp:308-311 / 323-326), then nG++, nT += len.
-__device__ __forceinline__ bool warp_add_basis(const BBParams& P, Env& e, int off, int len, WarpCounters& ct) {
-  const BBLayout& L = P.L;
-  const int lane = bb_lane();
-  const int m = e.nG;
-  if (m >= P.max_basis) { e.status = BB_STATUS_OVERFLOW_BASIS; return false; }
-  const uint64_t fk = e.tkey[off];
-  const uint32_t lc = e.tcoef[off];
-  if (!warp_update(P, e, fk, ct)) { e.status = BB_STATUS_OVERFLOW_PAIRS; return false; }
+  // reducer list
+  uint64_t* rlm = reinterpret_cast<uint64_t*>(base + P.o_rlm);
+  uint32_t* ridx = reinterpret_cast<uint32_t*>(base + P.o_ridx);
   int pos = m;
   if (P.sort_reducers) {
     int cnt = 0;  // reducers with LM <= new LM  <=>  key >= new key
-    for (int base = 0; base < m; base += 32) {
-      int r = base + lane;
-      cnt += __popc(__ballot_sync(BB_FULL, r < m && e.rlm[r] >= fk));
+    for (int b0 = 0; b0 < m; b0 += 32) {
+      const int r = b0 + lane;
+      cnt += __popc(__ballot_sync(BB_FULL, r < m && rlm[r] >= fk));
     }
     pos = cnt;
     for (int hi = m; hi > pos; hi -= 32) {
-      int lo = hi - 32 > pos ? hi - 32 : pos;
-      int idx = lo + lane;
-      bool v = idx < hi;
+      const int lo = hi - 32 > pos ? hi - 32 : pos;
+      const int idx = lo + lane;
+      const bool v = idx < hi;
       uint64_t k = 0; uint32_t ix = 0;
-      if (v) { k = e.rlm[idx]; ix = e.ridx[idx]; }
+      if (v) { k = rlm[idx]; ix = ridx[idx]; }
       __syncwarp();
-      if (v) { e.rlm[idx + 1] = k; e.ridx[idx + 1] = ix; }
+      if (v) { rlm[idx + 1] = k; ridx[idx + 1] = ix; }
       __syncwarp();
     }
   }
   if (lane == 0) {
-    e.rlm[pos] = fk; e.ridx[pos] = (uint32_t)m;
-    e.lm[m] = fk; e.invlc[m] = bb_invmod(L, lc);
-    e.pmeta[m] = make_uint2((unsigned)off, (unsigned)len);
+    rlm[pos] = fk; ridx[pos] = (uint32_t)m;
+    lm[m] = fk;
+    GHead* g = reinterpret_cast<GHead*>(base + P.o_ghead) + m;
+    const uint32_t inv = bbf_invmod(P.F, lc);
+    reinterpret_cast<uint4*>(g)[0] = make_uint4((uint32_t)fk, (uint32_t)(fk >> 32), (uint32_t)k1, (uint32_t)(k1 >> 32));
+    reinterpret_cast<uint4*>(g)[1] = make_uint4(inv, len > 1 ? c1 : 0u, (uint32_t)off, (uint32_t)len);
   }
-  e.nG = m + 1;
-  e.nT = off + len;
   __syncwarp();
-  return true;
+  return ((long long)emitted << 32) | (long long)nP;
 }
 
 // ---------------------------------------------------------------------------------------------------- step
@@ -380,48 +485,72 @@ __device__ __forceinline__ bool warp_add_basis(const BBParams& P, Env& e, int of
 // :318-329): erase the pair, s = spoly(G[i], G[j]) (:18-21), (r, steps) = reduce(s, G_), if r != 0 update + sorted
 // insert.  Returns the number of polynomial additions 1 + steps (reward = -(1+steps) under Additions, -1 under
 // Reductions).  *pi, *pj receive the pair.
-__device__ __forceinline__ int warp_step(const BBParams& P, Env& e, int row, int* pi, int* pj, WarpCounters& ct) {
-  const BBLayout& L = P.L;
+template <int NV>
+__device__ __forceinline__ int warp_step(const BBParams& P, Env& e, int row, int* pi, int* pj, Ctr& ct) {
+  typedef KL<NV> K;
+  const BBField F = P.F;
   const int lane = bb_lane();
-  if (row < 0 || row >= e.nP) { e.status = BB_STATUS_BAD_ACTION; *pi = -1; *pj = -1; return 0; }
-  const uint32_t pr = e.pairs[row];
+  if ((unsigned)row >= (unsigned)e.nP) { e.status = BB_STATUS_BAD_ACTION; *pi = -1; *pj = -1; return 0; }
+  uint32_t* pairs = ENV_PTR(uint32_t, e, P, o_pairs);
+  uint64_t* plcm = ENV_PTR(uint64_t, e, P, o_plcm);
+  const uint32_t pr = pairs[row];
+  const uint64_t gam = plcm[row];  // key of lcm(LM f, LM g), computed when the pair was created
   const int i = pr & 0xffffu, j = pr >> 16;
   *pi = i; *pj = j;
+  __syncwarp();
   // erase the pair, keeping order (:319)
-  for (int base = row; base < e.nP - 1; base += 32) {
-    int idx = base + lane;
-    bool v = idx < e.nP - 1;
-    uint32_t x = v ? e.pairs[idx + 1] : 0u;
+  for (int b0 = row; b0 < e.nP - 1; b0 += 32) {
+    const int idx = b0 + lane;
+    const bool v = idx < e.nP - 1;
+    uint32_t x = 0u; uint64_t y = 0ull;
+    if (v) { x = pairs[idx + 1]; y = plcm[idx + 1]; }
     __syncwarp();
-    if (v) e.pairs[idx] = x;
+    if (v) { pairs[idx] = x; plcm[idx] = y; }
   }
   e.nP--;
   // S-polynomial: lead terms cancel exactly, so s = (gamma/LT f) tail(f) - (gamma/LT g) tail(g)
-  const uint2 mf = e.pmeta[i], mg = e.pmeta[j];
-  const uint64_t lf = e.lm[i], lg = e.lm[j];
-  const uint64_t gam = bb_lcm(L, lf, lg);
+  const GHead* gh = ENV_PTR(GHead, e, P, o_ghead);
+  const GHead hf = load_head(gh + i), hg = load_head(gh + j);
   e.guard |= gam;
-  int n = warp_merge(L, e.tkey + mf.x + 1, e.tcoef + mf.x + 1, (int)mf.y - 1, e.invlc[i], gam - lf,
-                     e.tkey + mg.x + 1, e.tcoef + mg.x + 1, (int)mg.y - 1, bb_negmod(L, e.invlc[j]), gam - lg,
-                     e.hkey, e.hcoef, P.max_poly_terms, e.guard);
-  ct.v[CT_STEPS]++;
-  if (n < 0) { e.status = BB_STATUS_OVERFLOW_SCRATCH; return 1; }
-  if (bb_guard_tripped(L, e.guard)) { e.status = BB_STATUS_OVERFLOW_EXPONENT; return 1; }
-  ct.v[CT_TREAD] += mf.y + mg.y;
-  ct.v[CT_TWRITE] += (unsigned)n;
-  __syncwarp();
+  ct.tread += hf.len + hg.len;
+  Dividend h;
+  h.k0 = h.k1 = 0; h.c0 = h.c1 = 0; h.n = 0; h.buf = 0; h.pos = 0; h.mem = false;
+  const uint64_t adjf = gam - hf.lm, adjg = gam - hg.lm;
+  const uint32_t cg = F.p - hg.invlc;  // -(1/LC g), invlc != 0
+  if (hf.len <= 2 && hg.len <= 2) {
+    const uint64_t ka = hf.k1 + adjf, kb = hg.k1 + adjg;
+    const bool hasA = hf.len == 2, hasB = hg.len == 2;
+    if (hasA) e.guard |= ka;
+    if (hasB) e.guard |= kb;
+    tiny_merge(F, hasA, ka, bbf_mulmod(F, hf.c1, hf.invlc), hasB, kb, bbf_mulmod(F, hg.c1, cg), h);
+  } else {
+    const uint64_t* tk = ENV_PTR(uint64_t, e, P, o_tkey);
+    const uint32_t* tc = ENV_PTR(uint32_t, e, P, o_tcoef);
+    const int n = warp_merge<NV>(F, tk + hf.off + 1, tc + hf.off + 1, (int)hf.len - 1, hf.invlc, adjf, tk + hg.off + 1,
+                                 tc + hg.off + 1, (int)hg.len - 1, cg, adjg, ENV_PTR(uint64_t, e, P, o_hkey),
+                                 ENV_PTR(uint32_t, e, P, o_hcoef), P.max_poly_terms);
+    if (n == -1) { e.status = BB_STATUS_OVERFLOW_SCRATCH; return 1; }
+    if (n < 0) { e.status = BB_STATUS_OVERFLOW_EXPONENT; return 1; }
+    dividend_from_scratch(P, e, h, n, 0);
+  }
+  if (e.guard & K::g_all) { e.status = BB_STATUS_OVERFLOW_EXPONENT; return 1; }
+  ct.twrite += (unsigned)h.n;
   int steps = 0;
-  int rlen = warp_reduce(P, e, e.hkey, e.hcoef, n, 0, e.rlm, e.ridx, e.nG, e.tkey + e.nT, e.tcoef + e.nT,
-                         P.max_terms - e.nT, steps, ct);
-  ct.v[CT_ADDS] += (unsigned)(1 + steps);
+  uint64_t r0k = 0, r1k = 0; uint32_t r0c = 0, r1c = 0;
+  const int rlen = warp_reduce<NV>(P, e, h, ENV_PTR(uint64_t, e, P, o_rlm), ENV_PTR(uint32_t, e, P, o_ridx), e.nG,
+                                   P.sort_reducers != 0, ENV_PTR(uint64_t, e, P, o_tkey) + e.nT,
+                                   ENV_PTR(uint32_t, e, P, o_tcoef) + e.nT, P.max_terms - e.nT, steps, r0k, r0c, r1k, r1c,
+                                   ct);
   if (rlen == -1) { e.status = BB_STATUS_OVERFLOW_SCRATCH; return 1 + steps; }
   if (rlen == -2) { e.status = BB_STATUS_OVERFLOW_TERMS; return 1 + steps; }
-  if (rlen == -3 || bb_guard_tripped(L, e.guard)) { e.status = BB_STATUS_OVERFLOW_EXPONENT; return 1 + steps; }
+  if (rlen == -3 || (e.guard & K::g_all)) { e.status = BB_STATUS_OVERFLOW_EXPONENT; return 1 + steps; }
   if (rlen > 0) {
-    ct.v[CT_NONZERO]++;
-    if (!warp_add_basis(P, e, e.nT, rlen, ct)) return 1 + steps;
-  } else {
-    ct.v[CT_ZERO]++;
+    ct.upb += (unsigned)e.nG; ct.upp += (unsigned)e.nP;
+    const long long r = warp_add_basis<NV>(P, e.base, e.nG, e.nP, e.nT, rlen, r0k, r0c, r1k, r1c);
+    if (r < 0) { e.status = (r == -1) ? BB_STATUS_OVERFLOW_PAIRS : BB_STATUS_OVERFLOW_BASIS; return 1 + steps; }
+    e.nP = (int)(r & 0xffffffffll);
+    ct.upp += (unsigned)(r >> 32);
+    e.nG++; e.nT += rlen;
   }
   if (e.nP == 0) e.status = BB_STATUS_DONE;
   return 1 + steps;
@@ -429,113 +558,124 @@ __device__ __forceinline__ int warp_step(const BBParams& P, Env& e, int row, int
 
 // ---------------------------------------------------------------------------------------------------- select
 // First / Degree / Normal pair selection (buchberger.cpp:165-186); ties go to the first pair in P, which is
-// what the (j,i) tie-break selects because P is always sorted by (j,i).
+// what the (j,i) tie-break selects because P is always sorted by (j,i).  Reads only the cached lcm keys.
+template <int NV>
 __device__ __forceinline__ int warp_select(const BBParams& P, const Env& e, int strategy) {
-  const BBLayout& L = P.L;
+  typedef KL<NV> K;
   const int lane = bb_lane();
   if (strategy == BB_SELECT_FIRST || e.nP <= 1) return 0;
+  const uint64_t* plcm = ENV_PTR(uint64_t, e, P, o_plcm);
   if (strategy == BB_SELECT_DEGREE) {
-    uint32_t best = 0xffffffffu;
+    // smallest degree == largest complemented-degree field; lowest row on ties
+    uint32_t best = 0u;
     for (int idx = lane; idx < e.nP; idx += 32) {
-      uint32_t pr = e.pairs[idx];
-      uint32_t d = bb_sum_fields(L, bb_lcm_exps(L, e.lm[pr & 0xffffu], e.lm[pr >> 16]));
-      uint32_t v = (d << 16) | (uint32_t)idx;
-      best = v < best ? v : best;
+      const uint32_t v = ((uint32_t)(plcm[idx] >> K::dshift) << 16) | (0xffffu - (uint32_t)idx);
+      best = v > best ? v : best;
     }
-    best = __reduce_min_sync(BB_FULL, best);
-    return (int)(best & 0xffffu);
+    best = __reduce_max_sync(BB_FULL, best);
+    return (int)(0xffffu - (best & 0xffffu));
   }
   // Normal: smallest lcm in grevlex == LARGEST key; lowest row on ties
-  uint64_t bk = 0; int bi = 0x7fffffff;
+  uint64_t bk = 0; uint32_t bi = 0xffffffffu;
   for (int idx = lane; idx < e.nP; idx += 32) {
-    uint32_t pr = e.pairs[idx];
-    uint64_t k = bb_lcm(L, e.lm[pr & 0xffffu], e.lm[pr >> 16]);
-    if (k > bk) { bk = k; bi = idx; }  // strided ascending idx: first occurrence kept on ties
+    const uint64_t k = plcm[idx];
+    if (k > bk) { bk = k; bi = (uint32_t)idx; }  // strided ascending idx: first occurrence kept on ties
   }
-#pragma unroll
-  for (int o = 16; o; o >>= 1) {
-    uint64_t ok = bb_shfl64(bk, lane ^ o);
-    int oi = __shfl_xor_sync(BB_FULL, bi, o);
-    if (ok > bk || (ok == bk && oi < bi)) { bk = ok; bi = oi; }
-  }
-  return bi;
+  const uint32_t hi = __reduce_max_sync(BB_FULL, (uint32_t)(bk >> 32));
+  const bool c1 = (uint32_t)(bk >> 32) == hi && bi != 0xffffffffu;
+  const uint32_t lo = __reduce_max_sync(BB_FULL, c1 ? (uint32_t)bk : 0u);
+  const bool c2 = c1 && (uint32_t)bk == lo;
+  return (int)__reduce_min_sync(BB_FULL, c2 ? bi : 0xffffffffu);
 }
 
 // ---------------------------------------------------------------------------------------------------- observe
 // Row r of the state matrix = first k exponent vectors of G[i] then of G[j], zero padded
 // (lead_monomials_vector, buchberger.cpp:354-370; rows in P order, :402-406); rows [|P|, pmax) are -1.
-__device__ __forceinline__ void warp_observe(const BBParams& P, const Env& e, int32_t* obs, int pmax,
-                                             WarpCounters& ct) {
-  const BBLayout& L = P.L;
+template <int NV>
+__device__ __forceinline__ void warp_observe(const BBParams& P, const Env& e, int32_t* obs, int pmax, Ctr& ct) {
+  typedef KL<NV> K;
   const int lane = bb_lane();
-  const int cols = P.cols, half = P.L.n * P.k, n = P.L.n;
+  const int cols = P.cols, half = NV * P.k;
   const int rows = e.nP < pmax ? e.nP : pmax;
   const int live = rows * cols, total = pmax * cols;
+  const uint32_t* pairs = ENV_PTR(uint32_t, e, P, o_pairs);
+  const GHead* gh = ENV_PTR(GHead, e, P, o_ghead);
+  const uint64_t* tk = ENV_PTR(uint64_t, e, P, o_tkey);
   for (int x = lane; x < live; x += 32) {
-    int row = x / cols, c = x - row * cols;
-    uint32_t pr = e.pairs[row];
-    int side = c >= half;
-    int cc = c - side * half;
-    int t = cc / n, v = cc - t * n;
-    uint2 meta = e.pmeta[side ? (pr >> 16) : (pr & 0xffffu)];
-    obs[x] = (t < (int)meta.y) ? (int32_t)bb_exp(L, e.tkey[meta.x + t], v) : 0;
+    const int row = x / cols, c = x - row * cols;
+    const uint32_t pr = pairs[row];
+    const int side = c >= half;
+    const int cc = c - side * half;
+    const int t = cc / NV, v = cc - t * NV;
+    const GHead* g = gh + (side ? (pr >> 16) : (pr & 0xffffu));
+    int32_t val = 0;
+    if (t < (int)g->len) val = (int32_t)K::exp(t == 0 ? g->lm : (t == 1 ? g->k1 : tk[g->off + t]), v);
+    obs[x] = val;
   }
   for (int x = live + lane; x < total; x += 32) obs[x] = -1;
-  ct.v[CT_OBS] += (unsigned)rows;
+  ct.obs += (unsigned)rows;
 }
 
 // ---------------------------------------------------------------------------------------------------- generator
 // minstd_rand0 + libstdc++ distributions restated (ideals.h:177-179): the streams must match
 // the reference generator bit for bit because "identical seeded inputs" is part of the parity contract.
-__device__ __forceinline__ unsigned long long rng_seed(int seed) {
+// The engine state is < 2^31, so everything is 32-bit arithmetic except the 46-bit product.
+__device__ __forceinline__ uint32_t rng_seed(int seed) {
   unsigned long long s = (unsigned long long)(long long)seed % 2147483647ULL;  // int -> unsigned long, then mod m
-  return s == 0 ? 1ULL : s;
+  return s == 0 ? 1u : (uint32_t)s;
 }
-__device__ __forceinline__ unsigned long long rng_next(unsigned long long& x) { x = (x * 16807ULL) % 2147483647ULL; return x; }
+__device__ __forceinline__ uint32_t rng_next(uint32_t& x) {
+  const unsigned long long pr = (unsigned long long)x * 16807ULL;       // < 2^46
+  uint32_t r = (uint32_t)(pr & 0x7fffffffULL) + (uint32_t)(pr >> 31);  // 2^31 == 1 (mod 2^31 - 1)
+  if (r >= 2147483647u) r -= 2147483647u;
+  x = r;
+  return r;
+}
 // uniform_int_distribution<int>(a,b): "fallback (2 divisions)" branch of bits/uniform_int_dist.h
-__device__ __forceinline__ int rng_uniform(unsigned long long& x, int a, int b) {
-  const unsigned long long urngrange = 2147483645ULL;
-  unsigned long long uerange = (unsigned long long)(unsigned)(b - a) + 1ULL;
-  unsigned long long scaling = urngrange / uerange, past = uerange * scaling, ret;
-  do ret = rng_next(x) - 1ULL; while (ret >= past);
+__device__ __forceinline__ int rng_uniform(uint32_t& x, int a, int b) {
+  const uint32_t urngrange = 2147483645u;
+  const uint32_t uerange = (uint32_t)(b - a) + 1u;
+  const uint32_t scaling = urngrange / uerange, past = uerange * scaling;
+  uint32_t ret;
+  do ret = rng_next(x) - 1u; while (ret >= past);
   return a + (int)(ret / scaling);
 }
 // generate_canonical<double,53>: two draws, (u1-1) + (u2-1)*R over R*R, all in round-to-nearest double ops
-__device__ __forceinline__ double rng_canonical(unsigned long long& x) {
+__device__ __forceinline__ double rng_canonical(uint32_t& x) {
   const double R = 2147483646.0;
-  double s = __dmul_rn((double)(rng_next(x) - 1ULL), 1.0);
-  s = __dadd_rn(s, __dmul_rn((double)(rng_next(x) - 1ULL), R));
+  double s = (double)(rng_next(x) - 1u);
+  s = __dadd_rn(s, __dmul_rn((double)(rng_next(x) - 1u), R));
   double r = __ddiv_rn(s, __dmul_rn(R, R));
   if (r >= 1.0) r = __longlong_as_double(0x3FEFFFFFFFFFFFFFLL);  // nextafter(1,0)
   return r;
 }
-__device__ __forceinline__ int rng_degree(const BBDist& D, unsigned long long& x) {
+__device__ __forceinline__ int rng_degree(const BBDist& D, uint32_t& x) {
   if (D.ncp < 2) return 0;
-  double p = rng_canonical(x);
+  const double p = rng_canonical(x);
   int lo = 0, hi = D.ncp;
   while (lo < hi) { int mid = (lo + hi) >> 1; if (D.cp[mid] < p) lo = mid + 1; else hi = mid; }
   return lo;
 }
 // RandomBinomialIdealGenerator::next (ideals.cpp:168-201), executed by lane 0 into the slot's staging area.
 // Returns false if 1000 trials fail (the reference throws).
-__device__ __forceinline__ bool gen_binomial_ideal(const BBParams& P, int slot, unsigned long long& x) {
+__device__ __forceinline__ bool gen_binomial_ideal(const BBParams& P, int slot, uint32_t& x) {
   const BBDist& D = P.dist;
   uint64_t* ik = P.in_key + (size_t)slot * P.max_gen_terms;
   uint32_t* ic = P.in_coef + (size_t)slot * P.max_gen_terms;
   int* io = P.in_off + (size_t)slot * (P.max_gens + 1);
   io[0] = 0;
   for (int i = 0; i < D.s; i++) {
-    uint32_t c = D.pure ? (P.L.p - 1u) : (uint32_t)rng_uniform(x, 1, (int)P.L.p - 1);
+    const uint32_t c = D.pure ? (P.F.p - 1u) : (uint32_t)rng_uniform(x, 1, (int)P.F.p - 1);
     int d1, d2;
     if (D.homogeneous) d1 = d2 = rng_degree(D, x);
     else { d1 = rng_degree(D, x); d2 = rng_degree(D, x); }
+    const int o1 = D.basis_off[d1], n1 = D.basis_off[d1 + 1] - o1, o2 = D.basis_off[d2], n2 = D.basis_off[d2 + 1] - o2;
     bool ok = false;
     for (int trials = 0; trials < 1000 && !ok; trials++) {
-      int n1 = D.basis_off[d1 + 1] - D.basis_off[d1], n2 = D.basis_off[d2 + 1] - D.basis_off[d2];
-      uint64_t m1 = D.basis[D.basis_off[d1] + rng_uniform(x, 0, n1 - 1)];
-      uint64_t m2 = D.basis[D.basis_off[d2] + rng_uniform(x, 0, n2 - 1)];
+      const uint64_t m1 = D.basis[o1 + rng_uniform(x, 0, n1 - 1)];
+      const uint64_t m2 = D.basis[o2 + rng_uniform(x, 0, n2 - 1)];
       if (m1 != m2) {  // larger monomial (smaller key) leads with coefficient 1
-        uint64_t hi = m1 < m2 ? m1 : m2, lo = m1 < m2 ? m2 : m1;
+        const uint64_t hi = m1 < m2 ? m1 : m2, lo = m1 < m2 ? m2 : m1;
         ik[2 * i] = hi; ic[2 * i] = 1u; ik[2 * i + 1] = lo; ic[2 * i + 1] = c;
         ok = true;
       }
@@ -548,15 +688,18 @@ __device__ __forceinline__ bool gen_binomial_ideal(const BBParams& P, int slot, 
 }
 
 // ---------------------------------------------------------------------------------------------------- reset
-// BuchbergerEnv::reset (buchberger.cpp:299-315) from the slot's staged ideal: generators are added one by one
-// through update() and into the reducer list.  sort_input orders them by ascending lead monomial first (stable).
-// `src` is the staging slot the ideal is read from (never written while fixed ideals are in use).
-__device__ __forceinline__ void warp_load_ideal(const BBParams& P, int src_slot, Env& e, WarpCounters& ct) {
+// BuchbergerEnv::reset (buchberger.cpp:299-315) from staged ideal `src_slot` into slot `slot`: generators are added
+// one by one through update() and into the reducer list.  sort_input orders them by ascending lead monomial first
+// (stable).  Leaves (nG, nP, nT, status) in e.
+template <int NV>
+__device__ __forceinline__ void warp_load_ideal(const BBParams& P, int src_slot, Env& e, Ctr& ct) {
   const int lane = bb_lane();
   const uint64_t* ik = P.in_key + (size_t)src_slot * P.max_gen_terms;
   const uint32_t* ic = P.in_coef + (size_t)src_slot * P.max_gen_terms;
   const int* io = P.in_off + (size_t)src_slot * (P.max_gens + 1);
   const int np = P.in_np[src_slot];
+  uint64_t* tk = ENV_PTR(uint64_t, e, P, o_tkey);
+  uint32_t* tc = ENV_PTR(uint32_t, e, P, o_tcoef);
   e.nG = 0; e.nP = 0; e.nT = 0; e.guard = 0;
   e.status = BB_STATUS_RUNNING;
   for (int q = 0; q < np; q++) {
@@ -564,45 +707,65 @@ __device__ __forceinline__ void warp_load_ideal(const BBParams& P, int src_slot,
     if (P.sort_input) {  // the generator whose stable ascending-LM rank is q
       int mine = -1;
       for (int g = lane; g < np; g += 32) {
-        uint64_t kg = ik[io[g]];
+        const uint64_t kg = ik[io[g]];
         int rank = 0;
-        for (int o = 0; o < np; o++) { uint64_t ko = ik[io[o]]; rank += (ko > kg) || (ko == kg && o < g); }
+        for (int o = 0; o < np; o++) { const uint64_t ko = ik[io[o]]; rank += (ko > kg) || (ko == kg && o < g); }
         if (rank == q) mine = g;
       }
-      uint32_t b = __ballot_sync(BB_FULL, mine >= 0);
+      const uint32_t b = __ballot_sync(BB_FULL, mine >= 0);
       src = __shfl_sync(BB_FULL, mine, __ffs(b) - 1);
     }
     const int off = io[src], len = io[src + 1] - off;
     if (e.nT + len > P.max_terms) { e.status = BB_STATUS_OVERFLOW_TERMS; return; }
-    for (int t = lane; t < len; t += 32) { e.tkey[e.nT + t] = ik[off + t]; e.tcoef[e.nT + t] = ic[off + t]; }
+    for (int t = lane; t < len; t += 32) { tk[e.nT + t] = ik[off + t]; tc[e.nT + t] = ic[off + t]; }
     __syncwarp();
-    if (!warp_add_basis(P, e, e.nT, len, ct)) return;
+    const uint64_t k1 = len > 1 ? ik[off + 1] : 0ull;
+    const uint32_t c1 = len > 1 ? ic[off + 1] : 0u;
+    ct.upb += (unsigned)e.nG; ct.upp += (unsigned)e.nP;
+    const long long r = warp_add_basis<NV>(P, e.base, e.nG, e.nP, e.nT, len, ik[off], ic[off], k1, c1);
+    if (r < 0) { e.status = (r == -1) ? BB_STATUS_OVERFLOW_PAIRS : BB_STATUS_OVERFLOW_BASIS; return; }
+    e.nP = (int)(r & 0xffffffffll);
+    ct.upp += (unsigned)(r >> 32);
+    e.nG++; e.nT += len;
   }
   if (e.nP == 0) e.status = BB_STATUS_DONE;
 }
 
-// Full reset of a slot: draws from the slot's stream when a distribution is set (re-rolling while P comes out
-// empty, buchberger.cpp:313-314), else replays the staged ideal.
-// rng: the slot's minstd_rand0 state (only lane 0's copy advances); rerolls counts skipped ideals.
-// fixed_src: staging slot to replay when no distribution is set.
-__device__ __forceinline__ void warp_reset(const BBParams& P, int slot, int fixed_src, Env& e, unsigned long long& rng,
-                                           int& rerolls, WarpCounters& ct) {
+// Full reset of a slot: draws from stream state `rng` when a distribution is set (re-rolling while P comes out
+// empty, buchberger.cpp:313-314), else replays staged ideal `fixed_src`.  Out of line (cold): the results go to
+// the slot's state record -- (nG, nP, nT, status), rng, rerolls -- and the caller reloads them.
+template <int NV>
+__device__ __noinline__ void warp_reset_slot(const BBParams& P, int slot, int fixed_src, uint32_t rng,
+                                             unsigned long long* ctrow) {
   const int lane = bb_lane();
-  rerolls = 0;
+  Env e;
+  e.base = P.arena + (size_t)slot * P.slot_stride;
+  e.nG = e.nP = e.nT = 0; e.status = BB_STATUS_EMPTY; e.guard = 0;
+  Ctr ct; ct.clear();
+  int rerolls = 0;
   if (P.dist.enabled) {
     for (;;) {
       int ok = 1;
       if (lane == 0) ok = gen_binomial_ideal(P, slot, rng) ? 1 : 0;
       ok = __shfl_sync(BB_FULL, ok, 0);
       __syncwarp();
-      if (!ok) { e.nG = e.nP = e.nT = 0; e.status = BB_STATUS_EMPTY; return; }
-      warp_load_ideal(P, slot, e, ct);
-      if (e.status != BB_STATUS_DONE) return;
+      if (!ok) { e.nG = e.nP = e.nT = 0; e.status = BB_STATUS_EMPTY; break; }
+      warp_load_ideal<NV>(P, slot, e, ct);
+      if (e.status != BB_STATUS_DONE) break;
       rerolls++;
     }
   } else {
-    warp_load_ideal(P, fixed_src, e, ct);
+    warp_load_ideal<NV>(P, fixed_src, e, ct);
   }
+  env_store(P, slot, e);
+  if (lane == 0) {
+    BBEnvState& S = P.st[slot];
+    S.rng = rng; S.rerolls = rerolls;
+    S.steps = 0; S.adds = 0; S.zero = 0; S.nonzero = 0; S.truncated = 0;
+    S.trace_hash = 0; S.disc_return = 0.0; S.discount = 1.0;
+  }
+  ct.spill(ctrow);
+  __syncwarp();
 }
 
 // ---------------------------------------------------------------------------------------------------- hashes
@@ -611,25 +774,25 @@ __device__ __forceinline__ unsigned long long trace_hash_item(int i, int j, int 
   return bb_hash_item_impl((uint64_t)(uint32_t)i | ((uint64_t)(uint32_t)j << 16) | ((uint64_t)(uint32_t)adds << 32),
                            (uint64_t)t);
 }
-__device__ __forceinline__ unsigned long long warp_terms_hash(const BBLayout& L, const uint64_t* tk, const uint32_t* tc,
-                                                              int nT, const int* lens_or_null, const uint2* meta_or_null,
-                                                              int npoly) {
+// lens: polynomial lengths as an int array with the given stride (in ints)
+template <int NV>
+__device__ __noinline__ unsigned long long warp_terms_hash(const uint64_t* tk, const uint32_t* tc, int nT, const int* lens,
+                                                           int lens_stride, int npoly) {
+  typedef KL<NV> K;
   const int lane = bb_lane();
   unsigned long long h = 0;
   for (int t = lane; t < nT; t += 32) {
-    uint64_t k = tk[t];
+    const uint64_t k = tk[t];
     uint64_t elo = 0, ehi = 0;
-    for (int v = 0; v < L.n; v++) {
-      uint64_t x = bb_exp(L, k, v);
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+      const uint64_t x = K::exp(k, v);
       if (v < 4) elo |= x << (16 * v); else ehi |= x << (16 * (v - 4));
     }
     h += bb_hash_item_impl((uint64_t)tc[t], 3ull * t) + bb_hash_item_impl(elo, 3ull * t + 1) +
          bb_hash_item_impl(ehi, 3ull * t + 2);
   }
-  for (int p = lane; p < npoly; p += 32) {
-    uint64_t len = lens_or_null ? (uint64_t)lens_or_null[p] : (uint64_t)meta_or_null[p].y;
-    h += bb_mix64(len + BB_GOLD2 * (uint64_t)(p + 1));
-  }
+  for (int p = lane; p < npoly; p += 32) h += bb_mix64((uint64_t)lens[(size_t)p * lens_stride] + BB_GOLD2 * (uint64_t)(p + 1));
 #pragma unroll
   for (int o = 16; o; o >>= 1) h += bb_shfl64(h, lane ^ o);
   return h;
@@ -640,61 +803,80 @@ __device__ __forceinline__ unsigned long long warp_terms_hash(const BBLayout& L,
 // g kept iff no kept lead monomial divides LM g  <=>  no f with LM f strictly dividing LM g and no earlier f
 // with the same lead monomial (every lead monomial is divisible by a kept one, by induction along the order).
 // interreduce: g <- (1/LC g) * (LT g + reduce(g - LT g, Gmin)), Gmin scanned in ascending-LM order.
-// Output goes to the slot's GB arena (gkey/gcoef/glen/gcount); returns false on overflow.  O(m^2/32) once per
-// episode; does not modify the environment.
-__device__ __forceinline__ bool warp_final_gb(const BBParams& P, int slot, Env& e, WarpCounters& ct) {
-  const BBLayout& L = P.L;
+// Output goes to the slot's GB arena (gkey/gcoef/glen/gcount).  O(m^2/32) once per episode; reads the slot's state
+// record, does not modify the environment.  Returns 1, or 0 on overflow.  Out of line (cold).
+template <int NV>
+__device__ __noinline__ int warp_final_gb(const BBParams& P, int slot, unsigned long long* ctrow) {
+  typedef KL<NV> K;
   const int lane = bb_lane();
+  Env e; env_load(P, slot, e);
+  Ctr ct; ct.clear();
   const int m = e.nG;
+  const uint64_t* lm = ENV_PTR(uint64_t, e, P, o_lm);
+  const GHead* gh = ENV_PTR(GHead, e, P, o_ghead);
   uint64_t* gk = P.gkey + (size_t)slot * P.max_terms;
   uint32_t* gc = P.gcoef + (size_t)slot * P.max_terms;
   int* gl = P.glen + (size_t)slot * P.max_basis;
   uint64_t* rlm2 = P.grlm + (size_t)slot * P.max_basis;    // lead monomials of Gmin, ascending
   uint32_t* ridx2 = P.gridx + (size_t)slot * P.max_basis;  // their basis indices
   uint32_t* flag = P.gflag + (size_t)slot * P.max_basis;   // kept flags by basis index
-  for (int base = 0; base < m; base += 32) {
-    int g = base + lane;
+  for (int b0 = 0; b0 < m; b0 += 32) {
+    const int g = b0 + lane;
     if (g < m) {
-      uint64_t kg = e.lm[g];
+      const uint64_t kg = lm[g];
       bool kept = true;
       for (int o = 0; o < m; o++) {
-        uint64_t ko = e.lm[o];
+        const uint64_t ko = lm[o];
         if (ko == kg) kept &= !(o < g);
-        else kept &= !bb_divides(L, ko, kg);
+        else kept &= !K::divides(ko, kg);
       }
       flag[g] = kept ? 1u : 0u;
     }
   }
   __syncwarp();
   int nmin = 0;
-  for (int base = 0; base < m; base += 32) {
-    int g = base + lane;
-    bool kept = g < m && flag[g] != 0u;
+  for (int b0 = 0; b0 < m; b0 += 32) {
+    const int g = b0 + lane;
+    const bool kept = g < m && flag[g] != 0u;
     if (kept) {
-      uint64_t kg = e.lm[g];
+      const uint64_t kg = lm[g];
       int rank = 0;  // kept elements with a smaller lead monomial (larger key); kept lead monomials are distinct
-      for (int o = 0; o < m; o++) rank += (flag[o] != 0u) && (e.lm[o] > kg);
+      for (int o = 0; o < m; o++) rank += (flag[o] != 0u) && (lm[o] > kg);
       rlm2[rank] = kg; ridx2[rank] = (uint32_t)g;
     }
     nmin += __popc(__ballot_sync(BB_FULL, kept));
   }
   __syncwarp();
-  int gT = 0;
-  for (int q = 0; q < nmin; q++) {
+  int gT = 0, ok = 1;
+  uint64_t* hk = ENV_PTR(uint64_t, e, P, o_hkey);
+  uint32_t* hc = ENV_PTR(uint32_t, e, P, o_hcoef);
+  const uint64_t* tk = ENV_PTR(uint64_t, e, P, o_tkey);
+  const uint32_t* tc = ENV_PTR(uint32_t, e, P, o_tcoef);
+  for (int q = 0; q < nmin && ok; q++) {
     const int g = (int)ridx2[q];
-    const uint2 meta = e.pmeta[g];
-    if (gT + 1 > P.max_terms) return false;
+    const GHead f = load_head(gh + g);
+    if (gT + 1 > P.max_terms) { ok = 0; break; }
+    // dividend = g - LT g: copy the tail into scratch half 0
+    const int n = (int)f.len - 1;
+    if (n > P.max_poly_terms) { ok = 0; break; }
+    for (int t = lane; t < n; t += 32) { hk[t] = tk[f.off + 1 + t]; hc[t] = tc[f.off + 1 + t]; }
+    __syncwarp();
+    Dividend h;
+    h.k0 = h.k1 = 0; h.c0 = h.c1 = 0;
+    dividend_from_scratch(P, e, h, n, 0);
     int steps;
-    int rlen = warp_reduce(P, e, e.tkey + meta.x + 1, e.tcoef + meta.x + 1, (int)meta.y - 1, -1, rlm2, ridx2, nmin,
-                           gk + gT + 1, gc + gT + 1, P.max_terms - gT - 1, steps, ct);
-    if (rlen < 0) return false;
-    const uint32_t inv = e.invlc[g];
-    if (lane == 0) { gk[gT] = e.lm[g]; gc[gT] = 1u; gl[q] = 1 + rlen; }
-    for (int t = lane; t < rlen; t += 32) gc[gT + 1 + t] = bb_mulmod(L, gc[gT + 1 + t], inv);
+    uint64_t r0k, r1k; uint32_t r0c, r1c;
+    const int rlen = warp_reduce<NV>(P, e, h, rlm2, ridx2, nmin, true, gk + gT + 1, gc + gT + 1, P.max_terms - gT - 1, steps,
+                                     r0k, r0c, r1k, r1c, ct);
+    if (rlen < 0) { ok = 0; break; }
+    if (lane == 0) { gk[gT] = f.lm; gc[gT] = 1u; gl[q] = 1 + rlen; }
+    for (int t = lane; t < rlen; t += 32) gc[gT + 1 + t] = bbf_mulmod(P.F, gc[gT + 1 + t], f.invlc);
     gT += 1 + rlen;
     __syncwarp();
   }
+  if (e.guard & K::g_all) ok = 0;
   if (lane == 0) { P.gcount[2 * slot] = nmin; P.gcount[2 * slot + 1] = gT; }
+  ct.spill(ctrow);
   __syncwarp();
-  return true;
+  return ok;
 }

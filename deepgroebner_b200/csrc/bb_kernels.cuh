@@ -1,0 +1,261 @@
+// bb_kernels.cuh -- the kernels of libbbenv.so, templated on the number of variables NV (compile-time monomial
+// layout), and the per-NV launch table the host API (bbenv.cu) dispatches through.  sm_100a only.
+//
+// Kernels (one warp per environment slot, BB_WARPS warps per CTA):
+//   k_reset    BuchbergerEnv::reset          buchberger.cpp:299-315  (+ on-device ideal generator, ideals.cpp:168-201)
+//   k_step     LeadMonomialsEnv::step(int)   buchberger.cpp:398-408 -> :318-329 (spoly, reduce, update, insert)
+//   k_select   First/Degree/Normal           buchberger.cpp:165-186
+//   k_observe  state matrix                  buchberger.cpp:354-370, 402-406
+//   k_run      persistent: episodes pulled from a queue and run to completion with on-device selection
+//              (the loop of buchberger(), buchberger.cpp:243-263); finished slots refill at once.
+//   k_final_gb interreduce(minimalize(G))    buchberger.cpp:102-122
+#pragma once
+#include "bb_device.cuh"
+
+#define BB_WARPS 8
+#define BB_THREADS (BB_WARPS * 32)
+#ifndef BB_MIN_BLOCKS
+#define BB_MIN_BLOCKS 4  // register cap 64 -> 32 resident warps per SM
+#endif
+
+struct BBRunArgs {
+  int strategy, episodes, seed_base;
+  const int* seeds;
+  int max_steps;
+  double gamma;
+  int compute_gb;
+  bb_episode_stats* out;
+  int32_t* trace;
+  int trace_eps, trace_cap;
+  int* queue;
+};
+
+struct BBKernelTable {
+  int nvars, w, dw, dshift, eshift;
+  cudaError_t (*reset)(const BBParams&, const uint8_t* mask, int nwarps, cudaStream_t);
+  cudaError_t (*step)(const BBParams&, const int* actions, double* reward, uint8_t* done, int nwarps, cudaStream_t);
+  cudaError_t (*select)(const BBParams&, int strategy, int* actions, int nwarps, cudaStream_t);
+  cudaError_t (*observe)(const BBParams&, int32_t* obs, int32_t* lengths, int pmax, int nwarps, cudaStream_t);
+  cudaError_t (*final_gb)(const BBParams&, int slot, int* ok_out, cudaStream_t);
+  cudaError_t (*run)(const BBParams&, const BBRunArgs&, int nwarps, cudaStream_t);
+  int (*run_blocks_per_sm)(void);
+};
+
+const BBKernelTable* bb_kernel_table(int nvars);  // bbenv.cu; NULL if nvars is outside 1..8
+
+#ifdef BB_NV  // ---------------------------------------------------------------------- per-NV translation unit only
+
+// warp rows -> one global atomic per CTA and counter
+__device__ __forceinline__ void counters_flush(const BBParams& P, unsigned long long (*sh)[CT_COUNT]) {
+  __syncthreads();
+  if (threadIdx.x < CT_COUNT) {
+    unsigned long long s = 0;
+#pragma unroll
+    for (int w = 0; w < BB_WARPS; w++) s += sh[w][threadIdx.x];
+    if (s) atomicAdd(&P.counters[threadIdx.x], s);
+  }
+}
+__device__ __forceinline__ unsigned long long* counters_row(unsigned long long (*sh)[CT_COUNT]) {
+  unsigned long long* row = sh[threadIdx.x >> 5];
+  if (bb_lane() < CT_COUNT) row[bb_lane()] = 0ull;
+  __syncwarp();
+  return row;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_reset(const __grid_constant__ BBParams P, const uint8_t* mask) {
+  __shared__ unsigned long long sh[BB_WARPS][CT_COUNT];
+  unsigned long long* row = counters_row(sh);
+  const int slot = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
+  if (slot < P.num_envs && (!mask || mask[slot])) warp_reset_slot<NV>(P, slot, slot, (uint32_t)P.st[slot].rng, row);
+  counters_flush(P, sh);
+}
+
+template <int NV>
+__global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_step(const __grid_constant__ BBParams P,
+                                                                   const int* __restrict__ actions,
+                                                                   double* __restrict__ reward, uint8_t* __restrict__ done) {
+  __shared__ unsigned long long sh[BB_WARPS][CT_COUNT];
+  unsigned long long* row = counters_row(sh);
+  const int slot = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
+  if (slot < P.num_envs) {
+    Env e; env_load(P, slot, e);
+    Ctr ct; ct.clear();
+    double r = 0.0;
+    if (e.status == BB_STATUS_RUNNING) {
+      int pi, pj;
+      const int g0 = e.nG;
+      const int adds = warp_step<NV>(P, e, actions[slot], &pi, &pj, ct);
+      if (pi >= 0) {
+        r = (P.rewards == BB_REWARD_ADDITIONS) ? -(double)adds : -1.0;
+        if (bb_lane() == 0) {
+          BBEnvState& S = P.st[slot];
+          S.trace_hash += trace_hash_item(pi, pj, adds, S.steps);
+          S.steps += 1; S.adds += adds;
+          if (e.nG > g0) S.nonzero += 1; else S.zero += 1;
+          row[CT_STEPS] += 1; row[CT_ADDS] += (unsigned)adds;
+          row[e.nG > g0 ? CT_NONZERO : CT_ZERO] += 1;
+          if (e.status == BB_STATUS_DONE) row[CT_EPISODES] += 1;
+        }
+      }
+      env_store(P, slot, e);
+    }
+    if (bb_lane() == 0) {
+      if (reward) reward[slot] = r;
+      if (done) done[slot] = (e.status != BB_STATUS_RUNNING) ? 1 : 0;
+    }
+    ct.spill(row);
+  }
+  counters_flush(P, sh);
+}
+
+template <int NV>
+__global__ void __launch_bounds__(BB_THREADS) k_select(const __grid_constant__ BBParams P, int strategy,
+                                                       int* __restrict__ actions) {
+  const int slot = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
+  if (slot >= P.num_envs) return;
+  Env e; env_load(P, slot, e);
+  const int a = (e.status == BB_STATUS_RUNNING) ? warp_select<NV>(P, e, strategy) : 0;
+  if (bb_lane() == 0) actions[slot] = a;
+}
+
+template <int NV>
+__global__ void __launch_bounds__(BB_THREADS) k_observe(const __grid_constant__ BBParams P, int32_t* __restrict__ obs,
+                                                        int32_t* __restrict__ lengths, int pmax) {
+  __shared__ unsigned long long sh[BB_WARPS][CT_COUNT];
+  unsigned long long* row = counters_row(sh);
+  const int slot = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
+  if (slot < P.num_envs) {
+    Env e; env_load(P, slot, e);
+    Ctr ct; ct.clear();
+    if (obs) warp_observe<NV>(P, e, obs + (size_t)slot * pmax * P.cols, pmax, ct);
+    if (lengths && bb_lane() == 0) lengths[slot] = e.nP;
+    ct.spill(row);
+  }
+  counters_flush(P, sh);
+}
+
+template <int NV>
+__global__ void __launch_bounds__(32) k_final_gb(const __grid_constant__ BBParams P, int slot, int* ok_out) {
+  __shared__ unsigned long long sh[1][CT_COUNT];
+  if (bb_lane() < CT_COUNT) sh[0][bb_lane()] = 0ull;
+  __syncwarp();
+  const int ok = warp_final_gb<NV>(P, slot, sh[0]);
+  if (bb_lane() == 0) *ok_out = ok;
+}
+
+// Persistent episode runner.  Each warp owns slot = its global warp index and loops: pop an episode, reset from
+// that episode's stream, select/step until P is empty (or max_steps), write the episode record, repeat.
+template <int NV>
+__global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_run(const __grid_constant__ BBParams P,
+                                                                  const __grid_constant__ BBRunArgs A) {
+  typedef KL<NV> K;
+  __shared__ unsigned long long sh[BB_WARPS][CT_COUNT];
+  unsigned long long* row = counters_row(sh);
+  const int slot = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
+  const int lane = bb_lane();
+  if (slot < P.num_envs) {
+    const int nstaged = P.num_envs;
+    Ctr ct; ct.clear();
+    for (;;) {
+      int ep = 0;
+      if (lane == 0) ep = atomicAdd(A.queue, 1);
+      ep = __shfl_sync(BB_FULL, ep, 0);
+      if (ep >= A.episodes) break;
+      // fixed ideals: episode ep replays the ideal staged for slot (ep mod N), read in place (staging is immutable)
+      warp_reset_slot<NV>(P, slot, ep % nstaged, rng_seed(A.seeds ? A.seeds[ep] : A.seed_base + ep), row);
+      Env e; env_load(P, slot, e);
+      const int g_start = e.nG;
+      int steps = 0, adds = 0;
+      unsigned long long th = 0;
+      double ret = 0.0, disc = 1.0;
+      while (e.status == BB_STATUS_RUNNING && (A.max_steps == 0 || steps < A.max_steps)) {
+        const int prow = warp_select<NV>(P, e, A.strategy);
+        int pi, pj;
+        const int a = warp_step<NV>(P, e, prow, &pi, &pj, ct);
+        th += trace_hash_item(pi, pj, a, steps);
+        const double r = (P.rewards == BB_REWARD_ADDITIONS) ? -(double)a : -1.0;
+        ret += disc * r; disc *= A.gamma;
+        if (A.trace && ep < A.trace_eps && steps < A.trace_cap && lane == 0)
+          reinterpret_cast<int4*>(A.trace)[(size_t)ep * A.trace_cap + steps] = make_int4(pi, pj, a, e.nP);
+        steps++; adds += a;
+      }
+      const int nonzero = e.nG - g_start, zero = steps - nonzero;
+      env_store(P, slot, e);
+      __syncwarp();
+      const GHead* gh = ENV_PTR(GHead, e, P, o_ghead);
+      const unsigned long long bh = warp_terms_hash<NV>(ENV_PTR(uint64_t, e, P, o_tkey), ENV_PTR(uint32_t, e, P, o_tcoef),
+                                                        e.nT, reinterpret_cast<const int*>(&gh[0].len),
+                                                        (int)(sizeof(GHead) / sizeof(int)), e.nG);
+      unsigned long long gbh = 0; int gp = 0, gt = 0;
+      int status = e.status;
+      if (A.compute_gb && status == BB_STATUS_DONE) {
+        if (warp_final_gb<NV>(P, slot, row)) {
+          gp = P.gcount[2 * slot]; gt = P.gcount[2 * slot + 1];
+          gbh = warp_terms_hash<NV>(P.gkey + (size_t)slot * P.max_terms, P.gcoef + (size_t)slot * P.max_terms, gt,
+                                    P.glen + (size_t)slot * P.max_basis, 1, gp);
+        } else {
+          status = BB_STATUS_OVERFLOW_SCRATCH;
+        }
+      }
+      if (lane == 0) {
+        bb_episode_stats o;
+        o.steps = steps; o.additions = adds; o.zero_reductions = zero; o.nonzero_reductions = nonzero;
+        o.nbasis = e.nG; o.nterms = e.nT; o.status = status; o.rerolls = P.st[slot].rerolls;
+        o.trace_hash = th; o.basis_hash = bh; o.gb_hash = gbh; o.gb_polys = gp; o.gb_terms = gt;
+        o.discounted_return = ret;
+        A.out[ep] = o;
+        BBEnvState& S = P.st[slot];
+        S.status = status; S.steps = steps; S.adds = adds; S.zero = zero; S.nonzero = nonzero; S.trace_hash = th;
+        S.disc_return = ret;
+        row[CT_STEPS] += (unsigned)steps; row[CT_ADDS] += (unsigned)adds; row[CT_NONZERO] += (unsigned)nonzero;
+        row[CT_ZERO] += (unsigned)zero; row[CT_EPISODES] += 1;
+      }
+      ct.spill(row);
+      __syncwarp();
+    }
+  }
+  counters_flush(P, sh);
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+static inline int grid_for_warps(int nwarps) { return (nwarps + BB_WARPS - 1) / BB_WARPS; }
+
+template <int NV>
+struct BBLaunch {
+  static cudaError_t reset(const BBParams& P, const uint8_t* mask, int nwarps, cudaStream_t s) {
+    k_reset<NV><<<grid_for_warps(nwarps), BB_THREADS, 0, s>>>(P, mask);
+    return cudaGetLastError();
+  }
+  static cudaError_t step(const BBParams& P, const int* actions, double* reward, uint8_t* done, int nwarps, cudaStream_t s) {
+    k_step<NV><<<grid_for_warps(nwarps), BB_THREADS, 0, s>>>(P, actions, reward, done);
+    return cudaGetLastError();
+  }
+  static cudaError_t select(const BBParams& P, int strategy, int* actions, int nwarps, cudaStream_t s) {
+    k_select<NV><<<grid_for_warps(nwarps), BB_THREADS, 0, s>>>(P, strategy, actions);
+    return cudaGetLastError();
+  }
+  static cudaError_t observe(const BBParams& P, int32_t* obs, int32_t* lengths, int pmax, int nwarps, cudaStream_t s) {
+    k_observe<NV><<<grid_for_warps(nwarps), BB_THREADS, 0, s>>>(P, obs, lengths, pmax);
+    return cudaGetLastError();
+  }
+  static cudaError_t final_gb(const BBParams& P, int slot, int* ok_out, cudaStream_t s) {
+    k_final_gb<NV><<<1, 32, 0, s>>>(P, slot, ok_out);
+    return cudaGetLastError();
+  }
+  static cudaError_t run(const BBParams& P, const BBRunArgs& A, int nwarps, cudaStream_t s) {
+    k_run<NV><<<grid_for_warps(nwarps), BB_THREADS, 0, s>>>(P, A);
+    return cudaGetLastError();
+  }
+  static int run_blocks_per_sm() {
+    int blocks = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_run<NV>, BB_THREADS, 0) != cudaSuccess) return -1;
+    return blocks;
+  }
+  static const BBKernelTable* table() {
+    static const BBKernelTable t = {NV, KL<NV>::w, KL<NV>::dw, KL<NV>::dshift, KL<NV>::eshift,
+                                    &reset, &step, &select, &observe, &final_gb, &run, &run_blocks_per_sm};
+    return &t;
+  }
+};
+#endif  // BB_NV

@@ -41,21 +41,27 @@ struct BBLayout {
   uint32_t mu;      // floor(2^32 / p) for Barrett reduction of x < 2^32
 };
 
+// Field widths as a function of n alone, shared by the runtime layout (host side) and the compile-time one
+// (device side, KL<NV> below) so that the two can never disagree.
+constexpr int bb_field_width(int n) { return 64 / (n + 1) > 16 ? 16 : 64 / (n + 1); }
+constexpr int bb_degree_width(int n) { return 64 - n * bb_field_width(n) > 16 ? 16 : 64 - n * bb_field_width(n); }
+constexpr uint64_t bb_fields_mask(int n, uint64_t per_field) {
+  uint64_t m = 0;
+  const int w = bb_field_width(n), eshift = 64 - bb_degree_width(n) - n * w;
+  for (int i = 0; i < n; i++) m |= per_field << (eshift + i * w);
+  return m;
+}
+
 inline BBLayout bb_make_layout(int n, uint32_t p) {
   BBLayout L;
   L.n = n;
-  L.w = 64 / (n + 1);
-  if (L.w > 16) L.w = 16;
-  L.dw = 64 - n * L.w;
-  if (L.dw > 16) L.dw = 16;
+  L.w = bb_field_width(n);
+  L.dw = bb_degree_width(n);
   L.dshift = 64 - L.dw;
   L.eshift = L.dshift - n * L.w;
   L.fmask = (1u << L.w) - 1u;
-  L.ex_mask = 0; L.ge_mask = 0;
-  for (int i = 0; i < n; i++) {
-    L.ex_mask |= (uint64_t)L.fmask << (L.eshift + i * L.w);
-    L.ge_mask |= (uint64_t)1 << (L.eshift + i * L.w + L.w - 1);
-  }
+  L.ex_mask = bb_fields_mask(n, (uint64_t)L.fmask);
+  L.ge_mask = bb_fields_mask(n, (uint64_t)1 << (L.w - 1));
   L.g_all = L.ge_mask | ((uint64_t)1 << 63);
   L.dmax = (1u << (L.dw - 1)) - 1u;
   L.emax = (1u << (L.w - 1)) - 1u;
@@ -63,6 +69,80 @@ inline BBLayout bb_make_layout(int n, uint32_t p) {
   L.p = p;
   L.mu = (uint32_t)(((uint64_t)1 << 32) / p);
   return L;
+}
+
+// Compile-time layout for the device code: every mask and shift is an immediate, loops over variables unroll.
+template <int NV>
+struct KL {
+  static constexpr int n = NV;
+  static constexpr int w = bb_field_width(NV);
+  static constexpr int dw = bb_degree_width(NV);
+  static constexpr int dshift = 64 - dw;
+  static constexpr int eshift = dshift - NV * w;
+  static constexpr uint32_t fmask = (1u << w) - 1u;
+  static constexpr uint64_t ex_mask = bb_fields_mask(NV, (uint64_t)fmask);
+  static constexpr uint64_t ge_mask = bb_fields_mask(NV, (uint64_t)1 << (w - 1));
+  static constexpr uint64_t g_all = ge_mask | ((uint64_t)1 << 63);
+  static constexpr uint32_t dmax = (1u << (dw - 1)) - 1u;
+  static constexpr uint32_t emax = (1u << (w - 1)) - 1u;
+  static constexpr uint64_t bias = (uint64_t)dmax << dshift;
+
+  static BB_HD uint32_t exp(uint64_t k, int i) { return (uint32_t)(k >> (eshift + i * w)) & fmask; }
+  static BB_HD uint32_t deg(uint64_t k) { return dmax - (uint32_t)(k >> dshift); }
+  // true iff b divides a (degree fields are ignored)
+  static BB_HD bool divides(uint64_t b, uint64_t a) {
+    return ((((a & ex_mask) | ge_mask) - (b & ex_mask)) & ge_mask) == ge_mask;
+  }
+  static BB_HD uint64_t lcm_exps(uint64_t a, uint64_t b) {
+    uint64_t ea = a & ex_mask, eb = b & ex_mask;
+    uint64_t t = ((ea | ge_mask) - eb) & ge_mask;  // guard set where a_i >= b_i
+    uint64_t sel = t - (t >> (w - 1));             // value bits of those fields
+    return (ea & sel) | (eb & ~sel);
+  }
+  static BB_HD bool coprime(uint64_t a, uint64_t b) {
+    uint64_t ea = a & ex_mask, eb = b & ex_mask;
+    uint64_t t = ((ea | ge_mask) - eb) & ge_mask;
+    uint64_t sel = t - (t >> (w - 1));
+    return ((eb & sel) | (ea & ~sel)) == 0;        // field-wise min is zero everywhere
+  }
+  static BB_HD uint32_t sum_fields(uint64_t exps) {
+    uint32_t s = 0;
+    uint64_t x = exps >> eshift;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 0; i < NV; i++) { s += (uint32_t)x & fmask; x >>= w; }
+    return s;
+  }
+  static BB_HD uint64_t key_from_exps(uint64_t exps) { return exps | ((uint64_t)(dmax - sum_fields(exps)) << dshift); }
+};
+
+// GF(p) parameters as the kernels carry them
+struct BBField {
+  uint32_t p, mu;
+};
+BB_HD uint32_t bbf_mulmod(const BBField& F, uint32_t a, uint32_t b) {
+  uint32_t x = a * b;  // < 2^32 because p < 2^16
+#if defined(__CUDA_ARCH__)
+  uint32_t q = __umulhi(x, F.mu);
+#else
+  uint32_t q = (uint32_t)(((uint64_t)x * F.mu) >> 32);
+#endif
+  uint32_t r = x - q * F.p;  // in [0, 2p)
+  return r >= F.p ? r - F.p : r;
+}
+BB_HD uint32_t bbf_addmod(const BBField& F, uint32_t a, uint32_t b) { uint32_t r = a + b; return r >= F.p ? r - F.p : r; }
+BB_HD uint32_t bbf_negmod(const BBField& F, uint32_t a) { return a ? F.p - a : 0u; }
+// a^(p-2): the unique inverse, hence bit-identical to the extended-Euclid inverse of polynomials.cpp:11-23
+BB_HD uint32_t bbf_invmod(const BBField& F, uint32_t a) {
+  if (a == 1u) return 1u;
+  uint32_t r = 1, b = a, e = F.p - 2;
+  while (e) {
+    if (e & 1u) r = bbf_mulmod(F, r, b);
+    b = bbf_mulmod(F, b, b);
+    e >>= 1;
+  }
+  return r;
 }
 
 // ---- monomials -----------------------------------------------------------------------------------------------

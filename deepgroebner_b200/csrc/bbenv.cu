@@ -1,13 +1,5 @@
-// bbenv.cu -- kernels and the extern "C" ABI (include/bbenv.h) of libbbenv.so.  sm_100a only.
-//
-// Kernels (one warp per environment slot, 8 warps per CTA):
-//   k_reset    BuchbergerEnv::reset          buchberger.cpp:299-315  (+ on-device ideal generator, ideals.cpp:168-201)
-//   k_step     LeadMonomialsEnv::step(int)   buchberger.cpp:398-408 -> :318-329 (spoly, reduce, update, insert)
-//   k_select   First/Degree/Normal           buchberger.cpp:165-186
-//   k_observe  state matrix                  buchberger.cpp:354-370, 402-406
-//   k_run      persistent: episodes pulled from a queue and run to completion with on-device selection
-//              (the loop of buchberger(), buchberger.cpp:243-263); finished slots refill at once.
-//   k_final_gb interreduce(minimalize(G))    buchberger.cpp:102-122
+// bbenv.cu -- the extern "C" ABI (include/bbenv.h) of libbbenv.so: handle, arenas, host views, and dispatch to the
+// per-NV kernel tables (bb_kernels.cuh, compiled in bb_nv.cu once per number of variables).  sm_100a only.
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -16,114 +8,27 @@
 #include <string>
 #include <vector>
 
-#include "bb_device.cuh"
+#include "bb_kernels.cuh"
 
-#define BB_WARPS 8
-#define BB_THREADS (BB_WARPS * 32)
-
-// ------------------------------------------------------------------------------------------------ counters
-__device__ __forceinline__ void counters_flush(const BBParams& P, const WarpCounters& ct, unsigned long long* sh) {
-  // warp -> CTA (shared atomics) -> one global atomic per CTA and counter
-  if (threadIdx.x < CT_COUNT) sh[threadIdx.x] = 0ull;
-  __syncthreads();
-  if (bb_lane() == 0) {
-#pragma unroll
-    for (int i = 0; i < CT_COUNT; i++)
-      if (ct.v[i]) atomicAdd(&sh[i], ct.v[i]);
-  }
-  __syncthreads();
-  if (threadIdx.x < CT_COUNT && sh[threadIdx.x]) atomicAdd(&P.counters[threadIdx.x], sh[threadIdx.x]);
-}
-
-// ------------------------------------------------------------------------------------------------ kernels
+// ------------------------------------------------------------------------------------------------ layout-free kernels
 __global__ void __launch_bounds__(BB_THREADS) k_seed(BBParams P, const int* seeds, int base) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e < P.num_envs) P.st[e].rng = rng_seed(seeds ? seeds[e] : base + e);
-}
-
-__global__ void __launch_bounds__(BB_THREADS) k_reset(BBParams P, const uint8_t* mask) {
-  __shared__ unsigned long long sh[CT_COUNT];
-  const int slot = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
-  WarpCounters ct; ct.clear();
-  if (slot < P.num_envs && (!mask || mask[slot])) {
-    Env e; env_bind(P, slot, e);
-    BBEnvState& S = P.st[slot];
-    unsigned long long rng = S.rng;
-    int rerolls = 0;
-    warp_reset(P, slot, slot, e, rng, rerolls, ct);
-    if (bb_lane() == 0) {
-      S.rng = rng; S.rerolls = rerolls;
-      S.steps = 0; S.adds = 0; S.zero = 0; S.nonzero = 0; S.truncated = 0;
-      S.trace_hash = 0; S.disc_return = 0.0; S.discount = 1.0;
-    }
-    env_store(P, slot, e);
-  }
-  counters_flush(P, ct, sh);
-}
-
-__global__ void __launch_bounds__(BB_THREADS) k_step(BBParams P, const int* __restrict__ actions,
-                                                     double* __restrict__ reward, uint8_t* __restrict__ done) {
-  __shared__ unsigned long long sh[CT_COUNT];
-  const int slot = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
-  WarpCounters ct; ct.clear();
-  if (slot < P.num_envs) {
-    Env e; env_load(P, slot, e);
-    double r = 0.0;
-    if (e.status == BB_STATUS_RUNNING) {
-      int pi, pj;
-      int adds = warp_step(P, e, actions[slot], &pi, &pj, ct);
-      if (pi >= 0) {
-        r = (P.rewards == BB_REWARD_ADDITIONS) ? -(double)adds : -1.0;
-        if (bb_lane() == 0) {
-          BBEnvState& S = P.st[slot];
-          S.trace_hash += trace_hash_item(pi, pj, adds, S.steps);
-          S.steps += 1; S.adds += adds;
-          if (e.nG > S.nG) S.nonzero += 1; else S.zero += 1;
-        }
-      }
-      env_store(P, slot, e);
-    }
-    if (bb_lane() == 0) {
-      if (reward) reward[slot] = r;
-      if (done) done[slot] = (e.status != BB_STATUS_RUNNING) ? 1 : 0;
-    }
-  }
-  counters_flush(P, ct, sh);
-}
-
-__global__ void __launch_bounds__(BB_THREADS) k_select(BBParams P, int strategy, int* __restrict__ actions) {
-  const int slot = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
-  if (slot >= P.num_envs) return;
-  Env e; env_load(P, slot, e);
-  int a = (e.status == BB_STATUS_RUNNING) ? warp_select(P, e, strategy) : 0;
-  if (bb_lane() == 0) actions[slot] = a;
-}
-
-__global__ void __launch_bounds__(BB_THREADS) k_observe(BBParams P, int32_t* __restrict__ obs,
-                                                        int32_t* __restrict__ lengths, int pmax) {
-  __shared__ unsigned long long sh[CT_COUNT];
-  const int slot = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
-  WarpCounters ct; ct.clear();
-  if (slot < P.num_envs) {
-    Env e; env_load(P, slot, e);
-    if (obs) warp_observe(P, e, obs + (size_t)slot * pmax * P.cols, pmax, ct);
-    if (lengths && bb_lane() == 0) lengths[slot] = e.nP;
-  }
-  counters_flush(P, ct, sh);
 }
 
 __global__ void __launch_bounds__(BB_THREADS) k_pairs(BBParams P, int32_t* __restrict__ out,
                                                       int32_t* __restrict__ lengths, int pmax) {
   const int slot = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
   if (slot >= P.num_envs) return;
-  Env e; env_load(P, slot, e);
+  const int nP = P.st[slot].nP;
+  const uint32_t* pairs = SLOT_PTR(uint32_t, P, slot, o_pairs);
   int32_t* o = out + (size_t)slot * pmax * 2;
   for (int r = bb_lane(); r < pmax; r += 32) {
     int i = -1, j = -1;
-    if (r < e.nP) { uint32_t pr = e.pairs[r]; i = pr & 0xffffu; j = pr >> 16; }
+    if (r < nP) { uint32_t pr = pairs[r]; i = pr & 0xffffu; j = pr >> 16; }
     o[2 * r] = i; o[2 * r + 1] = j;
   }
-  if (lengths && bb_lane() == 0) lengths[slot] = e.nP;
+  if (lengths && bb_lane() == 0) lengths[slot] = nP;
 }
 
 __global__ void __launch_bounds__(BB_THREADS) k_status(BBParams P, int32_t* status, bb_episode_stats* stats) {
@@ -141,93 +46,28 @@ __global__ void __launch_bounds__(BB_THREADS) k_status(BBParams P, int32_t* stat
   }
 }
 
-__global__ void __launch_bounds__(32) k_final_gb(BBParams P, int slot, int* ok_out) {
-  WarpCounters ct; ct.clear();
-  Env e; env_load(P, slot, e);
-  bool ok = warp_final_gb(P, slot, e, ct);
-  if (bb_guard_tripped(P.L, e.guard)) ok = false;
-  if (bb_lane() == 0) *ok_out = ok ? 1 : 0;
-}
+// ------------------------------------------------------------------------------------------------ kernel tables
+const BBKernelTable* bb_kernel_table_nv1(); const BBKernelTable* bb_kernel_table_nv2();
+const BBKernelTable* bb_kernel_table_nv3(); const BBKernelTable* bb_kernel_table_nv4();
+const BBKernelTable* bb_kernel_table_nv5(); const BBKernelTable* bb_kernel_table_nv6();
+const BBKernelTable* bb_kernel_table_nv7(); const BBKernelTable* bb_kernel_table_nv8();
 
-// Persistent episode runner.  Each warp owns slot = its global warp index and loops: pop an episode, reset from
-// that episode's stream, select/step until P is empty (or max_steps), write the episode record, repeat.
-__global__ void __launch_bounds__(BB_THREADS) k_run(BBParams P, int strategy, int episodes, int seed_base,
-                                                    const int* __restrict__ seeds, int max_steps, double gamma,
-                                                    int compute_gb, bb_episode_stats* __restrict__ out,
-                                                    int32_t* __restrict__ trace, int trace_eps, int trace_cap,
-                                                    int* queue) {
-  __shared__ unsigned long long sh[CT_COUNT];
-  const int slot = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
-  const int lane = bb_lane();
-  WarpCounters ct; ct.clear();
-  if (slot < P.num_envs) {
-    Env e; env_bind(P, slot, e);
-    e.nG = e.nP = e.nT = 0; e.status = BB_STATUS_EMPTY;
-    const int nstaged = P.num_envs;
-    int last_steps = 0, last_adds = 0, last_zero = 0, last_nonzero = 0, last_rerolls = 0;
-    unsigned long long last_hash = 0; double last_ret = 0.0;
-    for (;;) {
-      int ep = 0;
-      if (lane == 0) ep = atomicAdd(queue, 1);
-      ep = __shfl_sync(BB_FULL, ep, 0);
-      if (ep >= episodes) break;
-      unsigned long long rng = rng_seed(seeds ? seeds[ep] : seed_base + ep);
-      int rerolls = 0;
-      // fixed ideals: episode ep replays the ideal staged for slot (ep mod N), read in place (staging is immutable)
-      warp_reset(P, slot, ep % nstaged, e, rng, rerolls, ct);
-      int steps = 0, adds = 0, zero = 0, nonzero = 0;
-      unsigned long long th = 0;
-      double ret = 0.0, disc = 1.0;
-      while (e.status == BB_STATUS_RUNNING && (max_steps == 0 || steps < max_steps)) {
-        const int row = warp_select(P, e, strategy);
-        const int g0 = e.nG;
-        int pi, pj;
-        const int a = warp_step(P, e, row, &pi, &pj, ct);
-        th += trace_hash_item(pi, pj, a, steps);
-        const double r = (P.rewards == BB_REWARD_ADDITIONS) ? -(double)a : -1.0;
-        ret += disc * r; disc *= gamma;
-        if (trace && ep < trace_eps && steps < trace_cap && lane == 0)
-          reinterpret_cast<int4*>(trace)[(size_t)ep * trace_cap + steps] = make_int4(pi, pj, a, e.nP);
-        steps++; adds += a;
-        if (e.nG > g0) nonzero++; else zero++;
-      }
-      ct.v[CT_EPISODES]++;
-      const unsigned long long bh = warp_terms_hash(P.L, e.tkey, e.tcoef, e.nT, nullptr, e.pmeta, e.nG);
-      unsigned long long gh = 0; int gp = 0, gt = 0;
-      if (compute_gb && e.status == BB_STATUS_DONE) {
-        if (warp_final_gb(P, slot, e, ct) && !bb_guard_tripped(P.L, e.guard)) {
-          gp = P.gcount[2 * slot]; gt = P.gcount[2 * slot + 1];
-          gh = warp_terms_hash(P.L, P.gkey + (size_t)slot * P.max_terms, P.gcoef + (size_t)slot * P.max_terms, gt,
-                               P.glen + (size_t)slot * P.max_basis, nullptr, gp);
-        } else {
-          e.status = BB_STATUS_OVERFLOW_SCRATCH;
-        }
-      }
-      if (lane == 0) {
-        bb_episode_stats o;
-        o.steps = steps; o.additions = adds; o.zero_reductions = zero; o.nonzero_reductions = nonzero;
-        o.nbasis = e.nG; o.nterms = e.nT; o.status = e.status; o.rerolls = rerolls;
-        o.trace_hash = th; o.basis_hash = bh; o.gb_hash = gh; o.gb_polys = gp; o.gb_terms = gt;
-        o.discounted_return = ret;
-        out[ep] = o;
-      }
-      last_steps = steps; last_adds = adds; last_zero = zero; last_nonzero = nonzero; last_rerolls = rerolls;
-      last_hash = th; last_ret = ret;
-    }
-    env_store(P, slot, e);
-    if (lane == 0) {
-      BBEnvState& S = P.st[slot];
-      S.steps = last_steps; S.adds = last_adds; S.zero = last_zero; S.nonzero = last_nonzero;
-      S.rerolls = last_rerolls; S.trace_hash = last_hash; S.disc_return = last_ret;
-    }
+const BBKernelTable* bb_kernel_table(int nvars) {
+  switch (nvars) {
+    case 1: return bb_kernel_table_nv1(); case 2: return bb_kernel_table_nv2();
+    case 3: return bb_kernel_table_nv3(); case 4: return bb_kernel_table_nv4();
+    case 5: return bb_kernel_table_nv5(); case 6: return bb_kernel_table_nv6();
+    case 7: return bb_kernel_table_nv7(); case 8: return bb_kernel_table_nv8();
   }
-  counters_flush(P, ct, sh);
+  return nullptr;
 }
 
 // ------------------------------------------------------------------------------------------------ host side
 struct bb_handle {
   bb_config cfg;
   BBParams P;
+  BBLayout L;               // host-side (runtime) copy of the packed-monomial layout
+  const BBKernelTable* K;   // kernels compiled for cfg.nvars
   int sm_count;
   std::vector<void*> allocs;
   std::string err;
@@ -260,7 +100,7 @@ static cudaError_t dev_alloc(bb_handle* h, T** p, size_t count) {
   return cudaMemset(q, 0, count * sizeof(T) + 16);
 }
 
-static inline int grid_for_warps(int nwarps) { return (nwarps + BB_WARPS - 1) / BB_WARPS; }
+static inline int grid_for_warps_host(int nwarps) { return (nwarps + BB_WARPS - 1) / BB_WARPS; }
 
 extern "C" {
 
@@ -272,11 +112,14 @@ int bb_num_envs(const bb_handle* h) { return h->P.num_envs; }
 int bb_sm_count(const bb_handle* h) { return h->sm_count; }
 uint64_t bb_hash_item(uint64_t x, uint64_t pos) { return bb_hash_item_impl(x, pos); }
 
-int bb_resident_envs(int device) {
-  int sms = 0, blocks = 0;
+int bb_resident_envs(int device, int nvars) {
+  int sms = 0;
+  const BBKernelTable* K = bb_kernel_table(nvars);
+  if (!K) return -1;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) return -1;
   if (cudaSetDevice(device) != cudaSuccess) return -1;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_run, BB_THREADS, 0) != cudaSuccess) return -1;
+  const int blocks = K->run_blocks_per_sm();
+  if (blocks <= 0) return -1;
   return sms * blocks * BB_WARPS;
 }
 
@@ -322,24 +165,36 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
   h->sm_count = prop.multiProcessorCount;
   BBParams& P = h->P;
   memset(&P, 0, sizeof P);
-  P.L = bb_make_layout(cfg->nvars, (uint32_t)cfg->prime);
+  h->L = bb_make_layout(cfg->nvars, (uint32_t)cfg->prime);
+  h->K = bb_kernel_table(cfg->nvars);
+  if (!h->K || h->K->w != h->L.w || h->K->dw != h->L.dw || h->K->dshift != h->L.dshift || h->K->eshift != h->L.eshift) {
+    h->err = "bb_create: kernel table / layout mismatch"; return bail(-6);
+  }
+  P.F.p = h->L.p; P.F.mu = h->L.mu; P.nvars = cfg->nvars;
   P.num_envs = cfg->num_envs; P.k = cfg->k; P.cols = 2 * cfg->nvars * cfg->k;
   P.elimination = cfg->elimination; P.rewards = cfg->rewards;
   P.sort_input = cfg->sort_input ? 1 : 0; P.sort_reducers = cfg->sort_reducers ? 1 : 0;
   P.max_basis = cfg->max_basis; P.max_pairs = cfg->max_pairs; P.max_terms = cfg->max_terms;
   P.max_poly_terms = cfg->max_poly_terms; P.max_gens = cfg->max_gens; P.max_gen_terms = cfg->max_gen_terms;
   const size_t N = (size_t)cfg->num_envs;
-  CKC(dev_alloc(h, &P.tkey, N * P.max_terms));
-  CKC(dev_alloc(h, &P.tcoef, N * P.max_terms));
-  CKC(dev_alloc(h, &P.pmeta, N * P.max_basis));
-  CKC(dev_alloc(h, &P.lm, N * P.max_basis));
-  CKC(dev_alloc(h, &P.invlc, N * P.max_basis));
-  CKC(dev_alloc(h, &P.rlm, N * P.max_basis));
-  CKC(dev_alloc(h, &P.ridx, N * P.max_basis));
-  CKC(dev_alloc(h, &P.pairs, N * P.max_pairs));
-  CKC(dev_alloc(h, &P.hkey, N * 2 * P.max_poly_terms));
-  CKC(dev_alloc(h, &P.hcoef, N * 2 * P.max_poly_terms));
-  CKC(dev_alloc(h, &P.lscr, N * P.max_basis));
+  {  // one contiguous arena per slot; 8-byte arrays first, every array 32-byte aligned, stride a multiple of 128
+    size_t o = 0;
+    auto take = [&o](size_t bytes) { size_t at = o; o = (o + bytes + 31) & ~(size_t)31; return (unsigned)at; };
+    P.o_ghead = take(sizeof(GHead) * (size_t)P.max_basis);
+    P.o_lm = take(8 * (size_t)P.max_basis);
+    P.o_rlm = take(8 * (size_t)P.max_basis);
+    P.o_lscr = take(8 * (size_t)P.max_basis);
+    P.o_plcm = take(8 * (size_t)P.max_pairs);
+    P.o_tkey = take(8 * (size_t)P.max_terms);
+    P.o_hkey = take(8 * 2 * (size_t)P.max_poly_terms);
+    P.o_ridx = take(4 * (size_t)P.max_basis);
+    P.o_pairs = take(4 * (size_t)P.max_pairs);
+    P.o_tcoef = take(4 * (size_t)P.max_terms);
+    P.o_hcoef = take(4 * 2 * (size_t)P.max_poly_terms);
+    if (o >= ((size_t)1 << 31)) { h->err = "bb_create: per-environment arena exceeds 2 GiB"; return bail(-1); }
+    P.slot_stride = (o + 127) & ~(size_t)127;
+  }
+  CKC(dev_alloc(h, &P.arena, N * P.slot_stride));
   CKC(dev_alloc(h, &P.st, N));
   CKC(dev_alloc(h, &P.in_key, N * P.max_gen_terms));
   CKC(dev_alloc(h, &P.in_coef, N * P.max_gen_terms));
@@ -382,9 +237,9 @@ int bb_set_distribution(bb_handle* h, int d, int s, int dist, int constants, int
   if (d < 0 || s < 1) return fail(h, "bb_set_distribution: need d >= 0 and s >= 1");
   if (s > P.max_gens || 2 * s > P.max_gen_terms) return fail(h, "bb_set_distribution: s exceeds max_gens/max_gen_terms");
   if ((unsigned)dist > 2u) return fail(h, "bb_set_distribution: bad dist");
-  if ((unsigned)d > P.L.emax || (unsigned)d > P.L.dmax) return fail(h, "bb_set_distribution: degree does not fit the packed layout");
+  if ((unsigned)d > h->L.emax || (unsigned)d > h->L.dmax) return fail(h, "bb_set_distribution: degree does not fit the packed layout");
   CK(cudaSetDevice(h->cfg.device));
-  const int n = P.L.n;
+  const int n = h->L.n;
   // degree_distribution counts (ideals.cpp:75-100)
   std::vector<double> prob;
   prob.push_back(constants ? 1.0 : 0.0);
@@ -407,7 +262,7 @@ int bb_set_distribution(bb_handle* h, int d, int s, int dist, int constants, int
   for (int deg = 0; deg <= d; deg++) {
     off.push_back((int)basis.size());
     int e[8] = {0};
-    basis_rec(P.L, n, 0, deg, e, basis);
+    basis_rec(h->L, n, 0, deg, e, basis);
   }
   off.push_back((int)basis.size());
   double* d_cp = nullptr; uint64_t* d_basis = nullptr; int* d_off = nullptr;
@@ -443,7 +298,8 @@ int bb_set_ideals(bb_handle* h, const int32_t* env_ids, int count, const int32_t
   BBParams& P = h->P;
   if (count < 0 || !ideal_offsets || !poly_offsets || !exps || !coefs) return fail(h, "bb_set_ideals: null argument");
   CK(cudaSetDevice(h->cfg.device));
-  const int n = P.L.n;
+  const int n = h->L.n;
+  const BBLayout& L = h->L;
   std::vector<uint64_t> keys((size_t)P.max_gen_terms);
   std::vector<uint32_t> cf((size_t)P.max_gen_terms);
   std::vector<int> off((size_t)P.max_gens + 1);
@@ -465,14 +321,14 @@ int bb_set_ideals(bb_handle* h, const int32_t* env_ids, int count, const int32_t
         uint32_t deg = 0;
         for (int v = 0; v < n; v++) {
           int x = exps[(size_t)t * n + v];
-          if (x < 0 || (uint32_t)x > P.L.emax) return fail(h, "bb_set_ideals: exponent does not fit the packed layout");
+          if (x < 0 || (uint32_t)x > L.emax) return fail(h, "bb_set_ideals: exponent does not fit the packed layout");
           deg += (uint32_t)x;
         }
-        if (deg > P.L.dmax) return fail(h, "bb_set_ideals: degree does not fit the packed layout");
-        long long cc = coefs[t] % (long long)P.L.p;
-        if (cc < 0) cc += P.L.p;
+        if (deg > L.dmax) return fail(h, "bb_set_ideals: degree does not fit the packed layout");
+        long long cc = coefs[t] % (long long)L.p;
+        if (cc < 0) cc += L.p;
         if (cc == 0) return fail(h, "bb_set_ideals: zero coefficient");
-        terms.push_back({bb_pack(P.L, exps + (size_t)t * n), (uint32_t)cc});
+        terms.push_back({bb_pack(L, exps + (size_t)t * n), (uint32_t)cc});
       }
       std::stable_sort(terms.begin(), terms.end(), [](const auto& a, const auto& b) { return a.first < b.first; });
       for (size_t t = 1; t < terms.size(); t++)
@@ -492,8 +348,7 @@ int bb_set_ideals(bb_handle* h, const int32_t* env_ids, int count, const int32_t
 int bb_reset(bb_handle* h, const uint8_t* mask_dev, void* stream) {
   if (!h) return -1;
   CK(cudaSetDevice(h->cfg.device));
-  k_reset<<<grid_for_warps(h->P.num_envs), BB_THREADS, 0, (cudaStream_t)stream>>>(h->P, mask_dev);
-  CK(cudaGetLastError());
+  CK(h->K->reset(h->P, mask_dev, h->P.num_envs, (cudaStream_t)stream));
   return 0;
 }
 
@@ -501,8 +356,7 @@ int bb_step(bb_handle* h, const int32_t* actions_dev, double* reward_dev, uint8_
   if (!h) return -1;
   if (!actions_dev) return fail(h, "bb_step: null actions");
   CK(cudaSetDevice(h->cfg.device));
-  k_step<<<grid_for_warps(h->P.num_envs), BB_THREADS, 0, (cudaStream_t)stream>>>(h->P, actions_dev, reward_dev, done_dev);
-  CK(cudaGetLastError());
+  CK(h->K->step(h->P, actions_dev, reward_dev, done_dev, h->P.num_envs, (cudaStream_t)stream));
   return 0;
 }
 
@@ -510,8 +364,7 @@ int bb_select(bb_handle* h, int strategy, int32_t* actions_dev, void* stream) {
   if (!h) return -1;
   if ((unsigned)strategy > 2u || !actions_dev) return fail(h, "bb_select: bad argument");
   CK(cudaSetDevice(h->cfg.device));
-  k_select<<<grid_for_warps(h->P.num_envs), BB_THREADS, 0, (cudaStream_t)stream>>>(h->P, strategy, actions_dev);
-  CK(cudaGetLastError());
+  CK(h->K->select(h->P, strategy, actions_dev, h->P.num_envs, (cudaStream_t)stream));
   return 0;
 }
 
@@ -519,8 +372,7 @@ int bb_observe(bb_handle* h, int32_t* obs_dev, int32_t* lengths_dev, int pmax, v
   if (!h) return -1;
   if (pmax < 0 || (obs_dev && pmax == 0)) return fail(h, "bb_observe: bad pmax");
   CK(cudaSetDevice(h->cfg.device));
-  k_observe<<<grid_for_warps(h->P.num_envs), BB_THREADS, 0, (cudaStream_t)stream>>>(h->P, obs_dev, lengths_dev, pmax);
-  CK(cudaGetLastError());
+  CK(h->K->observe(h->P, obs_dev, lengths_dev, pmax, h->P.num_envs, (cudaStream_t)stream));
   return 0;
 }
 
@@ -528,7 +380,7 @@ int bb_pairs(bb_handle* h, int32_t* pairs_dev, int32_t* lengths_dev, int pmax, v
   if (!h) return -1;
   if (!pairs_dev || pmax < 1) return fail(h, "bb_pairs: bad argument");
   CK(cudaSetDevice(h->cfg.device));
-  k_pairs<<<grid_for_warps(h->P.num_envs), BB_THREADS, 0, (cudaStream_t)stream>>>(h->P, pairs_dev, lengths_dev, pmax);
+  k_pairs<<<grid_for_warps_host(h->P.num_envs), BB_THREADS, 0, (cudaStream_t)stream>>>(h->P, pairs_dev, lengths_dev, pmax);
   CK(cudaGetLastError());
   return 0;
 }
@@ -559,17 +411,18 @@ int bb_run(bb_handle* h, int strategy, int episodes, int seed_base, const int32_
   CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int), s));
   int workers = h->P.num_envs < episodes ? h->P.num_envs : episodes;
   if (workers < 1) return 0;
-  k_run<<<grid_for_warps(workers), BB_THREADS, 0, s>>>(h->P, strategy, episodes, seed_base, seeds_dev, max_steps, gamma,
-                                                      compute_gb, stats_dev, trace_dev, trace_dev ? trace_episodes : 0,
-                                                      trace_cap, h->d_queue);
-  CK(cudaGetLastError());
+  BBRunArgs A;
+  A.strategy = strategy; A.episodes = episodes; A.seed_base = seed_base; A.seeds = seeds_dev; A.max_steps = max_steps;
+  A.gamma = gamma; A.compute_gb = compute_gb; A.out = stats_dev; A.trace = trace_dev;
+  A.trace_eps = trace_dev ? trace_episodes : 0; A.trace_cap = trace_cap; A.queue = h->d_queue;
+  CK(h->K->run(h->P, A, workers, s));
   return 0;
 }
 
 static int unpack_polys(bb_handle* h, const std::vector<uint64_t>& keys, const std::vector<uint32_t>& cf,
                         const std::vector<int>& plen, int32_t* lens, int cap_polys, int32_t* exps, int32_t* coefs,
                         int cap_terms, int* nterms_out) {
-  const BBLayout& L = h->P.L;
+  const BBLayout& L = h->L;
   int np = (int)plen.size(), nt = 0;
   for (int q = 0; q < np; q++) nt += plen[q];
   if (nterms_out) *nterms_out = nt;
@@ -591,17 +444,18 @@ int bb_download_basis(bb_handle* h, int env, int32_t* lens, int cap_polys, int32
   CK(cudaDeviceSynchronize());
   BBEnvState S;
   CK(cudaMemcpy(&S, P.st + env, sizeof S, cudaMemcpyDeviceToHost));
-  std::vector<uint2> meta((size_t)std::max(S.nG, 1));
+  std::vector<GHead> meta((size_t)std::max(S.nG, 1));
   std::vector<uint64_t> keys((size_t)std::max(S.nT, 1));
   std::vector<uint32_t> cf((size_t)std::max(S.nT, 1));
-  if (S.nG) CK(cudaMemcpy(meta.data(), P.pmeta + (size_t)env * P.max_basis, sizeof(uint2) * S.nG, cudaMemcpyDeviceToHost));
+  const unsigned char* base = P.arena + (size_t)env * P.slot_stride;
+  if (S.nG) CK(cudaMemcpy(meta.data(), base + P.o_ghead, sizeof(GHead) * S.nG, cudaMemcpyDeviceToHost));
   if (S.nT) {
-    CK(cudaMemcpy(keys.data(), P.tkey + (size_t)env * P.max_terms, sizeof(uint64_t) * S.nT, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(cf.data(), P.tcoef + (size_t)env * P.max_terms, sizeof(uint32_t) * S.nT, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(keys.data(), base + P.o_tkey, sizeof(uint64_t) * S.nT, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(cf.data(), base + P.o_tcoef, sizeof(uint32_t) * S.nT, cudaMemcpyDeviceToHost));
   }
   // polynomials are stored back to back in insertion order
   std::vector<int> plen;
-  for (int q = 0; q < S.nG; q++) plen.push_back((int)meta[q].y);
+  for (int q = 0; q < S.nG; q++) plen.push_back((int)meta[q].len);
   return unpack_polys(h, keys, cf, plen, lens, cap_polys, exps, coefs, cap_terms, nterms_out);
 }
 
@@ -611,8 +465,7 @@ int bb_final_gb(bb_handle* h, int env, int32_t* lens, int cap_polys, int32_t* ex
   BBParams& P = h->P;
   if (env < 0 || env >= P.num_envs) return fail(h, "bb_final_gb: environment index out of range");
   CK(cudaSetDevice(h->cfg.device));
-  k_final_gb<<<1, 32>>>(P, env, h->d_ok);
-  CK(cudaGetLastError());
+  CK(h->K->final_gb(P, env, h->d_ok, (cudaStream_t)0));
   CK(cudaDeviceSynchronize());
   int ok = 0, cnt[2] = {0, 0};
   CK(cudaMemcpy(&ok, h->d_ok, sizeof(int), cudaMemcpyDeviceToHost));

@@ -123,8 +123,8 @@ int bb_cols(const bb_handle* h);               /* 2*n*k, LeadMonomialsEnv::cols 
 int bb_num_envs(const bb_handle* h);
 int bb_sm_count(const bb_handle* h);
 /* Number of environment slots (warps) of the persistent episode runner that are co-resident on `device`
- * (occupancy of k_run x SM count).  Creating the handle with this many slots keeps bb_run to a single wave. */
-int bb_resident_envs(int device);
+ * (occupancy of k_run<nvars> x SM count).  Creating the handle with this many slots keeps bb_run to a single wave. */
+int bb_resident_envs(int device, int nvars);
 
 /* ---- input ideals
  * bb_set_distribution: the analogue of parse_ideal_dist("n-d-s-{uniform,weighted,maximum}[-consts][-homog][-pure]")
