@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libbbenv.so")
+# BBENV_LIB selects another build of the SAME library (A/B runs of kernel variants); it is never a fallback.
+LIB_PATH = os.environ.get("BBENV_LIB") or os.path.join(HERE, "libbbenv.so")
 
 BB_ABI_VERSION = 1
 

@@ -86,6 +86,7 @@ struct BBParams {
   int* gcount;                          // [num_envs][2] = (npolys, nterms)
   uint64_t* grlm; uint32_t* gridx; uint32_t* gflag;  // [num_envs][max_basis] scratch of warp_final_gb
   BBDist dist;
+  const uint16_t* invtab;               // [p] multiplicative inverses in GF(p) (invtab[0] = 0)
   unsigned long long* counters;         // bb_counters as 12 x u64
 };
 
@@ -235,14 +236,14 @@ __device__ __noinline__ int warp_merge(BBField F, const uint64_t* __restrict__ A
 struct Dividend {
   uint64_t k0, k1;
   uint32_t c0, c1;
-  int n, buf, pos;
-  bool mem;
+  int n;
+  int loc;  // -1: registers only (n <= 2); else index of the lead term in the scratch (half * max_poly_terms + pos)
 };
 
 // a + b for lists of at most one term each, entirely in (uniform) registers
 __device__ __forceinline__ void tiny_merge(const BBField& F, bool hasA, uint64_t ka, uint32_t ca, bool hasB, uint64_t kb,
                                            uint32_t cb, Dividend& o) {
-  o.mem = false;
+  o.loc = -1;
   if (hasA && hasB) {
     if (ka == kb) {
       const uint32_t c = bbf_addmod(F, ca, cb);
@@ -262,7 +263,7 @@ __device__ __forceinline__ void tiny_merge(const BBField& F, bool hasA, uint64_t
 __device__ __forceinline__ void dividend_from_scratch(const BBParams& P, const Env& e, Dividend& h, int n, int buf) {
   const uint64_t* hk = ENV_PTR(uint64_t, e, P, o_hkey) + (size_t)buf * P.max_poly_terms;
   const uint32_t* hc = ENV_PTR(uint32_t, e, P, o_hcoef) + (size_t)buf * P.max_poly_terms;
-  h.n = n; h.buf = buf; h.pos = 0; h.mem = true;
+  h.n = n; h.loc = buf * P.max_poly_terms;
   if (n > 0) { h.k0 = hk[0]; h.c0 = hc[0]; }
   if (n > 1) { h.k1 = hk[1]; h.c1 = hc[1]; }
 }
@@ -271,7 +272,7 @@ __device__ __forceinline__ void dividend_from_scratch(const BBParams& P, const E
 // Division algorithm of buchberger.cpp:24-49 on the dividend h.  Reducers are scanned IN ORDER (rlm[0..nR)), the
 // first whose lead monomial divides LM(h) is used (h <- h - (LT h / LT f) f, steps++); otherwise LT(h) moves to the
 // remainder, which is written to (rk, rc) [cap rcap].  Returns its length or -1 (scratch overflow) / -2 (remainder
-// overflow) / -3 (exponent overflow detected).  (r0k,r0c,r1k,r1c) receive the remainder's first two terms.
+// overflow) / -3 (exponent overflow detected).
 // `sorted`: the reducer list is ascending in lead monomial, so the scan may stop at the first reducer whose lead
 // monomial exceeds LM(h) (it and everything after it cannot divide); the count of examined lead monomials that
 // feeds the traffic model stays the reference's (found + 1, or all of them).
@@ -279,7 +280,7 @@ template <int NV>
 __device__ __forceinline__ int warp_reduce(const BBParams& P, Env& e, Dividend& h, const uint64_t* __restrict__ rlm,
                                            const uint32_t* __restrict__ ridx, int nR, bool sorted,
                                            uint64_t* __restrict__ rk, uint32_t* __restrict__ rc, int rcap, int& steps,
-                                           uint64_t& r0k, uint32_t& r0c, uint64_t& r1k, uint32_t& r1c, Ctr& ct) {
+                                           Ctr& ct) {
   typedef KL<NV> K;
   const BBField F = P.F;
   const int lane = bb_lane();
@@ -312,13 +313,13 @@ __device__ __forceinline__ int warp_reduce(const BBParams& P, Env& e, Dividend& 
       } else {
         uint64_t* hk = ENV_PTR(uint64_t, e, P, o_hkey);
         uint32_t* hc = ENV_PTR(uint32_t, e, P, o_hcoef);
-        if (!h.mem) {  // the register-resident dividend (n <= 2) goes to scratch half 0; only its tail is read
-          h.buf = 0; h.pos = 0; h.mem = true;
+        if (h.loc < 0) {  // the register-resident dividend (n <= 2) goes to scratch half 0; only its tail is read
+          h.loc = 0;
           if (lane == 0 && h.n == 2) { hk[1] = h.k1; hc[1] = h.c1; }
           __syncwarp();
         }
-        const int ob = h.buf ^ 1;
-        const size_t ho = (size_t)h.buf * P.max_poly_terms + h.pos, oo = (size_t)ob * P.max_poly_terms;
+        const int ob = h.loc >= P.max_poly_terms ? 0 : 1;
+        const size_t ho = (size_t)h.loc, oo = (size_t)ob * P.max_poly_terms;
         const uint64_t* tk = ENV_PTR(uint64_t, e, P, o_tkey);
         const uint32_t* tc = ENV_PTR(uint32_t, e, P, o_tcoef);
         const int n2 = warp_merge<NV>(F, hk + ho + 1, hc + ho + 1, h.n - 1, 1u, 0ull, tk + f.off + 1, tc + f.off + 1,
@@ -331,16 +332,13 @@ __device__ __forceinline__ int warp_reduce(const BBParams& P, Env& e, Dividend& 
     } else {
       if (rlen >= rcap) return -2;
       if (lane == 0) { rk[rlen] = lead; rc[rlen] = h.c0; }
-      if (rlen == 0) { r0k = lead; r0c = h.c0; }
-      if (rlen == 1) { r1k = lead; r1c = h.c0; }
       rlen++;
       ct.moves++;
       h.n--; h.k0 = h.k1; h.c0 = h.c1;  // drop the lead term
-      if (h.mem) {
-        h.pos++;
+      if (h.loc >= 0) {
+        h.loc++;
         if (h.n > 1) {
-          const size_t o = (size_t)h.buf * P.max_poly_terms + h.pos + 1;
-          h.k1 = ENV_PTR(uint64_t, e, P, o_hkey)[o]; h.c1 = ENV_PTR(uint32_t, e, P, o_hcoef)[o];
+          h.k1 = ENV_PTR(uint64_t, e, P, o_hkey)[h.loc + 1]; h.c1 = ENV_PTR(uint32_t, e, P, o_hcoef)[h.loc + 1];
         }
       }
     }
@@ -362,25 +360,31 @@ __device__ __forceinline__ int warp_reduce(const BBParams& P, Env& e, Dividend& 
 // (5) new pairs in ascending i (:86), appended after the survivors (:91-92).
 // Every pair carries the key of its lcm (plcm), so step (1) and the selection strategies read one array.
 // One out-of-line copy shared by step and reset.  Returns (emitted << 32) | new |P|, or -1 on pair-list overflow /
-// -2 when the basis is full; the caller bumps nG and nT.
+// -2 when the basis is full / -3 when an lcm's degree does not fit the packed layout; the caller bumps nG and nT.
 template <int NV>
-__device__ __noinline__ long long warp_add_basis(const BBParams& P, unsigned char* base, int m, int nP, int off, int len,
-                                                 uint64_t fk, uint32_t lc, uint64_t k1, uint32_t c1) {
+__device__ __noinline__ long long warp_add_basis(const BBParams& P, unsigned char* base, int m, int nP, int off, int len) {
   typedef KL<NV> K;
   const int lane = bb_lane();
   const uint32_t ltm = bb_lt_mask();
   if (m >= P.max_basis) return -2;
+  const uint64_t* tk = reinterpret_cast<const uint64_t*>(base + P.o_tkey) + off;
+  const uint32_t* tc = reinterpret_cast<const uint32_t*>(base + P.o_tcoef) + off;
+  const uint64_t fk = tk[0];
   uint64_t* lm = reinterpret_cast<uint64_t*>(base + P.o_lm);
   uint64_t* lscr = reinterpret_cast<uint64_t*>(base + P.o_lscr);
   uint64_t* plcm = reinterpret_cast<uint64_t*>(base + P.o_plcm);
   uint32_t* pairs = reinterpret_cast<uint32_t*>(base + P.o_pairs);
   int emitted = 0;
   if (P.elimination == BB_ELIM_GEBAUERMOELLER) {
-    // L_i for every basis element (also the scratch the old-pair filter gathers from)
+    // lscr[i] = key of L_i = lcm(LM_i, LM f), for every basis element (the old-pair filter gathers from it)
+    bool ovf = false;  // deg(L_i) must fit the degree field: bit 63 is a tag below, never a silently wrapped degree
     for (int i = lane; i < m; i += 32) {
-      const uint64_t li = lm[i];
-      lscr[i] = K::lcm_exps(li, fk) | (K::coprime(li, fk) ? (1ull << 63) : 0ull);
+      const uint64_t le = K::lcm_exps(lm[i], fk);
+      const uint32_t dg = K::sum_fields(le);
+      ovf |= dg > K::dmax;
+      lscr[i] = le | ((uint64_t)(K::dmax - dg) << K::dshift);
     }
+    if (__any_sync(BB_FULL, ovf)) return -3;
     __syncwarp();
     const uint64_t fe = fk & K::ex_mask;
     int w = 0;
@@ -404,28 +408,55 @@ __device__ __noinline__ long long warp_add_basis(const BBParams& P, unsigned cha
       __syncwarp();
     }
     nP = w;
+    // Steps (2)-(4) by peeling: the smallest remaining L (largest key; lowest index among equals = the group's
+    // v[0]) cannot be strictly divided by anything still alive, so it is one of the reference's min_lcms.  It
+    // kills every multiple (strict or equal), and its pair is emitted unless a member of its group is coprime to f.
+    // One sweep over lscr per kept lcm instead of m sweeps: lscr[i] = key while undecided, 0 once dead,
+    // key | 1<<63 once chosen for emission.
+    uint64_t kk = 0ull, kkey = 0ull;   // exponents / key of the current killer
+    int kidx = -1;
+    for (;;) {
+      uint64_t bk = 0ull; int bi = 0x7fffffff;
+      uint32_t grp_cop = 0u;
+      for (int b0 = 0; b0 < m; b0 += 32) {
+        const int i = b0 + lane;
+        uint64_t v = i < m ? lscr[i] : 0ull;
+        bool und = v != 0ull && (long long)v > 0;  // undecided
+        if (kidx >= 0) {
+          const uint64_t ei = v & K::ex_mask;
+          const bool eq = v != 0ull && ei == kk;    // the killer itself included
+          if (und && ((((ei | K::ge_mask) - kk) & K::ge_mask) == K::ge_mask)) { lscr[i] = 0ull; und = false; }
+          bool cop = false;
+          if (eq) cop = K::coprime(lm[i], fk);
+          grp_cop |= __ballot_sync(BB_FULL, cop);
+        }
+        if (und && v > bk) { bk = v; bi = i; }  // ascending i per lane: first occurrence kept on ties
+      }
+      if (kidx >= 0 && lane == 0) lscr[kidx] = grp_cop ? 0ull : (kkey | (1ull << 63));
+      if (!__any_sync(BB_FULL, bk != 0ull)) break;  // nothing undecided
+      // next killer: largest key, lowest index among equals
+      const uint32_t hi = __reduce_max_sync(BB_FULL, (uint32_t)(bk >> 32));
+      const bool c1 = (uint32_t)(bk >> 32) == hi;
+      const uint32_t lo = __reduce_max_sync(BB_FULL, c1 ? (uint32_t)bk : 0u);
+      const bool c2 = c1 && (uint32_t)bk == lo;
+      kidx = (int)__reduce_min_sync(BB_FULL, c2 ? (uint32_t)bi : 0x7fffffffu);
+      kkey = ((uint64_t)hi << 32) | lo;
+      kk = kkey & K::ex_mask;
+      if (lane == 0) lscr[kidx] |= (1ull << 63);  // decided: out of the undecided set while it sweeps
+      __syncwarp();
+    }
+    __syncwarp();
     for (int b0 = 0; b0 < m; b0 += 32) {
       const int i = b0 + lane;
-      const bool valid = i < m;
-      const uint64_t Li = valid ? (lscr[i] & K::ex_mask) : 0ull;
-      const uint64_t LiG = Li | K::ge_mask;
-      bool bad = !valid;
-#pragma unroll 4
-      for (int j = 0; j < m; j++) {
-        const uint64_t Lj = lscr[j];
-        const uint64_t ej = Lj & K::ex_mask;
-        const bool div = ((LiG - ej) & K::ge_mask) == K::ge_mask;
-        const bool eq = ej == Li;
-        bad |= div && (!eq || j < i || (long long)Lj < 0);
-      }
-      const bool keep = !bad;
+      const uint64_t v = i < m ? lscr[i] : 0ull;
+      const bool keep = (long long)v < 0;
       const uint32_t km = __ballot_sync(BB_FULL, keep);
       const int cnt = __popc(km);
       if (nP + cnt > P.max_pairs) return -1;
       if (keep) {
         const int pos = nP + __popc(km & ltm);
         pairs[pos] = ((uint32_t)m << 16) | (uint32_t)i;
-        plcm[pos] = K::key_from_exps(Li);
+        plcm[pos] = v & ~(1ull << 63);
       }
       nP += cnt; emitted += cnt;
     }
@@ -472,9 +503,11 @@ __device__ __noinline__ long long warp_add_basis(const BBParams& P, unsigned cha
     rlm[pos] = fk; ridx[pos] = (uint32_t)m;
     lm[m] = fk;
     GHead* g = reinterpret_cast<GHead*>(base + P.o_ghead) + m;
-    const uint32_t inv = bbf_invmod(P.F, lc);
+    const uint32_t inv = P.invtab[tc[0]];  // 1/LC: one table load instead of a 15-step power ladder
+    const uint64_t k1 = len > 1 ? tk[1] : 0ull;
+    const uint32_t c1 = len > 1 ? tc[1] : 0u;
     reinterpret_cast<uint4*>(g)[0] = make_uint4((uint32_t)fk, (uint32_t)(fk >> 32), (uint32_t)k1, (uint32_t)(k1 >> 32));
-    reinterpret_cast<uint4*>(g)[1] = make_uint4(inv, len > 1 ? c1 : 0u, (uint32_t)off, (uint32_t)len);
+    reinterpret_cast<uint4*>(g)[1] = make_uint4(inv, c1, (uint32_t)off, (uint32_t)len);
   }
   __syncwarp();
   return ((long long)emitted << 32) | (long long)nP;
@@ -514,7 +547,7 @@ __device__ __forceinline__ int warp_step(const BBParams& P, Env& e, int row, int
   e.guard |= gam;
   ct.tread += hf.len + hg.len;
   Dividend h;
-  h.k0 = h.k1 = 0; h.c0 = h.c1 = 0; h.n = 0; h.buf = 0; h.pos = 0; h.mem = false;
+  h.k0 = h.k1 = 0; h.c0 = h.c1 = 0; h.n = 0; h.loc = -1;
   const uint64_t adjf = gam - hf.lm, adjg = gam - hg.lm;
   const uint32_t cg = F.p - hg.invlc;  // -(1/LC g), invlc != 0
   if (hf.len <= 2 && hg.len <= 2) {
@@ -536,18 +569,19 @@ __device__ __forceinline__ int warp_step(const BBParams& P, Env& e, int row, int
   if (e.guard & K::g_all) { e.status = BB_STATUS_OVERFLOW_EXPONENT; return 1; }
   ct.twrite += (unsigned)h.n;
   int steps = 0;
-  uint64_t r0k = 0, r1k = 0; uint32_t r0c = 0, r1c = 0;
   const int rlen = warp_reduce<NV>(P, e, h, ENV_PTR(uint64_t, e, P, o_rlm), ENV_PTR(uint32_t, e, P, o_ridx), e.nG,
                                    P.sort_reducers != 0, ENV_PTR(uint64_t, e, P, o_tkey) + e.nT,
-                                   ENV_PTR(uint32_t, e, P, o_tcoef) + e.nT, P.max_terms - e.nT, steps, r0k, r0c, r1k, r1c,
-                                   ct);
+                                   ENV_PTR(uint32_t, e, P, o_tcoef) + e.nT, P.max_terms - e.nT, steps, ct);
   if (rlen == -1) { e.status = BB_STATUS_OVERFLOW_SCRATCH; return 1 + steps; }
   if (rlen == -2) { e.status = BB_STATUS_OVERFLOW_TERMS; return 1 + steps; }
   if (rlen == -3 || (e.guard & K::g_all)) { e.status = BB_STATUS_OVERFLOW_EXPONENT; return 1 + steps; }
   if (rlen > 0) {
     ct.upb += (unsigned)e.nG; ct.upp += (unsigned)e.nP;
-    const long long r = warp_add_basis<NV>(P, e.base, e.nG, e.nP, e.nT, rlen, r0k, r0c, r1k, r1c);
-    if (r < 0) { e.status = (r == -1) ? BB_STATUS_OVERFLOW_PAIRS : BB_STATUS_OVERFLOW_BASIS; return 1 + steps; }
+    const long long r = warp_add_basis<NV>(P, e.base, e.nG, e.nP, e.nT, rlen);
+    if (r < 0) {
+      e.status = (r == -1) ? BB_STATUS_OVERFLOW_PAIRS : (r == -2 ? BB_STATUS_OVERFLOW_BASIS : BB_STATUS_OVERFLOW_EXPONENT);
+      return 1 + steps;
+    }
     e.nP = (int)(r & 0xffffffffll);
     ct.upp += (unsigned)(r >> 32);
     e.nG++; e.nT += rlen;
@@ -719,11 +753,12 @@ __device__ __forceinline__ void warp_load_ideal(const BBParams& P, int src_slot,
     if (e.nT + len > P.max_terms) { e.status = BB_STATUS_OVERFLOW_TERMS; return; }
     for (int t = lane; t < len; t += 32) { tk[e.nT + t] = ik[off + t]; tc[e.nT + t] = ic[off + t]; }
     __syncwarp();
-    const uint64_t k1 = len > 1 ? ik[off + 1] : 0ull;
-    const uint32_t c1 = len > 1 ? ic[off + 1] : 0u;
     ct.upb += (unsigned)e.nG; ct.upp += (unsigned)e.nP;
-    const long long r = warp_add_basis<NV>(P, e.base, e.nG, e.nP, e.nT, len, ik[off], ic[off], k1, c1);
-    if (r < 0) { e.status = (r == -1) ? BB_STATUS_OVERFLOW_PAIRS : BB_STATUS_OVERFLOW_BASIS; return; }
+    const long long r = warp_add_basis<NV>(P, e.base, e.nG, e.nP, e.nT, len);
+    if (r < 0) {
+      e.status = (r == -1) ? BB_STATUS_OVERFLOW_PAIRS : (r == -2 ? BB_STATUS_OVERFLOW_BASIS : BB_STATUS_OVERFLOW_EXPONENT);
+      return;
+    }
     e.nP = (int)(r & 0xffffffffll);
     ct.upp += (unsigned)(r >> 32);
     e.nG++; e.nT += len;
@@ -865,9 +900,8 @@ __device__ __noinline__ int warp_final_gb(const BBParams& P, int slot, unsigned 
     h.k0 = h.k1 = 0; h.c0 = h.c1 = 0;
     dividend_from_scratch(P, e, h, n, 0);
     int steps;
-    uint64_t r0k, r1k; uint32_t r0c, r1c;
     const int rlen = warp_reduce<NV>(P, e, h, rlm2, ridx2, nmin, true, gk + gT + 1, gc + gT + 1, P.max_terms - gT - 1, steps,
-                                     r0k, r0c, r1k, r1c, ct);
+                                     ct);
     if (rlen < 0) { ok = 0; break; }
     if (lane == 0) { gk[gT] = f.lm; gc[gT] = 1u; gl[q] = 1 + rlen; }
     for (int t = lane; t < rlen; t += 32) gc[gT + 1 + t] = bbf_mulmod(P.F, gc[gT + 1 + t], f.invlc);

@@ -30,6 +30,11 @@ struct BBRunArgs {
   int* queue;
 };
 
+struct BBEpisodeAcc {
+  unsigned long long th;
+  double ret, disc;
+};
+
 struct BBKernelTable {
   int nvars, w, dw, dshift, eshift;
   cudaError_t (*reset)(const BBParams&, const uint8_t* mask, int nwarps, cudaStream_t);
@@ -151,7 +156,9 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_run(const __grid_
                                                                   const __grid_constant__ BBRunArgs A) {
   typedef KL<NV> K;
   __shared__ unsigned long long sh[BB_WARPS][CT_COUNT];
+  __shared__ BBEpisodeAcc acc_sh[BB_WARPS];  // per-episode accumulators only lane 0 touches: kept out of registers
   unsigned long long* row = counters_row(sh);
+  BBEpisodeAcc& acc = acc_sh[threadIdx.x >> 5];
   const int slot = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
   const int lane = bb_lane();
   if (slot < P.num_envs) {
@@ -167,17 +174,19 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_run(const __grid_
       Env e; env_load(P, slot, e);
       const int g_start = e.nG;
       int steps = 0, adds = 0;
-      unsigned long long th = 0;
-      double ret = 0.0, disc = 1.0;
+      if (lane == 0) { acc.th = 0ull; acc.ret = 0.0; acc.disc = 1.0; }
       while (e.status == BB_STATUS_RUNNING && (A.max_steps == 0 || steps < A.max_steps)) {
         const int prow = warp_select<NV>(P, e, A.strategy);
         int pi, pj;
         const int a = warp_step<NV>(P, e, prow, &pi, &pj, ct);
-        th += trace_hash_item(pi, pj, a, steps);
-        const double r = (P.rewards == BB_REWARD_ADDITIONS) ? -(double)a : -1.0;
-        ret += disc * r; disc *= A.gamma;
-        if (A.trace && ep < A.trace_eps && steps < A.trace_cap && lane == 0)
-          reinterpret_cast<int4*>(A.trace)[(size_t)ep * A.trace_cap + steps] = make_int4(pi, pj, a, e.nP);
+        if (lane == 0) {
+          acc.th += trace_hash_item(pi, pj, a, steps);
+          const double r = (P.rewards == BB_REWARD_ADDITIONS) ? -(double)a : -1.0;
+          const double d = acc.disc;  // discounted_return += discount * reward; discount *= gamma  (buchberger.cpp:250-251)
+          acc.ret = __dadd_rn(acc.ret, __dmul_rn(d, r)); acc.disc = __dmul_rn(d, A.gamma);
+          if (A.trace && ep < A.trace_eps && steps < A.trace_cap)
+            reinterpret_cast<int4*>(A.trace)[(size_t)ep * A.trace_cap + steps] = make_int4(pi, pj, a, e.nP);
+        }
         steps++; adds += a;
       }
       const int nonzero = e.nG - g_start, zero = steps - nonzero;
@@ -199,6 +208,7 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_run(const __grid_
         }
       }
       if (lane == 0) {
+        const unsigned long long th = acc.th; const double ret = acc.ret;
         bb_episode_stats o;
         o.steps = steps; o.additions = adds; o.zero_reductions = zero; o.nonzero_reductions = nonzero;
         o.nbasis = e.nG; o.nterms = e.nT; o.status = status; o.rerolls = P.st[slot].rerolls;

@@ -16,6 +16,12 @@ __global__ void __launch_bounds__(BB_THREADS) k_seed(BBParams P, const int* seed
   if (e < P.num_envs) P.st[e].rng = rng_seed(seeds ? seeds[e] : base + e);
 }
 
+// inverse table: every lane of a warp takes one residue; a^(p-2) by square and multiply
+__global__ void __launch_bounds__(BB_THREADS) k_invtab(BBField F, uint16_t* tab) {
+  uint32_t a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a < F.p) tab[a] = a ? (uint16_t)bbf_invmod(F, a) : 0;
+}
+
 __global__ void __launch_bounds__(BB_THREADS) k_pairs(BBParams P, int32_t* __restrict__ out,
                                                       int32_t* __restrict__ lengths, int pmax) {
   const int slot = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
@@ -208,6 +214,13 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
   CKC(dev_alloc(h, &P.gridx, N * P.max_basis));
   CKC(dev_alloc(h, &P.gflag, N * P.max_basis));
   CKC(dev_alloc(h, &P.counters, (size_t)CT_COUNT));
+  {
+    uint16_t* tab = nullptr;
+    CKC(dev_alloc(h, &tab, (size_t)cfg->prime));
+    k_invtab<<<(cfg->prime + BB_THREADS - 1) / BB_THREADS, BB_THREADS>>>(P.F, tab);
+    CKC(cudaGetLastError());
+    P.invtab = tab;
+  }
   CKC(dev_alloc(h, &h->d_queue, (size_t)4));
   CKC(dev_alloc(h, &h->d_ok, (size_t)4));
   k_seed<<<(cfg->num_envs + BB_THREADS - 1) / BB_THREADS, BB_THREADS>>>(P, nullptr, 0);

@@ -29,3 +29,27 @@ print("--- by samples")
 for o in sorted(out, key=lambda o: -o[4])[:top]:
     st = sorted(o[5].items(), key=lambda x: -x[1])[:2]
     print("%5.1f%% s %5.1f%% i  %s:%d  %s   %s" % (100.0 * o[4] / ts, 100.0 * o[3] / ti, o[0], o[1], o[2], st))
+
+# optional: aggregate by function (line ranges found by scanning the source for "__device__" / "__global__")
+if len(sys.argv) > 3:
+    import re, os
+    src_dir = sys.argv[3]
+    bounds = {}
+    for fn in set(o[0] for o in out):
+        path = os.path.join(src_dir, fn)
+        if not os.path.exists(path): continue
+        marks = []
+        lines = open(path).read().splitlines()
+        for ln, text in enumerate(lines, 1):
+            m = re.search(r'(?:__device__|__global__|static BB_HD|^BB_HD)[^;]*?\b([A-Za-z_][A-Za-z_0-9]*)\s*\(', text)
+            if m and not text.strip().startswith("//"): marks.append((ln, m.group(1)))
+        bounds[fn] = marks
+    agg = {}
+    for o in out:
+        name = o[0]
+        for ln, nm in bounds.get(o[0], []):
+            if ln <= o[1]: name = o[0] + ":" + nm
+        a = agg.setdefault(name, [0, 0]); a[0] += o[3]; a[1] += o[4]
+    print("--- by function")
+    for k, v in sorted(agg.items(), key=lambda x: -x[1][0])[:30]:
+        print("%5.1f%% i %5.1f%% s  %s" % (100.0 * v[0] / ti, 100.0 * v[1] / ts, k))
