@@ -20,6 +20,8 @@
 
 struct BBRunArgs {
   int strategy, episodes, seed_base;
+  int ep_base;      // first episode of this batch: episode ids are ep_base .. ep_base + episodes - 1
+  int nstaged;      // fixed ideals: number of staged ideals (episode e replays ideal e mod nstaged)
   const int* seeds;
   int max_steps;
   double gamma;
@@ -42,7 +44,8 @@ struct BBKernelTable {
   cudaError_t (*select)(const BBParams&, int strategy, int* actions, int nwarps, cudaStream_t);
   cudaError_t (*observe)(const BBParams&, int32_t* obs, int32_t* lengths, int pmax, int nwarps, cudaStream_t);
   cudaError_t (*final_gb)(const BBParams&, int slot, int* ok_out, cudaStream_t);
-  cudaError_t (*run)(const BBParams&, const BBRunArgs&, int nwarps, cudaStream_t);
+  cudaError_t (*prepare)(const BBParams& stage, const BBRunArgs&, cudaStream_t);
+  cudaError_t (*run)(const BBParams&, const BBParams& stage, const BBRunArgs&, int nwarps, cudaStream_t);
   int (*run_blocks_per_sm)(void);
 };
 
@@ -149,10 +152,35 @@ __global__ void __launch_bounds__(32) k_final_gb(const __grid_constant__ BBParam
   if (bb_lane() == 0) *ok_out = ok;
 }
 
-// Persistent episode runner.  Each warp owns slot = its global warp index and loops: pop an episode, reset from
-// that episode's stream, select/step until P is empty (or max_steps), write the episode record, repeat.
+// Episode preparation: warp b of the batch draws episode (ep_base + b)'s ideal from its stream and runs
+// BuchbergerEnv::reset on it (re-rolls included) inside the compact staging arena S (one small slot per episode of
+// the batch).  Keeping this out of k_run keeps the generator / reset code out of the step loop's instruction
+// working set (profiles/r01_v2: instruction fetch was the top stall) and runs it with every warp in the same code.
+template <int NV>
+__global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_prepare(const __grid_constant__ BBParams S,
+                                                                      const __grid_constant__ BBRunArgs A) {
+  __shared__ unsigned long long sh[BB_WARPS][CT_COUNT];
+  unsigned long long* row = counters_row(sh);
+  const int b = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
+  if (b < A.episodes) {
+    const int ep = A.ep_base + b;
+    warp_reset_slot<NV>(S, b, S.dist.enabled ? b : ep % A.nstaged, rng_seed(A.seeds ? A.seeds[ep] : A.seed_base + ep), row);
+  }
+  counters_flush(S, sh);
+}
+
+// copy n 32-bit words, lane-strided
+__device__ __forceinline__ void warp_copy_words(uint32_t* __restrict__ d, const uint32_t* __restrict__ s, int n) {
+#pragma unroll 1
+  for (int t = bb_lane(); t < n; t += 32) d[t] = s[t];
+}
+
+// Persistent episode runner.  Each warp owns slot = its global warp index and loops: pop an episode, copy its
+// prepared initial state from the staging arena, select/step until P is empty (or max_steps), write the episode
+// record, repeat.
 template <int NV>
 __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_run(const __grid_constant__ BBParams P,
+                                                                  const __grid_constant__ BBParams S,
                                                                   const __grid_constant__ BBRunArgs A) {
   typedef KL<NV> K;
   __shared__ unsigned long long sh[BB_WARPS][CT_COUNT];
@@ -162,16 +190,28 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_run(const __grid_
   const int slot = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
   const int lane = bb_lane();
   if (slot < P.num_envs) {
-    const int nstaged = P.num_envs;
     Ctr ct; ct.clear();
     for (;;) {
-      int ep = 0;
-      if (lane == 0) ep = atomicAdd(A.queue, 1);
-      ep = __shfl_sync(BB_FULL, ep, 0);
-      if (ep >= A.episodes) break;
-      // fixed ideals: episode ep replays the ideal staged for slot (ep mod N), read in place (staging is immutable)
-      warp_reset_slot<NV>(P, slot, ep % nstaged, rng_seed(A.seeds ? A.seeds[ep] : A.seed_base + ep), row);
-      Env e; env_load(P, slot, e);
+      int b = 0;
+      if (lane == 0) b = atomicAdd(A.queue, 1);
+      b = __shfl_sync(BB_FULL, b, 0);
+      if (b >= A.episodes) break;
+      const int ep = A.ep_base + b;
+      Env e; env_load(S, b, e);  // the prepared state; e.base still points into the staging arena here
+      {
+        const unsigned char* sb = e.base;
+        unsigned char* db = P.arena + (size_t)slot * P.slot_stride;
+        warp_copy_words((uint32_t*)(db + P.o_ghead), (const uint32_t*)(sb + S.o_ghead), e.nG * 8);
+        warp_copy_words((uint32_t*)(db + P.o_lm), (const uint32_t*)(sb + S.o_lm), e.nG * 2);
+        warp_copy_words((uint32_t*)(db + P.o_rlm), (const uint32_t*)(sb + S.o_rlm), e.nG * 2);
+        warp_copy_words((uint32_t*)(db + P.o_ridx), (const uint32_t*)(sb + S.o_ridx), e.nG);
+        warp_copy_words((uint32_t*)(db + P.o_pairs), (const uint32_t*)(sb + S.o_pairs), e.nP);
+        warp_copy_words((uint32_t*)(db + P.o_plcm), (const uint32_t*)(sb + S.o_plcm), e.nP * 2);
+        warp_copy_words((uint32_t*)(db + P.o_tkey), (const uint32_t*)(sb + S.o_tkey), e.nT * 2);
+        warp_copy_words((uint32_t*)(db + P.o_tcoef), (const uint32_t*)(sb + S.o_tcoef), e.nT);
+        e.base = db;
+        __syncwarp();
+      }
       const int g_start = e.nG;
       int steps = 0, adds = 0;
       if (lane == 0) { acc.th = 0ull; acc.ret = 0.0; acc.disc = 1.0; }
@@ -211,13 +251,13 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_run(const __grid_
         const unsigned long long th = acc.th; const double ret = acc.ret;
         bb_episode_stats o;
         o.steps = steps; o.additions = adds; o.zero_reductions = zero; o.nonzero_reductions = nonzero;
-        o.nbasis = e.nG; o.nterms = e.nT; o.status = status; o.rerolls = P.st[slot].rerolls;
+        o.nbasis = e.nG; o.nterms = e.nT; o.status = status; o.rerolls = S.st[b].rerolls;
         o.trace_hash = th; o.basis_hash = bh; o.gb_hash = gbh; o.gb_polys = gp; o.gb_terms = gt;
         o.discounted_return = ret;
         A.out[ep] = o;
-        BBEnvState& S = P.st[slot];
-        S.status = status; S.steps = steps; S.adds = adds; S.zero = zero; S.nonzero = nonzero; S.trace_hash = th;
-        S.disc_return = ret;
+        BBEnvState& St = P.st[slot];
+        St.status = status; St.steps = steps; St.adds = adds; St.zero = zero; St.nonzero = nonzero; St.trace_hash = th;
+        St.disc_return = ret; St.rerolls = o.rerolls;
         row[CT_STEPS] += (unsigned)steps; row[CT_ADDS] += (unsigned)adds; row[CT_NONZERO] += (unsigned)nonzero;
         row[CT_ZERO] += (unsigned)zero; row[CT_EPISODES] += 1;
       }
@@ -253,8 +293,12 @@ struct BBLaunch {
     k_final_gb<NV><<<1, 32, 0, s>>>(P, slot, ok_out);
     return cudaGetLastError();
   }
-  static cudaError_t run(const BBParams& P, const BBRunArgs& A, int nwarps, cudaStream_t s) {
-    k_run<NV><<<grid_for_warps(nwarps), BB_THREADS, 0, s>>>(P, A);
+  static cudaError_t prepare(const BBParams& S, const BBRunArgs& A, cudaStream_t s) {
+    k_prepare<NV><<<grid_for_warps(A.episodes), BB_THREADS, 0, s>>>(S, A);
+    return cudaGetLastError();
+  }
+  static cudaError_t run(const BBParams& P, const BBParams& S, const BBRunArgs& A, int nwarps, cudaStream_t s) {
+    k_run<NV><<<grid_for_warps(nwarps), BB_THREADS, 0, s>>>(P, S, A);
     return cudaGetLastError();
   }
   static int run_blocks_per_sm() {
@@ -264,7 +308,7 @@ struct BBLaunch {
   }
   static const BBKernelTable* table() {
     static const BBKernelTable t = {NV, KL<NV>::w, KL<NV>::dw, KL<NV>::dshift, KL<NV>::eshift,
-                                    &reset, &step, &select, &observe, &final_gb, &run, &run_blocks_per_sm};
+                                    &reset, &step, &select, &observe, &final_gb, &prepare, &run, &run_blocks_per_sm};
     return &t;
   }
 };

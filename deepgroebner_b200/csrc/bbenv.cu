@@ -79,6 +79,11 @@ struct bb_handle {
   std::string err;
   int* d_queue;
   int* d_ok;
+  // staging arena of bb_run: one compact slot per episode of a batch, holding the state right after reset()
+  int stage_cap;                    // episodes it can hold (0 = not allocated yet)
+  std::vector<void*> stage_allocs;
+  unsigned char* stage_arena; BBEnvState* stage_st;
+  uint64_t* stage_in_key; uint32_t* stage_in_coef; int* stage_in_off; int* stage_in_np;
   // host mirrors of the distribution tables
   std::vector<double> cp;
 };
@@ -104,6 +109,27 @@ static cudaError_t dev_alloc(bb_handle* h, T** p, size_t count) {
   h->allocs.push_back(q);
   *p = (T*)q;
   return cudaMemset(q, 0, count * sizeof(T) + 16);
+}
+
+// One contiguous arena per slot from the capacities in P: 8-byte arrays first, every array 32-byte aligned, stride a
+// multiple of 128.  Returns false if a slot would exceed 2 GiB.
+static bool layout_arena(BBParams& P) {
+  size_t o = 0;
+  auto take = [&o](size_t bytes) { size_t at = o; o = (o + bytes + 31) & ~(size_t)31; return (unsigned)at; };
+  P.o_ghead = take(sizeof(GHead) * (size_t)P.max_basis);
+  P.o_lm = take(8 * (size_t)P.max_basis);
+  P.o_rlm = take(8 * (size_t)P.max_basis);
+  P.o_lscr = take(8 * (size_t)P.max_basis);
+  P.o_plcm = take(8 * (size_t)P.max_pairs);
+  P.o_tkey = take(8 * (size_t)P.max_terms);
+  P.o_hkey = take(8 * 2 * (size_t)P.max_poly_terms);
+  P.o_ridx = take(4 * (size_t)P.max_basis);
+  P.o_pairs = take(4 * (size_t)P.max_pairs);
+  P.o_tcoef = take(4 * (size_t)P.max_terms);
+  P.o_hcoef = take(4 * 2 * (size_t)P.max_poly_terms);
+  if (o >= ((size_t)1 << 31)) return false;
+  P.slot_stride = (o + 127) & ~(size_t)127;
+  return true;
 }
 
 static inline int grid_for_warps_host(int nwarps) { return (nwarps + BB_WARPS - 1) / BB_WARPS; }
@@ -133,6 +159,7 @@ void bb_destroy(bb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
   for (void* p : h->allocs) cudaFree(p);
+  for (void* p : h->stage_allocs) cudaFree(p);
   delete h;
 }
 
@@ -159,6 +186,7 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
   h = new bb_handle();
   h->cfg = *cfg;
   h->d_queue = nullptr; h->d_ok = nullptr;
+  h->stage_cap = 0; h->stage_arena = nullptr; h->stage_st = nullptr;
   auto bail = [&](int code) { g_create_err = h->err; bb_destroy(h); return code; };
 #define CKC(call)                                                                                     \
   do {                                                                                                \
@@ -183,23 +211,7 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
   P.max_basis = cfg->max_basis; P.max_pairs = cfg->max_pairs; P.max_terms = cfg->max_terms;
   P.max_poly_terms = cfg->max_poly_terms; P.max_gens = cfg->max_gens; P.max_gen_terms = cfg->max_gen_terms;
   const size_t N = (size_t)cfg->num_envs;
-  {  // one contiguous arena per slot; 8-byte arrays first, every array 32-byte aligned, stride a multiple of 128
-    size_t o = 0;
-    auto take = [&o](size_t bytes) { size_t at = o; o = (o + bytes + 31) & ~(size_t)31; return (unsigned)at; };
-    P.o_ghead = take(sizeof(GHead) * (size_t)P.max_basis);
-    P.o_lm = take(8 * (size_t)P.max_basis);
-    P.o_rlm = take(8 * (size_t)P.max_basis);
-    P.o_lscr = take(8 * (size_t)P.max_basis);
-    P.o_plcm = take(8 * (size_t)P.max_pairs);
-    P.o_tkey = take(8 * (size_t)P.max_terms);
-    P.o_hkey = take(8 * 2 * (size_t)P.max_poly_terms);
-    P.o_ridx = take(4 * (size_t)P.max_basis);
-    P.o_pairs = take(4 * (size_t)P.max_pairs);
-    P.o_tcoef = take(4 * (size_t)P.max_terms);
-    P.o_hcoef = take(4 * 2 * (size_t)P.max_poly_terms);
-    if (o >= ((size_t)1 << 31)) { h->err = "bb_create: per-environment arena exceeds 2 GiB"; return bail(-1); }
-    P.slot_stride = (o + 127) & ~(size_t)127;
-  }
+  if (!layout_arena(P)) { h->err = "bb_create: per-environment arena exceeds 2 GiB"; return bail(-1); }
   CKC(dev_alloc(h, &P.arena, N * P.slot_stride));
   CKC(dev_alloc(h, &P.st, N));
   CKC(dev_alloc(h, &P.in_key, N * P.max_gen_terms));
@@ -414,6 +426,42 @@ int bb_stats(bb_handle* h, bb_episode_stats* stats_dev, void* stream) {
   return 0;
 }
 
+// Staging parameters for a batch: a copy of P whose arena is the compact per-episode one (capacity: the input
+// ideal only -- max_gens polynomials, all their pairs, max_gen_terms terms).
+#define BB_RUN_BATCH 65536
+static int stage_params(bb_handle* h, int batch, BBParams& S) {
+  const BBParams& P = h->P;
+  S = P;
+  S.max_basis = P.max_gens;
+  S.max_pairs = std::max(1, P.max_gens * (P.max_gens - 1) / 2);
+  S.max_terms = P.max_gen_terms;
+  S.max_poly_terms = 1;
+  if (!layout_arena(S)) return fail(h, "bb_run: staging slot too large");
+  if (batch > h->stage_cap) {
+    for (void* p : h->stage_allocs) cudaFree(p);
+    h->stage_allocs.clear();
+    h->stage_cap = 0;
+    const size_t n = (size_t)batch;
+    auto alloc = [&](void** out, size_t bytes) {
+      cudaError_t e = cudaMalloc(out, bytes + 16);
+      if (e == cudaSuccess) { h->stage_allocs.push_back(*out); e = cudaMemset(*out, 0, bytes + 16); }
+      return e;
+    };
+    CK(alloc((void**)&h->stage_arena, n * S.slot_stride));
+    CK(alloc((void**)&h->stage_st, n * sizeof(BBEnvState)));
+    CK(alloc((void**)&h->stage_in_key, n * P.max_gen_terms * sizeof(uint64_t)));
+    CK(alloc((void**)&h->stage_in_coef, n * P.max_gen_terms * sizeof(uint32_t)));
+    CK(alloc((void**)&h->stage_in_off, n * (P.max_gens + 1) * sizeof(int)));
+    CK(alloc((void**)&h->stage_in_np, n * sizeof(int)));
+    h->stage_cap = batch;
+  }
+  S.arena = h->stage_arena; S.st = h->stage_st; S.num_envs = batch;
+  if (P.dist.enabled) {  // generated ideals are staged per episode; fixed ideals are read in place from the handle
+    S.in_key = h->stage_in_key; S.in_coef = h->stage_in_coef; S.in_off = h->stage_in_off; S.in_np = h->stage_in_np;
+  }
+  return 0;
+}
+
 int bb_run(bb_handle* h, int strategy, int episodes, int seed_base, const int32_t* seeds_dev, int max_steps,
            double gamma, int compute_gb, bb_episode_stats* stats_dev, int32_t* trace_dev, int trace_episodes,
            int trace_cap, void* stream) {
@@ -421,14 +469,23 @@ int bb_run(bb_handle* h, int strategy, int episodes, int seed_base, const int32_
   if ((unsigned)strategy > 2u || episodes < 0 || !stats_dev) return fail(h, "bb_run: bad argument");
   CK(cudaSetDevice(h->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
-  CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int), s));
-  int workers = h->P.num_envs < episodes ? h->P.num_envs : episodes;
-  if (workers < 1) return 0;
-  BBRunArgs A;
-  A.strategy = strategy; A.episodes = episodes; A.seed_base = seed_base; A.seeds = seeds_dev; A.max_steps = max_steps;
-  A.gamma = gamma; A.compute_gb = compute_gb; A.out = stats_dev; A.trace = trace_dev;
-  A.trace_eps = trace_dev ? trace_episodes : 0; A.trace_cap = trace_cap; A.queue = h->d_queue;
-  CK(h->K->run(h->P, A, workers, s));
+  if (episodes == 0) return 0;
+  const int batch_cap = std::min(episodes, BB_RUN_BATCH);
+  BBParams S;
+  if (batch_cap > h->stage_cap) CK(cudaStreamSynchronize(s));  // the staging arena is about to be replaced
+  int rc = stage_params(h, std::max(batch_cap, h->stage_cap), S);
+  if (rc < 0) return rc;
+  for (int base = 0; base < episodes; base += BB_RUN_BATCH) {
+    BBRunArgs A;
+    A.strategy = strategy; A.episodes = std::min(BB_RUN_BATCH, episodes - base); A.seed_base = seed_base;
+    A.ep_base = base; A.nstaged = h->P.num_envs;
+    A.seeds = seeds_dev; A.max_steps = max_steps; A.gamma = gamma; A.compute_gb = compute_gb; A.out = stats_dev;
+    A.trace = trace_dev; A.trace_eps = trace_dev ? trace_episodes : 0; A.trace_cap = trace_cap; A.queue = h->d_queue;
+    CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int), s));
+    CK(h->K->prepare(S, A, s));
+    const int workers = std::min(h->P.num_envs, A.episodes);
+    CK(h->K->run(h->P, S, A, workers, s));
+  }
   return 0;
 }
 
