@@ -177,6 +177,7 @@ __device__ __noinline__ int warp_merge(BBField F, const uint64_t* __restrict__ A
     const uint64_t* Sk = nB == 0 ? Ak : Bk; const uint32_t* Sc = nB == 0 ? Ac : Bc;
     const int nS = nB == 0 ? nA : nB; const uint32_t cS = nB == 0 ? cA : cB; const uint64_t adjS = nB == 0 ? adjA : adjB;
     if (nS > cap) return -1;
+#pragma unroll 1
     for (int t = lane; t < nS; t += 32) {
       uint64_t k = Sk[t] + adjS; guard |= k;
       Ok[t] = k; Oc[t] = (cS == 1u) ? Sc[t] : bbf_mulmod(F, Sc[t], cS);
@@ -290,6 +291,7 @@ __device__ __forceinline__ int warp_reduce(const BBParams& P, Env& e, Dividend& 
   while (h.n > 0) {
     const uint64_t lead = h.k0;
     int found = -1;
+#pragma unroll 1
     for (int base = 0; base < nR; base += 32) {
       const int r = base + lane;
       const uint64_t rl = r < nR ? rlm[r] : ~0ull;
@@ -378,6 +380,7 @@ __device__ __noinline__ long long warp_add_basis(const BBParams& P, unsigned cha
   if (P.elimination == BB_ELIM_GEBAUERMOELLER) {
     // lscr[i] = key of L_i = lcm(LM_i, LM f), for every basis element (the old-pair filter gathers from it)
     bool ovf = false;  // deg(L_i) must fit the degree field: bit 63 is a tag below, never a silently wrapped degree
+#pragma unroll 1
     for (int i = lane; i < m; i += 32) {
       const uint64_t le = K::lcm_exps(lm[i], fk);
       const uint32_t dg = K::sum_fields(le);
@@ -388,6 +391,7 @@ __device__ __noinline__ long long warp_add_basis(const BBParams& P, unsigned cha
     __syncwarp();
     const uint64_t fe = fk & K::ex_mask;
     int w = 0;
+#pragma unroll 1
     for (int b0 = 0; b0 < nP; b0 += 32) {
       const int idx = b0 + lane;
       const bool valid = idx < nP;
@@ -418,6 +422,7 @@ __device__ __noinline__ long long warp_add_basis(const BBParams& P, unsigned cha
     for (;;) {
       uint64_t bk = 0ull; int bi = 0x7fffffff;
       uint32_t grp_cop = 0u;
+#pragma unroll 1
       for (int b0 = 0; b0 < m; b0 += 32) {
         const int i = b0 + lane;
         uint64_t v = i < m ? lscr[i] : 0ull;
@@ -446,6 +451,7 @@ __device__ __noinline__ long long warp_add_basis(const BBParams& P, unsigned cha
       __syncwarp();
     }
     __syncwarp();
+#pragma unroll 1
     for (int b0 = 0; b0 < m; b0 += 32) {
       const int i = b0 + lane;
       const uint64_t v = i < m ? lscr[i] : 0ull;
@@ -461,6 +467,7 @@ __device__ __noinline__ long long warp_add_basis(const BBParams& P, unsigned cha
       nP += cnt; emitted += cnt;
     }
   } else {
+#pragma unroll 1
     for (int b0 = 0; b0 < m; b0 += 32) {
       const int i = b0 + lane;
       bool keep = i < m;
@@ -483,11 +490,13 @@ __device__ __noinline__ long long warp_add_basis(const BBParams& P, unsigned cha
   int pos = m;
   if (P.sort_reducers) {
     int cnt = 0;  // reducers with LM <= new LM  <=>  key >= new key
+#pragma unroll 1
     for (int b0 = 0; b0 < m; b0 += 32) {
       const int r = b0 + lane;
       cnt += __popc(__ballot_sync(BB_FULL, r < m && rlm[r] >= fk));
     }
     pos = cnt;
+#pragma unroll 1
     for (int hi = m; hi > pos; hi -= 32) {
       const int lo = hi - 32 > pos ? hi - 32 : pos;
       const int idx = lo + lane;
@@ -517,21 +526,22 @@ __device__ __noinline__ long long warp_add_basis(const BBParams& P, unsigned cha
 // BuchbergerEnv::step for the pair in row `row` of P (LeadMonomialsEnv::step(int), buchberger.cpp:398-408 ->
 // :318-329): erase the pair, s = spoly(G[i], G[j]) (:18-21), (r, steps) = reduce(s, G_), if r != 0 update + sorted
 // insert.  Returns the number of polynomial additions 1 + steps (reward = -(1+steps) under Additions, -1 under
-// Reductions).  *pi, *pj receive the pair.
+// Reductions).  `pair` receives (j << 16) | i, or 0xffffffff for a bad action.
 template <int NV>
-__device__ __forceinline__ int warp_step(const BBParams& P, Env& e, int row, int* pi, int* pj, Ctr& ct) {
+__device__ __forceinline__ int warp_step(const BBParams& P, Env& e, int row, uint32_t& pair, Ctr& ct) {
   typedef KL<NV> K;
   const BBField F = P.F;
   const int lane = bb_lane();
-  if ((unsigned)row >= (unsigned)e.nP) { e.status = BB_STATUS_BAD_ACTION; *pi = -1; *pj = -1; return 0; }
+  if ((unsigned)row >= (unsigned)e.nP) { e.status = BB_STATUS_BAD_ACTION; pair = 0xffffffffu; return 0; }
   uint32_t* pairs = ENV_PTR(uint32_t, e, P, o_pairs);
   uint64_t* plcm = ENV_PTR(uint64_t, e, P, o_plcm);
   const uint32_t pr = pairs[row];
   const uint64_t gam = plcm[row];  // key of lcm(LM f, LM g), computed when the pair was created
   const int i = pr & 0xffffu, j = pr >> 16;
-  *pi = i; *pj = j;
+  pair = pr;  // (j << 16) | i; never 0xffffffff because i < j
   __syncwarp();
   // erase the pair, keeping order (:319)
+#pragma unroll 1
   for (int b0 = row; b0 < e.nP - 1; b0 += 32) {
     const int idx = b0 + lane;
     const bool v = idx < e.nP - 1;
@@ -602,6 +612,7 @@ __device__ __forceinline__ int warp_select(const BBParams& P, const Env& e, int 
   if (strategy == BB_SELECT_DEGREE) {
     // smallest degree == largest complemented-degree field; lowest row on ties
     uint32_t best = 0u;
+#pragma unroll 1
     for (int idx = lane; idx < e.nP; idx += 32) {
       const uint32_t v = ((uint32_t)(plcm[idx] >> K::dshift) << 16) | (0xffffu - (uint32_t)idx);
       best = v > best ? v : best;
@@ -611,6 +622,7 @@ __device__ __forceinline__ int warp_select(const BBParams& P, const Env& e, int 
   }
   // Normal: smallest lcm in grevlex == LARGEST key; lowest row on ties
   uint64_t bk = 0; uint32_t bi = 0xffffffffu;
+#pragma unroll 1
   for (int idx = lane; idx < e.nP; idx += 32) {
     const uint64_t k = plcm[idx];
     if (k > bk) { bk = k; bi = (uint32_t)idx; }  // strided ascending idx: first occurrence kept on ties
@@ -751,6 +763,7 @@ __device__ __forceinline__ void warp_load_ideal(const BBParams& P, int src_slot,
     }
     const int off = io[src], len = io[src + 1] - off;
     if (e.nT + len > P.max_terms) { e.status = BB_STATUS_OVERFLOW_TERMS; return; }
+#pragma unroll 1
     for (int t = lane; t < len; t += 32) { tk[e.nT + t] = ik[off + t]; tc[e.nT + t] = ic[off + t]; }
     __syncwarp();
     ct.upb += (unsigned)e.nG; ct.upp += (unsigned)e.nP;
@@ -816,6 +829,7 @@ __device__ __noinline__ unsigned long long warp_terms_hash(const uint64_t* tk, c
   typedef KL<NV> K;
   const int lane = bb_lane();
   unsigned long long h = 0;
+#pragma unroll 1
   for (int t = lane; t < nT; t += 32) {
     const uint64_t k = tk[t];
     uint64_t elo = 0, ehi = 0;
@@ -894,6 +908,7 @@ __device__ __noinline__ int warp_final_gb(const BBParams& P, int slot, unsigned 
     // dividend = g - LT g: copy the tail into scratch half 0
     const int n = (int)f.len - 1;
     if (n > P.max_poly_terms) { ok = 0; break; }
+#pragma unroll 1
     for (int t = lane; t < n; t += 32) { hk[t] = tk[f.off + 1 + t]; hc[t] = tc[f.off + 1 + t]; }
     __syncwarp();
     Dividend h;
@@ -904,6 +919,7 @@ __device__ __noinline__ int warp_final_gb(const BBParams& P, int slot, unsigned 
                                      ct);
     if (rlen < 0) { ok = 0; break; }
     if (lane == 0) { gk[gT] = f.lm; gc[gT] = 1u; gl[q] = 1 + rlen; }
+#pragma unroll 1
     for (int t = lane; t < rlen; t += 32) gc[gT + 1 + t] = bbf_mulmod(P.F, gc[gT + 1 + t], f.invlc);
     gT += 1 + rlen;
     __syncwarp();

@@ -12,7 +12,9 @@
 #pragma once
 #include "bb_device.cuh"
 
+#ifndef BB_WARPS
 #define BB_WARPS 8
+#endif
 #define BB_THREADS (BB_WARPS * 32)
 #ifndef BB_MIN_BLOCKS
 #define BB_MIN_BLOCKS 4  // register cap 64 -> 32 resident warps per SM
@@ -91,10 +93,11 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_step(const __grid
     Ctr ct; ct.clear();
     double r = 0.0;
     if (e.status == BB_STATUS_RUNNING) {
-      int pi, pj;
+      uint32_t pr;
       const int g0 = e.nG;
-      const int adds = warp_step<NV>(P, e, actions[slot], &pi, &pj, ct);
-      if (pi >= 0) {
+      const int adds = warp_step<NV>(P, e, actions[slot], pr, ct);
+      if (pr != 0xffffffffu) {
+        const int pi = pr & 0xffffu, pj = pr >> 16;
         r = (P.rewards == BB_REWARD_ADDITIONS) ? -(double)adds : -1.0;
         if (bb_lane() == 0) {
           BBEnvState& S = P.st[slot];
@@ -217,9 +220,10 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_run(const __grid_
       if (lane == 0) { acc.th = 0ull; acc.ret = 0.0; acc.disc = 1.0; }
       while (e.status == BB_STATUS_RUNNING && (A.max_steps == 0 || steps < A.max_steps)) {
         const int prow = warp_select<NV>(P, e, A.strategy);
-        int pi, pj;
-        const int a = warp_step<NV>(P, e, prow, &pi, &pj, ct);
+        uint32_t pr;
+        const int a = warp_step<NV>(P, e, prow, pr, ct);
         if (lane == 0) {
+          const int pi = pr & 0xffffu, pj = pr >> 16;
           acc.th += trace_hash_item(pi, pj, a, steps);
           const double r = (P.rewards == BB_REWARD_ADDITIONS) ? -(double)a : -1.0;
           const double d = acc.disc;  // discounted_return += discount * reward; discount *= gamma  (buchberger.cpp:250-251)
