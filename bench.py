@@ -207,7 +207,7 @@ def gpu_arm(args):
     lib = eng.lib
 
     def launch(gb):
-        rc = lib.bb_run(eng.h, _lib.SELECTION[STRATEGY], EPISODES, 0, C.c_void_p(seeds_dev.data_ptr()), 0, 0.99, gb,
+        rc = lib.bb_run(eng.h, _lib.SELECTION[STRATEGY], EPISODES, 0, C.c_void_p(seeds_dev.data_ptr()), 0, 0, 0.99, gb,
                         C.c_void_p(stats_dev.data_ptr()), None, 0, 0,
                         C.c_void_p(torch.cuda.current_stream().cuda_stream))
         if rc < 0:

@@ -10,11 +10,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # BBENV_LIB selects another build of the SAME library (A/B runs of kernel variants); it is never a fallback.
 LIB_PATH = os.environ.get("BBENV_LIB") or os.path.join(HERE, "libbbenv.so")
 
-BB_ABI_VERSION = 1
+BB_ABI_VERSION = 2
 
 ELIMINATION = {"gebauermoeller": 0, "lcm": 1, "none": 2}
 REWARDS = {"additions": 0, "reductions": 1}
-SELECTION = {"first": 0, "degree": 1, "normal": 2}
+SELECTION = {"first": 0, "degree": 1, "normal": 2, "sugar": 3, "random": 4, "last": 5, "codegree": 6, "strange": 7,
+             "spice": 8}
+VALUE_SAMPLE = 100  # bb_value only: value("sample")
 DISTRIBUTION = {"uniform": 0, "weighted": 1, "maximum": 2}
 
 STATUS_NAMES = {0: "empty", 1: "running", 2: "done", 3: "bad_action", 4: "overflow_basis", 5: "overflow_pairs",
@@ -54,6 +56,7 @@ EXPORTS = [
     "bb_abi_version", "bb_resident_envs", "bb_create", "bb_destroy", "bb_last_error", "bb_cols", "bb_num_envs", "bb_sm_count",
     "bb_set_distribution", "bb_seed", "bb_set_ideals", "bb_reset", "bb_step", "bb_select", "bb_observe", "bb_pairs",
     "bb_status", "bb_stats", "bb_run", "bb_download_basis", "bb_final_gb", "bb_counters_read", "bb_hash_item",
+    "bb_seed_selection", "bb_value", "bb_copy_env",
 ]
 
 _lib = None
@@ -89,6 +92,8 @@ def load():
     lib.bb_set_distribution.argtypes = [vp, i, i, i, i, i, i]
     lib.bb_seed.restype = i
     lib.bb_seed.argtypes = [vp, ip, i]
+    lib.bb_seed_selection.restype = i
+    lib.bb_seed_selection.argtypes = [vp, ip, i]
     lib.bb_set_ideals.restype = i
     lib.bb_set_ideals.argtypes = [vp, ip, i, ip, ip, ip, ip]
     lib.bb_reset.restype = i
@@ -106,7 +111,11 @@ def load():
     lib.bb_stats.restype = i
     lib.bb_stats.argtypes = [vp, vp, vp]
     lib.bb_run.restype = i
-    lib.bb_run.argtypes = [vp, i, i, i, vp, i, C.c_double, i, vp, vp, i, i, vp]
+    lib.bb_run.argtypes = [vp, i, i, i, vp, i, i, C.c_double, i, vp, vp, i, i, vp]
+    lib.bb_value.restype = i
+    lib.bb_value.argtypes = [vp, i, C.c_double, i, i, i, vp, vp]
+    lib.bb_copy_env.restype = i
+    lib.bb_copy_env.argtypes = [vp, i, vp, i, vp]
     lib.bb_download_basis.restype = i
     lib.bb_download_basis.argtypes = [vp, i, ip, i, ip, ip, i, C.POINTER(C.c_int)]
     lib.bb_final_gb.restype = i

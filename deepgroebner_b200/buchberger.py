@@ -51,6 +51,8 @@ class BuchbergerEngine:
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise ValueError("device must be a CUDA device")
+        self._ctor = dict(ideal_dist=ideal_dist, elimination=elimination, rewards=rewards, sort_input=sort_input,
+                          sort_reducers=sort_reducers, k=k, device=device, prime=prime, capacity=capacity, **caps)
         self.spec = ideal_dist if isinstance(ideal_dist, (BinomialSpec, FixedIdealGenerator)) \
             else parse_ideal_dist(ideal_dist, prime)
         self.n = self.spec.n if isinstance(self.spec, BinomialSpec) else self.spec.nvars()
@@ -104,6 +106,15 @@ class BuchbergerEngine:
             a = np.ascontiguousarray(seed, dtype=np.int32)
             assert a.shape == (self.num_envs,)
             self._ck(self.lib.bb_seed(self.h, a.ctypes.data_as(C.POINTER(C.c_int32)), 0), "bb_seed")
+
+    def seed_selection(self, seed=0):
+        """Seeds the per-environment stream that 'random' selection draws from (buchberger(..., seed))."""
+        if np.ndim(seed) == 0:
+            self._ck(self.lib.bb_seed_selection(self.h, None, int(seed)), "bb_seed_selection")
+        else:
+            a = np.ascontiguousarray(seed, dtype=np.int32)
+            assert a.shape == (self.num_envs,)
+            self._ck(self.lib.bb_seed_selection(self.h, a.ctypes.data_as(C.POINTER(C.c_int32)), 0), "bb_seed_selection")
 
     def set_ideals(self, ideals, env_ids=None):
         """ideals: list (one per environment) of lists of polynomials [(coef, exps), ...]."""
@@ -187,7 +198,7 @@ class BuchbergerEngine:
 
     # ---- whole episodes
     def run_episodes(self, strategy="degree", episodes=None, seed_base=0, seeds=None, max_steps=0, gamma=0.99,
-                     compute_gb=False, trace_episodes=0, trace_cap=0, to_host=True):
+                     compute_gb=False, trace_episodes=0, trace_cap=0, to_host=True, selection_seed=0):
         """Runs `episodes` episodes to completion with on-device selection (bb_run).  Returns (stats, trace):
         stats is a structured array of bb_episode_stats (numpy if to_host else a uint8 cuda tensor), trace an
         int32 [trace_episodes, trace_cap, 4] array of (i, j, additions, |P| after), -1 padded."""
@@ -202,12 +213,36 @@ class BuchbergerEngine:
                 d_seeds = torch.as_tensor(np.ascontiguousarray(seeds, np.int32), device=self.device)
                 assert d_seeds.numel() == episodes
             self._ck(self.lib.bb_run(self.h, _lib.SELECTION[strategy], episodes, int(seed_base), _ptr(d_seeds),
-                                     int(max_steps), float(gamma), int(bool(compute_gb)), _ptr(buf), _ptr(trace),
+                                     int(selection_seed), int(max_steps), float(gamma), int(bool(compute_gb)),
+                                     _ptr(buf), _ptr(trace),
                                      int(trace_episodes), int(trace_cap), _stream()), "bb_run")
             if not to_host:
                 return buf, trace
             stats = buf.cpu().numpy().view(np.dtype(_lib.STATS_DTYPE))[:episodes]
             return stats, (trace.cpu().numpy() if trace is not None else None)
+
+    def value(self, strategy="degree", gamma=0.99, rollouts=1, selection_seed=0, max_steps=0, out=None):
+        """BuchbergerEnv.value for every environment (bb_value): float64 cuda tensor [N].  strategy is a selection
+        name or 'sample' (1 Degree + 100 Random rollouts, best kept)."""
+        code = _lib.VALUE_SAMPLE if strategy == "sample" else _lib.SELECTION[strategy]
+        with torch.cuda.device(self.device):
+            if out is None:
+                out = torch.empty(self.num_envs, dtype=torch.float64, device=self.device)
+            self._ck(self.lib.bb_value(self.h, code, float(gamma), int(rollouts), int(selection_seed), int(max_steps),
+                                       _ptr(out), _stream()), "bb_value")
+        return out
+
+    def copy_env(self, dst_env, src, src_env):
+        """Environment src_env of engine `src` -> environment dst_env of this engine (bb_copy_env)."""
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.bb_copy_env(self.h, int(dst_env), src.h, int(src_env), _stream()), "bb_copy_env")
+
+    def clone(self):
+        """A new engine with the same configuration and a copy of every environment (the copy constructor)."""
+        other = BuchbergerEngine(num_envs=self.num_envs, **self._ctor)
+        for e in range(self.num_envs):
+            other.copy_env(e, self, e)
+        return other
 
     # ---- host views
     def _polys_out(self, fn, env, what):
@@ -280,9 +315,18 @@ class LeadMonomialsEnv:
             return state, float(reward.item()), bool(done.item()), {}
         return state, reward, done.bool(), {}
 
-    def value(self, strategy="degree", gamma=0.99):
-        raise NotImplementedError("value() from a live state needs slot forking (SURVEY 8(f) row 2); "
-                                  "use BuchbergerEngine.run_episodes for whole-episode rollouts")
+    def value(self, strategy="degree", gamma=0.99, **kw):
+        """Discounted return of finishing from the current state under `strategy` (wrapped.pyx:32-33,
+        buchberger.cpp:332-351); a float for num_envs == 1, else a float64 cuda tensor [N]."""
+        v = self.engine.value(strategy, gamma, **kw)
+        return float(v.item()) if self.num_envs == 1 else v
+
+    def copy(self):
+        """Deep copy including the ideal stream (wrapped.pyx:35-38)."""
+        other = object.__new__(type(self))
+        other.__dict__.update(self.__dict__)
+        other.engine = self.engine.clone()
+        return other
 
 
 class BuchbergerEnv:
@@ -305,6 +349,17 @@ class BuchbergerEnv:
 
     def basis(self, env=0):
         return self.engine.basis(env)
+
+    def value(self, strategy="degree", gamma=0.99, **kw):
+        """buchberger.py:380-387 / buchberger.cpp:332-351."""
+        v = self.engine.value(strategy, gamma, **kw)
+        return float(v.item()) if self.num_envs == 1 else v
+
+    def copy(self):
+        other = object.__new__(type(self))
+        other.__dict__.update(self.__dict__)
+        other.engine = self.engine.clone()
+        return other
 
     def _state(self):
         if self.num_envs == 1:
@@ -334,7 +389,8 @@ class BuchbergerEnv:
 
 
 class BuchbergerAgent:
-    """First / Degree / Normal selection computed on device (buchberger.py:397-439, buchberger.cpp:165-186)."""
+    """Built-in selection strategies computed on device (buchberger.py:397-439, buchberger.cpp:160-241):
+    first, degree, normal, sugar, random, last, codegree, strange, spice."""
 
     def __init__(self, selection="normal"):
         self.strategy = selection

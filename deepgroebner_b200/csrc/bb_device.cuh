@@ -32,7 +32,8 @@
 struct __align__(16) BBEnvState {  // one per slot, 96 bytes
   int nG, nP, nT, status;
   int steps, adds, zero, nonzero;
-  int rerolls, episode, truncated, pad1;
+  int rerolls, episode, truncated;
+  unsigned sel_rng;              // minstd_rand0 state of Random selection (buchberger.cpp:190-197)
   unsigned long long trace_hash;
   unsigned long long rng;        // minstd_rand0 state of this environment's ideal stream
   double disc_return, discount;
@@ -40,13 +41,19 @@ struct __align__(16) BBEnvState {  // one per slot, 96 bytes
 };
 
 // Head record of a basis element: everything a 2-term polynomial needs, and the arena range of the full term list.
-struct __align__(32) GHead {
+// Head record of a basis element as it sits in the arena (32 bytes, two 128-bit loads) ...
+struct __align__(32) GHeadMem {
   uint64_t lm;     // lead monomial key
   uint64_t k1;     // second term's key (undefined when len == 1)
-  uint32_t invlc;  // 1 / lead coefficient
-  uint32_t c1;     // second term's coefficient (0 when len == 1)
+  uint32_t ic;     // (1 / lead coefficient) | (second term's coefficient << 16): both are < p < 2^16
+  uint32_t sug;    // sugar degree (Polynomial::sug, polynomials.h:93)
   uint32_t off;    // first term's index in the slot's term arena
   uint32_t len;    // number of terms
+};
+// ... and unpacked in (warp-uniform) registers
+struct GHead {
+  uint64_t lm, k1;
+  uint32_t invlc, c1, sug, off, len;
 };
 
 struct BBDist {           // RandomBinomialIdealGenerator parameters (ideals.cpp:157-201)
@@ -64,7 +71,7 @@ struct BBParams {
   // one contiguous arena per slot: base = arena + slot * slot_stride; byte offsets of the arrays inside it
   unsigned char* arena;
   unsigned long long slot_stride;
-  unsigned o_ghead;   // GHead   [max_basis]          by basis index
+  unsigned o_ghead;   // GHeadMem[max_basis]          by basis index
   unsigned o_lm;      // u64     [max_basis]          lead monomial key by basis index
   unsigned o_rlm;     // u64     [max_basis]          reducer list G_ in scan order: lead monomial key
   unsigned o_lscr;    // u64     [max_basis]          update() scratch: lcm(LM_i, LM f) exponents | coprime << 63
@@ -148,12 +155,53 @@ __device__ __forceinline__ void env_load(const BBParams& P, int slot, Env& e) {
 __device__ __forceinline__ void env_store(const BBParams& P, int slot, const Env& e) {
   if (bb_lane() == 0) *reinterpret_cast<int4*>(&P.st[slot]) = make_int4(e.nG, e.nP, e.nT, e.status);
 }
-__device__ __forceinline__ GHead load_head(const GHead* g) {
+__device__ __forceinline__ GHead load_head(const GHeadMem* g) {
   const uint4 a = reinterpret_cast<const uint4*>(g)[0], b = reinterpret_cast<const uint4*>(g)[1];
   GHead h;
   h.lm = ((uint64_t)a.y << 32) | a.x; h.k1 = ((uint64_t)a.w << 32) | a.z;
-  h.invlc = b.x; h.c1 = b.y; h.off = b.z; h.len = b.w;
+  h.invlc = b.x & 0xffffu; h.c1 = b.x >> 16; h.sug = b.y; h.off = b.z; h.len = b.w;
   return h;
+}
+
+// ---------------------------------------------------------------------------------------------------- random streams
+// minstd_rand0 + libstdc++ distributions restated (ideals.h:177-179; SURVEY Appendix B): the streams must match
+// the reference generator bit for bit because "identical seeded inputs" is part of the parity contract.
+// The engine state is < 2^31, so everything is 32-bit arithmetic except the 46-bit product.
+__device__ __forceinline__ uint32_t rng_seed(int seed) {
+  unsigned long long s = (unsigned long long)(long long)seed % 2147483647ULL;  // int -> unsigned long, then mod m
+  return s == 0 ? 1u : (uint32_t)s;
+}
+__device__ __forceinline__ uint32_t rng_next(uint32_t& x) {
+  const unsigned long long pr = (unsigned long long)x * 16807ULL;       // < 2^46
+  uint32_t r = (uint32_t)(pr & 0x7fffffffULL) + (uint32_t)(pr >> 31);  // 2^31 == 1 (mod 2^31 - 1)
+  if (r >= 2147483647u) r -= 2147483647u;
+  x = r;
+  return r;
+}
+// uniform_int_distribution<int>(a,b): "fallback (2 divisions)" branch of bits/uniform_int_dist.h
+__device__ __forceinline__ int rng_uniform(uint32_t& x, int a, int b) {
+  const uint32_t urngrange = 2147483645u;
+  const uint32_t uerange = (uint32_t)(b - a) + 1u;
+  const uint32_t scaling = urngrange / uerange, past = uerange * scaling;
+  uint32_t ret;
+  do ret = rng_next(x) - 1u; while (ret >= past);
+  return a + (int)(ret / scaling);
+}
+// generate_canonical<double,53>: two draws, (u1-1) + (u2-1)*R over R*R, all in round-to-nearest double ops
+__device__ __forceinline__ double rng_canonical(uint32_t& x) {
+  const double R = 2147483646.0;
+  double s = (double)(rng_next(x) - 1u);
+  s = __dadd_rn(s, __dmul_rn((double)(rng_next(x) - 1u), R));
+  double r = __ddiv_rn(s, __dmul_rn(R, R));
+  if (r >= 1.0) r = __longlong_as_double(0x3FEFFFFFFFFFFFFFLL);  // nextafter(1,0)
+  return r;
+}
+__device__ __forceinline__ int rng_degree(const BBDist& D, uint32_t& x) {
+  if (D.ncp < 2) return 0;
+  const double p = rng_canonical(x);
+  int lo = 0, hi = D.ncp;
+  while (lo < hi) { int mid = (lo + hi) >> 1; if (D.cp[mid] < p) lo = mid + 1; else hi = mid; }
+  return lo;
 }
 
 // ---------------------------------------------------------------------------------------------------- merge
@@ -238,6 +286,7 @@ struct Dividend {
   uint64_t k0, k1;
   uint32_t c0, c1;
   int n;
+  int sug;  // sugar of h: max over the additions that built it of deg(multiplier) + sugar(operand), polynomials.cpp:150,198
   int loc;  // -1: registers only (n <= 2); else index of the lead term in the scratch (half * max_poly_terms + pos)
 };
 
@@ -285,7 +334,7 @@ __device__ __forceinline__ int warp_reduce(const BBParams& P, Env& e, Dividend& 
   typedef KL<NV> K;
   const BBField F = P.F;
   const int lane = bb_lane();
-  const GHead* gh = ENV_PTR(GHead, e, P, o_ghead);
+  const GHeadMem* gh = ENV_PTR(GHeadMem, e, P, o_ghead);
   int rlen = 0;
   steps = 0;
   while (h.n > 0) {
@@ -305,6 +354,10 @@ __device__ __forceinline__ int warp_reduce(const BBParams& P, Env& e, Dividend& 
       const uint32_t c = bbf_mulmod(F, h.c0, f.invlc);
       const uint32_t nc = F.p - c;              // c != 0
       const uint64_t adj = lead - f.lm;         // key(LM h / LM f) - bias
+      {  // h.sug = max(h.sug, deg(LM h / LM f) + f.sug); term moves never raise it (sugar >= degree of every term)
+        const int sf = (int)f.sug + (int)(uint32_t)(f.lm >> K::dshift) - (int)(uint32_t)(lead >> K::dshift);
+        h.sug = sf > h.sug ? sf : h.sug;
+      }
       ct.tread += (unsigned)h.n + f.len;
       if (h.n <= 2 && f.len <= 2) {
         const uint64_t kb = f.k1 + adj;
@@ -364,7 +417,8 @@ __device__ __forceinline__ int warp_reduce(const BBParams& P, Env& e, Dividend& 
 // One out-of-line copy shared by step and reset.  Returns (emitted << 32) | new |P|, or -1 on pair-list overflow /
 // -2 when the basis is full / -3 when an lcm's degree does not fit the packed layout; the caller bumps nG and nT.
 template <int NV>
-__device__ __noinline__ long long warp_add_basis(const BBParams& P, unsigned char* base, int m, int nP, int off, int len) {
+__device__ __noinline__ long long warp_add_basis(const BBParams& P, unsigned char* base, int m, int nP, int off, int len,
+                                                 int sug) {
   typedef KL<NV> K;
   const int lane = bb_lane();
   const uint32_t ltm = bb_lt_mask();
@@ -511,12 +565,12 @@ __device__ __noinline__ long long warp_add_basis(const BBParams& P, unsigned cha
   if (lane == 0) {
     rlm[pos] = fk; ridx[pos] = (uint32_t)m;
     lm[m] = fk;
-    GHead* g = reinterpret_cast<GHead*>(base + P.o_ghead) + m;
+    GHeadMem* g = reinterpret_cast<GHeadMem*>(base + P.o_ghead) + m;
     const uint32_t inv = P.invtab[tc[0]];  // 1/LC: one table load instead of a 15-step power ladder
     const uint64_t k1 = len > 1 ? tk[1] : 0ull;
     const uint32_t c1 = len > 1 ? tc[1] : 0u;
     reinterpret_cast<uint4*>(g)[0] = make_uint4((uint32_t)fk, (uint32_t)(fk >> 32), (uint32_t)k1, (uint32_t)(k1 >> 32));
-    reinterpret_cast<uint4*>(g)[1] = make_uint4(inv, c1, (uint32_t)off, (uint32_t)len);
+    reinterpret_cast<uint4*>(g)[1] = make_uint4(inv | (c1 << 16), (uint32_t)sug, (uint32_t)off, (uint32_t)len);
   }
   __syncwarp();
   return ((long long)emitted << 32) | (long long)nP;
@@ -552,12 +606,17 @@ __device__ __forceinline__ int warp_step(const BBParams& P, Env& e, int row, uin
   }
   e.nP--;
   // S-polynomial: lead terms cancel exactly, so s = (gamma/LT f) tail(f) - (gamma/LT g) tail(g)
-  const GHead* gh = ENV_PTR(GHead, e, P, o_ghead);
+  const GHeadMem* gh = ENV_PTR(GHeadMem, e, P, o_ghead);
   const GHead hf = load_head(gh + i), hg = load_head(gh + j);
   e.guard |= gam;
   ct.tread += hf.len + hg.len;
   Dividend h;
   h.k0 = h.k1 = 0; h.c0 = h.c1 = 0; h.n = 0; h.loc = -1;
+  {  // sugar of the S-polynomial: max(deg(gamma / LM f) + sug f, deg(gamma / LM g) + sug g)
+    const int cg0 = (int)(uint32_t)(gam >> K::dshift);
+    const int sf = (int)hf.sug + (int)(uint32_t)(hf.lm >> K::dshift) - cg0, sg = (int)hg.sug + (int)(uint32_t)(hg.lm >> K::dshift) - cg0;
+    h.sug = sf > sg ? sf : sg;
+  }
   const uint64_t adjf = gam - hf.lm, adjg = gam - hg.lm;
   const uint32_t cg = F.p - hg.invlc;  // -(1/LC g), invlc != 0
   if (hf.len <= 2 && hg.len <= 2) {
@@ -587,7 +646,7 @@ __device__ __forceinline__ int warp_step(const BBParams& P, Env& e, int row, uin
   if (rlen == -3 || (e.guard & K::g_all)) { e.status = BB_STATUS_OVERFLOW_EXPONENT; return 1 + steps; }
   if (rlen > 0) {
     ct.upb += (unsigned)e.nG; ct.upp += (unsigned)e.nP;
-    const long long r = warp_add_basis<NV>(P, e.base, e.nG, e.nP, e.nT, rlen);
+    const long long r = warp_add_basis<NV>(P, e.base, e.nG, e.nP, e.nT, rlen, h.sug);
     if (r < 0) {
       e.status = (r == -1) ? BB_STATUS_OVERFLOW_PAIRS : (r == -2 ? BB_STATUS_OVERFLOW_BASIS : BB_STATUS_OVERFLOW_EXPONENT);
       return 1 + steps;
@@ -601,13 +660,94 @@ __device__ __forceinline__ int warp_step(const BBParams& P, Env& e, int row, uin
 }
 
 // ---------------------------------------------------------------------------------------------------- select
-// First / Degree / Normal pair selection (buchberger.cpp:165-186); ties go to the first pair in P, which is
-// what the (j,i) tie-break selects because P is always sorted by (j,i).  Reads only the cached lcm keys.
+// Pair selection, buchberger.cpp:160-241.  Every comparator ends in (j, i), and P is always sorted by (j, i), so
+// "first minimal element" is the lowest row among ties for the ascending strategies (First, Degree, Normal, Sugar)
+// and the HIGHEST row among ties for the reversed ones (Last, Codegree, Strange, Spice: min_element under '>').
+// Reads only the cached lcm keys, except Sugar / Spice which gather the two head records of each pair.
+
+// argmax of a 64-bit value with an index tie-break (low: lowest index wins, else highest); lanes without a
+// candidate pass idx = 0xffffffff
+__device__ __forceinline__ int warp_argmax64(uint64_t v, uint32_t idx, bool low) {
+  const bool has = idx != 0xffffffffu;
+  const uint32_t hi = __reduce_max_sync(BB_FULL, has ? (uint32_t)(v >> 32) : 0u);
+  const bool c1 = has && (uint32_t)(v >> 32) == hi;
+  const uint32_t lo = __reduce_max_sync(BB_FULL, c1 ? (uint32_t)v : 0u);
+  const bool c2 = c1 && (uint32_t)v == lo;
+  return low ? (int)__reduce_min_sync(BB_FULL, c2 ? idx : 0xffffffffu) : (int)__reduce_max_sync(BB_FULL, c2 ? idx : 0u);
+}
+
+// sugar of pair (i, j) with lcm key l: max(sug_i + deg(l / LM_i), sug_j + deg(l / LM_j))   (buchberger.cpp:189-192)
 template <int NV>
-__device__ __forceinline__ int warp_select(const BBParams& P, const Env& e, int strategy) {
+__device__ __forceinline__ int pair_sugar(const GHeadMem* gh, uint32_t pr, uint64_t l) {
+  typedef KL<NV> K;
+  const GHeadMem* a = gh + (pr & 0xffffu); const GHeadMem* b = gh + (pr >> 16);
+  const int cl = (int)(uint32_t)(l >> K::dshift);
+  const int sa = (int)a->sug + (int)(uint32_t)(a->lm >> K::dshift) - cl, sb = (int)b->sug + (int)(uint32_t)(b->lm >> K::dshift) - cl;
+  return sa > sb ? sa : sb;
+}
+
+// the strategies outside the benchmarked three: one out-of-line copy
+template <int NV>
+__device__ __noinline__ int warp_select_rare(const BBParams& P, unsigned char* base, int nP, int strategy, uint32_t* rng) {
   typedef KL<NV> K;
   const int lane = bb_lane();
-  if (strategy == BB_SELECT_FIRST || e.nP <= 1) return 0;
+  const uint64_t* plcm = reinterpret_cast<const uint64_t*>(base + P.o_plcm);
+  if (strategy == BB_SELECT_RANDOM) {  // choice(): uniform_int_distribution<>(0, |P|-1)(rng), ideals.h:68-73
+    uint32_t x = *rng;                        // rng: shared or global memory, one word per environment
+    const int r = rng_uniform(x, 0, nP - 1);  // every lane runs the same stream
+    __syncwarp();
+    if (lane == 0) *rng = x;
+    __syncwarp();
+    return r;
+  }
+  if (strategy == BB_SELECT_LAST) return nP - 1;
+  if (strategy == BB_SELECT_CODEGREE) {  // largest degree == smallest complemented-degree field; highest row on ties
+    uint32_t best = 0u;
+#pragma unroll 1
+    for (int idx = lane; idx < nP; idx += 32) {
+      const uint32_t v = ((K::dmax - (uint32_t)(plcm[idx] >> K::dshift)) << 16) | (uint32_t)idx;
+      best = v > best ? v : best;
+    }
+    return (int)(__reduce_max_sync(BB_FULL, best) & 0xffffu);
+  }
+  if (strategy == BB_SELECT_STRANGE) {  // largest lcm in grevlex == SMALLEST key; highest row on ties
+    uint64_t bk = 0; uint32_t bi = 0xffffffffu;
+#pragma unroll 1
+    for (int idx = lane; idx < nP; idx += 32) {
+      const uint64_t k = ~plcm[idx];
+      if (k >= bk) { bk = k; bi = (uint32_t)idx; }  // ascending idx per lane: last occurrence kept on ties
+    }
+    return warp_argmax64(bk, bi, false);
+  }
+  // Sugar: min (sugar, lcm, j, i); Spice: max of the same tuple
+  const bool spice = strategy == BB_SELECT_SPICE;
+  const uint32_t* pairs = reinterpret_cast<const uint32_t*>(base + P.o_pairs);
+  const GHeadMem* gh = reinterpret_cast<const GHeadMem*>(base + P.o_ghead);
+  int bs = spice ? -1 : 0x7fffffff;
+#pragma unroll 1
+  for (int idx = lane; idx < nP; idx += 32) {
+    const int sg = pair_sugar<NV>(gh, pairs[idx], plcm[idx]);
+    bs = spice ? (sg > bs ? sg : bs) : (sg < bs ? sg : bs);
+  }
+  bs = spice ? (int)__reduce_max_sync(BB_FULL, (uint32_t)(bs + 1)) - 1 : (int)__reduce_min_sync(BB_FULL, (uint32_t)bs);
+  uint64_t bk = 0; uint32_t bi = 0xffffffffu;
+#pragma unroll 1
+  for (int idx = lane; idx < nP; idx += 32) {
+    const uint64_t l = plcm[idx];
+    if (pair_sugar<NV>(gh, pairs[idx], l) != bs) continue;
+    const uint64_t k = spice ? ~l : l;  // Sugar: smallest lcm == largest key; Spice: largest lcm == smallest key
+    if (bi == 0xffffffffu || (spice ? k >= bk : k > bk)) { bk = k; bi = (uint32_t)idx; }
+  }
+  return warp_argmax64(bk, bi, !spice);
+}
+
+template <int NV>
+__device__ __forceinline__ int warp_select(const BBParams& P, const Env& e, int strategy, uint32_t* rng) {
+  typedef KL<NV> K;
+  const int lane = bb_lane();
+  if (strategy == BB_SELECT_FIRST) return 0;
+  if (strategy > BB_SELECT_NORMAL) return warp_select_rare<NV>(P, e.base, e.nP, strategy, rng);
+  if (e.nP <= 1) return 0;
   const uint64_t* plcm = ENV_PTR(uint64_t, e, P, o_plcm);
   if (strategy == BB_SELECT_DEGREE) {
     // smallest degree == largest complemented-degree field; lowest row on ties
@@ -627,11 +767,7 @@ __device__ __forceinline__ int warp_select(const BBParams& P, const Env& e, int 
     const uint64_t k = plcm[idx];
     if (k > bk) { bk = k; bi = (uint32_t)idx; }  // strided ascending idx: first occurrence kept on ties
   }
-  const uint32_t hi = __reduce_max_sync(BB_FULL, (uint32_t)(bk >> 32));
-  const bool c1 = (uint32_t)(bk >> 32) == hi && bi != 0xffffffffu;
-  const uint32_t lo = __reduce_max_sync(BB_FULL, c1 ? (uint32_t)bk : 0u);
-  const bool c2 = c1 && (uint32_t)bk == lo;
-  return (int)__reduce_min_sync(BB_FULL, c2 ? bi : 0xffffffffu);
+  return warp_argmax64(bk, bi, true);
 }
 
 // ---------------------------------------------------------------------------------------------------- observe
@@ -645,7 +781,7 @@ __device__ __forceinline__ void warp_observe(const BBParams& P, const Env& e, in
   const int rows = e.nP < pmax ? e.nP : pmax;
   const int live = rows * cols, total = pmax * cols;
   const uint32_t* pairs = ENV_PTR(uint32_t, e, P, o_pairs);
-  const GHead* gh = ENV_PTR(GHead, e, P, o_ghead);
+  const GHeadMem* gh = ENV_PTR(GHeadMem, e, P, o_ghead);
   const uint64_t* tk = ENV_PTR(uint64_t, e, P, o_tkey);
   for (int x = lane; x < live; x += 32) {
     const int row = x / cols, c = x - row * cols;
@@ -653,7 +789,7 @@ __device__ __forceinline__ void warp_observe(const BBParams& P, const Env& e, in
     const int side = c >= half;
     const int cc = c - side * half;
     const int t = cc / NV, v = cc - t * NV;
-    const GHead* g = gh + (side ? (pr >> 16) : (pr & 0xffffu));
+    const GHeadMem* g = gh + (side ? (pr >> 16) : (pr & 0xffffu));
     int32_t val = 0;
     if (t < (int)g->len) val = (int32_t)K::exp(t == 0 ? g->lm : (t == 1 ? g->k1 : tk[g->off + t]), v);
     obs[x] = val;
@@ -663,45 +799,6 @@ __device__ __forceinline__ void warp_observe(const BBParams& P, const Env& e, in
 }
 
 // ---------------------------------------------------------------------------------------------------- generator
-// minstd_rand0 + libstdc++ distributions restated (ideals.h:177-179; SURVEY Appendix B): the streams must match
-// the reference generator bit for bit because "identical seeded inputs" is part of the parity contract.
-// The engine state is < 2^31, so everything is 32-bit arithmetic except the 46-bit product.
-__device__ __forceinline__ uint32_t rng_seed(int seed) {
-  unsigned long long s = (unsigned long long)(long long)seed % 2147483647ULL;  // int -> unsigned long, then mod m
-  return s == 0 ? 1u : (uint32_t)s;
-}
-__device__ __forceinline__ uint32_t rng_next(uint32_t& x) {
-  const unsigned long long pr = (unsigned long long)x * 16807ULL;       // < 2^46
-  uint32_t r = (uint32_t)(pr & 0x7fffffffULL) + (uint32_t)(pr >> 31);  // 2^31 == 1 (mod 2^31 - 1)
-  if (r >= 2147483647u) r -= 2147483647u;
-  x = r;
-  return r;
-}
-// uniform_int_distribution<int>(a,b): "fallback (2 divisions)" branch of bits/uniform_int_dist.h
-__device__ __forceinline__ int rng_uniform(uint32_t& x, int a, int b) {
-  const uint32_t urngrange = 2147483645u;
-  const uint32_t uerange = (uint32_t)(b - a) + 1u;
-  const uint32_t scaling = urngrange / uerange, past = uerange * scaling;
-  uint32_t ret;
-  do ret = rng_next(x) - 1u; while (ret >= past);
-  return a + (int)(ret / scaling);
-}
-// generate_canonical<double,53>: two draws, (u1-1) + (u2-1)*R over R*R, all in round-to-nearest double ops
-__device__ __forceinline__ double rng_canonical(uint32_t& x) {
-  const double R = 2147483646.0;
-  double s = (double)(rng_next(x) - 1u);
-  s = __dadd_rn(s, __dmul_rn((double)(rng_next(x) - 1u), R));
-  double r = __ddiv_rn(s, __dmul_rn(R, R));
-  if (r >= 1.0) r = __longlong_as_double(0x3FEFFFFFFFFFFFFFLL);  // nextafter(1,0)
-  return r;
-}
-__device__ __forceinline__ int rng_degree(const BBDist& D, uint32_t& x) {
-  if (D.ncp < 2) return 0;
-  const double p = rng_canonical(x);
-  int lo = 0, hi = D.ncp;
-  while (lo < hi) { int mid = (lo + hi) >> 1; if (D.cp[mid] < p) lo = mid + 1; else hi = mid; }
-  return lo;
-}
 // RandomBinomialIdealGenerator::next (ideals.cpp:168-201), executed by lane 0 into the slot's staging area.
 // Returns false if 1000 trials fail (the reference throws).
 __device__ __forceinline__ bool gen_binomial_ideal(const BBParams& P, int slot, uint32_t& x) {
@@ -767,7 +864,8 @@ __device__ __forceinline__ void warp_load_ideal(const BBParams& P, int src_slot,
     for (int t = lane; t < len; t += 32) { tk[e.nT + t] = ik[off + t]; tc[e.nT + t] = ic[off + t]; }
     __syncwarp();
     ct.upb += (unsigned)e.nG; ct.upp += (unsigned)e.nP;
-    const long long r = warp_add_basis<NV>(P, e.base, e.nG, e.nP, e.nT, len);
+    const long long r = warp_add_basis<NV>(P, e.base, e.nG, e.nP, e.nT, len,
+                                               (int)KL<NV>::deg(ik[off]));  // ctor: sug = deg LM (polynomials.cpp:136,144)
     if (r < 0) {
       e.status = (r == -1) ? BB_STATUS_OVERFLOW_PAIRS : (r == -2 ? BB_STATUS_OVERFLOW_BASIS : BB_STATUS_OVERFLOW_EXPONENT);
       return;
@@ -862,7 +960,7 @@ __device__ __noinline__ int warp_final_gb(const BBParams& P, int slot, unsigned 
   Ctr ct; ct.clear();
   const int m = e.nG;
   const uint64_t* lm = ENV_PTR(uint64_t, e, P, o_lm);
-  const GHead* gh = ENV_PTR(GHead, e, P, o_ghead);
+  const GHeadMem* gh = ENV_PTR(GHeadMem, e, P, o_ghead);
   uint64_t* gk = P.gkey + (size_t)slot * P.max_terms;
   uint32_t* gc = P.gcoef + (size_t)slot * P.max_terms;
   int* gl = P.glen + (size_t)slot * P.max_basis;
@@ -912,7 +1010,7 @@ __device__ __noinline__ int warp_final_gb(const BBParams& P, int slot, unsigned 
     for (int t = lane; t < n; t += 32) { hk[t] = tk[f.off + 1 + t]; hc[t] = tc[f.off + 1 + t]; }
     __syncwarp();
     Dividend h;
-    h.k0 = h.k1 = 0; h.c0 = h.c1 = 0;
+    h.k0 = h.k1 = 0; h.c0 = h.c1 = 0; h.sug = 0;
     dividend_from_scratch(P, e, h, n, 0);
     int steps;
     const int rlen = warp_reduce<NV>(P, e, h, rlm2, ridx2, nmin, true, gk + gT + 1, gc + gT + 1, P.max_terms - gT - 1, steps,

@@ -22,6 +22,7 @@
 
 struct BBRunArgs {
   int strategy, episodes, seed_base;
+  int sel_seed_base;  // Random selection: episode e draws choice() from minstd_rand0 seeded sel_seed_base + e
   int ep_base;      // first episode of this batch: episode ids are ep_base .. ep_base + episodes - 1
   int nstaged;      // fixed ideals: number of staged ideals (episode e replays ideal e mod nstaged)
   const int* seeds;
@@ -37,6 +38,18 @@ struct BBRunArgs {
 struct BBEpisodeAcc {
   unsigned long long th;
   double ret, disc;
+  uint32_t sel_rng, pad;
+};
+
+struct BBValueArgs {
+  int strategy;       // BB_SELECT_* or BB_VALUE_SAMPLE
+  int rollouts;       // rollouts per environment (max of their returns); SAMPLE: 1 Degree + (rollouts - 1) Random
+  int sel_seed_base;  // Random rollout r is seeded sel_seed_base + r (SAMPLE: sel_seed_base + r - 1)
+  int max_steps;
+  double gamma;
+  double* value;      // [num_envs], pre-filled with -inf
+  int* queue;
+  int ntasks;         // num_envs * rollouts
 };
 
 struct BBKernelTable {
@@ -48,6 +61,7 @@ struct BBKernelTable {
   cudaError_t (*final_gb)(const BBParams&, int slot, int* ok_out, cudaStream_t);
   cudaError_t (*prepare)(const BBParams& stage, const BBRunArgs&, cudaStream_t);
   cudaError_t (*run)(const BBParams&, const BBParams& stage, const BBRunArgs&, int nwarps, cudaStream_t);
+  cudaError_t (*value)(const BBParams&, const BBParams& fork, const BBValueArgs&, int nwarps, cudaStream_t);
   int (*run_blocks_per_sm)(void);
 };
 
@@ -126,7 +140,7 @@ __global__ void __launch_bounds__(BB_THREADS) k_select(const __grid_constant__ B
   const int slot = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
   if (slot >= P.num_envs) return;
   Env e; env_load(P, slot, e);
-  const int a = (e.status == BB_STATUS_RUNNING) ? warp_select<NV>(P, e, strategy) : 0;
+  const int a = (e.status == BB_STATUS_RUNNING) ? warp_select<NV>(P, e, strategy, &P.st[slot].sel_rng) : 0;
   if (bb_lane() == 0) actions[slot] = a;
 }
 
@@ -178,6 +192,41 @@ __device__ __forceinline__ void warp_copy_words(uint32_t* __restrict__ d, const 
   for (int t = bb_lane(); t < n; t += 32) d[t] = s[t];
 }
 
+// copy the live part of environment `src` (arena base sb, scalars in e) into the arena at db (same layout)
+__device__ __forceinline__ void warp_copy_env(const BBParams& D, unsigned char* db, const BBParams& S, const unsigned char* sb,
+                                              const Env& e) {
+  warp_copy_words((uint32_t*)(db + D.o_ghead), (const uint32_t*)(sb + S.o_ghead), e.nG * 8);
+  warp_copy_words((uint32_t*)(db + D.o_lm), (const uint32_t*)(sb + S.o_lm), e.nG * 2);
+  warp_copy_words((uint32_t*)(db + D.o_rlm), (const uint32_t*)(sb + S.o_rlm), e.nG * 2);
+  warp_copy_words((uint32_t*)(db + D.o_ridx), (const uint32_t*)(sb + S.o_ridx), e.nG);
+  warp_copy_words((uint32_t*)(db + D.o_pairs), (const uint32_t*)(sb + S.o_pairs), e.nP);
+  warp_copy_words((uint32_t*)(db + D.o_plcm), (const uint32_t*)(sb + S.o_plcm), e.nP * 2);
+  warp_copy_words((uint32_t*)(db + D.o_tkey), (const uint32_t*)(sb + S.o_tkey), e.nT * 2);
+  warp_copy_words((uint32_t*)(db + D.o_tcoef), (const uint32_t*)(sb + S.o_tcoef), e.nT);
+}
+
+// The loop of buchberger() (buchberger.cpp:243-263) on one environment: select, step, accumulate the trace checksum and
+// the discounted return (discounted_return += discount * reward; discount *= gamma, :250-251) until P is empty.
+template <int NV>
+__device__ __forceinline__ void run_episode(const BBParams& P, Env& e, int strategy, int max_steps, double gamma,
+                                            BBEpisodeAcc& acc, Ctr& ct, int& steps, int& adds, int4* trace, int trace_cap) {
+  const int lane = bb_lane();
+  while (e.status == BB_STATUS_RUNNING && (max_steps == 0 || steps < max_steps)) {
+    const int prow = warp_select<NV>(P, e, strategy, &acc.sel_rng);
+    uint32_t pr;
+    const int a = warp_step<NV>(P, e, prow, pr, ct);
+    if (lane == 0) {
+      const int pi = pr & 0xffffu, pj = pr >> 16;
+      acc.th += trace_hash_item(pi, pj, a, steps);
+      const double r = (P.rewards == BB_REWARD_ADDITIONS) ? -(double)a : -1.0;
+      const double d = acc.disc;
+      acc.ret = __dadd_rn(acc.ret, __dmul_rn(d, r)); acc.disc = __dmul_rn(d, gamma);
+      if (trace && steps < trace_cap) trace[steps] = make_int4(pi, pj, a, e.nP);
+    }
+    steps++; adds += a;
+  }
+}
+
 // Persistent episode runner.  Each warp owns slot = its global warp index and loops: pop an episode, copy its
 // prepared initial state from the staging arena, select/step until P is empty (or max_steps), write the episode
 // record, repeat.
@@ -202,44 +251,25 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_run(const __grid_
       const int ep = A.ep_base + b;
       Env e; env_load(S, b, e);  // the prepared state; e.base still points into the staging arena here
       {
-        const unsigned char* sb = e.base;
         unsigned char* db = P.arena + (size_t)slot * P.slot_stride;
-        warp_copy_words((uint32_t*)(db + P.o_ghead), (const uint32_t*)(sb + S.o_ghead), e.nG * 8);
-        warp_copy_words((uint32_t*)(db + P.o_lm), (const uint32_t*)(sb + S.o_lm), e.nG * 2);
-        warp_copy_words((uint32_t*)(db + P.o_rlm), (const uint32_t*)(sb + S.o_rlm), e.nG * 2);
-        warp_copy_words((uint32_t*)(db + P.o_ridx), (const uint32_t*)(sb + S.o_ridx), e.nG);
-        warp_copy_words((uint32_t*)(db + P.o_pairs), (const uint32_t*)(sb + S.o_pairs), e.nP);
-        warp_copy_words((uint32_t*)(db + P.o_plcm), (const uint32_t*)(sb + S.o_plcm), e.nP * 2);
-        warp_copy_words((uint32_t*)(db + P.o_tkey), (const uint32_t*)(sb + S.o_tkey), e.nT * 2);
-        warp_copy_words((uint32_t*)(db + P.o_tcoef), (const uint32_t*)(sb + S.o_tcoef), e.nT);
+        warp_copy_env(P, db, S, e.base, e);
         e.base = db;
         __syncwarp();
       }
       const int g_start = e.nG;
       int steps = 0, adds = 0;
-      if (lane == 0) { acc.th = 0ull; acc.ret = 0.0; acc.disc = 1.0; }
-      while (e.status == BB_STATUS_RUNNING && (A.max_steps == 0 || steps < A.max_steps)) {
-        const int prow = warp_select<NV>(P, e, A.strategy);
-        uint32_t pr;
-        const int a = warp_step<NV>(P, e, prow, pr, ct);
-        if (lane == 0) {
-          const int pi = pr & 0xffffu, pj = pr >> 16;
-          acc.th += trace_hash_item(pi, pj, a, steps);
-          const double r = (P.rewards == BB_REWARD_ADDITIONS) ? -(double)a : -1.0;
-          const double d = acc.disc;  // discounted_return += discount * reward; discount *= gamma  (buchberger.cpp:250-251)
-          acc.ret = __dadd_rn(acc.ret, __dmul_rn(d, r)); acc.disc = __dmul_rn(d, A.gamma);
-          if (A.trace && ep < A.trace_eps && steps < A.trace_cap)
-            reinterpret_cast<int4*>(A.trace)[(size_t)ep * A.trace_cap + steps] = make_int4(pi, pj, a, e.nP);
-        }
-        steps++; adds += a;
-      }
+      if (lane == 0) { acc.th = 0ull; acc.ret = 0.0; acc.disc = 1.0; acc.sel_rng = rng_seed(A.sel_seed_base + ep); }
+      __syncwarp();
+      run_episode<NV>(P, e, A.strategy, A.max_steps, A.gamma, acc, ct, steps, adds,
+                      (A.trace && ep < A.trace_eps) ? reinterpret_cast<int4*>(A.trace) + (size_t)ep * A.trace_cap : nullptr,
+                      A.trace_cap);
       const int nonzero = e.nG - g_start, zero = steps - nonzero;
       env_store(P, slot, e);
       __syncwarp();
-      const GHead* gh = ENV_PTR(GHead, e, P, o_ghead);
+      const GHeadMem* gh = ENV_PTR(GHeadMem, e, P, o_ghead);
       const unsigned long long bh = warp_terms_hash<NV>(ENV_PTR(uint64_t, e, P, o_tkey), ENV_PTR(uint32_t, e, P, o_tcoef),
                                                         e.nT, reinterpret_cast<const int*>(&gh[0].len),
-                                                        (int)(sizeof(GHead) / sizeof(int)), e.nG);
+                                                        (int)(sizeof(GHeadMem) / sizeof(int)), e.nG);
       unsigned long long gbh = 0; int gp = 0, gt = 0;
       int status = e.status;
       if (A.compute_gb && status == BB_STATUS_DONE) {
@@ -270,6 +300,67 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_run(const __grid_
     }
   }
   counters_flush(P, sh);
+}
+
+// max of doubles through a CAS loop (order independent, hence deterministic)
+__device__ __forceinline__ void atomic_max_double(double* addr, double v) {
+  unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+  unsigned long long old = *a;
+  while (__longlong_as_double((long long)old) < v) {
+    const unsigned long long seen = atomicCAS(a, old, (unsigned long long)__double_as_longlong(v));
+    if (seen == old) break;
+    old = seen;
+  }
+}
+
+// BuchbergerEnv::value (buchberger.cpp:332-351): the discounted return of finishing each environment's episode from
+// its CURRENT state under a built-in strategy.  Tasks (env, rollout) are pulled from a queue by persistent worker
+// warps; a worker forks the environment into its own arena F (the live environments are not modified), runs the
+// loop of buchberger() (:243-263) and folds the return into value[env] with max ("sample": :333-341).
+template <int NV>
+__global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_value(const __grid_constant__ BBParams P,
+                                                                    const __grid_constant__ BBParams F,
+                                                                    const __grid_constant__ BBValueArgs A) {
+  __shared__ unsigned long long sh[BB_WARPS][CT_COUNT];
+  __shared__ BBEpisodeAcc acc_sh[BB_WARPS];
+  unsigned long long* row = counters_row(sh);
+  BBEpisodeAcc& acc = acc_sh[threadIdx.x >> 5];
+  const int w = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
+  const int lane = bb_lane();
+  if (w < F.num_envs) {
+    Ctr ct; ct.clear();
+    for (;;) {
+      int t = 0;
+      if (lane == 0) t = atomicAdd(A.queue, 1);
+      t = __shfl_sync(BB_FULL, t, 0);
+      if (t >= A.ntasks) break;
+      const int env = t / A.rollouts, r = t - env * A.rollouts;
+      Env e; env_load(P, env, e);
+      double ret = 0.0;
+      if (e.status == BB_STATUS_RUNNING) {
+        unsigned char* db = F.arena + (size_t)w * F.slot_stride;
+        warp_copy_env(F, db, P, e.base, e);
+        e.base = db;
+        __syncwarp();
+        int strategy = A.strategy, seed = A.sel_seed_base + r;
+        if (strategy == BB_VALUE_SAMPLE) { strategy = r == 0 ? BB_SELECT_DEGREE : BB_SELECT_RANDOM; seed = A.sel_seed_base + r - 1; }
+        if (lane == 0) { acc.th = 0ull; acc.ret = 0.0; acc.disc = 1.0; acc.sel_rng = rng_seed(seed); }
+        __syncwarp();
+        int steps = 0, adds = 0;
+        run_episode<NV>(F, e, strategy, A.max_steps, A.gamma, acc, ct, steps, adds, nullptr, 0);
+        __syncwarp();
+        ret = acc.ret;
+        if (e.status != BB_STATUS_DONE && !(A.max_steps && steps >= A.max_steps)) ret = __longlong_as_double(0x7ff8000000000000LL);  // fault: NaN
+      }
+      if (lane == 0) {
+        if (ret != ret) A.value[env] = ret;  // NaN marks an overflowed rollout (never silently wrong)
+        else atomic_max_double(&A.value[env], ret);
+      }
+      ct.clear();  // rollouts of value() are not part of the environments' traffic counters
+      __syncwarp();
+    }
+  }
+  (void)row;
 }
 
 // ------------------------------------------------------------------------------------------------ launchers
@@ -305,6 +396,10 @@ struct BBLaunch {
     k_run<NV><<<grid_for_warps(nwarps), BB_THREADS, 0, s>>>(P, S, A);
     return cudaGetLastError();
   }
+  static cudaError_t value(const BBParams& P, const BBParams& F, const BBValueArgs& A, int nwarps, cudaStream_t s) {
+    k_value<NV><<<grid_for_warps(nwarps), BB_THREADS, 0, s>>>(P, F, A);
+    return cudaGetLastError();
+  }
   static int run_blocks_per_sm() {
     int blocks = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_run<NV>, BB_THREADS, 0) != cudaSuccess) return -1;
@@ -312,7 +407,7 @@ struct BBLaunch {
   }
   static const BBKernelTable* table() {
     static const BBKernelTable t = {NV, KL<NV>::w, KL<NV>::dw, KL<NV>::dshift, KL<NV>::eshift,
-                                    &reset, &step, &select, &observe, &final_gb, &prepare, &run, &run_blocks_per_sm};
+                                    &reset, &step, &select, &observe, &final_gb, &prepare, &run, &value, &run_blocks_per_sm};
     return &t;
   }
 };

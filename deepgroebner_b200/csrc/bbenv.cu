@@ -11,9 +11,16 @@
 #include "bb_kernels.cuh"
 
 // ------------------------------------------------------------------------------------------------ layout-free kernels
-__global__ void __launch_bounds__(BB_THREADS) k_seed(BBParams P, const int* seeds, int base) {
+__global__ void __launch_bounds__(BB_THREADS) k_seed(BBParams P, const int* seeds, int base, int selection) {
   int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < P.num_envs) P.st[e].rng = rng_seed(seeds ? seeds[e] : base + e);
+  if (e >= P.num_envs) return;
+  const uint32_t x = rng_seed(seeds ? seeds[e] : base + e);
+  if (selection) P.st[e].sel_rng = x; else P.st[e].rng = x;
+}
+
+__global__ void __launch_bounds__(BB_THREADS) k_fill_double(double* p, int n, double v) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n) p[e] = v;
 }
 
 // inverse table: every lane of a warp takes one residue; a^(p-2) by square and multiply
@@ -84,6 +91,10 @@ struct bb_handle {
   std::vector<void*> stage_allocs;
   unsigned char* stage_arena; BBEnvState* stage_st;
   uint64_t* stage_in_key; uint32_t* stage_in_coef; int* stage_in_off; int* stage_in_np;
+  // fork arena of bb_value: one full-size slot per worker warp
+  int fork_cap;
+  std::vector<void*> fork_allocs;
+  unsigned char* fork_arena; BBEnvState* fork_st;
   // host mirrors of the distribution tables
   std::vector<double> cp;
 };
@@ -116,7 +127,7 @@ static cudaError_t dev_alloc(bb_handle* h, T** p, size_t count) {
 static bool layout_arena(BBParams& P) {
   size_t o = 0;
   auto take = [&o](size_t bytes) { size_t at = o; o = (o + bytes + 31) & ~(size_t)31; return (unsigned)at; };
-  P.o_ghead = take(sizeof(GHead) * (size_t)P.max_basis);
+  P.o_ghead = take(sizeof(GHeadMem) * (size_t)P.max_basis);
   P.o_lm = take(8 * (size_t)P.max_basis);
   P.o_rlm = take(8 * (size_t)P.max_basis);
   P.o_lscr = take(8 * (size_t)P.max_basis);
@@ -160,6 +171,7 @@ void bb_destroy(bb_handle* h) {
   cudaSetDevice(h->cfg.device);
   for (void* p : h->allocs) cudaFree(p);
   for (void* p : h->stage_allocs) cudaFree(p);
+  for (void* p : h->fork_allocs) cudaFree(p);
   delete h;
 }
 
@@ -187,6 +199,7 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
   h->cfg = *cfg;
   h->d_queue = nullptr; h->d_ok = nullptr;
   h->stage_cap = 0; h->stage_arena = nullptr; h->stage_st = nullptr;
+  h->fork_cap = 0; h->fork_arena = nullptr; h->fork_st = nullptr;
   auto bail = [&](int code) { g_create_err = h->err; bb_destroy(h); return code; };
 #define CKC(call)                                                                                     \
   do {                                                                                                \
@@ -235,7 +248,8 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
   }
   CKC(dev_alloc(h, &h->d_queue, (size_t)4));
   CKC(dev_alloc(h, &h->d_ok, (size_t)4));
-  k_seed<<<(cfg->num_envs + BB_THREADS - 1) / BB_THREADS, BB_THREADS>>>(P, nullptr, 0);
+  k_seed<<<(cfg->num_envs + BB_THREADS - 1) / BB_THREADS, BB_THREADS>>>(P, nullptr, 0, 0);
+  k_seed<<<(cfg->num_envs + BB_THREADS - 1) / BB_THREADS, BB_THREADS>>>(P, nullptr, 0, 1);
   CKC(cudaGetLastError());
   CKC(cudaDeviceSynchronize());
 #undef CKC
@@ -302,7 +316,7 @@ int bb_set_distribution(bb_handle* h, int d, int s, int dist, int constants, int
   return 0;
 }
 
-int bb_seed(bb_handle* h, const int32_t* seeds, int base) {
+static int seed_impl(bb_handle* h, const int32_t* seeds, int base, int selection) {
   if (!h) return -1;
   CK(cudaSetDevice(h->cfg.device));
   int* d_seeds = nullptr;
@@ -310,12 +324,14 @@ int bb_seed(bb_handle* h, const int32_t* seeds, int base) {
     CK(cudaMalloc(&d_seeds, sizeof(int) * (size_t)h->P.num_envs));
     CK(cudaMemcpy(d_seeds, seeds, sizeof(int) * (size_t)h->P.num_envs, cudaMemcpyHostToDevice));
   }
-  k_seed<<<(h->P.num_envs + BB_THREADS - 1) / BB_THREADS, BB_THREADS>>>(h->P, d_seeds, base);
+  k_seed<<<(h->P.num_envs + BB_THREADS - 1) / BB_THREADS, BB_THREADS>>>(h->P, d_seeds, base, selection);
   cudaError_t e1 = cudaGetLastError(), e2 = cudaDeviceSynchronize();
   if (d_seeds) cudaFree(d_seeds);
   CK(e1); CK(e2);
   return 0;
 }
+int bb_seed(bb_handle* h, const int32_t* seeds, int base) { return seed_impl(h, seeds, base, 0); }
+int bb_seed_selection(bb_handle* h, const int32_t* seeds, int base) { return seed_impl(h, seeds, base, 1); }
 
 int bb_set_ideals(bb_handle* h, const int32_t* env_ids, int count, const int32_t* ideal_offsets,
                   const int32_t* poly_offsets, const int32_t* exps, const int32_t* coefs) {
@@ -387,7 +403,7 @@ int bb_step(bb_handle* h, const int32_t* actions_dev, double* reward_dev, uint8_
 
 int bb_select(bb_handle* h, int strategy, int32_t* actions_dev, void* stream) {
   if (!h) return -1;
-  if ((unsigned)strategy > 2u || !actions_dev) return fail(h, "bb_select: bad argument");
+  if ((unsigned)strategy > 8u || !actions_dev) return fail(h, "bb_select: bad argument");
   CK(cudaSetDevice(h->cfg.device));
   CK(h->K->select(h->P, strategy, actions_dev, h->P.num_envs, (cudaStream_t)stream));
   return 0;
@@ -462,11 +478,11 @@ static int stage_params(bb_handle* h, int batch, BBParams& S) {
   return 0;
 }
 
-int bb_run(bb_handle* h, int strategy, int episodes, int seed_base, const int32_t* seeds_dev, int max_steps,
-           double gamma, int compute_gb, bb_episode_stats* stats_dev, int32_t* trace_dev, int trace_episodes,
-           int trace_cap, void* stream) {
+int bb_run(bb_handle* h, int strategy, int episodes, int seed_base, const int32_t* seeds_dev, int sel_seed_base,
+           int max_steps, double gamma, int compute_gb, bb_episode_stats* stats_dev, int32_t* trace_dev,
+           int trace_episodes, int trace_cap, void* stream) {
   if (!h) return -1;
-  if ((unsigned)strategy > 2u || episodes < 0 || !stats_dev) return fail(h, "bb_run: bad argument");
+  if ((unsigned)strategy > 8u || episodes < 0 || !stats_dev) return fail(h, "bb_run: bad argument");
   CK(cudaSetDevice(h->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
   if (episodes == 0) return 0;
@@ -478,6 +494,7 @@ int bb_run(bb_handle* h, int strategy, int episodes, int seed_base, const int32_
   for (int base = 0; base < episodes; base += BB_RUN_BATCH) {
     BBRunArgs A;
     A.strategy = strategy; A.episodes = std::min(BB_RUN_BATCH, episodes - base); A.seed_base = seed_base;
+    A.sel_seed_base = sel_seed_base;
     A.ep_base = base; A.nstaged = h->P.num_envs;
     A.seeds = seeds_dev; A.max_steps = max_steps; A.gamma = gamma; A.compute_gb = compute_gb; A.out = stats_dev;
     A.trace = trace_dev; A.trace_eps = trace_dev ? trace_episodes : 0; A.trace_cap = trace_cap; A.queue = h->d_queue;
@@ -486,6 +503,87 @@ int bb_run(bb_handle* h, int strategy, int episodes, int seed_base, const int32_
     const int workers = std::min(h->P.num_envs, A.episodes);
     CK(h->K->run(h->P, S, A, workers, s));
   }
+  return 0;
+}
+
+// Fork arena: `workers` full-size slots (same layout as the handle's own), allocated on first use and kept.
+static int fork_params(bb_handle* h, int workers, BBParams& F) {
+  const BBParams& P = h->P;
+  F = P;
+  if (workers > h->fork_cap) {
+    for (void* p : h->fork_allocs) cudaFree(p);
+    h->fork_allocs.clear();
+    h->fork_cap = 0;
+    auto alloc = [&](void** out, size_t bytes) {
+      cudaError_t e = cudaMalloc(out, bytes + 16);
+      if (e == cudaSuccess) { h->fork_allocs.push_back(*out); e = cudaMemset(*out, 0, bytes + 16); }
+      return e;
+    };
+    CK(alloc((void**)&h->fork_arena, (size_t)workers * P.slot_stride));
+    CK(alloc((void**)&h->fork_st, (size_t)workers * sizeof(BBEnvState)));
+    h->fork_cap = workers;
+  }
+  F.arena = h->fork_arena; F.st = h->fork_st; F.num_envs = workers;
+  return 0;
+}
+
+int bb_value(bb_handle* h, int strategy, double gamma, int rollouts, int sel_seed_base, int max_steps,
+             double* value_dev, void* stream) {
+  if (!h) return -1;
+  if (!value_dev) return fail(h, "bb_value: null output");
+  if (strategy == BB_VALUE_SAMPLE) rollouts = rollouts > 0 ? rollouts : 101;  // 1 Degree + 100 Random (buchberger.cpp:333-341)
+  else if ((unsigned)strategy > 8u) return fail(h, "bb_value: bad strategy");
+  else if (strategy != BB_SELECT_RANDOM || rollouts < 1) rollouts = 1;
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const int N = h->P.num_envs;
+  const long long ntasks = (long long)N * rollouts;
+  if (ntasks > 0x7fffffffLL) return fail(h, "bb_value: too many rollouts");
+  // workers: one resident wave at most, and at most 8 GiB of fork arena
+  int workers = h->K->run_blocks_per_sm() * h->sm_count * BB_WARPS;
+  const long long by_mem = (long long)(((size_t)8 << 30) / h->P.slot_stride);
+  workers = (int)std::max(1LL, std::min((long long)workers, std::min(ntasks, by_mem)));
+  BBParams F;
+  if (workers > h->fork_cap) CK(cudaStreamSynchronize(s));
+  int rc = fork_params(h, std::max(workers, h->fork_cap), F);
+  if (rc < 0) return rc;
+  F.num_envs = workers;
+  BBValueArgs A;
+  A.strategy = strategy; A.rollouts = rollouts; A.sel_seed_base = sel_seed_base; A.max_steps = max_steps;
+  A.gamma = gamma; A.value = value_dev; A.queue = h->d_queue; A.ntasks = (int)ntasks;
+  CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int), s));
+  k_fill_double<<<(N + BB_THREADS - 1) / BB_THREADS, BB_THREADS, 0, s>>>(value_dev, N, -__builtin_inf());
+  CK(cudaGetLastError());
+  CK(h->K->value(h->P, F, A, workers, s));
+  return 0;
+}
+
+// BuchbergerEnv copy constructor (buchberger.cpp:279-283; wrapped.pyx:35-38 copy()): the whole environment --
+// basis, pair set, reducer list, staged ideal, both random streams and the episode record.
+int bb_copy_env(bb_handle* dst, int dst_env, bb_handle* src, int src_env, void* stream) {
+  bb_handle* h = dst;
+  if (!dst || !src) return -1;
+  if (dst_env < 0 || dst_env >= dst->P.num_envs || src_env < 0 || src_env >= src->P.num_envs)
+    return fail(h, "bb_copy_env: environment index out of range");
+  const bb_config &a = dst->cfg, &b = src->cfg;
+  if (a.device != b.device || a.nvars != b.nvars || a.prime != b.prime || a.max_basis != b.max_basis ||
+      a.max_pairs != b.max_pairs || a.max_terms != b.max_terms || a.max_poly_terms != b.max_poly_terms ||
+      a.max_gens != b.max_gens || a.max_gen_terms != b.max_gen_terms)
+    return fail(h, "bb_copy_env: handles differ in device, field, variables or capacities");
+  if (dst == src && dst_env == src_env) return 0;
+  CK(cudaSetDevice(a.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const BBParams &D = dst->P, &S = src->P;
+  CK(cudaMemcpyAsync(D.arena + (size_t)dst_env * D.slot_stride, S.arena + (size_t)src_env * S.slot_stride, S.slot_stride,
+                     cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(D.st + dst_env, S.st + src_env, sizeof(BBEnvState), cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(D.in_key + (size_t)dst_env * D.max_gen_terms, S.in_key + (size_t)src_env * S.max_gen_terms,
+                     sizeof(uint64_t) * S.max_gen_terms, cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(D.in_coef + (size_t)dst_env * D.max_gen_terms, S.in_coef + (size_t)src_env * S.max_gen_terms,
+                     sizeof(uint32_t) * S.max_gen_terms, cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(D.in_off + (size_t)dst_env * (D.max_gens + 1), S.in_off + (size_t)src_env * (S.max_gens + 1),
+                     sizeof(int) * (S.max_gens + 1), cudaMemcpyDeviceToDevice, s));
+  CK(cudaMemcpyAsync(D.in_np + dst_env, S.in_np + src_env, sizeof(int), cudaMemcpyDeviceToDevice, s));
   return 0;
 }
 
@@ -514,11 +612,11 @@ int bb_download_basis(bb_handle* h, int env, int32_t* lens, int cap_polys, int32
   CK(cudaDeviceSynchronize());
   BBEnvState S;
   CK(cudaMemcpy(&S, P.st + env, sizeof S, cudaMemcpyDeviceToHost));
-  std::vector<GHead> meta((size_t)std::max(S.nG, 1));
+  std::vector<GHeadMem> meta((size_t)std::max(S.nG, 1));
   std::vector<uint64_t> keys((size_t)std::max(S.nT, 1));
   std::vector<uint32_t> cf((size_t)std::max(S.nT, 1));
   const unsigned char* base = P.arena + (size_t)env * P.slot_stride;
-  if (S.nG) CK(cudaMemcpy(meta.data(), base + P.o_ghead, sizeof(GHead) * S.nG, cudaMemcpyDeviceToHost));
+  if (S.nG) CK(cudaMemcpy(meta.data(), base + P.o_ghead, sizeof(GHeadMem) * S.nG, cudaMemcpyDeviceToHost));
   if (S.nT) {
     CK(cudaMemcpy(keys.data(), base + P.o_tkey, sizeof(uint64_t) * S.nT, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(cf.data(), base + P.o_tcoef, sizeof(uint32_t) * S.nT, cudaMemcpyDeviceToHost));

@@ -12,8 +12,9 @@
  *   void reset()                         pxd:13             bb_reset / bb_set_ideals
  *   double step(int)                     pxd:14             bb_step
  *   vector[int] state, int cols          pxd:17-18          bb_observe, bb_cols
- *   double value(string,double)          pxd:16             bb_run (First/Degree/Normal rollouts to completion)
- *   LeadMonomialsEnv(const&)  (copy())   pxd:12             (next round: slot copy)
+ *   double value(string,double)          pxd:16             bb_value (fork + rollouts from the live state)
+ *   LeadMonomialsEnv(const&)  (copy())   pxd:12             bb_copy_env
+ *   buchberger(F, selection, ...)  buchberger.h:127-147     bb_run (whole episodes, all nine SelectionTypes)
  *   BuchbergerEnv::G, ::P   buchberger.h:195-196            bb_download_basis, bb_pairs
  *   buchberger(...) -> interreduce(minimalize(G))           bb_final_gb
  *       buchberger.cpp:265
@@ -35,14 +36,17 @@
 extern "C" {
 #endif
 
-#define BB_ABI_VERSION 1
+#define BB_ABI_VERSION 2
 
 /* EliminationType, buchberger.h:58 */
 enum { BB_ELIM_GEBAUERMOELLER = 0, BB_ELIM_LCM = 1, BB_ELIM_NONE = 2 };
 /* RewardType, buchberger.h:93 */
 enum { BB_REWARD_ADDITIONS = 0, BB_REWARD_REDUCTIONS = 1 };
-/* SelectionType, buchberger.h:111 (the deterministic ones that need no per-polynomial sugar) */
-enum { BB_SELECT_FIRST = 0, BB_SELECT_DEGREE = 1, BB_SELECT_NORMAL = 2 };
+/* SelectionType, buchberger.h:111 (same order).  BB_SELECT_RANDOM draws choice() (ideals.h:68-73) from a
+ * per-episode minstd_rand0 stream, i.e. buchberger(..., seed) of buchberger.cpp:190-197. */
+enum { BB_SELECT_FIRST = 0, BB_SELECT_DEGREE = 1, BB_SELECT_NORMAL = 2, BB_SELECT_SUGAR = 3, BB_SELECT_RANDOM = 4,
+       BB_SELECT_LAST = 5, BB_SELECT_CODEGREE = 6, BB_SELECT_STRANGE = 7, BB_SELECT_SPICE = 8,
+       BB_VALUE_SAMPLE = 100 /* bb_value only: value("sample"), buchberger.cpp:333-341 */ };
 /* DistributionType, ideals.h:40 */
 enum { BB_DIST_UNIFORM = 0, BB_DIST_WEIGHTED = 1, BB_DIST_MAXIMUM = 2 };
 
@@ -134,6 +138,9 @@ int bb_resident_envs(int device, int nvars);
  * seeds environment e with base + e. */
 int bb_set_distribution(bb_handle* h, int d, int s, int dist, int constants, int homogeneous, int pure);
 int bb_seed(bb_handle* h, const int32_t* seeds, int base);
+/* bb_seed_selection: the same for the per-environment stream BB_SELECT_RANDOM draws from in bb_select (the `seed`
+ * argument of buchberger(), buchberger.cpp:190-197).  Both streams are seeded with base + e at bb_create. */
+int bb_seed_selection(bb_handle* h, const int32_t* seeds, int base);
 
 /* bb_set_ideals: explicit ideals, the analogue of FixedIdealGenerator (ideals.h:116-138; buchberger.py:389-394).
  *   count          number of ideals; ideal c goes to environment env_ids[c] (env_ids == NULL: environment c)
@@ -152,7 +159,7 @@ int bb_reset(bb_handle* h, const uint8_t* mask_dev, void* stream);
  * buchberger.cpp:398-408).  reward_dev double[N] (-(1+steps) or -1), done_dev uint8[N] (|P| == 0).  Environments
  * that are not RUNNING are skipped (reward 0, done 1). */
 int bb_step(bb_handle* h, const int32_t* actions_dev, double* reward_dev, uint8_t* done_dev, void* stream);
-/* bb_select: built-in pair selection (buchberger.cpp:165-186; ties -> first in P): actions_dev int32[N]. */
+/* bb_select: built-in pair selection (buchberger.cpp:160-241, any BB_SELECT_*): actions_dev int32[N]. */
 int bb_select(bb_handle* h, int strategy, int32_t* actions_dev, void* stream);
 /* bb_observe: obs_dev int32[N, pmax, cols] padded with -1 (pg.py:217-226), lengths_dev int32[N] = |P|
  * (lead_monomials_vector rows, buchberger.cpp:354-370, 402-406).  Rows beyond pmax are dropped (lengths keeps |P|). */
@@ -169,10 +176,26 @@ int bb_stats(bb_handle* h, bb_episode_stats* stats_dev, void* stream);
  * draws its ideal from stream seed = seed_base + e (or seeds_dev[e]) when a distribution is set, or replays staged
  * ideal (e mod staged count).  stats_dev bb_episode_stats[episodes].  trace_dev (optional) int32[trace_episodes,
  * trace_cap, 4] = (i, j, additions, |P| after) for the first trace_episodes episodes, -1 padded.
- * max_steps truncates an episode (0 = unlimited); gamma feeds discounted_return. */
-int bb_run(bb_handle* h, int strategy, int episodes, int seed_base, const int32_t* seeds_dev, int max_steps,
-           double gamma, int compute_gb, bb_episode_stats* stats_dev, int32_t* trace_dev, int trace_episodes,
-           int trace_cap, void* stream);
+ * max_steps truncates an episode (0 = unlimited); gamma feeds discounted_return.  With BB_SELECT_RANDOM episode e
+ * draws its choices from a minstd_rand0 stream seeded sel_seed_base + e (buchberger(..., seed), buchberger.cpp:190-197). */
+int bb_run(bb_handle* h, int strategy, int episodes, int seed_base, const int32_t* seeds_dev, int sel_seed_base,
+           int max_steps, double gamma, int compute_gb, bb_episode_stats* stats_dev, int32_t* trace_dev,
+           int trace_episodes, int trace_cap, void* stream);
+
+/* bb_value: BuchbergerEnv::value(strategy, gamma) (buchberger.cpp:332-351) for every environment at once:
+ * value_dev double[N] = discounted return of finishing the episode from the CURRENT state under `strategy`
+ * (0.0 for an environment that is not running).  The environments are forked into a private arena; their own state
+ * is untouched.  strategy = BB_SELECT_RANDOM runs `rollouts` rollouts per environment (stream seeds sel_seed_base + r)
+ * and keeps the best; BB_VALUE_SAMPLE is value("sample"): one Degree rollout and rollouts-1 (default 100) Random
+ * rollouts seeded sel_seed_base + 0..99, best kept (:333-341; the reference seeds these from std::random_device).
+ * A rollout that overflows an arena yields NaN for its environment. */
+int bb_value(bb_handle* h, int strategy, double gamma, int rollouts, int sel_seed_base, int max_steps,
+             double* value_dev, void* stream);
+
+/* bb_copy_env: the copy constructor (buchberger.cpp:279-283; copy() of wrapped.pyx:35-38): environment src_env of
+ * `src` -> environment dst_env of `dst`, including both random streams and the staged ideal.  The handles must be on
+ * the same device with equal nvars, prime and capacities (they may be the same handle). */
+int bb_copy_env(bb_handle* dst, int dst_env, bb_handle* src, int src_env, void* stream);
 
 /* ---- host views (synchronising)
  * bb_download_basis: basis G of environment env in insertion order: lens[npoly], exps[nterms*n], coefs[nterms].

@@ -977,6 +977,28 @@ static double env_value(const Env* e, const char* strategy, double gamma) {
   return st.discounted_return;
 }
 
+/* same contract as ref_env_value_seeded (oracle/ref_shim.cpp): value() with explicit seeds for the random strategies */
+static double env_value_one(const Env* e, int sel, double gamma, int seed) {
+  Stats st;
+  PolyVec out = buchberger_from(&e->G, &e->P, sel, e->elimination, e->rewards, e->sort_reducers, gamma, seed, &st);
+  pv_free(&out);
+  return st.discounted_return;
+}
+double orc_env_value_seeded(void* h, int selection, double gamma, int seed, int rollouts) {
+  const Env* e = (const Env*)h;
+  double best;
+  if (selection == 100) {
+    if (rollouts <= 0) rollouts = 101;
+    best = env_value_one(e, 1, gamma, 0);
+    for (int r = 1; r < rollouts; r++) { double v = env_value_one(e, 4, gamma, seed + r - 1); if (v > best) best = v; }
+    return best;
+  }
+  if (selection != 4 || rollouts < 1) rollouts = 1;
+  best = env_value_one(e, selection, gamma, seed);
+  for (int r = 1; r < rollouts; r++) { double v = env_value_one(e, selection, gamma, seed + r); if (v > best) best = v; }
+  return best;
+}
+
 void* orc_env_create(const char* dist, int elimination, int rewards, int sort_input, int sort_reducers) {
   return env_new(dist, elimination, rewards, sort_input, sort_reducers);
 }

@@ -66,6 +66,7 @@ int orc_env_pairs(void* h, int* pairs, int cap);
 int orc_env_basis(void* h, int* oterms, int cap_terms, int* olens, int cap_polys);
 int orc_env_reducers(void* h, int* oterms, int cap_terms, int* olens, int cap_polys);
 double orc_env_value(void* h, const char* strategy, double gamma);
+double orc_env_value_seeded(void* h, int selection, double gamma, int seed, int rollouts);
 int orc_env_select(void* h, int selection);
 int orc_env_final_gb(void* h, int* oterms, int cap_terms, int* olens, int cap_polys);
 int orc_env_run(void* h, int selection, const int* actions, int nactions, int* trace, int cap_steps);

@@ -127,6 +127,7 @@ class Oracle:
         L("env_basis", _i, _vp, _ip, _i, _ip, _i)
         L("env_reducers", _i, _vp, _ip, _i, _ip, _i)
         L("env_value", C.c_double, _vp, _cp, C.c_double)
+        L("env_value_seeded", C.c_double, _vp, _i, C.c_double, _i, _i)
         L("env_select", _i, _vp, _i)
         L("env_final_gb", _i, _vp, _ip, _i, _ip, _i)
         L("env_run", _i, _vp, _i, _ip, _i, _ip, _i)
@@ -371,6 +372,11 @@ class Env:
 
     def value(self, strategy="degree", gamma=0.99):
         return self.o.c_env_value(self.h, strategy.encode(), gamma)
+
+    def value_seeded(self, strategy="degree", gamma=0.99, seed=0, rollouts=1):
+        """value() with explicit seeds for the random strategies; strategy may be 'sample'."""
+        code = 100 if strategy == "sample" else SELECT[strategy]
+        return self.o.c_env_value_seeded(self.h, code, gamma, seed, rollouts)
 
     def select(self, selection):
         return self.o.c_env_select(self.h, SELECT[selection])

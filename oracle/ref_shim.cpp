@@ -293,6 +293,28 @@ int ref_env_reducers(void* h, int* oterms, int cap_terms, int* olens, int cap_po
 double ref_env_value(void* h, const char* strategy, double gamma) {
   return static_cast<RefEnv*>(h)->env.value(std::string(strategy), gamma);
 }
+// value() with the random strategies made reproducible: BuchbergerEnv::value (buchberger.cpp:332-351) calls the
+// pair-set overload of buchberger() on (G, P); "random"/"sample" seed it from std::random_device there.  Here the
+// same overload is called with an explicit seed per rollout: selection 0..8 -> best of `rollouts` runs seeded
+// seed + r (rollouts is 1 unless Random); selection 100 -> "sample": one Degree run, then rollouts-1 (default 100)
+// Random runs seeded seed + 0.., best kept (:333-341).
+double ref_env_value_seeded(void* h, int selection, double gamma, int seed, int rollouts) {
+  auto& e = static_cast<RefEnv*>(h)->env;
+  auto run = [&](SelectionType sel, int sd) {
+    auto [G_, st] = buchberger(e.G, e.P, sel, e.elimination, e.rewards, e.sort_reducers, gamma, std::optional<int>(sd));
+    return st.discounted_return;
+  };
+  if (selection == 100) {
+    if (rollouts <= 0) rollouts = 101;
+    double best = run(SelectionType::Degree, 0);
+    for (int r = 1; r < rollouts; r++) best = std::max(best, run(SelectionType::Random, seed + r - 1));
+    return best;
+  }
+  if (selection != 4 || rollouts < 1) rollouts = 1;
+  double best = run(sel_of(selection), seed);
+  for (int r = 1; r < rollouts; r++) best = std::max(best, run(sel_of(selection), seed + r));
+  return best;
+}
 int ref_env_select(void* h, int selection) {
   auto& e = static_cast<RefEnv*>(h)->env;
   return select_row(e.G, e.P, selection);

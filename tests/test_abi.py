@@ -46,7 +46,7 @@ def test_create_fails_loudly_without_gpu():
     with pytest.raises(_lib.BBError):
         BuchbergerEngine("3-20-10-weighted")
     lib = _lib.load()
-    cfg = _lib.BBConfig(abi_version=1, device=0, nvars=3, k=1, prime=32003, elimination=0, rewards=0, sort_input=0,
+    cfg = _lib.BBConfig(abi_version=_lib.BB_ABI_VERSION, device=0, nvars=3, k=1, prime=32003, elimination=0, rewards=0, sort_input=0,
                         sort_reducers=1, num_envs=1, max_basis=64, max_pairs=64, max_terms=128, max_poly_terms=16,
                         max_gens=10, max_gen_terms=20)
     h = C.c_void_p()

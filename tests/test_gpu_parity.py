@@ -238,3 +238,143 @@ def test_full_size_properties_16384(torch_cuda):
         t = env.run(selection="degree")
         assert s1["steps"][e] == len(t) and int(s1["trace_hash"][e]) == trace_hash(t)
         assert int(s1["gb_hash"][e]) == polys_hash(env.final_gb())
+
+
+ALL_STRATEGIES = ["first", "degree", "normal", "sugar", "random", "last", "codegree", "strange", "spice"]
+
+
+@pytest.mark.parametrize("dist", ["3-20-10-weighted", "5-5-10-uniform"])
+@pytest.mark.parametrize("strategy", ALL_STRATEGIES)
+def test_all_selection_types_whole_episodes(torch_cuda, dist, strategy):
+    """bb_run under every SelectionType (buchberger.h:111) == buchberger(F, selection, ..., seed) of the reference:
+    reduction counts, additions, the discounted return (a gamma-weighted checksum of the reward sequence, exact in
+    double) and the reduced Groebner basis; for the deterministic strategies also the full pair sequence."""
+    from deepgroebner_b200.buchberger import BuchbergerEngine
+    orc = best_oracle()
+    port = __import__("oracle.oracle", fromlist=["x"]).load_port()
+    episodes, sel_seed = 48, 77
+    eng = BuchbergerEngine(dist, num_envs=episodes)
+    stats, trace = eng.run_episodes(strategy, episodes=episodes, seed_base=300, compute_gb=True, trace_episodes=episodes,
+                                    trace_cap=2048, selection_seed=sel_seed, gamma=0.99)
+    gen = orc.generator(dist)
+    penv = port.env(dist)
+    for e in range(episodes):
+        env = orc.env(dist)
+        env.seed(300 + e)
+        F, _ = env.reset()     # the ideal the environment settled on (re-rolls included)
+        gb, st = orc.buchberger(F, selection=strategy, gamma=0.99, seed=sel_seed + e)
+        s = stats[e]
+        assert s["status"] == 2
+        assert (s["zero_reductions"], s["nonzero_reductions"], s["additions"]) == \
+            (st["zero_reductions"], st["nonzero_reductions"], st["polynomial_additions"]), (e, strategy)
+        assert s["discounted_return"] == st["discounted_return"], (e, strategy)
+        assert int(s["gb_hash"]) == polys_hash(gb), (e, strategy)
+        if strategy != "random":
+            penv.seed(300 + e)
+            penv.reset()
+            t = penv.run(selection=strategy)
+            m = min(len(t), trace.shape[1])   # the reversed strategies run long: the trace is capped, the checksum is not
+            assert np.array_equal(trace[e, :m], t[:m, :4]), (e, strategy)
+            assert int(s["trace_hash"]) == trace_hash(t), (e, strategy)
+    del gen
+
+
+@pytest.mark.parametrize("strategy", ALL_STRATEGIES)
+def test_select_kernel_matches_oracle_row(torch_cuda, strategy):
+    """bb_select on live states == the row std::min_element picks (port restatement of buchberger.cpp:160-241)."""
+    if strategy == "random":
+        pytest.skip("covered by test_all_selection_types_whole_episodes and test_value")
+    from deepgroebner_b200.buchberger import BuchbergerEngine
+    port = __import__("oracle.oracle", fromlist=["x"]).load_port()
+    N = 64
+    eng = BuchbergerEngine("3-20-10-uniform", num_envs=N)
+    eng.seed(40)
+    eng.reset()
+    envs = []
+    for e in range(N):
+        r = port.env("3-20-10-uniform")
+        r.seed(40 + e)
+        r.reset()
+        envs.append(r)
+    rng = np.random.default_rng(1)
+    for step in range(25):
+        rows = eng.select(strategy).cpu().numpy()
+        lens = eng.lengths().cpu().numpy()
+        acts = np.zeros(N, np.int32)
+        for e in range(N):
+            if lens[e] == 0:
+                continue
+            assert rows[e] == envs[e].select(strategy), (step, e)
+            acts[e] = rng.integers(lens[e])
+            envs[e].step(envs[e].pairs()[acts[e]])
+        eng.step(torch_cuda.as_tensor(acts, device="cuda"))
+
+
+def test_value_matches_reference(torch_cuda):
+    """bb_value == BuchbergerEnv::value (buchberger.cpp:332-351) from live mid-episode states, bit-exact doubles;
+    the environments themselves are left untouched.  'random' / 'sample' use explicit seeds (the reference reads
+    std::random_device there): same buchberger(G, P, ...) overload, seed per rollout."""
+    from deepgroebner_b200 import LeadMonomialsEnv
+    orc = best_oracle()
+    N = 96
+    env = LeadMonomialsEnv("3-20-10-weighted", k=2, num_envs=N, pmax=128)
+    env.seed(np.arange(900, 900 + N))
+    refs = []
+    for e in range(N):
+        r = orc.env("3-20-10-weighted")
+        r.seed(900 + e)
+        r.reset()
+        refs.append(r)
+    obs, lengths = env.reset()
+    rng = np.random.default_rng(5)
+    for step in range(12):
+        lens = lengths.cpu().numpy()
+        if step in (0, 5, 11):
+            before = obs.clone()
+            for strat in ("first", "degree", "normal", "sugar", "last", "codegree", "strange", "spice"):
+                v = env.value(strat, 0.99).cpu().numpy()
+                for e in range(N):
+                    assert v[e] == refs[e].value_seeded(strat, 0.99), (step, strat, e)
+            v = env.value("random", 0.9, rollouts=5, selection_seed=31).cpu().numpy()
+            for e in range(0, N, 4):
+                assert v[e] == refs[e].value_seeded("random", 0.9, 31, 5), (step, e)
+            if step == 5:
+                v = env.value("sample", 0.99, selection_seed=17).cpu().numpy()
+                for e in range(0, N, 8):
+                    assert v[e] == refs[e].value_seeded("sample", 0.99, 17), (step, e)
+            o2, l2 = env.engine.observe(128)
+            assert torch_cuda.equal(o2, before) and torch_cuda.equal(l2, lengths)
+        acts = np.array([rng.integers(l) if l else 0 for l in lens], dtype=np.int32)
+        for e in range(N):
+            if lens[e]:
+                refs[e].step(refs[e].pairs()[acts[e]])
+        (obs, lengths), _, _, _ = env.step(torch_cuda.as_tensor(acts, device="cuda"))
+
+
+def test_value_single_env_matches_cython_docstring_case(torch_cuda):
+    """seed 123, reset, step(3) (reward -1.0), value('degree', 0.99) == -123.7032989562525."""
+    from deepgroebner_b200 import LeadMonomialsEnv
+    env = LeadMonomialsEnv("3-20-10-weighted", k=2)
+    env.seed(123)
+    env.reset()
+    _, reward, _, _ = env.step(3)
+    assert reward == -1.0
+    assert env.value("degree", 0.99) == -123.7032989562525
+
+
+def test_copy_is_deep_and_includes_the_ideal_stream(torch_cuda):
+    """copy() (wrapped.pyx:35-38, buchberger.cpp:279-283): the copy continues identically and independently, and its
+    next reset() draws the same next ideal as the original's."""
+    from deepgroebner_b200 import LeadMonomialsEnv
+    a = LeadMonomialsEnv("3-20-10-weighted", k=2)
+    a.seed(5)
+    a.reset()
+    a.step(1)
+    b = a.copy()
+    sa, ra, da, _ = a.step(2)
+    sb, rb, db, _ = b.step(2)
+    assert np.array_equal(sa, sb) and ra == rb and da == db
+    sa2, _, _, _ = a.step(0)
+    assert np.array_equal(b._state(), sb)          # stepping a did not move b
+    assert np.array_equal(a.reset(), b.reset())    # same generator stream position
+    assert a.value("normal") == b.value("normal")

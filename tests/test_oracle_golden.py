@@ -112,3 +112,28 @@ def test_port_vs_reference_episodes(port, ref, dist):
                 t = env.run(selection=sel)
                 out.append((G0, P0, v, t.tolist(), env.final_gb(), env.basis()))
             assert out[0] == out[1]
+
+
+@pytest.mark.parametrize("dist", ["3-20-10-weighted", "5-5-10-uniform", "cyclic-4"])
+def test_port_value_and_all_strategies_equal_reference(port, ref, dist):
+    """The seeded value() of both oracles (all nine SelectionTypes, best-of-random, 'sample') agree bit for bit, and
+    the unseeded deterministic strategies equal BuchbergerEnv::value itself."""
+    strategies = ["first", "degree", "normal", "sugar", "random", "last", "codegree", "strange", "spice"]
+    for seed in (1, 2, 3):
+        a, b = port.env(dist), ref.env(dist)
+        for env in (a, b):
+            env.seed(seed)
+            env.reset()
+        for pick in (0, 1, 0):
+            P = a.pairs()
+            if not P:
+                break
+            assert P == b.pairs()
+            for s in strategies:
+                assert a.value_seeded(s, 0.99, 9) == b.value_seeded(s, 0.99, 9), (dist, seed, s)
+            for s in ("first", "degree", "normal", "sugar"):
+                assert a.value_seeded(s, 0.9) == b.value(s, 0.9)
+            assert a.value_seeded("random", 0.99, 4, 6) == b.value_seeded("random", 0.99, 4, 6)
+            assert a.value_seeded("sample", 0.99, 2, 12) == b.value_seeded("sample", 0.99, 2, 12)
+            act = P[min(pick, len(P) - 1)]
+            assert a.step(act) == b.step(act)
