@@ -318,8 +318,115 @@ def gpu_arm(args):
         dist.destroy_process_group()
 
 
+def rollout_arm(args):
+    """BASELINE configs[3]: LeadMonomialsEnv(k=2) PPO rollout -- env step + PMLP(128) policy head sampling on device,
+    fused in one launch (bb_rollout), auto-reset.  Extra workload (`--workload rollout`); the default stays configs[1]."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from deepgroebner_b200 import LeadMonomialsEnv
+    from deepgroebner_b200.rollout import PairsPolicy
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    N, T = args.envs, args.horizon
+    env = LeadMonomialsEnv(DIST, k=2, num_envs=N, device="cuda:%d" % local, pmax=64)
+    env.seed(np.arange(rank * N, rank * N + N))
+    env.engine.set_auto_reset(True)
+    env.engine.reset()
+    net = PairsPolicy(env.engine.cols, 128, torch_seed=0, seed=1, device=dev)
+    out = env.engine.rollout(net, T)
+    host = {k: torch.empty_like(out[k], device="cpu").pin_memory() for k in ("reward", "done")}
+    w_host = [t.cpu().pin_memory() for t in net.parameters()]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for i in range(max(args.warmup, 3)):
+        flush.fill_(1)
+        env.engine.rollout(net, T, counter0=i * T, out=out)
+    torch.cuda.synchronize()
+    env.engine.counters(reset=True)
+    sampler = ClockSampler(local) if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for i, (a, b) in enumerate(ev):
+        flush.fill_(1)
+        a.record()
+        env.engine.rollout(net, T, counter0=(100 + i) * T, out=out)
+        b.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    counters = env.engine.counters(reset=True)
+    steps_done = counters["env_steps"]
+    # end to end: weights from pinned host memory, rewards + done flags back to the host
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        for t, h in zip(net.parameters(), w_host):
+            t.copy_(h, non_blocking=True)
+        env.engine.rollout(net, T, counter0=(200 + i) * T, out=out)
+        for k in host:
+            host[k].copy_(out[k], non_blocking=True)
+        torch.cuda.synchronize()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    e2e_steps = env.engine.counters(reset=True)["env_steps"]
+    t = torch.tensor([dev_ms, e2e_s * 1000.0], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(steps_done), float(e2e_steps)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        abytes = (algorithmic_bytes(counters) + 4 * 12 * counters["obs_rows"]) / args.steps
+        achieved = abytes / (dev_ms / 1000.0 / args.steps) / 1e9
+        line = {
+            "metric": "rollout_env_steps_per_sec", "value": float(tot[0]) / (float(t[0]) / 1000.0), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": float(t[0]) / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u64 packed monomials + u32 GF(32003) coefficients (integer); fp32 policy head",
+            "data": "synthetic (device generator, env e = stream seed e; PMLP(128) Glorot-initialised, torch seed 0)",
+            "config": {"workload": "%s LeadMonomialsEnv(k=2), %d envs x %d fused steps per launch, PMLP(128) sampling on "
+                                   "device, auto-reset (BASELINE configs[3])" % (DIST, N, T),
+                       "envs_per_gpu": N, "horizon": T, "l2": "256 MiB flush write between timed launches"},
+            "gpu_launches": args.steps, "clocks": clocks,
+            "e2e": {"value": float(tot[1]) / (float(t[1]) / 1000.0), "unit": UNIT,
+                    "h2d_bytes_per_step": sum(x.numel() * 4 for x in w_host),
+                    "d2h_bytes_per_step": sum(h.numel() * h.element_size() for h in host.values())},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None, "peak_source": peak_src, "kernel": "k_rollout",
+                         "algorithmic_bytes_per_launch": abytes},
+        }
+        if world == 1 and not args.no_cpu:
+            orc, kind = load_cpu_oracle()
+            if kind == "reference":
+                threads = host_threads()
+                r = orc.bench_random(DIST, 0, 2000 * threads, nthreads=threads)
+                line["cpu_baseline"] = {"value": r["steps"] / r["seconds"], "unit": UNIT, "cores": threads, "kind": kind,
+                                        "sample": "scripts/random_episodes.cpp loop (uniform-random actions, no network) on "
+                                                  "LeadMonomialsEnv(k=2), %d episodes, %.1f s" % (2000 * threads, r["seconds"])}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--workload", default="episodes", choices=["episodes", "rollout"])
+    ap.add_argument("--envs", type=int, default=16384, help="rollout workload: environments per GPU")
+    ap.add_argument("--horizon", type=int, default=128, help="rollout workload: fused steps per launch")
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
@@ -330,6 +437,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)
+    elif args.workload == "rollout":
+        rollout_arm(args)
     else:
         gpu_arm(args)
 

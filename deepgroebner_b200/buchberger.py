@@ -232,6 +232,48 @@ class BuchbergerEngine:
                                        _ptr(out), _stream()), "bb_value")
         return out
 
+    def set_auto_reset(self, on=True):
+        """Finished environments are reset inside step() / rollout() (vector-env semantics, bb_set_auto_reset)."""
+        self._ck(self.lib.bb_set_auto_reset(self.h, int(bool(on))), "bb_set_auto_reset")
+
+    def policy(self, net, counter=0, greedy=False, return_all=False, pmax=None):
+        """PMLP head + categorical sample on the current states (bb_policy_pmlp).  net: rollout.PairsPolicy.
+        Returns (actions int32 [N], logprob float32 [N][, logprobs float32 [N, pmax] padded with -inf])."""
+        with torch.cuda.device(self.device):
+            W1, b1, w2, b2 = net.device_weights(self.device, self.cols)
+            actions = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
+            logp = torch.empty(self.num_envs, dtype=torch.float32, device=self.device)
+            allp = None
+            if return_all:
+                pmax = int(pmax or self.caps["max_pairs"])
+                allp = torch.full((self.num_envs, pmax), float("-inf"), dtype=torch.float32, device=self.device)
+            self._ck(self.lib.bb_policy_pmlp(self.h, net.hidden, _ptr(W1), _ptr(b1), _ptr(w2), _ptr(b2), int(net.seed),
+                                             int(counter), int(bool(greedy)), _ptr(actions), _ptr(logp), _ptr(allp),
+                                             int(pmax or 0), _stream()), "bb_policy_pmlp")
+        return (actions, logp, allp) if return_all else (actions, logp)
+
+    def rollout(self, net, T, counter0=0, greedy=False, store_obs=False, pmax=None, out=None):
+        """T fused steps of every environment (bb_rollout).  Returns a dict of [N, T] cuda tensors: actions, logp,
+        reward, done, lengths (+ obs [N, T, pmax, cols] when store_obs)."""
+        N, dev = self.num_envs, self.device
+        with torch.cuda.device(dev):
+            W1, b1, w2, b2 = net.device_weights(dev, self.cols)
+            o = out or {}
+            o.setdefault("actions", torch.empty((N, T), dtype=torch.int32, device=dev))
+            o.setdefault("logp", torch.empty((N, T), dtype=torch.float32, device=dev))
+            o.setdefault("reward", torch.empty((N, T), dtype=torch.float32, device=dev))
+            o.setdefault("done", torch.empty((N, T), dtype=torch.uint8, device=dev))
+            o.setdefault("lengths", torch.empty((N, T), dtype=torch.int32, device=dev))
+            obs = None
+            if store_obs:
+                pmax = int(pmax or 64)
+                obs = o.setdefault("obs", torch.empty((N, T, pmax, self.cols), dtype=torch.int32, device=dev))
+            self._ck(self.lib.bb_rollout(self.h, net.hidden, _ptr(W1), _ptr(b1), _ptr(w2), _ptr(b2), int(net.seed),
+                                         int(counter0), int(bool(greedy)), int(T), _ptr(o["actions"]), _ptr(o["logp"]),
+                                         _ptr(o["reward"]), _ptr(o["done"]), _ptr(o["lengths"]), _ptr(obs),
+                                         int(pmax or 0), _stream()), "bb_rollout")
+        return o
+
     def copy_env(self, dst_env, src, src_env):
         """Environment src_env of engine `src` -> environment dst_env of this engine (bb_copy_env)."""
         with torch.cuda.device(self.device):

@@ -82,6 +82,8 @@ struct BBParams {
   unsigned o_pairs;   // u32     [max_pairs]          pair list P in order: (j << 16) | i
   unsigned o_tcoef;   // u32     [max_terms]          term arena: coefficients
   unsigned o_hcoef;   // u32     [2][max_poly_terms]
+  unsigned o_logit;   // f32     [max_pairs]          policy head scratch: one logit per pair row
+  int auto_reset;     // k_step / k_rollout: a finished environment is reset in the same call (vector-env semantics)
   BBEnvState* st;
   // staged input ideals, one per slot
   uint64_t* in_key; uint32_t* in_coef;  // [num_envs][max_gen_terms], each polynomial sorted descending

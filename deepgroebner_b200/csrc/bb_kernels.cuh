@@ -11,6 +11,7 @@
 //   k_final_gb interreduce(minimalize(G))    buchberger.cpp:102-122
 #pragma once
 #include "bb_device.cuh"
+#include "bb_policy.cuh"
 
 #ifndef BB_WARPS
 #define BB_WARPS 8
@@ -52,6 +53,15 @@ struct BBValueArgs {
   int ntasks;         // num_envs * rollouts
 };
 
+struct BBRolloutArgs {
+  BBPolicy W;
+  int T;                          // steps per environment
+  unsigned long long counter0;    // step t draws its uniform from (seed + env, counter0 + t)
+  // outputs, all [N, T] (environment-major: one trajectory is contiguous); any may be NULL
+  int32_t* actions; float* logp; float* reward; uint8_t* done; int32_t* lengths;
+  int32_t* obs; int pmax;         // optional [N, T, pmax, cols] state matrices BEFORE each step, padded with -1
+};
+
 struct BBKernelTable {
   int nvars, w, dw, dshift, eshift;
   cudaError_t (*reset)(const BBParams&, const uint8_t* mask, int nwarps, cudaStream_t);
@@ -62,6 +72,9 @@ struct BBKernelTable {
   cudaError_t (*prepare)(const BBParams& stage, const BBRunArgs&, cudaStream_t);
   cudaError_t (*run)(const BBParams&, const BBParams& stage, const BBRunArgs&, int nwarps, cudaStream_t);
   cudaError_t (*value)(const BBParams&, const BBParams& fork, const BBValueArgs&, int nwarps, cudaStream_t);
+  cudaError_t (*policy)(const BBParams&, const BBPolicy&, unsigned long long counter, int32_t* actions, float* logp,
+                        float* logits, int pmax, int nwarps, cudaStream_t);
+  cudaError_t (*rollout)(const BBParams&, const BBRolloutArgs&, int nwarps, cudaStream_t);
   int (*run_blocks_per_sm)(void);
 };
 
@@ -95,6 +108,28 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_reset(const __gri
   counters_flush(P, sh);
 }
 
+// One environment step with the bookkeeping k_step and k_rollout share: per-slot episode record, counters, reward.
+// Returns the reward (0 for a bad action).
+template <int NV>
+__device__ __forceinline__ double step_and_account(const BBParams& P, int slot, Env& e, int action, Ctr& ct,
+                                                   unsigned long long* row) {
+  uint32_t pr;
+  const int g0 = e.nG;
+  const int adds = warp_step<NV>(P, e, action, pr, ct);
+  if (pr == 0xffffffffu) return 0.0;
+  if (bb_lane() == 0) {
+    const int pi = pr & 0xffffu, pj = pr >> 16;
+    BBEnvState& S = P.st[slot];
+    S.trace_hash += trace_hash_item(pi, pj, adds, S.steps);
+    S.steps += 1; S.adds += adds;
+    if (e.nG > g0) S.nonzero += 1; else S.zero += 1;
+    row[CT_STEPS] += 1; row[CT_ADDS] += (unsigned)adds;
+    row[e.nG > g0 ? CT_NONZERO : CT_ZERO] += 1;
+    if (e.status == BB_STATUS_DONE) row[CT_EPISODES] += 1;
+  }
+  return (P.rewards == BB_REWARD_ADDITIONS) ? -(double)adds : -1.0;
+}
+
 template <int NV>
 __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_step(const __grid_constant__ BBParams P,
                                                                    const int* __restrict__ actions,
@@ -107,22 +142,7 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_step(const __grid
     Ctr ct; ct.clear();
     double r = 0.0;
     if (e.status == BB_STATUS_RUNNING) {
-      uint32_t pr;
-      const int g0 = e.nG;
-      const int adds = warp_step<NV>(P, e, actions[slot], pr, ct);
-      if (pr != 0xffffffffu) {
-        const int pi = pr & 0xffffu, pj = pr >> 16;
-        r = (P.rewards == BB_REWARD_ADDITIONS) ? -(double)adds : -1.0;
-        if (bb_lane() == 0) {
-          BBEnvState& S = P.st[slot];
-          S.trace_hash += trace_hash_item(pi, pj, adds, S.steps);
-          S.steps += 1; S.adds += adds;
-          if (e.nG > g0) S.nonzero += 1; else S.zero += 1;
-          row[CT_STEPS] += 1; row[CT_ADDS] += (unsigned)adds;
-          row[e.nG > g0 ? CT_NONZERO : CT_ZERO] += 1;
-          if (e.status == BB_STATUS_DONE) row[CT_EPISODES] += 1;
-        }
-      }
+      r = step_and_account<NV>(P, slot, e, actions[slot], ct, row);
       env_store(P, slot, e);
     }
     if (bb_lane() == 0) {
@@ -130,6 +150,10 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_step(const __grid
       if (done) done[slot] = (e.status != BB_STATUS_RUNNING) ? 1 : 0;
     }
     ct.spill(row);
+    if (P.auto_reset && e.status != BB_STATUS_RUNNING) {  // the caller sees done = 1 and the NEXT episode's first state
+      __syncwarp();
+      warp_reset_slot<NV>(P, slot, slot, (uint32_t)P.st[slot].rng, row);
+    }
   }
   counters_flush(P, sh);
 }
@@ -363,6 +387,73 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_value(const __gri
   (void)row;
 }
 
+// The policy head on the current state of every environment (see bb_policy.cuh).
+template <int NV, int UPL>
+__global__ void __launch_bounds__(BB_THREADS) k_policy(const __grid_constant__ BBParams P, const __grid_constant__ BBPolicy W,
+                                                       unsigned long long counter, int32_t* __restrict__ actions,
+                                                       float* __restrict__ logp, float* __restrict__ logits, int pmax) {
+  extern __shared__ float wsm[];
+  policy_load_weights(W, P.cols, wsm);
+  const int slot = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
+  if (slot >= P.num_envs) return;
+  Env e; env_load(P, slot, e);
+  int a = 0; float lp = 0.0f;
+  if (e.status == BB_STATUS_RUNNING)
+    a = warp_policy<NV, UPL>(P, e, wsm, W.greedy, policy_uniform(W.seed, (unsigned long long)slot, counter), lp,
+                             logits ? logits + (size_t)slot * pmax : nullptr, pmax);
+  if (bb_lane() == 0) { actions[slot] = a; if (logp) logp[slot] = lp; }
+}
+
+// Fused rollout (the loop of pg.Agent.run_episode, pg.py:451-472, for every environment at once): each warp runs T
+// steps of its environment -- policy head, categorical sample, step, auto-reset -- with no host round trip and no
+// synchronisation between environments.  Trajectories are written environment-major.
+template <int NV, int UPL>
+__global__ void __launch_bounds__(BB_THREADS, 3) k_rollout(const __grid_constant__ BBParams P,
+                                                           const __grid_constant__ BBRolloutArgs A) {
+  extern __shared__ float wsm[];
+  __shared__ unsigned long long sh[BB_WARPS][CT_COUNT];
+  policy_load_weights(A.W, P.cols, wsm);
+  unsigned long long* row = counters_row(sh);
+  const int slot = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
+  const int lane = bb_lane();
+  if (slot < P.num_envs) {
+    Env e; env_load(P, slot, e);
+    Ctr ct; ct.clear();
+    if (e.status != BB_STATUS_RUNNING && P.auto_reset) {  // a slot that was never reset (or finished before the call)
+      warp_reset_slot<NV>(P, slot, slot, (uint32_t)P.st[slot].rng, row);
+      env_load(P, slot, e);
+    }
+#pragma unroll 1
+    for (int t = 0; t < A.T; t++) {
+      const size_t o = (size_t)slot * A.T + t;
+      if (A.lengths && lane == 0) A.lengths[o] = e.nP;
+      if (A.obs) warp_observe<NV>(P, e, A.obs + o * A.pmax * P.cols, A.pmax, ct);
+      int a = -1; float lp = 0.0f; double r = 0.0;
+      if (e.status == BB_STATUS_RUNNING) {
+        a = warp_policy<NV, UPL>(P, e, wsm, A.W.greedy, policy_uniform(A.W.seed, (unsigned long long)slot, A.counter0 + t),
+                                 lp, nullptr, 0);
+        r = step_and_account<NV>(P, slot, e, a, ct, row);
+      }
+      const bool fin = e.status != BB_STATUS_RUNNING;
+      if (lane == 0) {
+        if (A.actions) A.actions[o] = a;
+        if (A.logp) A.logp[o] = lp;
+        if (A.reward) A.reward[o] = (float)r;
+        if (A.done) A.done[o] = fin ? 1 : 0;
+      }
+      if (fin && P.auto_reset) {  // same convention as k_step: the next state is the first state of the next episode
+        env_store(P, slot, e);
+        __syncwarp();
+        warp_reset_slot<NV>(P, slot, slot, (uint32_t)P.st[slot].rng, row);
+        env_load(P, slot, e);
+      }
+    }
+    env_store(P, slot, e);
+    ct.spill(row);
+  }
+  counters_flush(P, sh);
+}
+
 // ------------------------------------------------------------------------------------------------ launchers
 static inline int grid_for_warps(int nwarps) { return (nwarps + BB_WARPS - 1) / BB_WARPS; }
 
@@ -400,6 +491,40 @@ struct BBLaunch {
     k_value<NV><<<grid_for_warps(nwarps), BB_THREADS, 0, s>>>(P, F, A);
     return cudaGetLastError();
   }
+  static size_t policy_smem(const BBParams& P, int hidden) { return sizeof(float) * ((size_t)P.cols * hidden + 2 * hidden + 1); }
+  static cudaError_t policy(const BBParams& P, const BBPolicy& W, unsigned long long counter, int32_t* actions, float* logp,
+                            float* logits, int pmax, int nwarps, cudaStream_t s) {
+    const size_t sm = policy_smem(P, W.hidden);
+    const int g = grid_for_warps(nwarps);
+    switch (W.hidden >> 5) {
+      case 1: k_policy<NV, 1><<<g, BB_THREADS, sm, s>>>(P, W, counter, actions, logp, logits, pmax); break;
+      case 2: k_policy<NV, 2><<<g, BB_THREADS, sm, s>>>(P, W, counter, actions, logp, logits, pmax); break;
+      case 4: k_policy<NV, 4><<<g, BB_THREADS, sm, s>>>(P, W, counter, actions, logp, logits, pmax); break;
+      case 8: k_policy<NV, 8><<<g, BB_THREADS, sm, s>>>(P, W, counter, actions, logp, logits, pmax); break;
+      default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+  }
+  template <int UPL>
+  static cudaError_t rollout_upl(const BBParams& P, const BBRolloutArgs& A, int g, size_t sm, cudaStream_t s) {
+    if (sm > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(k_rollout<NV, UPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      if (e != cudaSuccess) return e;
+    }
+    k_rollout<NV, UPL><<<g, BB_THREADS, sm, s>>>(P, A);
+    return cudaGetLastError();
+  }
+  static cudaError_t rollout(const BBParams& P, const BBRolloutArgs& A, int nwarps, cudaStream_t s) {
+    const size_t sm = policy_smem(P, A.W.hidden);
+    const int g = grid_for_warps(nwarps);
+    switch (A.W.hidden >> 5) {
+      case 1: return rollout_upl<1>(P, A, g, sm, s);
+      case 2: return rollout_upl<2>(P, A, g, sm, s);
+      case 4: return rollout_upl<4>(P, A, g, sm, s);
+      case 8: return rollout_upl<8>(P, A, g, sm, s);
+    }
+    return cudaErrorInvalidValue;
+  }
   static int run_blocks_per_sm() {
     int blocks = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_run<NV>, BB_THREADS, 0) != cudaSuccess) return -1;
@@ -407,7 +532,8 @@ struct BBLaunch {
   }
   static const BBKernelTable* table() {
     static const BBKernelTable t = {NV, KL<NV>::w, KL<NV>::dw, KL<NV>::dshift, KL<NV>::eshift,
-                                    &reset, &step, &select, &observe, &final_gb, &prepare, &run, &value, &run_blocks_per_sm};
+                                    &reset, &step, &select, &observe, &final_gb, &prepare, &run, &value, &policy, &rollout,
+                                    &run_blocks_per_sm};
     return &t;
   }
 };

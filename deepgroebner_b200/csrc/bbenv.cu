@@ -138,6 +138,7 @@ static bool layout_arena(BBParams& P) {
   P.o_pairs = take(4 * (size_t)P.max_pairs);
   P.o_tcoef = take(4 * (size_t)P.max_terms);
   P.o_hcoef = take(4 * 2 * (size_t)P.max_poly_terms);
+  P.o_logit = take(4 * (size_t)P.max_pairs);
   if (o >= ((size_t)1 << 31)) return false;
   P.slot_stride = (o + 127) & ~(size_t)127;
   return true;
@@ -584,6 +585,50 @@ int bb_copy_env(bb_handle* dst, int dst_env, bb_handle* src, int src_env, void* 
   CK(cudaMemcpyAsync(D.in_off + (size_t)dst_env * (D.max_gens + 1), S.in_off + (size_t)src_env * (S.max_gens + 1),
                      sizeof(int) * (S.max_gens + 1), cudaMemcpyDeviceToDevice, s));
   CK(cudaMemcpyAsync(D.in_np + dst_env, S.in_np + src_env, sizeof(int), cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+int bb_set_auto_reset(bb_handle* h, int on) {
+  if (!h) return -1;
+  h->P.auto_reset = on ? 1 : 0;
+  return 0;
+}
+
+static int check_policy(bb_handle* h, int hidden, const float* W1, const float* b1, const float* w2, const float* b2) {
+  if (!W1 || !b1 || !w2 || !b2) return fail(h, "policy: null weight pointer");
+  if (hidden != 32 && hidden != 64 && hidden != 128 && hidden != 256) return fail(h, "policy: hidden must be 32, 64, 128 or 256");
+  if (h->P.cols > BB_POLICY_MAX_COLS) return fail(h, "policy: more than 64 state columns");
+  return 0;
+}
+
+int bb_policy_pmlp(bb_handle* h, int hidden, const float* W1_dev, const float* b1_dev, const float* w2_dev,
+                   const float* b2_dev, uint64_t seed, uint64_t counter, int greedy, int32_t* actions_dev,
+                   float* logprob_dev, float* logprobs_all_dev, int pmax, void* stream) {
+  if (!h) return -1;
+  int rc = check_policy(h, hidden, W1_dev, b1_dev, w2_dev, b2_dev);
+  if (rc < 0) return rc;
+  if (!actions_dev || (logprobs_all_dev && pmax < 1)) return fail(h, "bb_policy_pmlp: bad argument");
+  CK(cudaSetDevice(h->cfg.device));
+  BBPolicy W;
+  W.hidden = hidden; W.W1 = W1_dev; W.b1 = b1_dev; W.w2 = w2_dev; W.b2 = b2_dev; W.seed = seed; W.greedy = greedy ? 1 : 0;
+  CK(h->K->policy(h->P, W, counter, actions_dev, logprob_dev, logprobs_all_dev, pmax, h->P.num_envs, (cudaStream_t)stream));
+  return 0;
+}
+
+int bb_rollout(bb_handle* h, int hidden, const float* W1_dev, const float* b1_dev, const float* w2_dev, const float* b2_dev,
+               uint64_t seed, uint64_t counter0, int greedy, int T, int32_t* actions_dev, float* logprob_dev,
+               float* reward_dev, uint8_t* done_dev, int32_t* lengths_dev, int32_t* obs_dev, int pmax, void* stream) {
+  if (!h) return -1;
+  int rc = check_policy(h, hidden, W1_dev, b1_dev, w2_dev, b2_dev);
+  if (rc < 0) return rc;
+  if (T < 1 || (obs_dev && pmax < 1)) return fail(h, "bb_rollout: bad argument");
+  CK(cudaSetDevice(h->cfg.device));
+  BBRolloutArgs A;
+  A.W.hidden = hidden; A.W.W1 = W1_dev; A.W.b1 = b1_dev; A.W.w2 = w2_dev; A.W.b2 = b2_dev; A.W.seed = seed;
+  A.W.greedy = greedy ? 1 : 0;
+  A.T = T; A.counter0 = counter0; A.actions = actions_dev; A.logp = logprob_dev; A.reward = reward_dev; A.done = done_dev;
+  A.lengths = lengths_dev; A.obs = obs_dev; A.pmax = pmax;
+  CK(h->K->rollout(h->P, A, h->P.num_envs, (cudaStream_t)stream));
   return 0;
 }
 

@@ -15,6 +15,7 @@
  *   double value(string,double)          pxd:16             bb_value (fork + rollouts from the live state)
  *   LeadMonomialsEnv(const&)  (copy())   pxd:12             bb_copy_env
  *   buchberger(F, selection, ...)  buchberger.h:127-147     bb_run (whole episodes, all nine SelectionTypes)
+ *   policy_model(state) + categorical   pg.py:323-326       bb_policy_pmlp / bb_rollout (PMLP head, networks.py:522-571)
  *   BuchbergerEnv::G, ::P   buchberger.h:195-196            bb_download_basis, bb_pairs
  *   buchberger(...) -> interreduce(minimalize(G))           bb_final_gb
  *       buchberger.cpp:265
@@ -196,6 +197,35 @@ int bb_value(bb_handle* h, int strategy, double gamma, int rollouts, int sel_see
  * `src` -> environment dst_env of `dst`, including both random streams and the staged ideal.  The handles must be on
  * the same device with equal nvars, prime and capacities (they may be the same handle). */
 int bb_copy_env(bb_handle* dst, int dst_env, bb_handle* src, int src_env, void* stream);
+
+/* ---- vector-environment conveniences
+ * bb_set_auto_reset(on): with on != 0, bb_step and bb_rollout reset an environment in the same call in which it
+ * finishes: the caller sees done = 1 for that transition and the first state of the NEXT episode (drawn from the
+ * environment's own ideal stream) afterwards -- the loop of pg.Agent.run_episodes (pg.py:477-503) without a host
+ * round trip, and no idle slots. */
+int bb_set_auto_reset(bb_handle* h, int on);
+
+/* ---- the pairs policy head on device
+ * bb_policy_pmlp: ParallelMultilayerPerceptron([hidden]) (networks.py:522-571) evaluated on every environment's
+ * current state matrix, then tf.random.categorical (pg.py:323-326):
+ *     logit[r] = b2 + sum_u w2[u] * relu(b1[u] + sum_c W1[c*hidden + u] * state[r][c])        (fp32)
+ *     logp = log_softmax(logit over the |P| rows);  action = first row whose inclusive prefix sum of
+ *     exp(logit - max) exceeds u * total, u = (bb_hash_item(seed + env, counter) >> 40) * 2^-24   (greedy: argmax)
+ * W1 is [cols, hidden] row-major (the Keras Dense kernel), b1 [hidden], w2 [hidden] (Dense(1) kernel), b2 [1];
+ * hidden in {32, 64, 128, 256}.  actions_dev int32[N] (0 for environments that are not running), logprob_dev
+ * float[N] = logp[action] (optional), logprobs_all_dev float[N, pmax] (optional; rows >= |P| untouched). */
+int bb_policy_pmlp(bb_handle* h, int hidden, const float* W1_dev, const float* b1_dev, const float* w2_dev,
+                   const float* b2_dev, uint64_t seed, uint64_t counter, int greedy, int32_t* actions_dev,
+                   float* logprob_dev, float* logprobs_all_dev, int pmax, void* stream);
+
+/* bb_rollout: T steps of every environment in ONE launch -- policy head, sample, step, auto-reset (if enabled) --
+ * i.e. the loop of pg.Agent.run_episode (pg.py:451-472) fused on device.  Step t of environment e draws its uniform
+ * with counter counter0 + t.  Outputs are environment-major [N, T] (any may be NULL): actions (-1 where the
+ * environment was not running), logprob, reward (float: -(additions) or -1), done, lengths (|P| before the step);
+ * obs_dev (optional) int32 [N, T, pmax, cols] = the state matrix before each step, padded with -1 (pg.py:217-226). */
+int bb_rollout(bb_handle* h, int hidden, const float* W1_dev, const float* b1_dev, const float* w2_dev, const float* b2_dev,
+               uint64_t seed, uint64_t counter0, int greedy, int T, int32_t* actions_dev, float* logprob_dev,
+               float* reward_dev, uint8_t* done_dev, int32_t* lengths_dev, int32_t* obs_dev, int pmax, void* stream);
 
 /* ---- host views (synchronising)
  * bb_download_basis: basis G of environment env in insertion order: lens[npoly], exps[nterms*n], coefs[nterms].

@@ -253,7 +253,9 @@ def test_all_selection_types_whole_episodes(torch_cuda, dist, strategy):
     orc = best_oracle()
     port = __import__("oracle.oracle", fromlist=["x"]).load_port()
     episodes, sel_seed = 48, 77
-    eng = BuchbergerEngine(dist, num_envs=episodes)
+    # the reversed strategies build much larger bases than the default binomial preset holds
+    big = dict(max_basis=4096, max_pairs=32768, max_terms=12288) if strategy in ("last", "codegree", "strange", "spice") else {}
+    eng = BuchbergerEngine(dist, num_envs=episodes, **big)
     stats, trace = eng.run_episodes(strategy, episodes=episodes, seed_base=300, compute_gb=True, trace_episodes=episodes,
                                     trace_cap=2048, selection_seed=sel_seed, gamma=0.99)
     gen = orc.generator(dist)
