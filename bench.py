@@ -28,6 +28,16 @@ EPISODES = 16384
 METRIC = "env_steps_per_sec"
 UNIT = "env-steps/s"
 
+# name -> (ideal_dist, selection, episodes, "weak": per GPU | "strong": in total, BASELINE.json config it is)
+WORKLOADS = {
+    "episodes": ("3-20-10-weighted", "degree", 16384, "weak", "configs[1]"),
+    "u3": ("3-20-10-uniform", "degree", 65536, "strong", "configs[2]"),
+    "u5": ("5-5-10-uniform", "degree", 65536, "strong", "configs[2]"),
+    "cyclic6": ("cyclic-6", "random", 1024, "weak", "configs[4]"),
+}
+SCALING, CONFIG_ID, DATA_NOTE = "weak", "configs[1]", ""
+SEL_SEED = 1234  # Random selection: episode e draws choice() from minstd_rand0 seeded SEL_SEED + e
+
 
 def algorithmic_bytes(c):
     """12 B per term read/written by an addition, 8 B per reducer lead monomial examined,
@@ -46,15 +56,38 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
-    """DRAM bytes per launch of k_run from the committed ncu --set full capture, if any."""
+def ncu_capture():
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("k_run_dram_bytes_per_launch")
+            return json.load(open(p))
         except Exception:
-            return None
-    return None
+            return {}
+    return {}
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of k_run from the committed ncu --set full capture, if any."""
+    return ncu_capture().get("k_run_dram_bytes_per_launch")
+
+
+def int_pipe(launch_s, sm_mhz, sm_count):
+    """The secondary roofline BASELINE.json allows for this path (instruction issue / integer pipe):
+    warp instructions per launch of k_run (a property of the kernel + workload, from the committed ncu capture of the
+    same command) over the LIVE launch time, against the issue peak = SMs x 4 schedulers x SM clock sampled during
+    the timed region.  The pipe percentages are the capture's."""
+    c = ncu_capture()
+    inst = c.get("k_run_warp_instructions_per_launch")
+    if not inst or not sm_mhz:
+        return None
+    peak = sm_count * 4 * sm_mhz * 1e6
+    ach = inst / launch_s
+    return {"bound": "issue", "achieved": ach / 1e9, "peak": peak / 1e9, "unit": "G warp-inst/s", "frac": ach / peak,
+            "warp_instructions_per_launch": inst, "sm_mhz": sm_mhz,
+            "alu_pipe_pct_of_peak_while_active": c.get("k_run_alu_pipe_pct_active"),
+            "issue_slots_busy_pct": c.get("k_run_issue_active_pct"),
+            "threads_per_warp_instruction": c.get("k_run_threads_per_warp_instruction"),
+            "source": c.get("source")}
 
 
 class ClockSampler:
@@ -133,14 +166,25 @@ def cpu_sample(orc, kind, seconds, threads):
     bounded sample of the SAME workload (episodes seed 0..count-1), sized for about `seconds` of wall time."""
     if kind != "reference":
         threads = 1  # the C restatement is single-threaded
-    probe = orc.bench_selection(DIST, STRATEGY, 0, 64 * threads, nthreads=threads)
+    n0 = (64 if STRATEGY != "random" else 1) * threads
+    probe = cpu_run(orc, kind, 0, n0, threads)
     rate = probe["steps"] / max(probe["seconds"], 1e-9)
-    steps_per_ep = probe["steps"] / (64.0 * threads)
-    count = int(min(EPISODES, max(64 * threads, seconds * rate / steps_per_ep)))
+    steps_per_ep = probe["steps"] / float(n0)
+    count = int(min(EPISODES, max(n0, seconds * rate / steps_per_ep)))
     if count > EPISODES // 2:
         count = EPISODES  # the whole workload fits the budget: no sampling at all
-    r = orc.bench_selection(DIST, STRATEGY, 0, count, nthreads=threads)
+    r = cpu_run(orc, kind, 0, count, threads)
     return r, count, threads
+
+
+def cpu_run(orc, kind, seed0, count, threads):
+    """Episodes seed0 .. seed0+count-1 of the current workload on the host: the reference env stepped with the
+    selection comparators (First/Degree/Normal/Sugar), or the reference's own buchberger() loop for seeded Random."""
+    if STRATEGY == "random":
+        if kind != "reference":
+            raise SystemExit("the Random-selection CPU arm needs oracle/_ref (the unmodified reference)")
+        return orc.bench_buchberger(DIST, STRATEGY, seed0, count, nthreads=threads, sel_seed0=SEL_SEED + seed0)
+    return orc.bench_selection(DIST, STRATEGY, seed0, count, nthreads=threads)
 
 
 def reference_arm(args):
@@ -152,25 +196,28 @@ def reference_arm(args):
     # each step = the first `count` episodes of the workload, sized for ~4 s per step
     probe, count, threads = cpu_sample(orc, kind, 4.0, threads)
     for _ in range(args.warmup):
-        orc.bench_selection(DIST, STRATEGY, 0, max(count // 8, threads), nthreads=threads)
+        cpu_run(orc, kind, 0, max(count // 8, threads), threads)
     steps = adds = 0
     secs = 0.0
     for _ in range(args.steps):
-        r = orc.bench_selection(DIST, STRATEGY, 0, count, nthreads=threads)
+        r = cpu_run(orc, kind, 0, count, threads)
         steps += r["steps"]; adds += r["additions"]; secs += r["seconds"]
     value = steps / secs
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000.0 * secs / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "int32 (GF(32003) coefficients, int exponent vectors)",
-        "data": "synthetic (reference RandomBinomialIdealGenerator, env seed e for episode e)",
+        "scaling": SCALING, "vs_baseline": None, "dtype": "int32 (GF(32003) coefficients, int exponent vectors)",
+        "data": DATA_NOTE.replace("on-device restatement of the reference", "reference"),
         "config": {"workload": "%s, %s selection, episodes to completion; bounded sample: episodes 0..%d of %d per step"
                                % (DIST, STRATEGY, count - 1, EPISODES), "episodes_per_step": count,
                    "host_threads": threads},
         "additions_per_sec": adds / secs,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
                          "sample": "%d episodes (seeds 0..%d) x %d steps, one BuchbergerEnv per thread, "
-                                   "env.seed(e); reset(); Degree select + step until P empty" % (count, count - 1, args.steps)},
+                                   "env.seed(e); reset(); %s until P empty"
+                                   % (count, count - 1, args.steps,
+                                      "the reference buchberger() loop with seeded Random selection" if STRATEGY == "random"
+                                      else STRATEGY + " select + step")},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -193,12 +240,19 @@ def gpu_arm(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
-    slots = args.slots or resident_envs(local, 3)
+    from deepgroebner_b200 import sharding
+    from deepgroebner_b200.ideals import BinomialSpec, parse_ideal_dist
+    spec = parse_ideal_dist(DIST, 32003)
+    nvars = spec.n if isinstance(spec, BinomialSpec) else spec.nvars()
+    if SCALING == "weak":   # every rank runs its own EPISODES episodes, disjoint seeds
+        ep_first, ep_local = rank * EPISODES, EPISODES
+    else:                   # EPISODES in total, contiguous blocks (deepgroebner_b200/sharding.py)
+        ep_first, ep_local = sharding.shard_range(EPISODES, rank, world)
+    slots = args.slots or min(resident_envs(local, nvars), ep_local)
     eng = BuchbergerEngine(DIST, num_envs=slots, device="cuda:%d" % local)
-    seed_base = rank * EPISODES  # weak scaling: every rank runs its own 16384 episodes, disjoint seeds
-    seeds_host = torch.arange(seed_base, seed_base + EPISODES, dtype=torch.int32).pin_memory()
+    seeds_host = torch.arange(ep_first, ep_first + ep_local, dtype=torch.int32).pin_memory()
     seeds_dev = seeds_host.to(dev)
-    stats_bytes = EPISODES * 72
+    stats_bytes = ep_local * 72
     stats_dev = torch.empty(stats_bytes, dtype=torch.uint8, device=dev)
     stats_host = torch.empty(stats_bytes, dtype=torch.uint8).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -207,8 +261,8 @@ def gpu_arm(args):
     lib = eng.lib
 
     def launch(gb):
-        rc = lib.bb_run(eng.h, _lib.SELECTION[STRATEGY], EPISODES, 0, C.c_void_p(seeds_dev.data_ptr()), 0, 0, 0.99, gb,
-                        C.c_void_p(stats_dev.data_ptr()), None, 0, 0,
+        rc = lib.bb_run(eng.h, _lib.SELECTION[STRATEGY], ep_local, 0, C.c_void_p(seeds_dev.data_ptr()), SEL_SEED + ep_first,
+                        0, 0.99, gb, C.c_void_p(stats_dev.data_ptr()), None, 0, 0,
                         C.c_void_p(torch.cuda.current_stream().cuda_stream))
         if rc < 0:
             raise RuntimeError(lib.bb_last_error(eng.h))
@@ -270,12 +324,18 @@ def gpu_arm(args):
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         from hashing import trace_hash
         env = orc.env(DIST)
-        for e in range(0, EPISODES, 1024):
-            env.seed(e)
-            env.reset()
-            tr = env.run(selection=STRATEGY)
-            assert stats["steps"][e] == len(tr) and int(stats["trace_hash"][e]) == trace_hash(tr), \
-                "GPU episode %d differs from the %s oracle" % (e, kind)
+        for e in range(0, ep_local, max(1, ep_local // (4 if STRATEGY == "random" else 16))):
+            env.seed(ep_first + e)
+            F, _ = env.reset()
+            if STRATEGY == "random":   # the reference's own buchberger() loop with the episode's selection seed
+                _, st = orc.buchberger(F, selection="random", gamma=0.99, seed=SEL_SEED + ep_first + e)
+                ok = (stats["steps"][e] == st["zero_reductions"] + st["nonzero_reductions"]
+                      and stats["additions"][e] == st["polynomial_additions"]
+                      and stats["discounted_return"][e] == st["discounted_return"])
+            else:
+                tr = env.run(selection=STRATEGY)
+                ok = stats["steps"][e] == len(tr) and int(stats["trace_hash"][e]) == trace_hash(tr)
+            assert ok, "GPU episode %d differs from the %s oracle" % (ep_first + e, kind)
 
         peak, peak_src = measured_peak()
         abytes = algorithmic_bytes(counters) / args.steps
@@ -285,12 +345,13 @@ def gpu_arm(args):
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None,
+            "scaling": SCALING, "vs_baseline": None,
             "dtype": "u64 packed monomials + u32 GF(32003) coefficients (integer)",
-            "data": "synthetic (on-device restatement of the reference RandomBinomialIdealGenerator; episode e = stream seed e)",
-            "config": {"workload": "%s, %d episodes per GPU to completion, %s selection (BASELINE configs[1])"
-                                   % (DIST, EPISODES, STRATEGY),
-                       "episodes_per_gpu": EPISODES, "env_steps_per_launch": steps_per_launch, "slots": slots,
+            "data": DATA_NOTE,
+            "config": {"workload": "%s, %d episodes %s to completion, %s selection (BASELINE %s)"
+                                   % (DIST, EPISODES, "per GPU" if SCALING == "weak" else "in total, sharded", STRATEGY,
+                                      CONFIG_ID),
+                       "episodes_per_gpu": ep_local, "env_steps_per_launch": steps_per_launch, "slots": slots,
                        "parallelism": "episodes sharded across GPUs, no collective on the step path",
                        "l2": "256 MiB flush write between timed launches"},
             "additions_per_sec": total_adds * args.steps / (dev_ms_max / 1000.0),
@@ -299,13 +360,16 @@ def gpu_arm(args):
             "wall_s_timed_region": wall,
             "clocks": clocks,
             "e2e": {"value": total_steps * args.steps / (e2e_ms_max / 1000.0), "unit": UNIT,
-                    "h2d_bytes_per_step": EPISODES * 4, "d2h_bytes_per_step": stats_bytes},
+                    "h2d_bytes_per_step": ep_local * 4, "d2h_bytes_per_step": stats_bytes},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "k_run",
                          "algorithmic_bytes_per_launch": abytes,
                          "note": "latency/integer bound at binomial sizes (working set lives in L1/L2); see DESIGN.md"},
             "counters_per_launch": {k: v / args.steps for k, v in counters.items()},
         }
+        ip = int_pipe(launch_s, (clocks or {}).get("sm_mhz"), eng.sm_count) if args.workload == "episodes" else None
+        if ip:
+            line["int_pipe"] = ip
         if world == 1 and not args.no_cpu:
             threads = host_threads()
             r, count, threads = cpu_sample(orc, kind, args.cpu_seconds, threads)
@@ -424,7 +488,10 @@ def rollout_arm(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="episodes", choices=["episodes", "rollout"])
+    ap.add_argument("--workload", default="episodes", choices=sorted(WORKLOADS) + ["rollout"],
+                    help="episodes = BASELINE configs[1] (the headline); u3/u5 = configs[2]; cyclic6 = configs[4]; "
+                         "rollout = configs[3]")
+    ap.add_argument("--episodes", type=int, default=0, help="override the workload's episode count")
     ap.add_argument("--envs", type=int, default=16384, help="rollout workload: environments per GPU")
     ap.add_argument("--horizon", type=int, default=128, help="rollout workload: fused steps per launch")
     ap.add_argument("--gpus", type=int, default=1)
@@ -435,6 +502,13 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    global DIST, STRATEGY, EPISODES, SCALING, CONFIG_ID, DATA_NOTE
+    DIST, STRATEGY, EPISODES, SCALING, CONFIG_ID = WORKLOADS.get(args.workload, WORKLOADS["episodes"])
+    if args.episodes:
+        EPISODES = args.episodes
+    DATA_NOTE = ("synthetic (fixed ideal staged on device; episode e = Random-selection stream seed %d + e)" % SEL_SEED
+                 if STRATEGY == "random" else
+                 "synthetic (on-device restatement of the reference RandomBinomialIdealGenerator; episode e = stream seed e)")
     if args.impl == "reference":
         reference_arm(args)
     elif args.workload == "rollout":

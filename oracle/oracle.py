@@ -143,6 +143,7 @@ class Oracle:
         L("bench_selection", None, _cp, _i, _i, _i, _i, _i, _i, _dp)
         if prefix == "ref_":
             L("bench_random", None, _cp, _i, _i, _i, _dp)
+            L("bench_buchberger", None, _cp, _i, _i, _i, _i, _i, C.c_double, _dp)
         else:
             L("set_prime", None, _i)
 
@@ -291,6 +292,13 @@ class Oracle:
         out = np.zeros(3, np.float64)
         self.c_bench_selection(dist.encode(), SELECT[selection], seed0, count, nthreads, int(with_matrix), k,
                                out.ctypes.data_as(_dp))
+        return dict(steps=int(out[0]), additions=int(out[1]), seconds=float(out[2]))
+
+    def bench_buchberger(self, dist, selection, seed0, count, nthreads=1, sel_seed0=0, gamma=0.99):
+        """Whole episodes through the reference's buchberger() loop (any SelectionType, seeded Random); ref only."""
+        out = np.zeros(3, np.float64)
+        self.c_bench_buchberger(dist.encode(), SELECT[selection], seed0, count, nthreads, sel_seed0, gamma,
+                                out.ctypes.data_as(_dp))
         return dict(steps=int(out[0]), additions=int(out[1]), seconds=float(out[2]))
 
     def bench_random(self, dist, seed0, episodes, nthreads=1):

@@ -445,4 +445,35 @@ void ref_bench_random(const char* dist, int seed0, int episodes, int nthreads, d
   out[0] = (double)S; out[1] = -R; out[2] = std::chrono::duration<double>(t1 - t0).count();
 }
 
+// Whole episodes through the reference's own buchberger() loop (buchberger.cpp:125-266), any SelectionType incl.
+// seeded Random: episode e draws its ideal from the generator stream seed0 + e (first next() with a non-empty pair
+// set, like BuchbergerEnv::reset) and runs buchberger(F, selection, GebauerMoeller, Additions, false, true, gamma,
+// sel_seed0 + e).  One generator per thread.  out[0]=env steps (zero + nonzero reductions), out[1]=additions,
+// out[2]=seconds.
+void ref_bench_buchberger(const char* dist, int selection, int seed0, int count, int nthreads, int sel_seed0,
+                          double gamma, double* out) {
+  std::vector<long long> steps(nthreads, 0), adds(nthreads, 0);
+  auto t0 = std::chrono::steady_clock::now();
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthreads; t++) {
+    th.emplace_back([&, t]() {
+      BuchbergerEnv env{dist};
+      for (int e = t; e < count; e += nthreads) {
+        env.seed(seed0 + e);
+        env.reset();
+        std::vector<Polynomial> F = env.G;  // after reset() G holds exactly the generators (sort_input = false)
+        auto res = buchberger(F, sel_of(selection), EliminationType::GebauerMoeller, RewardType::Additions, false, true,
+                              gamma, std::optional<int>(sel_seed0 + e));
+        steps[t] += res.second.zero_reductions + res.second.nonzero_reductions;
+        adds[t] += res.second.polynomial_additions;
+      }
+    });
+  }
+  for (auto& x : th) x.join();
+  auto t1 = std::chrono::steady_clock::now();
+  long long S = 0, A = 0;
+  for (int t = 0; t < nthreads; t++) { S += steps[t]; A += adds[t]; }
+  out[0] = (double)S; out[1] = (double)A; out[2] = std::chrono::duration<double>(t1 - t0).count();
+}
+
 }  // extern "C"

@@ -380,3 +380,56 @@ def test_copy_is_deep_and_includes_the_ideal_stream(torch_cuda):
     assert np.array_equal(b._state(), sb)          # stepping a did not move b
     assert np.array_equal(a.reset(), b.reset())    # same generator stream position
     assert a.value("normal") == b.value("normal")
+
+
+def test_cyclic6_seeded_random_episodes(torch_cuda):
+    """BASELINE configs[4]: cyclic-6 over GF(32003), many episodes under seeded Random selection -- long reductions
+    (dividends of hundreds of terms through the general merge path), pair sets beyond 1000 entries, every warp on a
+    different trajectory.  Reduction counts, additions, the discounted return (a gamma-weighted checksum of the
+    reward sequence, exact in double) and the reduced Groebner basis equal buchberger(F, Random, ..., seed) of the
+    reference for every episode; Degree is checked with its full pair sequence."""
+    from deepgroebner_b200.buchberger import BuchbergerEngine
+    orc = best_oracle()
+    episodes, sel_seed = 24, 1234
+    eng = BuchbergerEngine("cyclic-6", num_envs=episodes)
+    stats, _ = eng.run_episodes("random", episodes=episodes, compute_gb=True, selection_seed=sel_seed, gamma=0.99)
+    env = orc.env("cyclic-6")
+    F, _ = env.reset()
+    seen = set()
+    for e in range(episodes):
+        gb, st = orc.buchberger(F, selection="random", gamma=0.99, seed=sel_seed + e)
+        s = stats[e]
+        assert s["status"] == 2, (e, s)
+        assert (s["zero_reductions"], s["nonzero_reductions"], s["additions"]) == \
+            (st["zero_reductions"], st["nonzero_reductions"], st["polynomial_additions"]), e
+        assert s["discounted_return"] == st["discounted_return"], e
+        assert (s["gb_polys"], s["gb_terms"]) == (len(gb), sum(len(g) for g in gb))
+        assert int(s["gb_hash"]) == polys_hash(gb), e
+        seen.add(int(s["steps"]))
+    assert len(seen) > episodes // 2   # the episodes really are different trajectories
+    stats, trace = eng.run_episodes("degree", episodes=2, compute_gb=True, trace_episodes=2, trace_cap=4096)
+    t = env.run(selection="degree")
+    for e in range(2):
+        assert stats["steps"][e] == len(t) and np.array_equal(trace[e, :len(t)], t[:, :4])
+        assert int(stats["trace_hash"][e]) == trace_hash(t) and int(stats["basis_hash"][e]) == polys_hash(env.basis())
+
+
+def test_sharded_blocks_equal_one_run(torch_cuda):
+    """an episode's record does not depend on how the episode range is cut into per-GPU blocks --
+    run_sharded over one rank == the concatenation of the blocks that 2 and 3 ranks would run."""
+    from deepgroebner_b200 import sharding
+    from deepgroebner_b200.buchberger import BuchbergerEngine
+    total = 301
+    eng = BuchbergerEngine("3-20-10-uniform", num_envs=128)
+    whole = sharding.run_sharded(eng, "normal", total, seed_base=50, compute_gb=True)
+    assert whole.shape == (total,) and (whole["status"] == 2).all()
+    for ws in (2, 3):
+        parts = []
+        for r in range(ws):
+            first, count = sharding.shard_range(total, r, ws)
+            st, _ = eng.run_episodes("normal", episodes=count, seed_base=50 + first, compute_gb=True)
+            parts.append(st)
+        cat = np.concatenate(parts)
+        for f in ("steps", "additions", "trace_hash", "basis_hash", "gb_hash", "discounted_return", "rerolls"):
+            assert np.array_equal(cat[f], whole[f]), (ws, f)
+    assert sharding.summarize(whole)["finished"] == total
