@@ -21,6 +21,8 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# stdout carries exactly one JSON line: NCCL's version / debug banner (NCCL_DEBUG=VERSION|INFO) goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 DIST = "3-20-10-weighted"
 STRATEGY = "degree"
