@@ -18,7 +18,7 @@ from .ideals import BinomialSpec, FixedIdealGenerator, parse_ideal_dist
 # arena capacities per environment: (max_basis, max_pairs, max_terms, max_poly_terms)
 CAPACITY_PRESETS = {
     "binomial": dict(max_basis=512, max_pairs=1024, max_terms=1536, max_poly_terms=64),
-    "general": dict(max_basis=2048, max_pairs=8192, max_terms=1 << 18, max_poly_terms=4096),
+    "general": dict(max_basis=2048, max_pairs=8192, max_terms=1 << 18, max_poly_terms=2048),
 }
 
 
@@ -235,6 +235,11 @@ class BuchbergerEngine:
     def set_auto_reset(self, on=True):
         """Finished environments are reset inside step() / rollout() (vector-env semantics, bb_set_auto_reset)."""
         self._ck(self.lib.bb_set_auto_reset(self.h, int(bool(on))), "bb_set_auto_reset")
+
+    def set_wide(self, mode=-1):
+        """Episode runner of run_episodes (bb_set_wide): -1 auto, 0 one warp per environment, 1 one CTA per
+        environment (long polynomials).  Results are identical; only speed differs."""
+        self._ck(self.lib.bb_set_wide(self.h, int(mode)), "bb_set_wide")
 
     def policy(self, net, counter=0, greedy=False, return_all=False, pmax=None):
         """PMLP head + categorical sample on the current states (bb_policy_pmlp).  net: rollout.PairsPolicy.

@@ -579,24 +579,15 @@ __device__ __noinline__ long long warp_add_basis(const BBParams& P, unsigned cha
 }
 
 // ---------------------------------------------------------------------------------------------------- step
-// BuchbergerEnv::step for the pair in row `row` of P (LeadMonomialsEnv::step(int), buchberger.cpp:398-408 ->
-// :318-329): erase the pair, s = spoly(G[i], G[j]) (:18-21), (r, steps) = reduce(s, G_), if r != 0 update + sorted
-// insert.  Returns the number of polynomial additions 1 + steps (reward = -(1+steps) under Additions, -1 under
-// Reductions).  `pair` receives (j << 16) | i, or 0xffffffff for a bad action.
-template <int NV>
-__device__ __forceinline__ int warp_step(const BBParams& P, Env& e, int row, uint32_t& pair, Ctr& ct) {
-  typedef KL<NV> K;
-  const BBField F = P.F;
+// Removes row `row` from the pair list keeping order (buchberger.cpp:319) and returns the pair ((j << 16) | i) and the
+// cached key of its lcm.  Caller guarantees 0 <= row < |P|.
+__device__ __forceinline__ void warp_take_pair(const BBParams& P, Env& e, int row, uint32_t& pr, uint64_t& gam) {
   const int lane = bb_lane();
-  if ((unsigned)row >= (unsigned)e.nP) { e.status = BB_STATUS_BAD_ACTION; pair = 0xffffffffu; return 0; }
   uint32_t* pairs = ENV_PTR(uint32_t, e, P, o_pairs);
   uint64_t* plcm = ENV_PTR(uint64_t, e, P, o_plcm);
-  const uint32_t pr = pairs[row];
-  const uint64_t gam = plcm[row];  // key of lcm(LM f, LM g), computed when the pair was created
-  const int i = pr & 0xffffu, j = pr >> 16;
-  pair = pr;  // (j << 16) | i; never 0xffffffff because i < j
+  pr = pairs[row];
+  gam = plcm[row];  // key of lcm(LM f, LM g), computed when the pair was created
   __syncwarp();
-  // erase the pair, keeping order (:319)
 #pragma unroll 1
   for (int b0 = row; b0 < e.nP - 1; b0 += 32) {
     const int idx = b0 + lane;
@@ -607,6 +598,21 @@ __device__ __forceinline__ int warp_step(const BBParams& P, Env& e, int row, uin
     if (v) { pairs[idx] = x; plcm[idx] = y; }
   }
   e.nP--;
+}
+
+// BuchbergerEnv::step for the pair in row `row` of P (LeadMonomialsEnv::step(int), buchberger.cpp:398-408 ->
+// :318-329): erase the pair, s = spoly(G[i], G[j]) (:18-21), (r, steps) = reduce(s, G_), if r != 0 update + sorted
+// insert.  Returns the number of polynomial additions 1 + steps (reward = -(1+steps) under Additions, -1 under
+// Reductions).  `pair` receives (j << 16) | i, or 0xffffffff for a bad action.
+template <int NV>
+__device__ __forceinline__ int warp_step(const BBParams& P, Env& e, int row, uint32_t& pair, Ctr& ct) {
+  typedef KL<NV> K;
+  const BBField F = P.F;
+  if ((unsigned)row >= (unsigned)e.nP) { e.status = BB_STATUS_BAD_ACTION; pair = 0xffffffffu; return 0; }
+  uint32_t pr; uint64_t gam;
+  warp_take_pair(P, e, row, pr, gam);
+  const int i = pr & 0xffffu, j = pr >> 16;
+  pair = pr;  // (j << 16) | i; never 0xffffffff because i < j
   // S-polynomial: lead terms cancel exactly, so s = (gamma/LT f) tail(f) - (gamma/LT g) tail(g)
   const GHeadMem* gh = ENV_PTR(GHeadMem, e, P, o_ghead);
   const GHead hf = load_head(gh + i), hg = load_head(gh + j);

@@ -12,6 +12,7 @@
 #pragma once
 #include "bb_device.cuh"
 #include "bb_policy.cuh"
+#include "bb_wide.cuh"
 
 #ifndef BB_WARPS
 #define BB_WARPS 8
@@ -33,8 +34,12 @@ struct BBRunArgs {
   bb_episode_stats* out;
   int32_t* trace;
   int trace_eps, trace_cap;
-  int* queue;
+  int* queue;        // [0]: next queue position; [BB_LPT_HIST .. +BB_LPT_BUCKETS): histogram of the cost keys of the batch, then as many cursors
+  int* order;        // [episodes] queue position -> episode of the batch, longest predicted first (k_order)
+  uint8_t* cost_key; // [episodes] predicted-cost bucket of each episode of the batch (k_prepare)
 };
+#define BB_LPT_BUCKETS 256
+#define BB_LPT_HIST 4
 
 struct BBEpisodeAcc {
   unsigned long long th;
@@ -69,8 +74,12 @@ struct BBKernelTable {
   cudaError_t (*select)(const BBParams&, int strategy, int* actions, int nwarps, cudaStream_t);
   cudaError_t (*observe)(const BBParams&, int32_t* obs, int32_t* lengths, int pmax, int nwarps, cudaStream_t);
   cudaError_t (*final_gb)(const BBParams&, int slot, int* ok_out, cudaStream_t);
-  cudaError_t (*prepare)(const BBParams& stage, const BBRunArgs&, cudaStream_t);
+  cudaError_t (*prepare)(const BBParams& stage, const BBRunArgs&, cudaStream_t);  // k_prepare + k_order
   cudaError_t (*run)(const BBParams&, const BBParams& stage, const BBRunArgs&, int nwarps, cudaStream_t);
+  // one CTA per environment (bb_wide.cuh); nctas worker CTAs; returns cudaErrorInvalidValue if the dividend buffers
+  // (2 x max_poly_terms terms) do not fit shared memory
+  cudaError_t (*run_wide)(const BBParams&, const BBParams& stage, const BBRunArgs&, int nctas, cudaStream_t);
+  int (*wide_ctas_per_sm)(int max_poly_terms);   // 0 if it does not fit
   cudaError_t (*value)(const BBParams&, const BBParams& fork, const BBValueArgs&, int nwarps, cudaStream_t);
   cudaError_t (*policy)(const BBParams&, const BBPolicy&, unsigned long long counter, int32_t* actions, float* logp,
                         float* logits, int pmax, int nwarps, cudaStream_t);
@@ -206,8 +215,43 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_prepare(const __g
   if (b < A.episodes) {
     const int ep = A.ep_base + b;
     warp_reset_slot<NV>(S, b, S.dist.enabled ? b : ep % A.nstaged, rng_seed(A.seeds ? A.seeds[ep] : A.seed_base + ep), row);
+    // Predicted cost of the episode, for the longest-first queue order: the summed degree of the generators' lead
+    // monomials (rank correlation with the episode length ~0.5 on the binomial distributions), scaled to a bucket.
+    // Only the ORDER in which episodes start depends on it, never a result.
+    const int nG = S.st[b].nG;
+    const uint64_t* lm = SLOT_PTR(uint64_t, S, b, o_lm);
+    uint32_t sd = 0;
+    for (int i = bb_lane(); i < nG; i += 32) sd += KL<NV>::deg(lm[i]);
+    sd = __reduce_add_sync(BB_FULL, sd);
+    if (bb_lane() == 0) {
+      // generated ideals: s generators of degree <= d; a fixed ideal is the same for every episode (one bucket)
+      uint32_t key = S.dist.enabled ? (sd * (BB_LPT_BUCKETS - 1)) / (uint32_t)max(1, S.dist.s * S.dist.d) : 0u;
+      key = key < BB_LPT_BUCKETS ? key : BB_LPT_BUCKETS - 1;
+      A.cost_key[b] = (uint8_t)key;
+      atomicAdd(&A.queue[BB_LPT_HIST + key], 1);
+    }
   }
   counters_flush(S, sh);
+}
+
+// Queue order of a batch: episodes sorted by cost bucket, largest first (counting sort).  Every CTA recomputes the
+// bucket starts from the histogram and places a slice of the batch through the global per-bucket cursors.  Within a
+// bucket the order is whatever the atomics produce -- it only decides which worker warp picks an episode up when.
+template <int NV>
+__global__ void __launch_bounds__(BB_LPT_BUCKETS) k_order(const __grid_constant__ BBRunArgs A) {
+  __shared__ int hist[BB_LPT_BUCKETS], start[BB_LPT_BUCKETS];
+  const int t = threadIdx.x;
+  hist[t] = A.queue[BB_LPT_HIST + t];
+  __syncthreads();
+  int before = 0;
+  for (int k = t + 1; k < BB_LPT_BUCKETS; k++) before += hist[k];
+  start[t] = before;
+  __syncthreads();
+  int* cursor = A.queue + BB_LPT_HIST + BB_LPT_BUCKETS;
+  for (int b = blockIdx.x * BB_LPT_BUCKETS + t; b < A.episodes; b += gridDim.x * BB_LPT_BUCKETS) {
+    const int key = A.cost_key[b];
+    A.order[start[key] + atomicAdd(&cursor[key], 1)] = b;
+  }
 }
 
 // copy n 32-bit words, lane-strided
@@ -269,9 +313,9 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_run(const __grid_
     Ctr ct; ct.clear();
     for (;;) {
       int b = 0;
-      if (lane == 0) b = atomicAdd(A.queue, 1);
+      if (lane == 0) { b = atomicAdd(A.queue, 1); b = b < A.episodes ? A.order[b] : -1; }
       b = __shfl_sync(BB_FULL, b, 0);
-      if (b >= A.episodes) break;
+      if (b < 0) break;
       const int ep = A.ep_base + b;
       Env e; env_load(S, b, e);  // the prepared state; e.base still points into the staging arena here
       {
@@ -324,6 +368,114 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_run(const __grid_
     }
   }
   counters_flush(P, sh);
+}
+
+// block-strided copy of n 32-bit words
+__device__ __forceinline__ void block_copy_words(uint32_t* __restrict__ d, const uint32_t* __restrict__ s, int n) {
+#pragma unroll 1
+  for (int t = threadIdx.x; t < n; t += BBW_THREADS) d[t] = s[t];
+}
+
+// Persistent episode runner, one CTA per environment slot (bb_wide.cuh): same queue, staging arena, episode record and
+// checksums as k_run; the step is block_step.  Dynamic shared memory: the two dividend buffers.
+template <int NV>
+__global__ void __launch_bounds__(BBW_THREADS, BBW_MIN_CTAS) k_run_wide(const __grid_constant__ BBParams P, const __grid_constant__ BBParams S,
+                                                          const __grid_constant__ BBRunArgs A) {
+  extern __shared__ __align__(16) unsigned char wide_smem[];
+  __shared__ unsigned long long sh[1][CT_COUNT];
+  __shared__ BBEpisodeAcc acc;
+  __shared__ WideShared ws;
+  __shared__ int next_b;
+  const int cap = P.max_poly_terms;
+  uint64_t* hk = reinterpret_cast<uint64_t*>(wide_smem);
+  uint32_t* hc = reinterpret_cast<uint32_t*>(wide_smem + (size_t)16 * cap);
+  const int tid = threadIdx.x;
+  const int slot = blockIdx.x;
+  if (tid < CT_COUNT) sh[0][tid] = 0ull;
+  __syncthreads();
+  unsigned long long* row = sh[0];
+  Ctr ct; ct.clear();
+  int bslot = 0;
+  for (;;) {
+    if (tid == 0) { int q = atomicAdd(A.queue, 1); next_b = q < A.episodes ? A.order[q] : -1; }
+    __syncthreads();
+    const int b = next_b;
+    if (b < 0) break;
+    const int ep = A.ep_base + b;
+    Env e; env_load(S, b, e);
+    {
+      unsigned char* db = P.arena + (size_t)slot * P.slot_stride;
+      const unsigned char* sb = e.base;
+      block_copy_words((uint32_t*)(db + P.o_ghead), (const uint32_t*)(sb + S.o_ghead), e.nG * 8);
+      block_copy_words((uint32_t*)(db + P.o_lm), (const uint32_t*)(sb + S.o_lm), e.nG * 2);
+      block_copy_words((uint32_t*)(db + P.o_rlm), (const uint32_t*)(sb + S.o_rlm), e.nG * 2);
+      block_copy_words((uint32_t*)(db + P.o_ridx), (const uint32_t*)(sb + S.o_ridx), e.nG);
+      block_copy_words((uint32_t*)(db + P.o_pairs), (const uint32_t*)(sb + S.o_pairs), e.nP);
+      block_copy_words((uint32_t*)(db + P.o_plcm), (const uint32_t*)(sb + S.o_plcm), e.nP * 2);
+      block_copy_words((uint32_t*)(db + P.o_tkey), (const uint32_t*)(sb + S.o_tkey), e.nT * 2);
+      block_copy_words((uint32_t*)(db + P.o_tcoef), (const uint32_t*)(sb + S.o_tcoef), e.nT);
+      e.base = db;
+    }
+    const int g_start = e.nG;
+    int steps = 0, adds = 0;
+    if (tid == 0) { acc.th = 0ull; acc.ret = 0.0; acc.disc = 1.0; acc.sel_rng = rng_seed(A.sel_seed_base + ep); }
+    __syncthreads();
+    int4* trace = (A.trace && ep < A.trace_eps) ? reinterpret_cast<int4*>(A.trace) + (size_t)ep * A.trace_cap : nullptr;
+    while (e.status == BB_STATUS_RUNNING && (A.max_steps == 0 || steps < A.max_steps)) {
+      uint32_t pr;
+      const int a = block_step<NV>(P, e, ws, bslot, hk, hc, cap, A.strategy, &acc.sel_rng, pr, ct);
+      if (tid == 0) {
+        const int pi = pr & 0xffffu, pj = pr >> 16;
+        acc.th += trace_hash_item(pi, pj, a, steps);
+        const double r = (P.rewards == BB_REWARD_ADDITIONS) ? -(double)a : -1.0;
+        const double d = acc.disc;
+        acc.ret = __dadd_rn(acc.ret, __dmul_rn(d, r)); acc.disc = __dmul_rn(d, A.gamma);
+        if (trace && steps < A.trace_cap) trace[steps] = make_int4(pi, pj, a, e.nP);
+      }
+      steps++; adds += a;
+    }
+    __syncthreads();
+    if (tid < 32) {   // warp 0: episode record, checksums, reduced Groebner basis (the warp routines of bb_device.cuh)
+      const int nonzero = e.nG - g_start, zero = steps - nonzero;
+      env_store(P, slot, e);
+      __syncwarp();
+      const GHeadMem* gh = ENV_PTR(GHeadMem, e, P, o_ghead);
+      const unsigned long long bh = warp_terms_hash<NV>(ENV_PTR(uint64_t, e, P, o_tkey), ENV_PTR(uint32_t, e, P, o_tcoef),
+                                                        e.nT, reinterpret_cast<const int*>(&gh[0].len),
+                                                        (int)(sizeof(GHeadMem) / sizeof(int)), e.nG);
+      unsigned long long gbh = 0; int gp = 0, gt = 0;
+      int status = e.status;
+      if (A.compute_gb && status == BB_STATUS_DONE) {
+        if (warp_final_gb<NV>(P, slot, row)) {
+          gp = P.gcount[2 * slot]; gt = P.gcount[2 * slot + 1];
+          gbh = warp_terms_hash<NV>(P.gkey + (size_t)slot * P.max_terms, P.gcoef + (size_t)slot * P.max_terms, gt,
+                                    P.glen + (size_t)slot * P.max_basis, 1, gp);
+        } else {
+          status = BB_STATUS_OVERFLOW_SCRATCH;
+        }
+      }
+      if (tid == 0) {
+        const unsigned long long th = acc.th; const double ret = acc.ret;
+        bb_episode_stats o;
+        o.steps = steps; o.additions = adds; o.zero_reductions = zero; o.nonzero_reductions = nonzero;
+        o.nbasis = e.nG; o.nterms = e.nT; o.status = status; o.rerolls = S.st[b].rerolls;
+        o.trace_hash = th; o.basis_hash = bh; o.gb_hash = gbh; o.gb_polys = gp; o.gb_terms = gt;
+        o.discounted_return = ret;
+        A.out[ep] = o;
+        BBEnvState& St = P.st[slot];
+        St.status = status; St.steps = steps; St.adds = adds; St.zero = zero; St.nonzero = nonzero; St.trace_hash = th;
+        St.disc_return = ret; St.rerolls = o.rerolls;
+        row[CT_STEPS] += (unsigned)steps; row[CT_ADDS] += (unsigned)adds; row[CT_NONZERO] += (unsigned)nonzero;
+        row[CT_ZERO] += (unsigned)zero; row[CT_EPISODES] += 1;
+      }
+      ct.spill(row);
+    } else {
+      ct.clear();
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (tid < CT_COUNT && sh[0][tid]) atomicAdd(&P.counters[tid], sh[0][tid]);
 }
 
 // max of doubles through a CAS loop (order independent, hence deterministic)
@@ -481,10 +633,28 @@ struct BBLaunch {
   }
   static cudaError_t prepare(const BBParams& S, const BBRunArgs& A, cudaStream_t s) {
     k_prepare<NV><<<grid_for_warps(A.episodes), BB_THREADS, 0, s>>>(S, A);
+    k_order<NV><<<std::min(64, (A.episodes + 1023) / 1024), BB_LPT_BUCKETS, 0, s>>>(A);
     return cudaGetLastError();
   }
   static cudaError_t run(const BBParams& P, const BBParams& S, const BBRunArgs& A, int nwarps, cudaStream_t s) {
     k_run<NV><<<grid_for_warps(nwarps), BB_THREADS, 0, s>>>(P, S, A);
+    return cudaGetLastError();
+  }
+  static size_t wide_smem(int max_poly_terms) { return (size_t)24 * max_poly_terms; }
+  static int wide_ctas_per_sm(int max_poly_terms) {
+    const size_t sm = wide_smem(max_poly_terms);
+    if (sm > 200 * 1024) return 0;
+    if (cudaFuncSetAttribute(k_run_wide<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return 0;
+    int blocks = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_run_wide<NV>, BBW_THREADS, sm) != cudaSuccess) return 0;
+    return blocks;
+  }
+  static cudaError_t run_wide(const BBParams& P, const BBParams& S, const BBRunArgs& A, int nctas, cudaStream_t s) {
+    const size_t sm = wide_smem(P.max_poly_terms);
+    if (sm > 200 * 1024) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(k_run_wide<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return e;
+    k_run_wide<NV><<<nctas, BBW_THREADS, sm, s>>>(P, S, A);
     return cudaGetLastError();
   }
   static cudaError_t value(const BBParams& P, const BBParams& F, const BBValueArgs& A, int nwarps, cudaStream_t s) {
@@ -532,7 +702,8 @@ struct BBLaunch {
   }
   static const BBKernelTable* table() {
     static const BBKernelTable t = {NV, KL<NV>::w, KL<NV>::dw, KL<NV>::dshift, KL<NV>::eshift,
-                                    &reset, &step, &select, &observe, &final_gb, &prepare, &run, &value, &policy, &rollout,
+                                    &reset, &step, &select, &observe, &final_gb, &prepare, &run, &run_wide, &wide_ctas_per_sm, &value, &policy,
+                                    &rollout,
                                     &run_blocks_per_sm};
     return &t;
   }

@@ -91,10 +91,12 @@ struct bb_handle {
   std::vector<void*> stage_allocs;
   unsigned char* stage_arena; BBEnvState* stage_st;
   uint64_t* stage_in_key; uint32_t* stage_in_coef; int* stage_in_off; int* stage_in_np;
+  int* stage_order; uint8_t* stage_cost_key;   // longest-predicted-first queue order of the batch (k_order)
   // fork arena of bb_value: one full-size slot per worker warp
   int fork_cap;
   std::vector<void*> fork_allocs;
   unsigned char* fork_arena; BBEnvState* fork_st;
+  int wide_mode;   // bb_run: -1 = one CTA per environment when the capacities ask for long polynomials, 0 = never, 1 = always
   // host mirrors of the distribution tables
   std::vector<double> cp;
 };
@@ -201,6 +203,7 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
   h->d_queue = nullptr; h->d_ok = nullptr;
   h->stage_cap = 0; h->stage_arena = nullptr; h->stage_st = nullptr;
   h->fork_cap = 0; h->fork_arena = nullptr; h->fork_st = nullptr;
+  h->wide_mode = -1;
   auto bail = [&](int code) { g_create_err = h->err; bb_destroy(h); return code; };
 #define CKC(call)                                                                                     \
   do {                                                                                                \
@@ -247,7 +250,7 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
     CKC(cudaGetLastError());
     P.invtab = tab;
   }
-  CKC(dev_alloc(h, &h->d_queue, (size_t)4));
+  CKC(dev_alloc(h, &h->d_queue, (size_t)(BB_LPT_HIST + 2 * BB_LPT_BUCKETS)));
   CKC(dev_alloc(h, &h->d_ok, (size_t)4));
   k_seed<<<(cfg->num_envs + BB_THREADS - 1) / BB_THREADS, BB_THREADS>>>(P, nullptr, 0, 0);
   k_seed<<<(cfg->num_envs + BB_THREADS - 1) / BB_THREADS, BB_THREADS>>>(P, nullptr, 0, 1);
@@ -470,6 +473,8 @@ static int stage_params(bb_handle* h, int batch, BBParams& S) {
     CK(alloc((void**)&h->stage_in_coef, n * P.max_gen_terms * sizeof(uint32_t)));
     CK(alloc((void**)&h->stage_in_off, n * (P.max_gens + 1) * sizeof(int)));
     CK(alloc((void**)&h->stage_in_np, n * sizeof(int)));
+    CK(alloc((void**)&h->stage_order, n * sizeof(int)));
+    CK(alloc((void**)&h->stage_cost_key, n));
     h->stage_cap = batch;
   }
   S.arena = h->stage_arena; S.st = h->stage_st; S.num_envs = batch;
@@ -499,10 +504,21 @@ int bb_run(bb_handle* h, int strategy, int episodes, int seed_base, const int32_
     A.ep_base = base; A.nstaged = h->P.num_envs;
     A.seeds = seeds_dev; A.max_steps = max_steps; A.gamma = gamma; A.compute_gb = compute_gb; A.out = stats_dev;
     A.trace = trace_dev; A.trace_eps = trace_dev ? trace_episodes : 0; A.trace_cap = trace_cap; A.queue = h->d_queue;
-    CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int), s));
+    A.order = h->stage_order; A.cost_key = h->stage_cost_key;
+    CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int) * (BB_LPT_HIST + 2 * BB_LPT_BUCKETS), s));
     CK(h->K->prepare(S, A, s));
-    const int workers = std::min(h->P.num_envs, A.episodes);
-    CK(h->K->run(h->P, S, A, workers, s));
+    // long polynomials (general capacities): one CTA per environment, dividend in shared memory (bb_wide.cuh)
+    int wide_ctas = 0;
+    if (h->wide_mode != 0 && (h->wide_mode == 1 || h->P.max_poly_terms >= 256))
+      wide_ctas = h->K->wide_ctas_per_sm(h->P.max_poly_terms) * h->sm_count;
+    if (h->wide_mode == 1 && wide_ctas <= 0)
+      return fail(h, "bb_run: the dividend buffers (24 bytes x max_poly_terms) do not fit shared memory");
+    if (wide_ctas > 0) {
+      CK(h->K->run_wide(h->P, S, A, std::min(std::min(h->P.num_envs, A.episodes), wide_ctas), s));
+    } else {
+      const int workers = std::min(h->P.num_envs, A.episodes);
+      CK(h->K->run(h->P, S, A, workers, s));
+    }
   }
   return 0;
 }
@@ -585,6 +601,13 @@ int bb_copy_env(bb_handle* dst, int dst_env, bb_handle* src, int src_env, void* 
   CK(cudaMemcpyAsync(D.in_off + (size_t)dst_env * (D.max_gens + 1), S.in_off + (size_t)src_env * (S.max_gens + 1),
                      sizeof(int) * (S.max_gens + 1), cudaMemcpyDeviceToDevice, s));
   CK(cudaMemcpyAsync(D.in_np + dst_env, S.in_np + src_env, sizeof(int), cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+int bb_set_wide(bb_handle* h, int mode) {
+  if (!h) return -1;
+  if (mode < -1 || mode > 1) return fail(h, "bb_set_wide: mode must be -1 (auto), 0 (off) or 1 (on)");
+  h->wide_mode = mode;
   return 0;
 }
 

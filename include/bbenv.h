@@ -183,6 +183,12 @@ int bb_run(bb_handle* h, int strategy, int episodes, int seed_base, const int32_
            int max_steps, double gamma, int compute_gb, bb_episode_stats* stats_dev, int32_t* trace_dev,
            int trace_episodes, int trace_cap, void* stream);
 
+/* bb_set_wide: which episode runner bb_run uses.  -1 (default): one warp per environment, except that capacities
+ * sized for long polynomials (max_poly_terms >= 256, e.g. cyclic-n) get one CTA per environment with the dividend in
+ * shared memory; 0: always one warp per environment; 1: always one CTA per environment (an error if 24 bytes x
+ * max_poly_terms exceed shared memory).  Both runners produce bit-identical episodes; this is a performance switch. */
+int bb_set_wide(bb_handle* h, int mode);
+
 /* bb_value: BuchbergerEnv::value(strategy, gamma) (buchberger.cpp:332-351) for every environment at once:
  * value_dev double[N] = discounted return of finishing the episode from the CURRENT state under `strategy`
  * (0.0 for an environment that is not running).  The environments are forked into a private arena; their own state

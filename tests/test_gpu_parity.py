@@ -433,3 +433,27 @@ def test_sharded_blocks_equal_one_run(torch_cuda):
         for f in ("steps", "additions", "trace_hash", "basis_hash", "gb_hash", "discounted_return", "rerolls"):
             assert np.array_equal(cat[f], whole[f]), (ws, f)
     assert sharding.summarize(whole)["finished"] == total
+
+
+@pytest.mark.parametrize("name,strategy", [("cyclic-5", "normal"), ("cyclic-6", "degree"), ("cyclic-6", "random"),
+                                           ("3-20-10-weighted", "degree")])
+def test_cta_per_environment_runner_equals_warp_runner(torch_cuda, name, strategy):
+    """bb_set_wide: the one-CTA-per-environment runner (bb_wide.cuh: dividend in shared memory, block-wide divisor
+    search and rank merge) and the one-warp-per-environment runner produce bit-identical episode records -- pair
+    sequence checksum, additions, final basis, reduced Groebner basis, discounted return -- and traffic counters."""
+    from deepgroebner_b200.buchberger import BuchbergerEngine
+    episodes = 12
+    eng = BuchbergerEngine(name, num_envs=episodes, **({} if name.startswith("cyclic") else dict(max_poly_terms=256)))
+    out = {}
+    for mode in (0, 1):
+        eng.set_wide(mode)
+        eng.counters(reset=True)
+        stats, trace = eng.run_episodes(strategy, episodes=episodes, seed_base=7, compute_gb=True, selection_seed=99,
+                                        trace_episodes=2, trace_cap=4096)
+        out[mode] = (stats, trace, eng.counters(reset=True))
+    (s0, t0, c0), (s1, t1, c1) = out[0], out[1]
+    assert (s0["status"] == 2).all() and (s1["status"] == 2).all()
+    for f in s0.dtype.names:
+        assert np.array_equal(s0[f], s1[f]), f
+    assert np.array_equal(t0, t1)
+    assert c0 == c1
