@@ -243,9 +243,9 @@ def gpu_arm(args):
     dev = torch.device("cuda", local)
 
     from deepgroebner_b200 import sharding
-    from deepgroebner_b200.ideals import BinomialSpec, parse_ideal_dist
+    from deepgroebner_b200.ideals import FixedIdealGenerator, parse_ideal_dist
     spec = parse_ideal_dist(DIST, 32003)
-    nvars = spec.n if isinstance(spec, BinomialSpec) else spec.nvars()
+    nvars = spec.nvars() if isinstance(spec, FixedIdealGenerator) else spec.n
     if SCALING == "weak":   # every rank runs its own EPISODES episodes, disjoint seeds
         ep_first, ep_local = rank * EPISODES, EPISODES
     else:                   # EPISODES in total, contiguous blocks (deepgroebner_b200/sharding.py)

@@ -4,9 +4,9 @@ Drop-in for the environment path of dylanpeifer/deepgroebner (BuchbergerEnv / Le
 vectorised over N episodes per GPU.  The CUDA library (libbbenv.so, C-ABI in include/bbenv.h) is required:
 there is no CPU fallback.  Importing this package does not load CUDA; constructing an environment does.
 """
-from .ideals import BinomialSpec, FixedIdealGenerator, cyclic, parse_ideal_dist  # noqa: F401
+from .ideals import BinomialSpec, FixedIdealGenerator, PolySpec, cyclic, parse_ideal_dist  # noqa: F401
 
-__all__ = ["BuchbergerEnv", "LeadMonomialsEnv", "BuchbergerEngine", "BuchbergerAgent", "BinomialSpec",
+__all__ = ["BuchbergerEnv", "LeadMonomialsEnv", "BuchbergerEngine", "BuchbergerAgent", "BinomialSpec", "PolySpec",
            "FixedIdealGenerator", "cyclic", "parse_ideal_dist"]
 
 

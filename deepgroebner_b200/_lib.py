@@ -54,9 +54,9 @@ STATS_DTYPE = [("steps", "<i4"), ("additions", "<i4"), ("zero_reductions", "<i4"
 
 EXPORTS = [
     "bb_abi_version", "bb_resident_envs", "bb_create", "bb_destroy", "bb_last_error", "bb_cols", "bb_num_envs", "bb_sm_count",
-    "bb_set_distribution", "bb_seed", "bb_set_ideals", "bb_reset", "bb_step", "bb_select", "bb_observe", "bb_pairs",
+    "bb_set_distribution", "bb_set_distribution_poly", "bb_seed", "bb_set_ideals", "bb_reset", "bb_step", "bb_select", "bb_observe", "bb_pairs",
     "bb_status", "bb_stats", "bb_run", "bb_download_basis", "bb_final_gb", "bb_counters_read", "bb_hash_item",
-    "bb_seed_selection", "bb_value", "bb_copy_env", "bb_set_auto_reset", "bb_set_wide", "bb_policy_pmlp", "bb_rollout",
+    "bb_seed_selection", "bb_value", "bb_copy_env", "bb_set_auto_reset", "bb_set_wide", "bb_set_selection_seed_stride", "bb_policy_pmlp", "bb_rollout",
 ]
 
 _lib = None
@@ -90,6 +90,8 @@ def load():
     lib.bb_resident_envs.argtypes = [i, i]
     lib.bb_set_distribution.restype = i
     lib.bb_set_distribution.argtypes = [vp, i, i, i, i, i, i]
+    lib.bb_set_distribution_poly.restype = i
+    lib.bb_set_distribution_poly.argtypes = [vp, i, i, C.c_double, i, i, i]
     lib.bb_seed.restype = i
     lib.bb_seed.argtypes = [vp, ip, i]
     lib.bb_seed_selection.restype = i
@@ -120,6 +122,8 @@ def load():
     lib.bb_set_auto_reset.argtypes = [vp, i]
     lib.bb_set_wide.restype = i
     lib.bb_set_wide.argtypes = [vp, i]
+    lib.bb_set_selection_seed_stride.restype = i
+    lib.bb_set_selection_seed_stride.argtypes = [vp, i]
     u64 = C.c_uint64
     lib.bb_policy_pmlp.restype = i
     lib.bb_policy_pmlp.argtypes = [vp, i, vp, vp, vp, vp, u64, u64, i, vp, vp, vp, i, vp]

@@ -13,11 +13,12 @@ import numpy as np
 import torch
 
 from . import _lib
-from .ideals import BinomialSpec, FixedIdealGenerator, parse_ideal_dist
+from .ideals import BinomialSpec, FixedIdealGenerator, PolySpec, parse_ideal_dist
 
 # arena capacities per environment: (max_basis, max_pairs, max_terms, max_poly_terms)
 CAPACITY_PRESETS = {
     "binomial": dict(max_basis=512, max_pairs=1024, max_terms=1536, max_poly_terms=64),
+    "poly": dict(max_basis=512, max_pairs=2048, max_terms=1 << 14, max_poly_terms=512),
     "general": dict(max_basis=2048, max_pairs=8192, max_terms=1 << 18, max_poly_terms=2048),
 }
 
@@ -53,18 +54,24 @@ class BuchbergerEngine:
             raise ValueError("device must be a CUDA device")
         self._ctor = dict(ideal_dist=ideal_dist, elimination=elimination, rewards=rewards, sort_input=sort_input,
                           sort_reducers=sort_reducers, k=k, device=device, prime=prime, capacity=capacity, **caps)
-        self.spec = ideal_dist if isinstance(ideal_dist, (BinomialSpec, FixedIdealGenerator)) \
+        self.spec = ideal_dist if isinstance(ideal_dist, (BinomialSpec, PolySpec, FixedIdealGenerator)) \
             else parse_ideal_dist(ideal_dist, prime)
-        self.n = self.spec.n if isinstance(self.spec, BinomialSpec) else self.spec.nvars()
+        self.n = self.spec.n if isinstance(self.spec, (BinomialSpec, PolySpec)) else self.spec.nvars()
         self.k, self.num_envs, self.prime = int(k), int(num_envs), int(prime)
         self.elimination, self.rewards = elimination, rewards
-        preset = dict(CAPACITY_PRESETS[capacity or ("binomial" if isinstance(self.spec, BinomialSpec) else "general")])
+        default = {BinomialSpec: "binomial", PolySpec: "poly"}.get(type(self.spec), "general")
+        preset = dict(CAPACITY_PRESETS[capacity or default])
+        gen_caps = {k_: caps.pop(k_) for k_ in ("max_gens", "max_gen_terms") if k_ in caps}
         preset.update(caps)
         if isinstance(self.spec, BinomialSpec):
             max_gens, max_gen_terms = self.spec.s, 2 * self.spec.s
+        elif isinstance(self.spec, PolySpec):
+            max_gens, max_gen_terms = self.spec.s, self.spec.max_gen_terms()
         else:
             max_gens = len(self.spec.F)
             max_gen_terms = sum(len(f) for f in self.spec.F)
+        max_gens = max(max_gens, int(gen_caps.get("max_gens", 0)))   # room for larger ideals staged later (set_ideals)
+        max_gen_terms = max(max_gen_terms, int(gen_caps.get("max_gen_terms", 0)))
         cfg = _lib.BBConfig(
             abi_version=_lib.BB_ABI_VERSION, device=self.device.index or 0, nvars=self.n, k=self.k, prime=self.prime,
             elimination=_lib.ELIMINATION[elimination], rewards=_lib.REWARDS[rewards], sort_input=int(sort_input),
@@ -82,6 +89,10 @@ class BuchbergerEngine:
             s = self.spec
             self._ck(self.lib.bb_set_distribution(self.h, s.d, s.s, _lib.DISTRIBUTION[s.dist], int(s.constants),
                                                   int(s.homogeneous), int(s.pure)), "bb_set_distribution")
+        elif isinstance(self.spec, PolySpec):
+            s = self.spec
+            self._ck(self.lib.bb_set_distribution_poly(self.h, s.d, s.s, float(s.lam), _lib.DISTRIBUTION[s.dist],
+                                                       int(s.constants), int(s.homogeneous)), "bb_set_distribution_poly")
         else:
             self.set_ideals([self.spec.F] * self.num_envs)
 
@@ -240,6 +251,11 @@ class BuchbergerEngine:
         """Episode runner of run_episodes (bb_set_wide): -1 auto, 0 one warp per environment, 1 one CTA per
         environment (long polynomials).  Results are identical; only speed differs."""
         self._ck(self.lib.bb_set_wide(self.h, int(mode)), "bb_set_wide")
+
+    def set_selection_seed_stride(self, stride=1):
+        """run_episodes seeds episode e's 'random' selection stream with selection_seed + e * stride
+        (0: one seed for every episode, as scripts/make_strat.cpp does)."""
+        self._ck(self.lib.bb_set_selection_seed_stride(self.h, int(stride)), "bb_set_selection_seed_stride")
 
     def policy(self, net, counter=0, greedy=False, return_all=False, pmax=None):
         """PMLP head + categorical sample on the current states (bb_policy_pmlp).  net: rollout.PairsPolicy.

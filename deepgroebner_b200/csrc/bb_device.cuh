@@ -56,8 +56,10 @@ struct GHead {
   uint32_t invlc, c1, sug, off, len;
 };
 
-struct BBDist {           // RandomBinomialIdealGenerator parameters (ideals.cpp:157-201)
+struct BBDist {           // RandomBinomialIdealGenerator / RandomIdealGenerator parameters (ideals.cpp:157-231)
   int enabled, d, s, homogeneous, pure, ncp;
+  int kind;               // 0: binomials (ideals.cpp:168-201); 1: Poisson-length polynomials (ideals.cpp:214-231)
+  double lm_thr;          // kind 1: exp(-lam), std::poisson_distribution::param_type::_M_lm_thr for mean < 12
   const double* cp;       // [d+1] cumulative degree probabilities (libstdc++ discrete_distribution::_M_cp)
   const uint64_t* basis;  // packed monomials of degree 0..d, lex-descending within a degree (ideals.cpp:39-64)
   const int* basis_off;   // [d+2]
@@ -838,6 +840,56 @@ __device__ __forceinline__ bool gen_binomial_ideal(const BBParams& P, int slot, 
   return true;
 }
 
+// RandomIdealGenerator::next (ideals.cpp:214-231), executed by lane 0 into the slot's staging area: per generator
+// terms = 2 + Poisson(lam) draws of (coefficient, monomial of the current degree) summed into f (equal monomials add,
+// a zero sum drops out: Polynomial operator+, polynomials.cpp:148-177), a fresh degree after every term unless homog,
+// then f / LC(f).  libstdc++'s poisson_distribution for mean < 12 multiplies canonicals until the product falls to
+// exp(-mean) (bits/random.tcc, the branch without _GLIBCXX_USE_C99_MATH_TR1's rejection method).
+// Returns 1, 0 if a polynomial cancelled to zero (f.LC() of an empty polynomial is undefined behaviour in the
+// reference), -1 if the ideal does not fit max_gen_terms.
+__device__ __forceinline__ int gen_random_ideal(const BBParams& P, int slot, uint32_t& x) {
+  const BBDist& D = P.dist;
+  const BBField F = P.F;
+  uint64_t* ik = P.in_key + (size_t)slot * P.max_gen_terms;
+  uint32_t* ic = P.in_coef + (size_t)slot * P.max_gen_terms;
+  int* io = P.in_off + (size_t)slot * (P.max_gens + 1);
+  io[0] = 0;
+  int nt = 0;
+  for (int i = 0; i < D.s; i++) {
+    int cnt = 0;
+    double prod = 1.0;
+    do { prod = __dmul_rn(prod, rng_canonical(x)); cnt++; } while (prod > D.lm_thr);
+    const int terms = 2 + (cnt - 1);
+    int d = rng_degree(D, x);
+    uint64_t* fk = ik + nt; uint32_t* fc = ic + nt;
+    int len = 0;
+    for (int j = 0; j < terms; j++) {
+      const uint32_t c = (uint32_t)rng_uniform(x, 1, (int)F.p - 1);
+      const int o = D.basis_off[d], nb = D.basis_off[d + 1] - o;
+      const uint64_t m = D.basis[o + rng_uniform(x, 0, nb - 1)];
+      int pos = 0;
+      while (pos < len && fk[pos] < m) pos++;
+      if (pos < len && fk[pos] == m) {
+        const uint32_t sum = bbf_addmod(F, fc[pos], c);
+        if (sum) fc[pos] = sum;
+        else { for (int t = pos; t + 1 < len; t++) { fk[t] = fk[t + 1]; fc[t] = fc[t + 1]; } len--; }
+      } else {
+        if (nt + len + 1 > P.max_gen_terms) return -1;
+        for (int t = len; t > pos; t--) { fk[t] = fk[t - 1]; fc[t] = fc[t - 1]; }
+        fk[pos] = m; fc[pos] = c; len++;
+      }
+      if (!D.homogeneous) d = rng_degree(D, x);
+    }
+    if (len == 0) return 0;
+    const uint32_t inv = P.invtab[fc[0]];
+    for (int t = 0; t < len; t++) fc[t] = bbf_mulmod(F, fc[t], inv);
+    nt += len;
+    io[i + 1] = nt;
+  }
+  P.in_np[slot] = D.s;
+  return 1;
+}
+
 // ---------------------------------------------------------------------------------------------------- reset
 // BuchbergerEnv::reset (buchberger.cpp:299-315) from staged ideal `src_slot` into slot `slot`: generators are added
 // one by one through update() and into the reducer list.  sort_input orders them by ascending lead monomial first
@@ -900,10 +952,10 @@ __device__ __noinline__ void warp_reset_slot(const BBParams& P, int slot, int fi
   if (P.dist.enabled) {
     for (;;) {
       int ok = 1;
-      if (lane == 0) ok = gen_binomial_ideal(P, slot, rng) ? 1 : 0;
+      if (lane == 0) ok = P.dist.kind ? gen_random_ideal(P, slot, rng) : (gen_binomial_ideal(P, slot, rng) ? 1 : 0);
       ok = __shfl_sync(BB_FULL, ok, 0);
       __syncwarp();
-      if (!ok) { e.nG = e.nP = e.nT = 0; e.status = BB_STATUS_EMPTY; break; }
+      if (ok <= 0) { e.nG = e.nP = e.nT = 0; e.status = ok ? BB_STATUS_OVERFLOW_TERMS : BB_STATUS_EMPTY; break; }
       warp_load_ideal<NV>(P, slot, e, ct);
       if (e.status != BB_STATUS_DONE) break;
       rerolls++;

@@ -24,7 +24,8 @@
 
 struct BBRunArgs {
   int strategy, episodes, seed_base;
-  int sel_seed_base;  // Random selection: episode e draws choice() from minstd_rand0 seeded sel_seed_base + e
+  int sel_seed_base;  // Random selection: episode e draws choice() from minstd_rand0 seeded sel_seed_base + e * sel_seed_stride
+  int sel_seed_stride;
   int ep_base;      // first episode of this batch: episode ids are ep_base .. ep_base + episodes - 1
   int nstaged;      // fixed ideals: number of staged ideals (episode e replays ideal e mod nstaged)
   const int* seeds;
@@ -326,7 +327,7 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_run(const __grid_
       }
       const int g_start = e.nG;
       int steps = 0, adds = 0;
-      if (lane == 0) { acc.th = 0ull; acc.ret = 0.0; acc.disc = 1.0; acc.sel_rng = rng_seed(A.sel_seed_base + ep); }
+      if (lane == 0) { acc.th = 0ull; acc.ret = 0.0; acc.disc = 1.0; acc.sel_rng = rng_seed(A.sel_seed_base + ep * A.sel_seed_stride); }
       __syncwarp();
       run_episode<NV>(P, e, A.strategy, A.max_steps, A.gamma, acc, ct, steps, adds,
                       (A.trace && ep < A.trace_eps) ? reinterpret_cast<int4*>(A.trace) + (size_t)ep * A.trace_cap : nullptr,
@@ -418,7 +419,7 @@ __global__ void __launch_bounds__(BBW_THREADS, BBW_MIN_CTAS) k_run_wide(const __
     }
     const int g_start = e.nG;
     int steps = 0, adds = 0;
-    if (tid == 0) { acc.th = 0ull; acc.ret = 0.0; acc.disc = 1.0; acc.sel_rng = rng_seed(A.sel_seed_base + ep); }
+    if (tid == 0) { acc.th = 0ull; acc.ret = 0.0; acc.disc = 1.0; acc.sel_rng = rng_seed(A.sel_seed_base + ep * A.sel_seed_stride); }
     __syncthreads();
     int4* trace = (A.trace && ep < A.trace_eps) ? reinterpret_cast<int4*>(A.trace) + (size_t)ep * A.trace_cap : nullptr;
     while (e.status == BB_STATUS_RUNNING && (A.max_steps == 0 || steps < A.max_steps)) {

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -96,6 +97,7 @@ struct bb_handle {
   int fork_cap;
   std::vector<void*> fork_allocs;
   unsigned char* fork_arena; BBEnvState* fork_st;
+  int sel_seed_stride;   // bb_run: episode e's Random-selection stream is seeded sel_seed_base + e * stride (default 1)
   int wide_mode;   // bb_run: -1 = one CTA per environment when the capacities ask for long polynomials, 0 = never, 1 = always
   // host mirrors of the distribution tables
   std::vector<double> cp;
@@ -204,6 +206,7 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
   h->stage_cap = 0; h->stage_arena = nullptr; h->stage_st = nullptr;
   h->fork_cap = 0; h->fork_arena = nullptr; h->fork_st = nullptr;
   h->wide_mode = -1;
+  h->sel_seed_stride = 1;
   auto bail = [&](int code) { g_create_err = h->err; bb_destroy(h); return code; };
 #define CKC(call)                                                                                     \
   do {                                                                                                \
@@ -274,11 +277,16 @@ static void basis_rec(const BBLayout& L, int n, int var, int left, int* e, std::
   for (int x = left; x >= 0; x--) { e[var] = x; basis_rec(L, n, var + 1, left - x, e, out); }
 }
 
-int bb_set_distribution(bb_handle* h, int d, int s, int dist, int constants, int homogeneous, int pure) {
+// kind 0: RandomBinomialIdealGenerator (ideals.cpp:157-201); kind 1: RandomIdealGenerator (ideals.cpp:204-231)
+static int set_distribution_impl(bb_handle* h, int kind, int d, int s, double lam, int dist, int constants, int homogeneous,
+                                 int pure) {
   if (!h) return -1;
   BBParams& P = h->P;
   if (d < 0 || s < 1) return fail(h, "bb_set_distribution: need d >= 0 and s >= 1");
   if (s > P.max_gens || 2 * s > P.max_gen_terms) return fail(h, "bb_set_distribution: s exceeds max_gens/max_gen_terms");
+  if (kind == 1 && !(lam >= 0.0 && lam < 12.0))
+    return fail(h, "bb_set_distribution_poly: lam must be in [0, 12) (libstdc++ switches to a rejection sampler at mean >= 12, "
+                   "which is not restated on device)");
   if ((unsigned)dist > 2u) return fail(h, "bb_set_distribution: bad dist");
   if ((unsigned)d > h->L.emax || (unsigned)d > h->L.dmax) return fail(h, "bb_set_distribution: degree does not fit the packed layout");
   CK(cudaSetDevice(h->cfg.device));
@@ -317,7 +325,15 @@ int bb_set_distribution(bb_handle* h, int d, int s, int dist, int constants, int
   CK(cudaMemcpy(d_off, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice));
   P.dist.enabled = 1; P.dist.d = d; P.dist.s = s; P.dist.homogeneous = homogeneous ? 1 : 0; P.dist.pure = pure ? 1 : 0;
   P.dist.ncp = (int)cp.size(); P.dist.cp = d_cp; P.dist.basis = d_basis; P.dist.basis_off = d_off;
+  P.dist.kind = kind; P.dist.lm_thr = kind == 1 ? std::exp(-lam) : 0.0;
   return 0;
+}
+
+int bb_set_distribution(bb_handle* h, int d, int s, int dist, int constants, int homogeneous, int pure) {
+  return set_distribution_impl(h, 0, d, s, 0.0, dist, constants, homogeneous, pure);
+}
+int bb_set_distribution_poly(bb_handle* h, int d, int s, double lam, int dist, int constants, int homogeneous) {
+  return set_distribution_impl(h, 1, d, s, lam, dist, constants, homogeneous, 0);
 }
 
 static int seed_impl(bb_handle* h, const int32_t* seeds, int base, int selection) {
@@ -500,7 +516,7 @@ int bb_run(bb_handle* h, int strategy, int episodes, int seed_base, const int32_
   for (int base = 0; base < episodes; base += BB_RUN_BATCH) {
     BBRunArgs A;
     A.strategy = strategy; A.episodes = std::min(BB_RUN_BATCH, episodes - base); A.seed_base = seed_base;
-    A.sel_seed_base = sel_seed_base;
+    A.sel_seed_base = sel_seed_base; A.sel_seed_stride = h->sel_seed_stride;
     A.ep_base = base; A.nstaged = h->P.num_envs;
     A.seeds = seeds_dev; A.max_steps = max_steps; A.gamma = gamma; A.compute_gb = compute_gb; A.out = stats_dev;
     A.trace = trace_dev; A.trace_eps = trace_dev ? trace_episodes : 0; A.trace_cap = trace_cap; A.queue = h->d_queue;
@@ -608,6 +624,12 @@ int bb_set_wide(bb_handle* h, int mode) {
   if (!h) return -1;
   if (mode < -1 || mode > 1) return fail(h, "bb_set_wide: mode must be -1 (auto), 0 (off) or 1 (on)");
   h->wide_mode = mode;
+  return 0;
+}
+
+int bb_set_selection_seed_stride(bb_handle* h, int stride) {
+  if (!h) return -1;
+  h->sel_seed_stride = stride;
   return 0;
 }
 

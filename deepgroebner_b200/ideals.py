@@ -2,8 +2,9 @@
 
 Mirrors what the environment constructor needs from the reference's ``parse_ideal_dist``
 (deepgroebner/ideals.cpp:103-143, deepgroebner/ideals.py:112-139) and ``FixedIdealGenerator``
-(ideals.h:116-138, ideals.py:142-166).  Random binomial ideals are NOT generated here: the spec is handed to the
-CUDA library, which draws them on device from per-environment minstd_rand0 streams (bb_set_distribution).
+(ideals.h:116-138, ideals.py:142-166).  Random ideals are NOT generated here: the spec is handed to the CUDA
+library, which draws them on device from per-environment minstd_rand0 streams (bb_set_distribution for binomials,
+bb_set_distribution_poly for Poisson-length polynomials).
 """
 from dataclasses import dataclass, field
 from typing import List, Sequence, Tuple
@@ -21,6 +22,24 @@ class BinomialSpec:
     constants: bool = False
     homogeneous: bool = False
     pure: bool = False
+
+
+@dataclass
+class PolySpec:
+    """'n-d-s-lam-{uniform,weighted,maximum}[-consts][-homog]' -> RandomIdealGenerator (ideals.cpp:204-231):
+    s monic polynomials of 2 + Poisson(lam) random terms each."""
+    n: int
+    d: int
+    s: int
+    lam: float
+    dist: str
+    constants: bool = False
+    homogeneous: bool = False
+
+    def max_gen_terms(self):
+        """Term capacity of one staged ideal: every polynomial at 2 + (lam + 10 sqrt(lam) + 10) terms -- a Poisson
+        tail of < 1e-9 per polynomial; an ideal beyond it is flagged BB_STATUS_OVERFLOW_TERMS, never truncated."""
+        return self.s * (2 + int(self.lam + 10.0 * self.lam ** 0.5 + 10.0))
 
 
 @dataclass
@@ -67,7 +86,6 @@ def parse_ideal_dist(ideal_dist: str, prime: int = 32003):
         return BinomialSpec(int(args[0]), int(args[1]), int(args[2]), args[3], "consts" in args, "homog" in args,
                             "pure" in args)
     if len(args) >= 5 and args[4] in ("uniform", "weighted", "maximum"):
-        raise NotImplementedError(
-            "'n-d-s-lam-dist' (RandomIdealGenerator, Poisson-length polynomials, ideals.cpp:204-231) is not on the "
-            "device generator yet; pass explicit ideals through FixedIdealGenerator / set_ideals")
+        return PolySpec(int(args[0]), int(args[1]), int(args[2]), float(args[3]), args[4], "consts" in args,
+                        "homog" in args)
     raise ValueError("cannot parse ideal_dist %r" % ideal_dist)

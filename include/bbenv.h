@@ -138,6 +138,11 @@ int bb_resident_envs(int device, int nvars);
  * bb_seed: stream[e] <- seeds[e] for every environment (BuchbergerEnv::seed, buchberger.h:189); seeds == NULL
  * seeds environment e with base + e. */
 int bb_set_distribution(bb_handle* h, int d, int s, int dist, int constants, int homogeneous, int pure);
+/* bb_set_distribution_poly: the same for "n-d-s-lam-{uniform,weighted,maximum}[-consts][-homog]", RandomIdealGenerator
+ * (ideals.cpp:204-231): s monic polynomials of 2 + Poisson(lam) random terms each, drawn on device with libstdc++'s
+ * poisson_distribution stream (mean < 12 branch; lam >= 12 is refused).  cfg.max_gen_terms bounds the terms of one
+ * ideal: an ideal that does not fit leaves its environment in BB_STATUS_OVERFLOW_TERMS. */
+int bb_set_distribution_poly(bb_handle* h, int d, int s, double lam, int dist, int constants, int homogeneous);
 int bb_seed(bb_handle* h, const int32_t* seeds, int base);
 /* bb_seed_selection: the same for the per-environment stream BB_SELECT_RANDOM draws from in bb_select (the `seed`
  * argument of buchberger(), buchberger.cpp:190-197).  Both streams are seeded with base + e at bb_create. */
@@ -182,6 +187,11 @@ int bb_stats(bb_handle* h, bb_episode_stats* stats_dev, void* stream);
 int bb_run(bb_handle* h, int strategy, int episodes, int seed_base, const int32_t* seeds_dev, int sel_seed_base,
            int max_steps, double gamma, int compute_gb, bb_episode_stats* stats_dev, int32_t* trace_dev,
            int trace_episodes, int trace_cap, void* stream);
+
+/* bb_set_selection_seed_stride: bb_run seeds episode e's BB_SELECT_RANDOM stream with sel_seed_base + e * stride.
+ * Default 1 (every episode its own stream); 0 gives every episode the SAME seed, which is what scripts/make_strat.cpp:66
+ * does (one `seed` argument for every ideal of the file). */
+int bb_set_selection_seed_stride(bb_handle* h, int stride);
 
 /* bb_set_wide: which episode runner bb_run uses.  -1 (default): one warp per environment, except that capacities
  * sized for long polynomials (max_poly_terms >= 256, e.g. cyclic-n) get one CTA per environment with the dividend in

@@ -453,6 +453,9 @@ def build(ref=True):
     subprocess.run(["make", "-s", "-C", HERE, "port"] + (["ref"] if ref else []), check=True)
 
 
+REF_MAKE_STRAT = os.path.join(HERE, "_ref", "make_strat")   # the reference's scripts/make_strat.cpp, unmodified
+
+
 def load_port():
     if not os.path.exists(PORT_SO):
         build(ref=False)

@@ -38,3 +38,9 @@ def run_on_oracle(orc, rec):
     else:
         trace = env.run(actions=rec["actions"])
     return G0, P0, np.asarray(trace), env.final_gb(), env.basis(), env
+
+
+def best_oracle():
+    """The unmodified reference when oracle/_ref is built, else the C restatement."""
+    from oracle import oracle as O
+    return O.load_ref() if O.have_ref() else O.load_port()

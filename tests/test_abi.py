@@ -64,8 +64,9 @@ def test_parse_ideal_dist_grammar():
     assert (s.n, s.d, s.s, s.dist, s.constants, s.homogeneous, s.pure) == (5, 5, 10, "uniform", True, True, True)
     g = parse_ideal_dist("cyclic-4")
     assert isinstance(g, FixedIdealGenerator) and g.nvars() == 4 and len(g.F) == 4
-    with pytest.raises(NotImplementedError):
-        parse_ideal_dist("3-20-10-0.5-uniform")
+    q = parse_ideal_dist("3-20-10-0.5-uniform-homog")   # RandomIdealGenerator, ideals.cpp:131-141
+    assert (q.n, q.d, q.s, q.lam, q.dist, q.constants, q.homogeneous) == (3, 20, 10, 0.5, "uniform", False, True)
+    assert q.max_gen_terms() >= 10 * (2 + 8)
     with pytest.raises(ValueError):
         parse_ideal_dist("banana")
 

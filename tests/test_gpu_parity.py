@@ -35,16 +35,11 @@ def test_step_api_replays_golden_episode(torch_cuda, rec):
     """reset()/select()/step() one call at a time, against episodes recorded from the unmodified reference."""
     from deepgroebner_b200.buchberger import BuchbergerEngine
     from deepgroebner_b200.ideals import FixedIdealGenerator
-    if rec.get("selection") == "sugar":
-        pytest.skip("sugar selection needs per-polynomial sugar (SURVEY 8(f) row 2)")
     n = rec["nvars"]
     ideal = trim(expand(rec["ideal"]), n)
     kw = dict(elimination=rec["elimination"], rewards=rec["rewards"], sort_input=rec["sort_input"],
               sort_reducers=rec["sort_reducers"], k=1, num_envs=1)
-    try:
-        eng = BuchbergerEngine(rec["dist"], **kw)
-    except NotImplementedError:  # Poisson-length generator: feed the recorded ideal explicitly
-        eng = BuchbergerEngine(FixedIdealGenerator(ideal, n), capacity="binomial", **kw)
+    eng = BuchbergerEngine(rec["dist"], **kw)   # every recorded distribution is drawn by the device generator
     eng.seed(rec["seed"])
     eng.reset()
     assert eng.basis(0) == ideal
@@ -95,6 +90,9 @@ def test_lead_monomials_env_matrices(torch_cuda, rec):
     ("3-20-10-weighted", "degree", 1024), ("3-20-10-weighted", "first", 512), ("3-20-10-weighted", "normal", 512),
     ("3-20-10-uniform", "degree", 256), ("5-5-10-uniform", "degree", 256), ("5-5-10-uniform", "normal", 128),
     ("4-6-8-maximum-homog", "first", 128), ("3-12-6-weighted-pure", "normal", 128), ("2-9-5-uniform-consts", "degree", 128),
+    # RandomIdealGenerator (Poisson-length polynomials, ideals.cpp:204-231) drawn on device
+    ("3-6-5-0.5-uniform", "degree", 128), ("4-4-4-1.5-weighted-homog", "normal", 64), ("2-8-6-3.0-maximum-consts", "first", 64),
+    ("3-5-4-0.5-weighted", "sugar", 64),
 ])
 def test_run_episodes_bit_exact_vs_oracle(torch_cuda, dist, strategy, episodes):
     """bb_run (persistent kernel, on-device generator + selection): every episode's pair sequence, rewards, length,
