@@ -21,8 +21,18 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# stdout carries exactly one JSON line: NCCL's version / debug banner (NCCL_DEBUG=VERSION|INFO) goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# stdout carries exactly ONE JSON line.  Libraries write to file descriptor 1 behind Python's back (NCCL prints its
+# version banner there under torchrun), so fd 1 is pointed at stderr for the whole run and the JSON line goes to a
+# private duplicate of the original stdout.
+_JSON_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+sys.stdout = sys.stderr
+
+
+def emit(line):
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
 
 DIST = "3-20-10-weighted"
 STRATEGY = "degree"
@@ -230,7 +240,7 @@ def reference_arm(args):
                                       else STRATEGY + " select + step")},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def gpu_arm(args):
@@ -388,7 +398,7 @@ def gpu_arm(args):
                 "value": r["steps"] / r["seconds"], "unit": UNIT, "cores": threads, "kind": kind,
                 "sample": "%d episodes (seeds 0..%d) of the same workload x %d passes, one reference BuchbergerEnv per "
                           "host thread, %.1f s" % (count, count - 1, r.get("reps", 1), r["seconds"])}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -492,7 +502,7 @@ def rollout_arm(args):
                 line["cpu_baseline"] = {"value": r["steps"] / r["seconds"], "unit": UNIT, "cores": threads, "kind": kind,
                                         "sample": "scripts/random_episodes.cpp loop (uniform-random actions, no network) on "
                                                   "LeadMonomialsEnv(k=2), %d episodes, %.1f s" % (2000 * threads, r["seconds"])}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

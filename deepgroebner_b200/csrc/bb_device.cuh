@@ -435,7 +435,80 @@ __device__ __noinline__ long long warp_add_basis(const BBParams& P, unsigned cha
   uint64_t* plcm = reinterpret_cast<uint64_t*>(base + P.o_plcm);
   uint32_t* pairs = reinterpret_cast<uint32_t*>(base + P.o_pairs);
   int emitted = 0;
-  if (P.elimination == BB_ELIM_GEBAUERMOELLER) {
+  if (P.elimination == BB_ELIM_GEBAUERMOELLER && m <= 64) {
+    // The common case (profiles/r01_v6: the sweep loop below was the largest single consumer of issue slots): with at
+    // most 64 basis elements every lane keeps L_lane and L_{lane+32} in registers, so the peeling needs no memory at
+    // all -- one candidate reduction and one two-register sweep per kept lcm.  Same algorithm as the general path.
+    const int i0 = lane, i1 = lane + 32;
+    const bool in0 = i0 < m, in1 = i1 < m;
+    uint64_t v0 = 0ull, v1 = 0ull;
+    bool cp0 = false, cp1 = false, ovf = false;
+    if (in0) {
+      const uint64_t l = lm[i0], le = K::lcm_exps(l, fk);
+      const uint32_t dg = K::sum_fields(le);
+      ovf |= dg > K::dmax;
+      v0 = le | ((uint64_t)(K::dmax - dg) << K::dshift);
+      cp0 = K::coprime(l, fk);
+      lscr[i0] = v0;
+    }
+    if (in1) {
+      const uint64_t l = lm[i1], le = K::lcm_exps(l, fk);
+      const uint32_t dg = K::sum_fields(le);
+      ovf |= dg > K::dmax;
+      v1 = le | ((uint64_t)(K::dmax - dg) << K::dshift);
+      cp1 = K::coprime(l, fk);
+      lscr[i1] = v1;
+    }
+    if (__any_sync(BB_FULL, ovf)) return -3;
+    __syncwarp();
+    const uint64_t fe = fk & K::ex_mask;
+    int w = 0;
+#pragma unroll 1
+    for (int b0 = 0; b0 < nP; b0 += 32) {   // step (1): old pairs, as in the general path
+      const int idx = b0 + lane;
+      const bool valid = idx < nP;
+      uint32_t pr = 0u; uint64_t pl = 0ull;
+      bool keep = false;
+      if (valid) {
+        pr = pairs[idx]; pl = plcm[idx];
+        const uint64_t l = pl & K::ex_mask;
+        const bool drop = K::divides(fe, l) && l != (lscr[pr & 0xffffu] & K::ex_mask) && l != (lscr[pr >> 16] & K::ex_mask);
+        keep = !drop;
+      }
+      const uint32_t km = __ballot_sync(BB_FULL, keep);
+      if (keep) {
+        const int pos = w + __popc(km & ltm);
+        pairs[pos] = pr; plcm[pos] = pl;
+      }
+      w += __popc(km);
+      __syncwarp();
+    }
+    nP = w;
+    const uint64_t e0 = v0 & K::ex_mask, e1 = v1 & K::ex_mask;
+    bool u0 = in0, u1 = in1, k0 = false, k1 = false;   // undecided / chosen for emission
+    for (;;) {
+      const bool p1 = u1 && (!u0 || v1 > v0);          // this lane's larger undecided key; the lower index on a tie
+      const uint64_t bk = p1 ? v1 : (u0 ? v0 : 0ull);
+      if (!__any_sync(BB_FULL, u0 || u1)) break;
+      const uint32_t hi = __reduce_max_sync(BB_FULL, (uint32_t)(bk >> 32));
+      const bool c1 = (u0 || u1) && (uint32_t)(bk >> 32) == hi;
+      const uint32_t lo = __reduce_max_sync(BB_FULL, c1 ? (uint32_t)bk : 0u);
+      const bool c2 = c1 && (uint32_t)bk == lo;
+      const int kidx = (int)__reduce_min_sync(BB_FULL, c2 ? (uint32_t)(p1 ? i1 : i0) : 0x7fffffffu);
+      const uint64_t kk = (((uint64_t)hi << 32) | lo) & K::ex_mask;
+      const bool d0 = u0 && ((((e0 | K::ge_mask) - kk) & K::ge_mask) == K::ge_mask);   // multiples of the killer, itself included
+      const bool d1 = u1 && ((((e1 | K::ge_mask) - kk) & K::ge_mask) == K::ge_mask);
+      const bool grp_cop = __any_sync(BB_FULL, (d0 && e0 == kk && cp0) || (d1 && e1 == kk && cp1));
+      u0 = u0 && !d0; u1 = u1 && !d1;
+      if (!grp_cop) { k0 = k0 || kidx == i0; k1 = k1 || kidx == i1; }
+    }
+    const uint32_t km0 = __ballot_sync(BB_FULL, k0), km1 = __ballot_sync(BB_FULL, k1);
+    const int cnt0 = __popc(km0), cnt1 = __popc(km1);
+    if (nP + cnt0 + cnt1 > P.max_pairs) return -1;
+    if (k0) { const int pos = nP + __popc(km0 & ltm); pairs[pos] = ((uint32_t)m << 16) | (uint32_t)i0; plcm[pos] = v0; }
+    if (k1) { const int pos = nP + cnt0 + __popc(km1 & ltm); pairs[pos] = ((uint32_t)m << 16) | (uint32_t)i1; plcm[pos] = v1; }
+    nP += cnt0 + cnt1; emitted = cnt0 + cnt1;
+  } else if (P.elimination == BB_ELIM_GEBAUERMOELLER) {
     // lscr[i] = key of L_i = lcm(LM_i, LM f), for every basis element (the old-pair filter gathers from it)
     bool ovf = false;  // deg(L_i) must fit the degree field: bit 63 is a tag below, never a silently wrapped degree
 #pragma unroll 1
@@ -546,7 +619,18 @@ __device__ __noinline__ long long warp_add_basis(const BBParams& P, unsigned cha
   uint64_t* rlm = reinterpret_cast<uint64_t*>(base + P.o_rlm);
   uint32_t* ridx = reinterpret_cast<uint32_t*>(base + P.o_ridx);
   int pos = m;
-  if (P.sort_reducers) {
+  if (P.sort_reducers && m <= 64) {   // both halves of the list in registers: count, then shift by one, no read-after-write hazard
+    const int i0 = lane, i1 = lane + 32;
+    uint64_t r0 = 0ull, r1 = 0ull; uint32_t x0 = 0u, x1 = 0u;
+    if (i0 < m) { r0 = rlm[i0]; x0 = ridx[i0]; }
+    if (i1 < m) { r1 = rlm[i1]; x1 = ridx[i1]; }
+    // reducers with LM <= new LM  <=>  key >= new key; the list is sorted, so they are a prefix
+    pos = __popc(__ballot_sync(BB_FULL, i0 < m && r0 >= fk)) + __popc(__ballot_sync(BB_FULL, i1 < m && r1 >= fk));
+    __syncwarp();
+    if (i0 < m && i0 >= pos) { rlm[i0 + 1] = r0; ridx[i0 + 1] = x0; }
+    if (i1 < m && i1 >= pos) { rlm[i1 + 1] = r1; ridx[i1 + 1] = x1; }
+    __syncwarp();
+  } else if (P.sort_reducers) {
     int cnt = 0;  // reducers with LM <= new LM  <=>  key >= new key
 #pragma unroll 1
     for (int b0 = 0; b0 < m; b0 += 32) {
