@@ -974,6 +974,56 @@ __device__ __forceinline__ int gen_random_ideal(const BBParams& P, int slot, uin
   return 1;
 }
 
+// The same generator with one lane per generator.  minstd_rand0 is a pure multiplicative congruence, so the state
+// before generator g is a^(g * draws_per_generator) * x provided every earlier generator consumed the nominal number
+// of draws (1 coefficient + 2 per degree + 1 per monomial pick).  It does unless a uniform_int draw was rejected
+// (p < 1e-5) or the two monomials coincided (p ~ 0.2 %): every lane checks that its own state advanced by exactly the
+// nominal power, and one deviation anywhere sends the whole ideal back to the serial restatement above.  x must be
+// warp-uniform; returns false without touching it when the serial path has to run.
+__device__ __forceinline__ uint32_t rng_mulmod(uint32_t a, uint32_t b) {
+  const unsigned long long pr = (unsigned long long)a * b;              // < 2^62
+  unsigned long long r = (pr & 0x7fffffffULL) + (pr >> 31);             // 2^31 == 1 (mod 2^31 - 1);  < 2^32
+  uint32_t q = (uint32_t)(r & 0x7fffffffULL) + (uint32_t)(r >> 31);     // <= 2^31
+  if (q >= 2147483647u) q -= 2147483647u;
+  return q;
+}
+__device__ __forceinline__ bool gen_binomial_ideal_warp(const BBParams& P, int slot, uint32_t& x) {
+  const BBDist& D = P.dist;
+  if (D.s > 32) return false;
+  const int lane = bb_lane();
+  const int nominal = (D.pure ? 0 : 1) + (D.ncp < 2 ? 0 : (D.homogeneous ? 2 : 4)) + 2;
+  uint32_t an = 1u;                                   // a^nominal
+  for (int k = 0; k < nominal; k++) rng_next(an);
+  uint32_t mult = 1u, sq = an;                        // a^(nominal * lane)
+  for (int e = lane; e; e >>= 1) { if (e & 1) mult = rng_mulmod(mult, sq); sq = rng_mulmod(sq, sq); }
+  uint32_t y = rng_mulmod(x, mult);
+  bool fine = true;
+  uint64_t hi = 0ull, lo = 0ull; uint32_t c = 0u;
+  if (lane < D.s) {
+    const uint32_t expect = rng_mulmod(y, an);
+    c = D.pure ? (P.F.p - 1u) : (uint32_t)rng_uniform(y, 1, (int)P.F.p - 1);
+    int d1, d2;
+    if (D.homogeneous) d1 = d2 = rng_degree(D, y);
+    else { d1 = rng_degree(D, y); d2 = rng_degree(D, y); }
+    const int o1 = D.basis_off[d1], n1 = D.basis_off[d1 + 1] - o1, o2 = D.basis_off[d2], n2 = D.basis_off[d2 + 1] - o2;
+    const uint64_t m1 = D.basis[o1 + rng_uniform(y, 0, n1 - 1)];
+    const uint64_t m2 = D.basis[o2 + rng_uniform(y, 0, n2 - 1)];
+    hi = m1 < m2 ? m1 : m2; lo = m1 < m2 ? m2 : m1;
+    fine = m1 != m2 && y == expect;
+  }
+  if (!__all_sync(BB_FULL, fine)) return false;
+  uint64_t* ik = P.in_key + (size_t)slot * P.max_gen_terms;
+  uint32_t* ic = P.in_coef + (size_t)slot * P.max_gen_terms;
+  int* io = P.in_off + (size_t)slot * (P.max_gens + 1);
+  if (lane < D.s) {
+    ik[2 * lane] = hi; ic[2 * lane] = 1u; ik[2 * lane + 1] = lo; ic[2 * lane + 1] = c;
+    io[lane + 1] = 2 * (lane + 1);
+  }
+  if (lane == 0) { io[0] = 0; P.in_np[slot] = D.s; }
+  x = __shfl_sync(BB_FULL, y, D.s - 1);
+  return true;
+}
+
 // ---------------------------------------------------------------------------------------------------- reset
 // BuchbergerEnv::reset (buchberger.cpp:299-315) from staged ideal `src_slot` into slot `slot`: generators are added
 // one by one through update() and into the reducer list.  sort_input orders them by ascending lead monomial first
@@ -1036,8 +1086,11 @@ __device__ __noinline__ void warp_reset_slot(const BBParams& P, int slot, int fi
   if (P.dist.enabled) {
     for (;;) {
       int ok = 1;
-      if (lane == 0) ok = P.dist.kind ? gen_random_ideal(P, slot, rng) : (gen_binomial_ideal(P, slot, rng) ? 1 : 0);
-      ok = __shfl_sync(BB_FULL, ok, 0);
+      if (P.dist.kind || !gen_binomial_ideal_warp(P, slot, rng)) {
+        if (lane == 0) ok = P.dist.kind ? gen_random_ideal(P, slot, rng) : (gen_binomial_ideal(P, slot, rng) ? 1 : 0);
+        ok = __shfl_sync(BB_FULL, ok, 0);
+        rng = __shfl_sync(BB_FULL, rng, 0);
+      }
       __syncwarp();
       if (ok <= 0) { e.nG = e.nP = e.nT = 0; e.status = ok ? BB_STATUS_OVERFLOW_TERMS : BB_STATUS_EMPTY; break; }
       warp_load_ideal<NV>(P, slot, e, ct);

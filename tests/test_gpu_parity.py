@@ -238,6 +238,35 @@ def test_full_size_properties_16384(torch_cuda):
         assert int(s1["gb_hash"][e]) == polys_hash(env.final_gb())
 
 
+@pytest.mark.parametrize("dist,s", [("3-20-10-uniform", 10), ("5-5-10-uniform", 10)])
+def test_full_size_properties_65536(torch_cuda, dist, s):
+    """BASELINE config 3 size: 65536 episodes of the uniform distributions to completion (one resident wave of slots,
+    like bench.py).  Size-independent properties -- every episode finished, counter identities, |G| = s + nonzero
+    reductions, a second run bit-identical -- and 64 episodes spread over the range against the oracle."""
+    from deepgroebner_b200.buchberger import BuchbergerEngine, resident_envs
+    orc = best_oracle()
+    E = 65536
+    eng = BuchbergerEngine(dist, num_envs=resident_envs(0, int(dist.split("-")[0])))
+    eng.counters(reset=True)
+    s1, _ = eng.run_episodes("degree", episodes=E, seed_base=0, compute_gb=True)
+    c = eng.counters(reset=True)
+    s2, _ = eng.run_episodes("degree", episodes=E, seed_base=0, compute_gb=True)
+    assert (s1["status"] == 2).all()
+    assert c["episodes"] == E and c["env_steps"] == int(s1["steps"].sum()) and c["additions"] == int(s1["additions"].sum())
+    assert c["zero_reductions"] + c["nonzero_reductions"] == c["env_steps"]
+    for f in ("steps", "additions", "trace_hash", "basis_hash", "gb_hash", "nbasis", "rerolls"):
+        assert np.array_equal(s1[f], s2[f]), f
+    assert (s1["additions"] >= s1["steps"]).all() and (s1["nbasis"] == s + s1["nonzero_reductions"]).all()
+    env = orc.env(dist)
+    for e in range(0, E, 1024):
+        env.seed(e)
+        env.reset()
+        t = env.run(selection="degree")
+        assert s1["steps"][e] == len(t) and int(s1["trace_hash"][e]) == trace_hash(t), e
+        assert int(s1["basis_hash"][e]) == polys_hash(env.basis()), e
+        assert int(s1["gb_hash"][e]) == polys_hash(env.final_gb()), e
+
+
 ALL_STRATEGIES = ["first", "degree", "normal", "sugar", "random", "last", "codegree", "strange", "spice"]
 
 
