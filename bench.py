@@ -337,6 +337,14 @@ def gpu_arm(args):
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     dev_ms_max, e2e_ms_max = float(t[0]), float(t[1])
     total_steps, total_adds = float(tot[0]), float(tot[1])
+    per_rank = None
+    if world > 1:   # diagnosis of the scaling figure: every rank's own device time, fastest single launch and work
+        mine = torch.tensor([dev_ms / args.steps, min(a.elapsed_time(b) for a, b in ev), float(steps_per_launch)],
+                            dtype=torch.float64, device=dev)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"ms_per_step": [round(float(x[0]), 4) for x in allr], "min_ms": [round(float(x[1]), 4) for x in allr],
+                    "env_steps_per_launch": [int(x[2]) for x in allr]}
 
     if rank == 0:
         # spot check (outside every timed region): a sample of the timed output against the CPU oracle
@@ -388,6 +396,8 @@ def gpu_arm(args):
                          "note": "latency/integer bound at binomial sizes (working set lives in L1/L2); see DESIGN.md"},
             "counters_per_launch": {k: v / args.steps for k, v in counters.items()},
         }
+        if per_rank:
+            line["per_rank"] = per_rank
         ip = int_pipe(launch_s, (clocks or {}).get("sm_mhz"), eng.sm_count) if args.workload == "episodes" else None
         if ip:
             line["int_pipe"] = ip

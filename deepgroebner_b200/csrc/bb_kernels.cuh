@@ -19,7 +19,7 @@
 #endif
 #define BB_THREADS (BB_WARPS * 32)
 #ifndef BB_MIN_BLOCKS
-#define BB_MIN_BLOCKS 4  // register cap 64 -> 32 resident warps per SM
+#define BB_MIN_BLOCKS 3  // register cap 80 -> 24 resident warps per SM (A/B on B200, profiles/README.md v8: 2 -> 702, 3 -> 763, 4 -> 728, 5 -> 693, 6 -> 657 M env-steps/s)
 #endif
 
 struct BBRunArgs {
