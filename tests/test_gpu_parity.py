@@ -217,7 +217,7 @@ def test_full_size_properties_16384(torch_cuda):
     spread over the range matches the oracle exactly."""
     from deepgroebner_b200.buchberger import BuchbergerEngine
     orc = best_oracle()
-    eng = BuchbergerEngine("3-20-10-weighted", num_envs=4736)
+    eng = BuchbergerEngine("3-20-10-weighted", num_envs=3552)
     eng.counters(reset=True)
     s1, _ = eng.run_episodes("degree", episodes=16384, seed_base=0, compute_gb=True)
     c = eng.counters(reset=True)
