@@ -390,6 +390,8 @@ __global__ void __launch_bounds__(BBW_THREADS, BBW_MIN_CTAS) k_run_wide(const __
   const int cap = P.max_poly_terms;
   uint64_t* hk = reinterpret_cast<uint64_t*>(wide_smem);
   uint32_t* hc = reinterpret_cast<uint32_t*>(wide_smem + (size_t)16 * cap);
+  uint64_t* sk = reinterpret_cast<uint64_t*>(wide_smem + (size_t)24 * cap);   // staging of a merge's f-side operand
+  uint32_t* sc = reinterpret_cast<uint32_t*>(wide_smem + (size_t)24 * cap + (size_t)8 * BBW_STAGE);
   const int tid = threadIdx.x;
   const int slot = blockIdx.x;
   if (tid < CT_COUNT) sh[0][tid] = 0ull;
@@ -424,7 +426,7 @@ __global__ void __launch_bounds__(BBW_THREADS, BBW_MIN_CTAS) k_run_wide(const __
     int4* trace = (A.trace && ep < A.trace_eps) ? reinterpret_cast<int4*>(A.trace) + (size_t)ep * A.trace_cap : nullptr;
     while (e.status == BB_STATUS_RUNNING && (A.max_steps == 0 || steps < A.max_steps)) {
       uint32_t pr;
-      const int a = block_step<NV>(P, e, ws, bslot, hk, hc, cap, A.strategy, &acc.sel_rng, pr, ct);
+      const int a = block_step<NV>(P, e, ws, bslot, hk, hc, cap, sk, sc, A.strategy, &acc.sel_rng, pr, ct);
       if (tid == 0) {
         const int pi = pr & 0xffffu, pj = pr >> 16;
         acc.th += trace_hash_item(pi, pj, a, steps);
@@ -641,7 +643,7 @@ struct BBLaunch {
     k_run<NV><<<grid_for_warps(nwarps), BB_THREADS, 0, s>>>(P, S, A);
     return cudaGetLastError();
   }
-  static size_t wide_smem(int max_poly_terms) { return (size_t)24 * max_poly_terms; }
+  static size_t wide_smem(int max_poly_terms) { return (size_t)24 * max_poly_terms + (size_t)12 * BBW_STAGE; }
   static int wide_ctas_per_sm(int max_poly_terms) {
     const size_t sm = wide_smem(max_poly_terms);
     if (sm > 200 * 1024) return 0;

@@ -22,48 +22,93 @@
 #include "bb_device.cuh"
 
 #ifndef BBW_WARPS
-#define BBW_WARPS 4
+#define BBW_WARPS 8
 #endif
 #define BBW_THREADS (BBW_WARPS * 32)
+static_assert(BBW_WARPS % 4 == 0, "per-warp partial results are read four at a time");
 #ifndef BBW_MIN_CTAS
-#define BBW_MIN_CTAS 7   // 1024 environments resident on 148 SMs
+#define BBW_MIN_CTAS 2   // 128 registers; A/B on cyclic-6 (profiles/README.md v9): 4 warps x 7 -> 1923 ms, 4 x 4 -> 1834, 8 x 3 -> 1524, 8 x 2 -> 1437
+#endif
+#ifndef BBW_PER
+#define BBW_PER 4        // merged positions per thread that block_merge keeps in registers
+#endif
+#ifndef BBW_STAGE
+#define BBW_STAGE 512    // terms of the staging buffer for the f-side operand of a merge (12 bytes each)
 #endif
 
 struct WideShared {
-  int wmin[2][BBW_WARPS];   // block_scan: per-warp minima (double-buffered, see block_first_divisor)
-  int wcnt[2][BBW_WARPS];   // block_merge: per-warp survivor counts (double-buffered)
+  // per-warp partial results, double-buffered (a slot is rewritten two barriers later, after every thread has read it)
+  __align__(16) uint32_t wmin[2][BBW_WARPS];   // divisor search: (position in G_ << 16) | basis index of each warp's first hit
+  __align__(16) int wcnt[2][BBW_WARPS];        // block_merge: per-warp survivor counts
   uint32_t pr; int row;     // the pair warp 0 took this step
   uint64_t gam;
   long long upd;            // result of warp_add_basis
   int status;
 };
 
-// First reducer (lowest position in G_) whose lead monomial divides `lead`, or -1.  `slot` alternates between calls:
-// a slot is rewritten two calls later, after every thread has passed the barrier of the call in between.
+// Divisor search (buchberger.cpp:27-32), split in two so that it can share a barrier with other work:
+// search_publish: every thread tests a strided slice of the reducer lead monomials, its first hit is its minimum, the
+// warp's minimum goes to sh.wmin[slot][warp] packed as (position in G_ << 16) | basis index (both < 65536; the basis
+// index ridx[r] is loaded next to the lead monomial so that the head record's address is known right after the
+// barrier); search_collect (after a block barrier): the block-wide first divisor, or -1.
+#define BBW_NONE 0xffffffffu
 template <int NV>
-__device__ __forceinline__ int block_first_divisor(WideShared& sh, int& slot, const uint64_t* __restrict__ rlm, int nR,
-                                                   uint64_t lead) {
+__device__ __forceinline__ void search_publish(WideShared& sh, int slot, const uint64_t* __restrict__ rlm,
+                                               const uint32_t* __restrict__ ridx, int nR, uint64_t lead, bool sorted) {
   typedef KL<NV> K;
-  int best = 0x7fffffff;
+  uint32_t best = BBW_NONE;
+  // sorted: G_ ascends in lead monomial (keys descend), so a thread may stop at its first reducer whose lead monomial
+  // exceeds `lead` (key below lead's): nothing after it can divide.  Same early exit as warp_reduce.
+  const uint64_t stop = sorted ? lead : 0ull;
 #pragma unroll 1
-  for (int r = threadIdx.x; r < nR; r += BBW_THREADS)
-    if (K::divides(rlm[r], lead)) { best = r; break; }   // ascending per thread: its first hit is its minimum
-  best = (int)__reduce_min_sync(BB_FULL, (unsigned)best);
+  for (int r = threadIdx.x; r < nR; r += BBW_THREADS) {
+    const uint64_t l = rlm[r];
+    const uint32_t ix = ridx[r];
+    if (l < stop) break;
+    if (K::divides(l, lead)) { best = ((uint32_t)r << 16) | ix; break; }
+  }
+  best = __reduce_min_sync(BB_FULL, best);
   if (bb_lane() == 0) sh.wmin[slot][threadIdx.x >> 5] = best;
-  __syncthreads();
-  int found = sh.wmin[slot][0];
+}
+__device__ __forceinline__ int search_collect(const WideShared& sh, int slot, uint32_t& gidx) {
+  uint32_t m = BBW_NONE;
 #pragma unroll
-  for (int w = 1; w < BBW_WARPS; w++) found = min(found, sh.wmin[slot][w]);
+  for (int w = 0; w < BBW_WARPS; w += 4) {
+    const uint4 v = *reinterpret_cast<const uint4*>(&sh.wmin[slot][w]);
+    m = min(min(m, min(v.x, v.y)), min(v.z, v.w));
+  }
+  gidx = m & 0xffffu;
+  return m == BBW_NONE ? -1 : (int)(m >> 16);
+}
+// sum of the warps' counts, and of the warps before `warp`
+__device__ __forceinline__ void counts_collect(const WideShared& sh, int slot, int warp, int& before, int& all) {
+  before = 0; all = 0;
+#pragma unroll
+  for (int w = 0; w < BBW_WARPS; w += 4) {
+    const int4 v = *reinterpret_cast<const int4*>(&sh.wcnt[slot][w]);
+    all += v.x + v.y + v.z + v.w;
+    before += (w < warp ? v.x : 0) + (w + 1 < warp ? v.y : 0) + (w + 2 < warp ? v.z : 0) + (w + 3 < warp ? v.w : 0);
+  }
+}
+template <int NV>
+__device__ __forceinline__ int block_first_divisor(WideShared& sh, int& slot, const uint64_t* __restrict__ rlm,
+                                                   const uint32_t* __restrict__ ridx, int nR, uint64_t lead, bool sorted,
+                                                   uint32_t& gidx) {
+  search_publish<NV>(sh, slot, rlm, ridx, nR, lead, sorted);
+  __syncthreads();
+  const int found = search_collect(sh, slot, gidx);
   slot ^= 1;
-  return found == 0x7fffffff ? -1 : found;
+  return found;
 }
 
 // out = cA * mA * A + cB * mB * B for term lists in ascending key order (see warp_merge in bb_device.cuh for the
 // conventions: adjX = key(mX) - bias, coefficients in [1,p), cancelled terms dropped).  A, B, O may be shared or global
 // memory; O must not alias A or B and needs room for nA + nB terms (`cap`).  Returns the number of output terms, -1 if
 // nA + nB > cap, -3 if a produced key has a guard bit set.  Ends with a block barrier: O is visible to every thread.
+// This is the merge by RANK (every term binary-searches the other list, then one chunked stream compaction): the
+// fallback of block_merge for a B operand longer than the staging buffer.
 template <int NV>
-__device__ __forceinline__ int block_merge(WideShared& sh, int& slot, BBField F, const uint64_t* Ak, const uint32_t* Ac,
+__device__ __noinline__ int block_merge_rank(WideShared& sh, int& slot, BBField F, const uint64_t* Ak, const uint32_t* Ac,
                                            int nA, uint32_t cA, uint64_t adjA, const uint64_t* Bk, const uint32_t* Bc, int nB,
                                            uint32_t cB, uint64_t adjB, uint64_t* Ok, uint32_t* Oc, int cap) {
   typedef KL<NV> K;
@@ -104,9 +149,8 @@ __device__ __forceinline__ int block_merge(WideShared& sh, int& slot, BBField F,
     const uint32_t live = __ballot_sync(BB_FULL, c != 0u);
     if (bb_lane() == 0) sh.wcnt[slot][warp] = __popc(live);
     __syncthreads();
-    int before = 0, all = 0;
-#pragma unroll
-    for (int w = 0; w < BBW_WARPS; w++) { const int n = sh.wcnt[slot][w]; all += n; before += w < warp ? n : 0; }
+    int before, all;
+    counts_collect(sh, slot, warp, before, all);
     if (c != 0u) { const int pos = no + before + __popc(live & ltm); Ok[pos] = k; Oc[pos] = c; }
     no += all;
     slot ^= 1;
@@ -115,12 +159,139 @@ __device__ __forceinline__ int block_merge(WideShared& sh, int& slot, BBField F,
   return bad ? -3 : no;
 }
 
+// out = cA * mA * A + cB * mB * B, same contract as block_merge_rank, by MERGE PATH.  sk / sc: BBW_STAGE terms of shared
+// memory.  B (the reducer's tail: ~33 terms on cyclic-6) is staged there with its multiplier applied in one coalesced
+// pass; thread t then owns the merged positions [t * per, (t + 1) * per): one binary search along its diagonal finds
+// where its slice starts in A and in B (at most log2(nB) steps on shared memory), a sequential walk merges the slice
+// (equal monomials: the A term carries the sum and the B term retires, a zero sum drops out), a block scan of the
+// slices' survivor counts gives every slice its output offset, and a second walk writes the survivors in place.  Three
+// barriers per addition whatever the length of the dividend; the rank merge needed log2(nB) dependent loads for EVERY
+// term of A and one barrier per BBW_THREADS merged terms, which is what bounded the longest cyclic-6 episodes
+// (profiles/README.md v6/v9).
+// One merged position: consumes the smaller of the two heads (a = A[ia] + adjA, b = staged B[ib]; ~0 past the end) and
+// returns its key k and coefficient c, c == 0 when nothing survives there (a cancelled sum, or a B term whose equal A
+// term carried the sum).
+__device__ __forceinline__ void merge_take(const BBField& F, const uint64_t* Ak, const uint32_t* Ac, int nA, uint32_t cA,
+                                           uint64_t adjA, const uint64_t* sk, const uint32_t* sc, int nB, int& ia, int& ib,
+                                           uint64_t& a, uint64_t& b, uint64_t& k, uint32_t& c) {
+  if (a <= b) {   // A first on ties
+    k = a;
+    c = (cA == 1u) ? Ac[ia] : bbf_mulmod(F, Ac[ia], cA);
+    if (a == b) c = bbf_addmod(F, c, sc[ib]);
+    ia++;
+    a = ia < nA ? Ak[ia] + adjA : ~0ull;
+  } else {        // its A partner, if any, is the A term just before it
+    k = b;
+    c = (ia > 0 && Ak[ia - 1] + adjA == b) ? 0u : sc[ib];
+    ib++;
+    b = ib < nB ? sk[ib] : ~0ull;
+  }
+}
+template <int NV, bool WRITE>
+__device__ __forceinline__ int merge_walk(BBField F, const uint64_t* Ak, const uint32_t* Ac, int nA, uint32_t cA, uint64_t adjA,
+                                          const uint64_t* sk, const uint32_t* sc, int nB, int ia, int ib, int count,
+                                          uint64_t* Ok, uint32_t* Oc, uint64_t& guard) {
+  int cnt = 0;
+  uint64_t a = ia < nA ? Ak[ia] + adjA : ~0ull, b = ib < nB ? sk[ib] : ~0ull;
+#pragma unroll 1
+  for (int d = 0; d < count; d++) {
+    uint64_t k; uint32_t c;
+    merge_take(F, Ak, Ac, nA, cA, adjA, sk, sc, nB, ia, ib, a, b, k, c);
+    if (!WRITE) guard |= k;
+    if (c != 0u) { if (WRITE) { Ok[cnt] = k; Oc[cnt] = c; } cnt++; }
+  }
+  return cnt;
+}
+
+template <int NV>
+__device__ __forceinline__ int block_merge(WideShared& sh, int& slot, BBField F, const uint64_t* Ak, const uint32_t* Ac,
+                                           int nA, uint32_t cA, uint64_t adjA, const uint64_t* Bk, const uint32_t* Bc, int nB,
+                                           uint32_t cB, uint64_t adjB, uint64_t* Ok, uint32_t* Oc, int cap, uint64_t* sk,
+                                           uint32_t* sc, const uint64_t* __restrict__ rlm, const uint32_t* __restrict__ ridx,
+                                           int nR, bool sorted, int& next_found, uint32_t& next_idx) {
+  typedef KL<NV> K;
+  next_found = -2;   // -2: the divisor of the result's lead monomial was not searched here
+  const int total = nA + nB;
+  if (total > cap) return -1;
+  if (nB > BBW_STAGE) return block_merge_rank<NV>(sh, slot, F, Ak, Ac, nA, cA, adjA, Bk, Bc, nB, cB, adjB, Ok, Oc, cap);
+  uint64_t guard = 0;
+#pragma unroll 1
+  for (int j = threadIdx.x; j < nB; j += BBW_THREADS) {
+    const uint64_t k = Bk[j] + adjB;
+    guard |= k;
+    sk[j] = k;
+    sc[j] = (cB == 1u) ? Bc[j] : bbf_mulmod(F, Bc[j], cB);
+  }
+  __syncthreads();
+  const int per = (total + BBW_THREADS - 1) / BBW_THREADS;
+  const int d0 = min((int)threadIdx.x * per, total), count = min(per, total - d0);
+  int lo = max(0, d0 - nB), hi = min(d0, nA);   // lo -> number of A terms among the first d0 merged terms
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (Ak[mid] + adjA <= sk[d0 - 1 - mid]) lo = mid + 1; else hi = mid;
+  }
+  const int ia = lo, ib = d0 - lo;
+  // The result's lead monomial is known before the merge runs unless the two heads coincide (their sum may cancel):
+  // it is the smaller head.  Its divisor search then shares the barrier of the survivor-count scan, which takes one
+  // barrier and the scan of the reducer lead monomials off the serial chain of an addition.
+  bool searched = false;
+  if (rlm != nullptr && total > 0) {
+    const uint64_t a0 = nA > 0 ? Ak[0] + adjA : ~0ull, b0 = nB > 0 ? sk[0] : ~0ull;
+    if (a0 != b0) { search_publish<NV>(sh, slot, rlm, ridx, nR, a0 < b0 ? a0 : b0, sorted); searched = true; }
+  }
+  // Slices of at most BBW_PER positions (dividends up to BBW_PER * BBW_THREADS terms: nearly all) are walked once and
+  // held in registers across the scan; longer ones are walked twice (count, then write).
+  uint64_t rk[BBW_PER]; uint32_t rc[BBW_PER];
+  int mine = 0;
+  const bool small = per <= BBW_PER;
+  if (small) {
+    int xa = ia, xb = ib;
+    uint64_t a = xa < nA ? Ak[xa] + adjA : ~0ull, b = xb < nB ? sk[xb] : ~0ull;
+#pragma unroll
+    for (int d = 0; d < BBW_PER; d++) {
+      rc[d] = 0u; rk[d] = 0ull;
+      if (d < count) {
+        merge_take(F, Ak, Ac, nA, cA, adjA, sk, sc, nB, xa, xb, a, b, rk[d], rc[d]);
+        guard |= rk[d];
+        mine += rc[d] != 0u;
+      }
+    }
+  } else {
+    mine = merge_walk<NV, false>(F, Ak, Ac, nA, cA, adjA, sk, sc, nB, ia, ib, count, Ok, Oc, guard);
+  }
+  int incl = mine;   // inclusive scan of the survivor counts inside the warp
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int v = __shfl_up_sync(BB_FULL, incl, o);
+    if (bb_lane() >= o) incl += v;
+  }
+  const int warp = threadIdx.x >> 5;
+  if (bb_lane() == 31) sh.wcnt[slot][warp] = incl;
+  const int bad = __syncthreads_or((guard & K::g_all) != 0ull);
+  int before, all;
+  counts_collect(sh, slot, warp, before, all);
+  if (searched) next_found = search_collect(sh, slot, next_idx);
+  slot ^= 1;
+  const int base = before + incl - mine;
+  if (small) {
+    int o = base;
+#pragma unroll
+    for (int d = 0; d < BBW_PER; d++)
+      if (rc[d] != 0u) { Ok[o] = rk[d]; Oc[o] = rc[d]; o++; }
+  } else {
+    merge_walk<NV, true>(F, Ak, Ac, nA, cA, adjA, sk, sc, nB, ia, ib, count, Ok + base, Oc + base, guard);
+  }
+  __syncthreads();
+  return bad ? -3 : all;
+}
+
 // One environment step by the whole CTA (BuchbergerEnv::step, buchberger.cpp:318-329, with the pair chosen by
 // `strategy`).  e and every scalar below are block-uniform.  hk / hc: the two shared dividend buffers of `cap` terms.
 // Returns the number of polynomial additions; `pair` receives (j << 16) | i.
 template <int NV>
 __device__ __forceinline__ int block_step(const BBParams& P, Env& e, WideShared& sh, int& slot, uint64_t* hk, uint32_t* hc,
-                                          int cap, int strategy, uint32_t* sel_rng, uint32_t& pair, Ctr& ct) {
+                                          int cap, uint64_t* sk, uint32_t* sc, int strategy, uint32_t* sel_rng,
+                                          uint32_t& pair, Ctr& ct) {
   typedef KL<NV> K;
   const BBField F = P.F;
   const int tid = threadIdx.x;
@@ -150,8 +321,10 @@ __device__ __forceinline__ int block_step(const BBParams& P, Env& e, WideShared&
   }
   // s = (gamma / LT f) tail(f) - (gamma / LT g) tail(g): the lead terms cancel exactly (buchberger.cpp:18-21)
   int cur = 0, pos = 0;
+  int found; uint32_t fidx;   // first divisor of the current lead monomial (found == -2: not searched yet)
   int n = block_merge<NV>(sh, slot, F, tk + hf.off + 1, tc + hf.off + 1, (int)hf.len - 1, hf.invlc, gam - hf.lm,
-                          tk + hg.off + 1, tc + hg.off + 1, (int)hg.len - 1, F.p - hg.invlc, gam - hg.lm, hk, hc, cap);
+                          tk + hg.off + 1, tc + hg.off + 1, (int)hg.len - 1, F.p - hg.invlc, gam - hg.lm, hk, hc, cap, sk, sc,
+                          ENV_PTR(uint64_t, e, P, o_rlm), ENV_PTR(uint32_t, e, P, o_ridx), e.nG, P.sort_reducers != 0, found, fidx);
   if (n < 0) { e.status = n == -1 ? BB_STATUS_OVERFLOW_SCRATCH : BB_STATUS_OVERFLOW_EXPONENT; return 1; }
   if (e.guard & K::g_all) { e.status = BB_STATUS_OVERFLOW_EXPONENT; return 1; }
   ct.twrite += (unsigned)n;
@@ -161,15 +334,17 @@ __device__ __forceinline__ int block_step(const BBParams& P, Env& e, WideShared&
   uint64_t* rk = ENV_PTR(uint64_t, e, P, o_tkey) + e.nT;
   uint32_t* rc = ENV_PTR(uint32_t, e, P, o_tcoef) + e.nT;
   const int rcap = P.max_terms - e.nT, nR = e.nG;
+  const bool sorted = P.sort_reducers != 0;
   int steps = 0, rlen = 0;
   while (n > 0) {
-    const uint64_t* ck = hk + (size_t)cur * cap + pos;
-    const uint32_t* cc = hc + (size_t)cur * cap + pos;
+    const int hb = cur * cap + pos;
+    const uint64_t* ck = hk + hb;
+    const uint32_t* cc = hc + hb;
     const uint64_t lead = ck[0];
-    const int found = block_first_divisor<NV>(sh, slot, rlm, nR, lead);
+    if (found == -2) found = block_first_divisor<NV>(sh, slot, rlm, ridx, nR, lead, sorted, fidx);
     ct.lms += (found >= 0) ? (unsigned)(found + 1) : (unsigned)nR;
     if (found >= 0) {
-      const GHead f = load_head(gh + ridx[found]);
+      const GHead f = load_head(gh + fidx);
       const uint32_t c = bbf_mulmod(F, cc[0], f.invlc);
       const uint32_t nc = F.p - c;              // c != 0
       const uint64_t adj = lead - f.lm;         // key(LM h / LM f) - bias
@@ -178,7 +353,7 @@ __device__ __forceinline__ int block_step(const BBParams& P, Env& e, WideShared&
       ct.tread += (unsigned)n + f.len;
       const int ob = cur ^ 1;
       const int n2 = block_merge<NV>(sh, slot, F, ck + 1, cc + 1, n - 1, 1u, 0ull, tk + f.off + 1, tc + f.off + 1,
-                                     (int)f.len - 1, nc, adj, hk + (size_t)ob * cap, hc + (size_t)ob * cap, cap);
+                                     (int)f.len - 1, nc, adj, hk + ob * cap, hc + ob * cap, cap, sk, sc, rlm, ridx, nR, sorted, found, fidx);
       if (n2 < 0) { e.status = n2 == -1 ? BB_STATUS_OVERFLOW_SCRATCH : BB_STATUS_OVERFLOW_EXPONENT; return 1 + steps; }
       n = n2; cur = ob; pos = 0;
       ct.twrite += (unsigned)n;
@@ -188,6 +363,7 @@ __device__ __forceinline__ int block_step(const BBParams& P, Env& e, WideShared&
       if (tid == 0) { rk[rlen] = lead; rc[rlen] = cc[0]; }
       rlen++; ct.moves++;
       pos++; n--;
+      found = -2;
     }
   }
   if (rlen > 0) {
