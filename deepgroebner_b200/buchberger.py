@@ -249,7 +249,8 @@ class BuchbergerEngine:
 
     def set_wide(self, mode=-1):
         """Episode runner of run_episodes (bb_set_wide): -1 auto, 0 one warp per environment, 1 one CTA per
-        environment (long polynomials).  Results are identical; only speed differs."""
+        environment (long polynomials); 2 / 3 as 1 with the block merge on its fallback paths (rank merge / two-walk
+        merge path).  Results are identical; only speed differs."""
         self._ck(self.lib.bb_set_wide(self.h, int(mode)), "bb_set_wide")
 
     def set_selection_seed_stride(self, stride=1):

@@ -35,6 +35,7 @@ struct BBRunArgs {
   bb_episode_stats* out;
   int32_t* trace;
   int trace_eps, trace_cap;
+  int wide_flags;    // k_run_wide: BBW_FLAG_* (bb_wide.cuh), the merge variants bb_set_wide(2 / 3) select
   int* queue;        // [0]: next queue position; [BB_LPT_HIST .. +BB_LPT_BUCKETS): histogram of the cost keys of the batch, then as many cursors
   int* order;        // [episodes] queue position -> episode of the batch, longest predicted first (k_order)
   uint8_t* cost_key; // [episodes] predicted-cost bucket of each episode of the batch (k_prepare)
@@ -426,7 +427,7 @@ __global__ void __launch_bounds__(BBW_THREADS, BBW_MIN_CTAS) k_run_wide(const __
     int4* trace = (A.trace && ep < A.trace_eps) ? reinterpret_cast<int4*>(A.trace) + (size_t)ep * A.trace_cap : nullptr;
     while (e.status == BB_STATUS_RUNNING && (A.max_steps == 0 || steps < A.max_steps)) {
       uint32_t pr;
-      const int a = block_step<NV>(P, e, ws, bslot, hk, hc, cap, sk, sc, A.strategy, &acc.sel_rng, pr, ct);
+      const int a = block_step<NV>(P, e, ws, bslot, hk, hc, cap, sk, sc, A.wide_flags, A.strategy, &acc.sel_rng, pr, ct);
       if (tid == 0) {
         const int pi = pr & 0xffffu, pj = pr >> 16;
         acc.th += trace_hash_item(pi, pj, a, steps);

@@ -32,6 +32,10 @@ static_assert(BBW_WARPS % 4 == 0, "per-warp partial results are read four at a t
 #ifndef BBW_PER
 #define BBW_PER 4        // merged positions per thread that block_merge keeps in registers
 #endif
+// merge variants (BBRunArgs::wide_flags).  Every variant is bit-identical; the flags exist so that the parity tests
+// reach the fallback paths that the benchmark ideals rarely or never take.
+#define BBW_FLAG_RANK_MERGE 1   // block_merge_rank for every addition (else: only when the reducer outgrows the staging buffer)
+#define BBW_FLAG_TWO_WALKS 2    // merge path with the count + write walks (else: only for slices longer than BBW_PER)
 #ifndef BBW_STAGE
 #define BBW_STAGE 512    // terms of the staging buffer for the f-side operand of a merge (12 bytes each)
 #endif
@@ -208,12 +212,12 @@ __device__ __forceinline__ int block_merge(WideShared& sh, int& slot, BBField F,
                                            int nA, uint32_t cA, uint64_t adjA, const uint64_t* Bk, const uint32_t* Bc, int nB,
                                            uint32_t cB, uint64_t adjB, uint64_t* Ok, uint32_t* Oc, int cap, uint64_t* sk,
                                            uint32_t* sc, const uint64_t* __restrict__ rlm, const uint32_t* __restrict__ ridx,
-                                           int nR, bool sorted, int& next_found, uint32_t& next_idx) {
+                                           int nR, bool sorted, int flags, int& next_found, uint32_t& next_idx) {
   typedef KL<NV> K;
   next_found = -2;   // -2: the divisor of the result's lead monomial was not searched here
   const int total = nA + nB;
   if (total > cap) return -1;
-  if (nB > BBW_STAGE) return block_merge_rank<NV>(sh, slot, F, Ak, Ac, nA, cA, adjA, Bk, Bc, nB, cB, adjB, Ok, Oc, cap);
+  if (nB > BBW_STAGE || (flags & BBW_FLAG_RANK_MERGE)) return block_merge_rank<NV>(sh, slot, F, Ak, Ac, nA, cA, adjA, Bk, Bc, nB, cB, adjB, Ok, Oc, cap);
   uint64_t guard = 0;
 #pragma unroll 1
   for (int j = threadIdx.x; j < nB; j += BBW_THREADS) {
@@ -243,7 +247,7 @@ __device__ __forceinline__ int block_merge(WideShared& sh, int& slot, BBField F,
   // held in registers across the scan; longer ones are walked twice (count, then write).
   uint64_t rk[BBW_PER]; uint32_t rc[BBW_PER];
   int mine = 0;
-  const bool small = per <= BBW_PER;
+  const bool small = per <= BBW_PER && !(flags & BBW_FLAG_TWO_WALKS);
   if (small) {
     int xa = ia, xb = ib;
     uint64_t a = xa < nA ? Ak[xa] + adjA : ~0ull, b = xb < nB ? sk[xb] : ~0ull;
@@ -290,7 +294,7 @@ __device__ __forceinline__ int block_merge(WideShared& sh, int& slot, BBField F,
 // Returns the number of polynomial additions; `pair` receives (j << 16) | i.
 template <int NV>
 __device__ __forceinline__ int block_step(const BBParams& P, Env& e, WideShared& sh, int& slot, uint64_t* hk, uint32_t* hc,
-                                          int cap, uint64_t* sk, uint32_t* sc, int strategy, uint32_t* sel_rng,
+                                          int cap, uint64_t* sk, uint32_t* sc, int flags, int strategy, uint32_t* sel_rng,
                                           uint32_t& pair, Ctr& ct) {
   typedef KL<NV> K;
   const BBField F = P.F;
@@ -324,7 +328,7 @@ __device__ __forceinline__ int block_step(const BBParams& P, Env& e, WideShared&
   int found; uint32_t fidx;   // first divisor of the current lead monomial (found == -2: not searched yet)
   int n = block_merge<NV>(sh, slot, F, tk + hf.off + 1, tc + hf.off + 1, (int)hf.len - 1, hf.invlc, gam - hf.lm,
                           tk + hg.off + 1, tc + hg.off + 1, (int)hg.len - 1, F.p - hg.invlc, gam - hg.lm, hk, hc, cap, sk, sc,
-                          ENV_PTR(uint64_t, e, P, o_rlm), ENV_PTR(uint32_t, e, P, o_ridx), e.nG, P.sort_reducers != 0, found, fidx);
+                          ENV_PTR(uint64_t, e, P, o_rlm), ENV_PTR(uint32_t, e, P, o_ridx), e.nG, P.sort_reducers != 0, flags, found, fidx);
   if (n < 0) { e.status = n == -1 ? BB_STATUS_OVERFLOW_SCRATCH : BB_STATUS_OVERFLOW_EXPONENT; return 1; }
   if (e.guard & K::g_all) { e.status = BB_STATUS_OVERFLOW_EXPONENT; return 1; }
   ct.twrite += (unsigned)n;
@@ -353,7 +357,7 @@ __device__ __forceinline__ int block_step(const BBParams& P, Env& e, WideShared&
       ct.tread += (unsigned)n + f.len;
       const int ob = cur ^ 1;
       const int n2 = block_merge<NV>(sh, slot, F, ck + 1, cc + 1, n - 1, 1u, 0ull, tk + f.off + 1, tc + f.off + 1,
-                                     (int)f.len - 1, nc, adj, hk + ob * cap, hc + ob * cap, cap, sk, sc, rlm, ridx, nR, sorted, found, fidx);
+                                     (int)f.len - 1, nc, adj, hk + ob * cap, hc + ob * cap, cap, sk, sc, rlm, ridx, nR, sorted, flags, found, fidx);
       if (n2 < 0) { e.status = n2 == -1 ? BB_STATUS_OVERFLOW_SCRATCH : BB_STATUS_OVERFLOW_EXPONENT; return 1 + steps; }
       n = n2; cur = ob; pos = 0;
       ct.twrite += (unsigned)n;

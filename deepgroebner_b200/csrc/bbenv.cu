@@ -525,9 +525,10 @@ int bb_run(bb_handle* h, int strategy, int episodes, int seed_base, const int32_
     CK(h->K->prepare(S, A, s));
     // long polynomials (general capacities): one CTA per environment, dividend in shared memory (bb_wide.cuh)
     int wide_ctas = 0;
-    if (h->wide_mode != 0 && (h->wide_mode == 1 || h->P.max_poly_terms >= 256))
+    A.wide_flags = h->wide_mode == 2 ? BBW_FLAG_RANK_MERGE : (h->wide_mode == 3 ? BBW_FLAG_TWO_WALKS : 0);
+    if (h->wide_mode != 0 && (h->wide_mode >= 1 || h->P.max_poly_terms >= 256))
       wide_ctas = h->K->wide_ctas_per_sm(h->P.max_poly_terms) * h->sm_count;
-    if (h->wide_mode == 1 && wide_ctas <= 0)
+    if (h->wide_mode >= 1 && wide_ctas <= 0)
       return fail(h, "bb_run: the dividend buffers (24 bytes x max_poly_terms) do not fit shared memory");
     if (wide_ctas > 0) {
       CK(h->K->run_wide(h->P, S, A, std::min(std::min(h->P.num_envs, A.episodes), wide_ctas), s));
@@ -622,7 +623,7 @@ int bb_copy_env(bb_handle* dst, int dst_env, bb_handle* src, int src_env, void* 
 
 int bb_set_wide(bb_handle* h, int mode) {
   if (!h) return -1;
-  if (mode < -1 || mode > 1) return fail(h, "bb_set_wide: mode must be -1 (auto), 0 (off) or 1 (on)");
+  if (mode < -1 || mode > 3) return fail(h, "bb_set_wide: mode must be -1 (auto), 0 (off), 1 (on), 2 or 3 (on, merge variants)");
   h->wide_mode = mode;
   return 0;
 }

@@ -196,7 +196,10 @@ int bb_set_selection_seed_stride(bb_handle* h, int stride);
 /* bb_set_wide: which episode runner bb_run uses.  -1 (default): one warp per environment, except that capacities
  * sized for long polynomials (max_poly_terms >= 256, e.g. cyclic-n) get one CTA per environment with the dividend in
  * shared memory; 0: always one warp per environment; 1: always one CTA per environment (an error if 24 bytes x
- * max_poly_terms exceed shared memory).  Both runners produce bit-identical episodes; this is a performance switch. */
+ * max_poly_terms exceed shared memory); 2 / 3: as 1 with the block merge forced onto its fallback paths (2: merge by
+ * rank, otherwise taken when a reducer outgrows the staging buffer; 3: merge path with two walks, otherwise taken for
+ * dividends beyond 1024 terms) so that tests reach them.  Every mode produces bit-identical episodes; this is a
+ * performance switch. */
 int bb_set_wide(bb_handle* h, int mode);
 
 /* bb_value: BuchbergerEnv::value(strategy, gamma) (buchberger.cpp:332-351) for every environment at once:

@@ -472,15 +472,17 @@ def test_cta_per_environment_runner_equals_warp_runner(torch_cuda, name, strateg
     episodes = 12
     eng = BuchbergerEngine(name, num_envs=episodes, **({} if name.startswith("cyclic") else dict(max_poly_terms=256)))
     out = {}
-    for mode in (0, 1):
+    for mode in (0, 1, 2, 3):
         eng.set_wide(mode)
         eng.counters(reset=True)
         stats, trace = eng.run_episodes(strategy, episodes=episodes, seed_base=7, compute_gb=True, selection_seed=99,
                                         trace_episodes=2, trace_cap=4096)
         out[mode] = (stats, trace, eng.counters(reset=True))
-    (s0, t0, c0), (s1, t1, c1) = out[0], out[1]
-    assert (s0["status"] == 2).all() and (s1["status"] == 2).all()
-    for f in s0.dtype.names:
-        assert np.array_equal(s0[f], s1[f]), f
-    assert np.array_equal(t0, t1)
-    assert c0 == c1
+    s0, t0, c0 = out[0]
+    assert (s0["status"] == 2).all()
+    for mode in (1, 2, 3):   # 2 / 3: the block merge's fallback paths (rank merge, two-walk merge path)
+        s1, t1, c1 = out[mode]
+        for f in s0.dtype.names:
+            assert np.array_equal(s0[f], s1[f]), (mode, f)
+        assert np.array_equal(t0, t1), mode
+        assert c0 == c1, mode
