@@ -665,19 +665,28 @@ struct BBLaunch {
     k_value<NV><<<grid_for_warps(nwarps), BB_THREADS, 0, s>>>(P, F, A);
     return cudaGetLastError();
   }
-  static size_t policy_smem(const BBParams& P, int hidden) { return sizeof(float) * ((size_t)P.cols * hidden + 2 * hidden + 1); }
+  static size_t policy_smem(const BBParams& P, int hidden) { return sizeof(float) * (size_t)policy_smem_floats(P.cols, hidden); }
+  template <int UPL>
+  static cudaError_t policy_upl(const BBParams& P, const BBPolicy& W, unsigned long long counter, int32_t* actions, float* logp,
+                                float* logits, int pmax, int g, size_t sm, cudaStream_t s) {
+    if (sm > 48 * 1024) {
+      cudaError_t e = cudaFuncSetAttribute(k_policy<NV, UPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      if (e != cudaSuccess) return e;
+    }
+    k_policy<NV, UPL><<<g, BB_THREADS, sm, s>>>(P, W, counter, actions, logp, logits, pmax);
+    return cudaGetLastError();
+  }
   static cudaError_t policy(const BBParams& P, const BBPolicy& W, unsigned long long counter, int32_t* actions, float* logp,
                             float* logits, int pmax, int nwarps, cudaStream_t s) {
     const size_t sm = policy_smem(P, W.hidden);
     const int g = grid_for_warps(nwarps);
     switch (W.hidden >> 5) {
-      case 1: k_policy<NV, 1><<<g, BB_THREADS, sm, s>>>(P, W, counter, actions, logp, logits, pmax); break;
-      case 2: k_policy<NV, 2><<<g, BB_THREADS, sm, s>>>(P, W, counter, actions, logp, logits, pmax); break;
-      case 4: k_policy<NV, 4><<<g, BB_THREADS, sm, s>>>(P, W, counter, actions, logp, logits, pmax); break;
-      case 8: k_policy<NV, 8><<<g, BB_THREADS, sm, s>>>(P, W, counter, actions, logp, logits, pmax); break;
-      default: return cudaErrorInvalidValue;
+      case 1: return policy_upl<1>(P, W, counter, actions, logp, logits, pmax, g, sm, s);
+      case 2: return policy_upl<2>(P, W, counter, actions, logp, logits, pmax, g, sm, s);
+      case 4: return policy_upl<4>(P, W, counter, actions, logp, logits, pmax, g, sm, s);
+      case 8: return policy_upl<8>(P, W, counter, actions, logp, logits, pmax, g, sm, s);
     }
-    return cudaGetLastError();
+    return cudaErrorInvalidValue;
   }
   template <int UPL>
   static cudaError_t rollout_upl(const BBParams& P, const BBRolloutArgs& A, int g, size_t sm, cudaStream_t s) {
