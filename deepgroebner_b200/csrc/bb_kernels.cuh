@@ -22,6 +22,10 @@
 #define BB_MIN_BLOCKS 3  // register cap 80 -> 24 resident warps per SM (A/B on B200, profiles/README.md v8: 2 -> 702, 3 -> 763, 4 -> 728, 5 -> 693, 6 -> 657 M env-steps/s)
 #endif
 
+#ifndef BB_ROLLOUT_MIN_BLOCKS
+#define BB_ROLLOUT_MIN_BLOCKS 2  // 128 registers, no spills, 16 warps/SM: 140 M env-steps/s against 132 M at 3 and 123 M at 4 (profiles/README.md v10)
+#endif
+
 struct BBRunArgs {
   int strategy, episodes, seed_base;
   int sel_seed_base;  // Random selection: episode e draws choice() from minstd_rand0 seeded sel_seed_base + e * sel_seed_stride
@@ -564,7 +568,7 @@ __global__ void __launch_bounds__(BB_THREADS) k_policy(const __grid_constant__ B
 // steps of its environment -- policy head, categorical sample, step, auto-reset -- with no host round trip and no
 // synchronisation between environments.  Trajectories are written environment-major.
 template <int NV, int UPL>
-__global__ void __launch_bounds__(BB_THREADS, 3) k_rollout(const __grid_constant__ BBParams P,
+__global__ void __launch_bounds__(BB_THREADS, BB_ROLLOUT_MIN_BLOCKS) k_rollout(const __grid_constant__ BBParams P,
                                                            const __grid_constant__ BBRolloutArgs A) {
   extern __shared__ float wsm[];
   __shared__ unsigned long long sh[BB_WARPS][CT_COUNT];
