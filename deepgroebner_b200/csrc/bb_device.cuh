@@ -1112,10 +1112,13 @@ __device__ __noinline__ void warp_reset_slot(const BBParams& P, int slot, int fi
 }
 
 // ---------------------------------------------------------------------------------------------------- hashes
-// Position-salted additive checksums (order-sensitive, but computable in parallel on both sides).
-__device__ __forceinline__ unsigned long long trace_hash_item(int i, int j, int adds, int t) {
-  return bb_hash_item_impl((uint64_t)(uint32_t)i | ((uint64_t)(uint32_t)j << 16) | ((uint64_t)(uint32_t)adds << 32),
-                           (uint64_t)t);
+// The per-step checksum of the (i, j, additions) sequence is a rolling polynomial hash mod 2^64,
+//   h <- h * 0x9E3779B97F4A7C15 + (i | j << 16 | additions << 32) + 1,
+// order-sensitive and one 64-bit multiply-add per step (the position-salted splitmix sum it replaces was 3.7 % of
+// k_run's instructions, profiles/README.md v10).  `pair` = (j << 16) | i as the step returns it.  The basis / GB
+// checksums below, computed once per episode over many terms in parallel, stay position-salted additive sums.
+__device__ __forceinline__ unsigned long long trace_hash_step(unsigned long long h, uint32_t pair, int adds) {
+  return h * BB_GOLD + ((((unsigned long long)(uint32_t)adds) << 32) | pair) + 1ull;
 }
 // lens: polynomial lengths as an int array with the given stride (in ints)
 template <int NV>

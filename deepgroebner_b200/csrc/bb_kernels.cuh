@@ -135,7 +135,7 @@ __device__ __forceinline__ double step_and_account(const BBParams& P, int slot, 
   if (bb_lane() == 0) {
     const int pi = pr & 0xffffu, pj = pr >> 16;
     BBEnvState& S = P.st[slot];
-    S.trace_hash += trace_hash_item(pi, pj, adds, S.steps);
+    S.trace_hash = trace_hash_step(S.trace_hash, pr, adds);
     S.steps += 1; S.adds += adds;
     if (e.nG > g0) S.nonzero += 1; else S.zero += 1;
     row[CT_STEPS] += 1; row[CT_ADDS] += (unsigned)adds;
@@ -291,7 +291,7 @@ __device__ __forceinline__ void run_episode(const BBParams& P, Env& e, int strat
     const int a = warp_step<NV>(P, e, prow, pr, ct);
     if (lane == 0) {
       const int pi = pr & 0xffffu, pj = pr >> 16;
-      acc.th += trace_hash_item(pi, pj, a, steps);
+      acc.th = trace_hash_step(acc.th, pr, a);
       const double r = (P.rewards == BB_REWARD_ADDITIONS) ? -(double)a : -1.0;
       const double d = acc.disc;
       acc.ret = __dadd_rn(acc.ret, __dmul_rn(d, r)); acc.disc = __dmul_rn(d, gamma);
@@ -434,7 +434,7 @@ __global__ void __launch_bounds__(BBW_THREADS, BBW_MIN_CTAS) k_run_wide(const __
       const int a = block_step<NV>(P, e, ws, bslot, hk, hc, cap, sk, sc, A.wide_flags, A.strategy, &acc.sel_rng, pr, ct);
       if (tid == 0) {
         const int pi = pr & 0xffffu, pj = pr >> 16;
-        acc.th += trace_hash_item(pi, pj, a, steps);
+        acc.th = trace_hash_step(acc.th, pr, a);
         const double r = (P.rewards == BB_REWARD_ADDITIONS) ? -(double)a : -1.0;
         const double d = acc.disc;
         acc.ret = __dadd_rn(acc.ret, __dmul_rn(d, r)); acc.disc = __dmul_rn(d, A.gamma);

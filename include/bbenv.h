@@ -261,7 +261,8 @@ int bb_counters_read(bb_handle* h, bb_counters* out, int reset);
 
 /* ---- checksums (so a host-side checker can recompute them from an oracle's episode)
  * item(x, pos) = splitmix64_finalizer(x + 0x9E3779B97F4A7C15 * (pos + 1));  all sums are mod 2^64.
- *   trace_hash = sum over steps t of item(i | j<<16 | additions<<32, t)
+ *   trace_hash = h_T, where h_0 = 0 and h_{t+1} = h_t * 0x9E3779B97F4A7C15 + (i | j<<16 | additions<<32) + 1 over the
+ *        steps in order (a rolling polynomial hash: one multiply-add per step on the device)
  *   basis_hash / gb_hash = sum over terms t (flattened over the polynomial list, in order) of
  *        item(coef, 3t) + item(e0 | e1<<16 | e2<<32 | e3<<48, 3t+1) + item(e4 | e5<<16 | e6<<32 | e7<<48, 3t+2)
  *      + sum over polynomials q of splitmix64_finalizer(len_q + 0xD1B54A32D192ED03 * (q + 1)) */

@@ -33,8 +33,11 @@ def trace_hash(trace):
     t = np.asarray(trace, dtype=np.uint64).reshape(-1, np.asarray(trace).shape[-1])
     if len(t) == 0:
         return 0
-    x = t[:, 0] | (t[:, 1] << np.uint64(16)) | (t[:, 2] << np.uint64(32))
-    return _sum(hash_item(x, np.arange(len(t), dtype=np.uint64)))
+    # h_T = sum_t x_t * GOLD^(T-1-t) mod 2^64  (h <- h * GOLD + x_t, include/bbenv.h "checksums")
+    with np.errstate(over="ignore"):
+        x = (t[:, 0] | (t[:, 1] << np.uint64(16)) | (t[:, 2] << np.uint64(32))) + np.uint64(1)
+        powers = np.cumprod(np.concatenate([np.ones(1, np.uint64), np.full(len(t) - 1, GOLD, np.uint64)]), dtype=np.uint64)[::-1]
+        return int(np.sum(x * powers, dtype=np.uint64))
 
 
 def polys_hash(polys):
