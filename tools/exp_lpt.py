@@ -1,5 +1,7 @@
 """Diagnostic: how much of k_run's time is queue-order tail?  Runs the 16384-episode workload with seeds in natural
-order, then sorted by (measured) episode length descending (perfect LPT) and ascending (worst case)."""
+order, then sorted by (measured) episode length descending (perfect LPT) and ascending (worst case).
+Historical (v5): since bb_run orders its queue itself (k_order, longest predicted first) the order of `seeds` no longer
+matters and all three runs take the same time."""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
