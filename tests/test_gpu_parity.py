@@ -270,6 +270,29 @@ def test_full_size_properties_65536(torch_cuda, dist, s):
 ALL_STRATEGIES = ["first", "degree", "normal", "sugar", "random", "last", "codegree", "strange", "spice"]
 
 
+def test_run_beyond_one_batch_of_65536(torch_cuda):
+    """bb_run splits a call into batches of 65536 episodes (staging arena, queue and order are reused, episode ids carry
+    on): 70000 episodes with explicit seeds give, episode by episode, what two separate calls over the same seeds give,
+    and a sample on both sides of the boundary equals the oracle."""
+    from deepgroebner_b200.buchberger import BuchbergerEngine
+    orc = best_oracle()
+    E, cut = 70000, 65536
+    seeds = (np.arange(E, dtype=np.int64) * 7 + 3).astype(np.int32)
+    eng = BuchbergerEngine("3-20-10-weighted", num_envs=2048)
+    whole, _ = eng.run_episodes("degree", episodes=E, seeds=seeds)
+    head, _ = eng.run_episodes("degree", episodes=cut, seeds=seeds[:cut])
+    tail, _ = eng.run_episodes("degree", episodes=E - cut, seeds=seeds[cut:])
+    assert (whole["status"] == 2).all()
+    for f in ("steps", "additions", "trace_hash", "basis_hash", "nbasis", "rerolls", "discounted_return"):
+        assert np.array_equal(whole[f][:cut], head[f]) and np.array_equal(whole[f][cut:], tail[f]), f
+    env = orc.env("3-20-10-weighted")
+    for e in list(range(cut - 8, cut + 8)) + [0, E - 1]:
+        env.seed(int(seeds[e]))
+        env.reset()
+        t = env.run(selection="degree")
+        assert whole["steps"][e] == len(t) and int(whole["trace_hash"][e]) == trace_hash(t), e
+
+
 @pytest.mark.parametrize("dist", ["3-20-10-weighted", "5-5-10-uniform"])
 @pytest.mark.parametrize("strategy", ALL_STRATEGIES)
 def test_all_selection_types_whole_episodes(torch_cuda, dist, strategy):
