@@ -440,6 +440,7 @@ __device__ __noinline__ long long warp_add_basis(const BBParams& P, unsigned cha
     // most 64 basis elements every lane keeps L_lane and L_{lane+32} in registers, so the peeling needs no memory at
     // all -- one candidate reduction and one two-register sweep per kept lcm.  Same algorithm as the general path.
     const int i0 = lane, i1 = lane + 32;
+    const bool two = m > 32;   // warp-uniform: the second register of every lane is in use (1 call in 5 on the binomial workloads)
     const bool in0 = i0 < m, in1 = i1 < m;
     uint64_t v0 = 0ull, v1 = 0ull;
     bool cp0 = false, cp1 = false, ovf = false;
@@ -486,27 +487,43 @@ __device__ __noinline__ long long warp_add_basis(const BBParams& P, unsigned cha
     nP = w;
     const uint64_t e0 = v0 & K::ex_mask, e1 = v1 & K::ex_mask;
     bool u0 = in0, u1 = in1, k0 = false, k1 = false;   // undecided / chosen for emission
-    for (;;) {
-      const bool p1 = u1 && (!u0 || v1 > v0);          // this lane's larger undecided key; the lower index on a tie
-      const uint64_t bk = p1 ? v1 : (u0 ? v0 : 0ull);
-      if (!__any_sync(BB_FULL, u0 || u1)) break;
-      const uint32_t hi = __reduce_max_sync(BB_FULL, (uint32_t)(bk >> 32));
-      const bool c1 = (u0 || u1) && (uint32_t)(bk >> 32) == hi;
-      const uint32_t lo = __reduce_max_sync(BB_FULL, c1 ? (uint32_t)bk : 0u);
-      const bool c2 = c1 && (uint32_t)bk == lo;
-      const int kidx = (int)__reduce_min_sync(BB_FULL, c2 ? (uint32_t)(p1 ? i1 : i0) : 0x7fffffffu);
-      const uint64_t kk = (((uint64_t)hi << 32) | lo) & K::ex_mask;
-      const bool d0 = u0 && ((((e0 | K::ge_mask) - kk) & K::ge_mask) == K::ge_mask);   // multiples of the killer, itself included
-      const bool d1 = u1 && ((((e1 | K::ge_mask) - kk) & K::ge_mask) == K::ge_mask);
-      const bool grp_cop = __any_sync(BB_FULL, (d0 && e0 == kk && cp0) || (d1 && e1 == kk && cp1));
-      u0 = u0 && !d0; u1 = u1 && !d1;
-      if (!grp_cop) { k0 = k0 || kidx == i0; k1 = k1 || kidx == i1; }
+    if (!two) {   // one lcm per lane: the same sweep without the second register (no code is shared on purpose: both loops are short)
+      for (;;) {
+        if (!__any_sync(BB_FULL, u0)) break;
+        const uint32_t hi = __reduce_max_sync(BB_FULL, u0 ? (uint32_t)(v0 >> 32) : 0u);
+        const bool c1 = u0 && (uint32_t)(v0 >> 32) == hi;
+        const uint32_t lo = __reduce_max_sync(BB_FULL, c1 ? (uint32_t)v0 : 0u);
+        const bool c2 = c1 && (uint32_t)v0 == lo;
+        const int kidx = (int)__reduce_min_sync(BB_FULL, c2 ? (uint32_t)i0 : 0x7fffffffu);
+        const uint64_t kk = (((uint64_t)hi << 32) | lo) & K::ex_mask;
+        const bool d0 = u0 && ((((e0 | K::ge_mask) - kk) & K::ge_mask) == K::ge_mask);
+        const bool grp_cop = __any_sync(BB_FULL, d0 && e0 == kk && cp0);
+        u0 = u0 && !d0;
+        if (!grp_cop) k0 = k0 || kidx == i0;
+      }
+    } else {
+      for (;;) {
+        const bool p1 = u1 && (!u0 || v1 > v0);          // this lane's larger undecided key; the lower index on a tie
+        const uint64_t bk = p1 ? v1 : (u0 ? v0 : 0ull);
+        if (!__any_sync(BB_FULL, u0 || u1)) break;
+        const uint32_t hi = __reduce_max_sync(BB_FULL, (uint32_t)(bk >> 32));
+        const bool c1 = (u0 || u1) && (uint32_t)(bk >> 32) == hi;
+        const uint32_t lo = __reduce_max_sync(BB_FULL, c1 ? (uint32_t)bk : 0u);
+        const bool c2 = c1 && (uint32_t)bk == lo;
+        const int kidx = (int)__reduce_min_sync(BB_FULL, c2 ? (uint32_t)(p1 ? i1 : i0) : 0x7fffffffu);
+        const uint64_t kk = (((uint64_t)hi << 32) | lo) & K::ex_mask;
+        const bool d0 = u0 && ((((e0 | K::ge_mask) - kk) & K::ge_mask) == K::ge_mask);   // multiples of the killer, itself included
+        const bool d1 = u1 && ((((e1 | K::ge_mask) - kk) & K::ge_mask) == K::ge_mask);
+        const bool grp_cop = __any_sync(BB_FULL, (d0 && e0 == kk && cp0) || (d1 && e1 == kk && cp1));
+        u0 = u0 && !d0; u1 = u1 && !d1;
+        if (!grp_cop) { k0 = k0 || kidx == i0; k1 = k1 || kidx == i1; }
+      }
     }
-    const uint32_t km0 = __ballot_sync(BB_FULL, k0), km1 = __ballot_sync(BB_FULL, k1);
+    const uint32_t km0 = __ballot_sync(BB_FULL, k0), km1 = two ? __ballot_sync(BB_FULL, k1) : 0u;
     const int cnt0 = __popc(km0), cnt1 = __popc(km1);
     if (nP + cnt0 + cnt1 > P.max_pairs) return -1;
     if (k0) { const int pos = nP + __popc(km0 & ltm); pairs[pos] = ((uint32_t)m << 16) | (uint32_t)i0; plcm[pos] = v0; }
-    if (k1) { const int pos = nP + cnt0 + __popc(km1 & ltm); pairs[pos] = ((uint32_t)m << 16) | (uint32_t)i1; plcm[pos] = v1; }
+    if (two && k1) { const int pos = nP + cnt0 + __popc(km1 & ltm); pairs[pos] = ((uint32_t)m << 16) | (uint32_t)i1; plcm[pos] = v1; }
     nP += cnt0 + cnt1; emitted = cnt0 + cnt1;
   } else if (P.elimination == BB_ELIM_GEBAUERMOELLER) {
     // lscr[i] = key of L_i = lcm(LM_i, LM f), for every basis element (the old-pair filter gathers from it)
@@ -622,13 +639,15 @@ __device__ __noinline__ long long warp_add_basis(const BBParams& P, unsigned cha
   if (P.sort_reducers && m <= 64) {   // both halves of the list in registers: count, then shift by one, no read-after-write hazard
     const int i0 = lane, i1 = lane + 32;
     uint64_t r0 = 0ull, r1 = 0ull; uint32_t x0 = 0u, x1 = 0u;
+    const bool two = m > 32;
     if (i0 < m) { r0 = rlm[i0]; x0 = ridx[i0]; }
-    if (i1 < m) { r1 = rlm[i1]; x1 = ridx[i1]; }
+    if (two && i1 < m) { r1 = rlm[i1]; x1 = ridx[i1]; }
     // reducers with LM <= new LM  <=>  key >= new key; the list is sorted, so they are a prefix
-    pos = __popc(__ballot_sync(BB_FULL, i0 < m && r0 >= fk)) + __popc(__ballot_sync(BB_FULL, i1 < m && r1 >= fk));
+    pos = __popc(__ballot_sync(BB_FULL, i0 < m && r0 >= fk));
+    if (two) pos += __popc(__ballot_sync(BB_FULL, i1 < m && r1 >= fk));
     __syncwarp();
     if (i0 < m && i0 >= pos) { rlm[i0 + 1] = r0; ridx[i0 + 1] = x0; }
-    if (i1 < m && i1 >= pos) { rlm[i1 + 1] = r1; ridx[i1 + 1] = x1; }
+    if (two && i1 < m && i1 >= pos) { rlm[i1 + 1] = r1; ridx[i1 + 1] = x1; }
     __syncwarp();
   } else if (P.sort_reducers) {
     int cnt = 0;  // reducers with LM <= new LM  <=>  key >= new key
