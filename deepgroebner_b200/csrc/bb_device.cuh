@@ -350,7 +350,7 @@ __device__ __forceinline__ int warp_reduce(const BBParams& P, Env& e, Dividend& 
       const uint64_t rl = r < nR ? rlm[r] : ~0ull;
       const uint32_t b = __ballot_sync(BB_FULL, r < nR && K::divides(rl, lead));
       if (b) { found = base + __ffs(b) - 1; break; }
-      if (sorted && __any_sync(BB_FULL, rl < lead)) break;  // larger lead monomials from here on
+      if (sorted && base + 32 < nR && __any_sync(BB_FULL, rl < lead)) break;  // larger lead monomials from here on (the last chunk ends the scan anyway)
     }
     ct.lms += (found >= 0) ? (found + 1) : nR;
     if (found >= 0) {
