@@ -754,9 +754,10 @@ __device__ __forceinline__ int warp_step(const BBParams& P, Env& e, int row, uin
   const int rlen = warp_reduce<NV>(P, e, h, ENV_PTR(uint64_t, e, P, o_rlm), ENV_PTR(uint32_t, e, P, o_ridx), e.nG,
                                    P.sort_reducers != 0, ENV_PTR(uint64_t, e, P, o_tkey) + e.nT,
                                    ENV_PTR(uint32_t, e, P, o_tcoef) + e.nT, P.max_terms - e.nT, steps, ct);
-  if (rlen == -1) { e.status = BB_STATUS_OVERFLOW_SCRATCH; return 1 + steps; }
-  if (rlen == -2) { e.status = BB_STATUS_OVERFLOW_TERMS; return 1 + steps; }
-  if (rlen == -3 || (e.guard & K::g_all)) { e.status = BB_STATUS_OVERFLOW_EXPONENT; return 1 + steps; }
+  if (rlen < 0 || (e.guard & K::g_all)) {   // one test on the hot path; which fault it was is sorted out here
+    e.status = rlen == -1 ? BB_STATUS_OVERFLOW_SCRATCH : (rlen == -2 ? BB_STATUS_OVERFLOW_TERMS : BB_STATUS_OVERFLOW_EXPONENT);
+    return 1 + steps;
+  }
   if (rlen > 0) {
     ct.upb += (unsigned)e.nG; ct.upp += (unsigned)e.nP;
     const long long r = warp_add_basis<NV>(P, e.base, e.nG, e.nP, e.nT, rlen, h.sug);
