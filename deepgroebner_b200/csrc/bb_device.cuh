@@ -344,17 +344,19 @@ __device__ __forceinline__ int warp_reduce(const BBParams& P, Env& e, Dividend& 
   while (h.n > 0) {
     const uint64_t lead = h.k0;
     int found = -1;
+    uint32_t fidx = 0u;   // basis index of the divisor: loaded next to its lead monomial, one dependent load less per addition
 #pragma unroll 1
     for (int base = 0; base < nR; base += 32) {
       const int r = base + lane;
       const uint64_t rl = r < nR ? rlm[r] : ~0ull;
+      const uint32_t ix = r < nR ? ridx[r] : 0u;
       const uint32_t b = __ballot_sync(BB_FULL, r < nR && K::divides(rl, lead));
-      if (b) { found = base + __ffs(b) - 1; break; }
+      if (b) { const int src = __ffs(b) - 1; found = base + src; fidx = __shfl_sync(BB_FULL, ix, src); break; }
       if (sorted && base + 32 < nR && __any_sync(BB_FULL, rl < lead)) break;  // larger lead monomials from here on (the last chunk ends the scan anyway)
     }
     ct.lms += (found >= 0) ? (found + 1) : nR;
     if (found >= 0) {
-      const GHead f = load_head(gh + ridx[found]);
+      const GHead f = load_head(gh + fidx);
       const uint32_t c = bbf_mulmod(F, h.c0, f.invlc);
       const uint32_t nc = F.p - c;              // c != 0
       const uint64_t adj = lead - f.lm;         // key(LM h / LM f) - bias
