@@ -144,6 +144,7 @@ class Oracle:
         if prefix == "ref_":
             L("bench_random", None, _cp, _i, _i, _i, _dp)
             L("bench_buchberger", None, _cp, _i, _i, _i, _i, _i, C.c_double, _dp)
+            L("run_records", _i, _cp, _i, _i, _i, _i, _i, _i, _ip, _i, _i, _i, _i, C.c_double, _i, _i, _vp)
         else:
             L("set_prime", None, _i)
 
@@ -300,6 +301,30 @@ class Oracle:
         self.c_bench_buchberger(dist.encode(), SELECT[selection], seed0, count, nthreads, sel_seed0, gamma,
                                 out.ctypes.data_as(_dp))
         return dict(steps=int(out[0]), additions=int(out[1]), seconds=float(out[2]))
+
+    # numpy view of one record = bb_episode_stats (include/bbenv.h); kept here so that oracle/ imports nothing of the product
+    RECORD_DTYPE = [("steps", "<i4"), ("additions", "<i4"), ("zero_reductions", "<i4"), ("nonzero_reductions", "<i4"),
+                    ("nbasis", "<i4"), ("nterms", "<i4"), ("status", "<i4"), ("rerolls", "<i4"), ("trace_hash", "<u8"),
+                    ("basis_hash", "<u8"), ("gb_hash", "<u8"), ("gb_polys", "<i4"), ("gb_terms", "<i4"),
+                    ("discounted_return", "<f8")]
+
+    def run_records(self, dist, selection, count, seed0=0, seeds=None, sel_seed0=0, sel_stride=1, max_steps=0,
+                    gamma=0.99, compute_gb=True, nthreads=0, elimination="gebauermoeller", sort_input=False,
+                    sort_reducers=True):
+        """Per-episode records (the layout bb_run writes) of episodes 0..count-1 from the unmodified reference env,
+        on `nthreads` host threads (0 = all): the exhaustive parity gate of bench.py and the full-size GPU tests."""
+        if self.prefix != "ref_":
+            raise RuntimeError("run_records needs oracle/_ref (the unmodified reference)")
+        if not nthreads:
+            nthreads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        out = np.zeros(count, dtype=np.dtype(self.RECORD_DTYPE))
+        sd = None if seeds is None else _np_i(seeds)
+        rc = self.c_run_records(dist.encode(), SELECT[selection], ELIM[elimination], 0, int(sort_input),
+                                int(sort_reducers), seed0, None if sd is None else _ptr(sd), count, sel_seed0, sel_stride,
+                                max_steps, gamma, int(compute_gb), nthreads, out.ctypes.data_as(_vp))
+        if rc < 0:
+            raise RuntimeError("ref_run_records failed (%d)" % rc)
+        return out
 
     def bench_random(self, dist, seed0, episodes, nthreads=1):
         out = np.zeros(3, np.float64)

@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <array>
+#include <atomic>
 #include <chrono>
 #include <cstring>
 #include <functional>
@@ -474,6 +475,119 @@ void ref_bench_buchberger(const char* dist, int selection, int seed0, int count,
   long long S = 0, A = 0;
   for (int t = 0; t < nthreads; t++) { S += steps[t]; A += adds[t]; }
   out[0] = (double)S; out[1] = (double)A; out[2] = std::chrono::duration<double>(t1 - t0).count();
+}
+
+// ---- whole-run parity records (bench.py's exhaustive gate and the full-size GPU tests) ----
+//
+// ref_run_records: for every episode e in [0, count) the record the CUDA path's bb_run writes (bb_episode_stats,
+// include/bbenv.h), computed from the UNMODIFIED reference env driven exactly as BuchbergerEnv::reset/step are
+// (buchberger.cpp:299-329) with the pair chosen by the comparators of buchberger.cpp:160-241 or, for Random, by
+// choice() (ideals.h:68-73) on a std::default_random_engine seeded sel_seed0 + e * sel_stride (buchberger.cpp:190-197).
+// Episode e draws its ideal from stream seed seeds[e] (or seed0 + e).  Checksums as include/bbenv.h "checksums".
+// Threads pull episodes from an atomic counter.  Layout of one record = bb_episode_stats (72 bytes).
+struct RefRecord {
+  int32_t steps, additions, zero_reductions, nonzero_reductions, nbasis, nterms, status, rerolls;
+  uint64_t trace_hash, basis_hash, gb_hash;
+  int32_t gb_polys, gb_terms;
+  double discounted_return;
+};
+static_assert(sizeof(RefRecord) == 72, "must match bb_episode_stats");
+
+static inline uint64_t rr_mix64(uint64_t z) {
+  z ^= z >> 30; z *= 0xbf58476d1ce4e5b9ULL;
+  z ^= z >> 27; z *= 0x94d049bb133111ebULL;
+  z ^= z >> 31;
+  return z;
+}
+static inline uint64_t rr_item(uint64_t x, uint64_t pos) { return rr_mix64(x + 0x9E3779B97F4A7C15ULL * (pos + 1)); }
+static uint64_t rr_polys_hash(const std::vector<Polynomial>& F, int* nterms_out) {
+  uint64_t h = 0, t = 0;
+  for (size_t q = 0; q < F.size(); q++) {
+    for (const Term& tm : F[q].terms) {
+      uint64_t elo = 0, ehi = 0;
+      for (int v = 0; v < N; v++) {
+        const uint64_t x = (uint64_t)tm.monom[v];
+        if (v < 4) elo |= x << (16 * v); else ehi |= x << (16 * (v - 4));
+      }
+      h += rr_item((uint64_t)coef_int(tm.coeff), 3 * t) + rr_item(elo, 3 * t + 1) + rr_item(ehi, 3 * t + 2);
+      t++;
+    }
+    h += rr_mix64((uint64_t)F[q].terms.size() + 0xD1B54A32D192ED03ULL * (uint64_t)(q + 1));
+  }
+  if (nterms_out) *nterms_out = (int)t;
+  return h;
+}
+
+int ref_run_records(const char* dist, int selection, int elimination, int rewards, int sort_input, int sort_reducers,
+                    int seed0, const int* seeds, int count, int sel_seed0, int sel_stride, int max_steps, double gamma,
+                    int compute_gb, int nthreads, void* out_records) {
+  RefRecord* out = static_cast<RefRecord*>(out_records);
+  if (rewards != 0) return -2;   // the record's addition count is read off the Additions reward
+  if (selection < 0 || selection > 4) return -1;   // the reversed strategies are covered through ref_buchberger
+  if (nthreads < 1) nthreads = 1;
+  std::atomic<int> next{0};
+  std::atomic<int> failed{0};
+  std::vector<std::thread> th;
+  for (int t = 0; t < nthreads; t++) {
+    th.emplace_back([&]() {
+      try {
+        BuchbergerEnv env{dist, elim_of(elimination), rew_of(rewards), sort_input != 0, sort_reducers != 0};
+        auto twin = parse_ideal_dist(std::string(dist));   // counts the re-rolls of reset() (buchberger.cpp:313-314)
+        for (;;) {
+          const int e = next.fetch_add(1);
+          if (e >= count) break;
+          const int sd = seeds ? seeds[e] : seed0 + e;
+          env.seed(sd);
+          env.reset();
+          RefRecord r;
+          std::memset(&r, 0, sizeof r);
+          {
+            twin->seed(sd);
+            int rolls = 0;
+            for (;; rolls++) {
+              std::vector<Polynomial> F = twin->next();
+              if (sort_input)
+                std::sort(F.begin(), F.end(), [](const Polynomial& f, const Polynomial& g) { return f.LM() < g.LM(); });
+              if (F == env.G || rolls > 1000) break;
+            }
+            r.rerolls = rolls;
+          }
+          std::default_random_engine rng(sel_seed0 + e * sel_stride);
+          uint64_t th_ = 0;
+          double ret = 0.0, disc = 1.0;
+          const int g0 = (int)env.G.size();
+          while (!env.P.empty() && (max_steps == 0 || r.steps < max_steps)) {
+            int row;
+            if (selection == 4) row = (int)(choice(env.P.begin(), env.P.end(), rng) - env.P.begin());
+            else row = select_row(env.G, env.P, selection);
+            const SPair p = env.P[row];
+            const double reward = env.step(p);
+            const int a = (int)(-reward);   // Additions rewards (checked on entry): reward = -(1 + reduction steps)
+            th_ = th_ * 0x9E3779B97F4A7C15ULL + ((((uint64_t)(uint32_t)a) << 32) | ((uint64_t)p.j << 16) | (uint64_t)p.i) + 1ULL;
+            ret += disc * reward;
+            disc *= gamma;
+            r.steps++;
+            r.additions += a;
+          }
+          r.nbasis = (int)env.G.size();
+          r.nonzero_reductions = r.nbasis - g0;
+          r.zero_reductions = r.steps - r.nonzero_reductions;
+          r.status = env.P.empty() ? 2 : 1;
+          r.trace_hash = th_;
+          r.basis_hash = rr_polys_hash(env.G, &r.nterms);
+          if (compute_gb && env.P.empty()) {
+            const std::vector<Polynomial> gb = interreduce(minimalize(env.G));
+            r.gb_hash = rr_polys_hash(gb, &r.gb_terms);
+            r.gb_polys = (int)gb.size();
+          }
+          r.discounted_return = ret;
+          out[e] = r;
+        }
+      } catch (...) { failed = 3; }
+    });
+  }
+  for (auto& x : th) x.join();
+  return -failed.load();
 }
 
 }  // extern "C"
