@@ -314,7 +314,8 @@ def gpu_arm(args):
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     counters = eng.counters(reset=True)
     stats = stats_dev.cpu().numpy().view(np.dtype(_lib.STATS_DTYPE))
-    assert (stats["status"] == 2).all(), "not every episode finished"
+    assert (stats["status"] == 2).all(), "not every episode finished: status histogram %r" % (
+        dict(zip(*[x.tolist() for x in np.unique(stats["status"], return_counts=True)])),)
     steps_per_launch = int(stats["steps"].sum())
     adds_per_launch = int(stats["additions"].sum())
     assert counters["env_steps"] == steps_per_launch * args.steps

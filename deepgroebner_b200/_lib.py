@@ -56,7 +56,7 @@ EXPORTS = [
     "bb_abi_version", "bb_resident_envs", "bb_create", "bb_destroy", "bb_last_error", "bb_cols", "bb_num_envs", "bb_sm_count",
     "bb_set_distribution", "bb_set_distribution_poly", "bb_seed", "bb_set_ideals", "bb_reset", "bb_step", "bb_select", "bb_observe", "bb_pairs",
     "bb_status", "bb_stats", "bb_run", "bb_download_basis", "bb_final_gb", "bb_counters_read", "bb_hash_item",
-    "bb_seed_selection", "bb_value", "bb_copy_env", "bb_set_auto_reset", "bb_set_wide", "bb_set_selection_seed_stride", "bb_policy_pmlp", "bb_rollout",
+    "bb_seed_selection", "bb_value", "bb_copy_env", "bb_set_auto_reset", "bb_step_observe", "bb_step_host", "bb_reset_host", "bb_observe_host", "bb_set_wide", "bb_set_prepare_mode", "bb_set_selection_seed_stride", "bb_policy_pmlp", "bb_rollout",
 ]
 
 _lib = None
@@ -102,6 +102,14 @@ def load():
     lib.bb_reset.argtypes = [vp, vp, vp]
     lib.bb_step.restype = i
     lib.bb_step.argtypes = [vp, vp, vp, vp, vp]
+    lib.bb_step_observe.restype = i
+    lib.bb_step_observe.argtypes = [vp, vp, vp, vp, vp, vp, i, vp]
+    lib.bb_step_host.restype = i
+    lib.bb_step_host.argtypes = [vp, vp, vp, vp, vp, vp, i, i, vp]
+    lib.bb_reset_host.restype = i
+    lib.bb_reset_host.argtypes = [vp, vp, vp, i, i, vp]
+    lib.bb_observe_host.restype = i
+    lib.bb_observe_host.argtypes = [vp, vp, vp, i, i, vp]
     lib.bb_select.restype = i
     lib.bb_select.argtypes = [vp, i, vp, vp]
     lib.bb_observe.restype = i
@@ -122,6 +130,8 @@ def load():
     lib.bb_set_auto_reset.argtypes = [vp, i]
     lib.bb_set_wide.restype = i
     lib.bb_set_wide.argtypes = [vp, i]
+    lib.bb_set_prepare_mode.restype = i
+    lib.bb_set_prepare_mode.argtypes = [vp, i]
     lib.bb_set_selection_seed_stride.restype = i
     lib.bb_set_selection_seed_stride.argtypes = [vp, i]
     u64 = C.c_uint64

@@ -19,7 +19,7 @@ from .ideals import BinomialSpec, FixedIdealGenerator, PolySpec, parse_ideal_dis
 CAPACITY_PRESETS = {
     "binomial": dict(max_basis=512, max_pairs=1024, max_terms=1536, max_poly_terms=64),
     "poly": dict(max_basis=512, max_pairs=2048, max_terms=1 << 14, max_poly_terms=512),
-    "general": dict(max_basis=2048, max_pairs=8192, max_terms=1 << 18, max_poly_terms=2048),
+    "general": dict(max_basis=2048, max_pairs=8192, max_terms=1 << 19, max_poly_terms=4096),
 }
 
 
@@ -165,6 +165,56 @@ class BuchbergerEngine:
             self._ck(self.lib.bb_step(self.h, _ptr(actions), _ptr(reward), _ptr(done), _stream()), "bb_step")
         return reward, done
 
+    def step_observe(self, actions, pmax, reward=None, done=None, obs=None, lengths=None):
+        """step() and the observation of the new state in ONE launch (bb_step_observe): LeadMonomialsEnv.step as a
+        whole.  Returns (obs[N, pmax, cols], lengths[N], reward[N], done[N]) as cuda tensors."""
+        with torch.cuda.device(self.device):
+            actions = torch.as_tensor(actions, device=self.device).to(torch.int32).contiguous().view(-1)
+            assert actions.numel() == self.num_envs
+            if reward is None:
+                reward = torch.empty(self.num_envs, dtype=torch.float64, device=self.device)
+            if done is None:
+                done = torch.empty(self.num_envs, dtype=torch.uint8, device=self.device)
+            if obs is None:
+                obs = torch.empty((self.num_envs, pmax, self.cols), dtype=torch.int32, device=self.device)
+            if lengths is None:
+                lengths = torch.empty(self.num_envs, dtype=torch.int32, device=self.device)
+            self._ck(self.lib.bb_step_observe(self.h, _ptr(actions), _ptr(reward), _ptr(done), _ptr(obs), _ptr(lengths),
+                                              int(pmax), _stream()), "bb_step_observe")
+        return obs, lengths, reward, done
+
+    # ---- the same calls with HOST buffers, as the reference's Cython binding makes them (one launch, one sync each)
+    def _host_buffers(self, pmax):
+        hb = getattr(self, "_hb", None)
+        if hb is None or hb["pmax"] != pmax:
+            N = self.num_envs
+            hb = dict(pmax=pmax, act=np.zeros(N, np.int32), rew=np.zeros(N, np.float64), done=np.zeros(N, np.uint8),
+                      len=np.zeros(N, np.int32), obs=np.full((N, pmax, self.cols), -1, np.int32))
+            for k_ in ("act", "rew", "done", "len", "obs"):
+                hb["p_" + k_] = C.c_void_p(hb[k_].ctypes.data)
+            self._hb = hb
+        return hb
+
+    def step_host(self, actions, pmax, pad=True):
+        """bb_step_host: actions from host memory; returns numpy views (obs[N, pmax, cols], lengths[N], reward[N],
+        done[N]) that the next call overwrites.  pad=False leaves the rows beyond |P| undefined."""
+        hb = self._host_buffers(int(pmax))
+        hb["act"][...] = actions
+        self._ck(self.lib.bb_step_host(self.h, hb["p_act"], hb["p_rew"], hb["p_done"], hb["p_obs"], hb["p_len"],
+                                       hb["pmax"], int(pad), _stream()), "bb_step_host")
+        return hb["obs"], hb["len"], hb["rew"], hb["done"]
+
+    def reset_host(self, pmax, pad=True):
+        """bb_reset_host: reset() of every environment and the first observation, to host memory."""
+        hb = self._host_buffers(int(pmax))
+        self._ck(self.lib.bb_reset_host(self.h, hb["p_obs"], hb["p_len"], hb["pmax"], int(pad), _stream()), "bb_reset_host")
+        return hb["obs"], hb["len"]
+
+    def observe_host(self, pmax, pad=True):
+        hb = self._host_buffers(int(pmax))
+        self._ck(self.lib.bb_observe_host(self.h, hb["p_obs"], hb["p_len"], hb["pmax"], int(pad), _stream()), "bb_observe_host")
+        return hb["obs"], hb["len"]
+
     def select(self, strategy="degree", out=None):
         with torch.cuda.device(self.device):
             if out is None:
@@ -249,9 +299,15 @@ class BuchbergerEngine:
 
     def set_wide(self, mode=-1):
         """Episode runner of run_episodes (bb_set_wide): -1 auto, 0 one warp per environment, 1 one CTA per
-        environment (long polynomials); 2 / 3 as 1 with the block merge on its fallback paths (rank merge / two-walk
-        merge path).  Results are identical; only speed differs."""
+        environment (long polynomials); 2 / 3 as 1 with the block merge on its fallback paths (2: merge by rank for
+        every addition, 3: the zero-coefficient compaction after every addition).  Results are identical; only speed
+        differs."""
         self._ck(self.lib.bb_set_wide(self.h, int(mode)), "bb_set_wide")
+
+    def set_prepare_mode(self, by_warp=False):
+        """Episode preparation of run_episodes (bb_set_prepare_mode): one thread per episode where it applies
+        (default) or always one warp per episode.  Results are identical; only speed differs."""
+        self._ck(self.lib.bb_set_prepare_mode(self.h, int(bool(by_warp))), "bb_set_prepare_mode")
 
     def set_selection_seed_stride(self, stride=1):
         """run_episodes seeds episode e's 'random' selection stream with selection_seed + e * stride
@@ -363,21 +419,23 @@ class LeadMonomialsEnv:
 
     def _state(self):
         if self.num_envs == 1:
-            n = int(self.engine.lengths().item())
-            obs, _ = self.engine.observe(max(n, 1))
-            return obs[0, :n].cpu().numpy().astype(self.dtype)
+            obs, lengths = self.engine.observe_host(self.pmax, pad=False)
+            return obs[0, :int(lengths[0])].astype(self.dtype)
         return self.engine.observe(self.pmax)
 
     def reset(self):
+        if self.num_envs == 1:   # one launch pair, one synchronisation (wrapped.pyx:18-21)
+            obs, lengths = self.engine.reset_host(self.pmax, pad=False)
+            return obs[0, :int(lengths[0])].astype(self.dtype)
         self.engine.reset()
         return self._state()
 
     def step(self, action):
-        reward, done = self.engine.step(action)
-        state = self._state()
-        if self.num_envs == 1:
-            return state, float(reward.item()), bool(done.item()), {}
-        return state, reward, done.bool(), {}
+        if self.num_envs == 1:   # one launch, one synchronisation, the action in the launch parameters (wrapped.pyx:23-26)
+            obs, lengths, reward, done = self.engine.step_host(action, self.pmax, pad=False)
+            return obs[0, :int(lengths[0])].astype(self.dtype), float(reward[0]), bool(done[0]), {}
+        obs, lengths, reward, done = self.engine.step_observe(action, self.pmax)
+        return (obs, lengths), reward, done.bool(), {}
 
     def value(self, strategy="degree", gamma=0.99, **kw):
         """Discounted return of finishing from the current state under `strategy` (wrapped.pyx:32-33,

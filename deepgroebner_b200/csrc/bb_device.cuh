@@ -25,6 +25,9 @@
 #include "bb_layout.cuh"
 
 #define BB_FULL 0xffffffffu
+#ifndef BB_ADD_BASIS_INLINE
+#define BB_ADD_BASIS_INLINE __noinline__   // A/B switch: __forceinline__ puts update() into every caller
+#endif
 #define BB_GOLD 0x9E3779B97F4A7C15ULL
 #define BB_GOLD2 0xD1B54A32D192ED03ULL
 
@@ -126,8 +129,15 @@ struct Env {
   uint64_t guard;  // OR of every produced monomial key: any guard bit set => exponent/degree overflow
 };
 
-#define ENV_PTR(T, e, P, off) (reinterpret_cast<T*>((e).base + (P).off))
-#define SLOT_PTR(T, P, slot, off) (reinterpret_cast<T*>((P).arena + (size_t)(slot) * (P).slot_stride + (P).off))
+// Every arena lives in global memory: saying so lets the compiler emit LDG / STG instead of generic LD / ST (whose
+// address-space resolution sits on the latency chain of every dependent load of the step).
+template <class T>
+__device__ __forceinline__ T* bb_global(T* p) {
+  __builtin_assume(__isGlobal(p));
+  return p;
+}
+#define ENV_PTR(T, e, P, off) (bb_global(reinterpret_cast<T*>((e).base + (P).off)))
+#define SLOT_PTR(T, P, slot, off) (bb_global(reinterpret_cast<T*>((P).arena + (size_t)(slot) * (P).slot_stride + (P).off)))
 
 __device__ __forceinline__ int bb_lane() { return threadIdx.x & 31; }
 __device__ __forceinline__ uint32_t bb_lt_mask() { return (1u << bb_lane()) - 1u; }
@@ -151,8 +161,8 @@ __host__ __device__ __forceinline__ uint64_t bb_hash_item_impl(uint64_t x, uint6
 }
 
 __device__ __forceinline__ void env_load(const BBParams& P, int slot, Env& e) {
-  e.base = P.arena + (size_t)slot * P.slot_stride;
-  const int4 s = *reinterpret_cast<const int4*>(&P.st[slot]);
+  e.base = bb_global(P.arena + (size_t)slot * P.slot_stride);
+  const int4 s = *reinterpret_cast<const int4*>(bb_global(&P.st[slot]));
   e.nG = s.x; e.nP = s.y; e.nT = s.z; e.status = s.w;
   e.guard = 0;
 }
@@ -423,12 +433,13 @@ __device__ __forceinline__ int warp_reduce(const BBParams& P, Env& e, Dividend& 
 // One out-of-line copy shared by step and reset.  Returns (emitted << 32) | new |P|, or -1 on pair-list overflow /
 // -2 when the basis is full / -3 when an lcm's degree does not fit the packed layout; the caller bumps nG and nT.
 template <int NV>
-__device__ __noinline__ long long warp_add_basis(const BBParams& P, unsigned char* base, int m, int nP, int off, int len,
+__device__ BB_ADD_BASIS_INLINE long long warp_add_basis(const BBParams& P, unsigned char* base, int m, int nP, int off, int len,
                                                  int sug) {
   typedef KL<NV> K;
   const int lane = bb_lane();
   const uint32_t ltm = bb_lt_mask();
   if (m >= P.max_basis) return -2;
+  base = bb_global(base);
   const uint64_t* tk = reinterpret_cast<const uint64_t*>(base + P.o_tkey) + off;
   const uint32_t* tc = reinterpret_cast<const uint32_t*>(base + P.o_tcoef) + off;
   const uint64_t fk = tk[0];
@@ -675,7 +686,7 @@ __device__ __noinline__ long long warp_add_basis(const BBParams& P, unsigned cha
     rlm[pos] = fk; ridx[pos] = (uint32_t)m;
     lm[m] = fk;
     GHeadMem* g = reinterpret_cast<GHeadMem*>(base + P.o_ghead) + m;
-    const uint32_t inv = P.invtab[tc[0]];  // 1/LC: one table load instead of a 15-step power ladder
+    const uint32_t inv = bb_global(P.invtab)[tc[0]];  // 1/LC: one table load instead of a 15-step power ladder
     const uint64_t k1 = len > 1 ? tk[1] : 0ull;
     const uint32_t c1 = len > 1 ? tc[1] : 0u;
     reinterpret_cast<uint4*>(g)[0] = make_uint4((uint32_t)fk, (uint32_t)(fk >> 32), (uint32_t)k1, (uint32_t)(k1 >> 32));
@@ -807,6 +818,7 @@ template <int NV>
 __device__ __noinline__ int warp_select_rare(const BBParams& P, unsigned char* base, int nP, int strategy, uint32_t* rng) {
   typedef KL<NV> K;
   const int lane = bb_lane();
+  base = bb_global(base);
   const uint64_t* plcm = reinterpret_cast<const uint64_t*>(base + P.o_plcm);
   if (strategy == BB_SELECT_RANDOM) {  // choice(): uniform_int_distribution<>(0, |P|-1)(rng), ideals.h:68-73
     uint32_t x = *rng;                        // rng: shared or global memory, one word per environment

@@ -39,6 +39,7 @@ struct BBRunArgs {
   bb_episode_stats* out;
   int32_t* trace;
   int trace_eps, trace_cap;
+  int prepare_by_warp;  // 1: k_prepare (one warp per episode) even where k_prepare_lanes applies (tests compare the two)
   int wide_flags;    // k_run_wide: BBW_FLAG_* (bb_wide.cuh), the merge variants bb_set_wide(2 / 3) select
   int* queue;        // [0]: next queue position; [BB_LPT_HIST .. +BB_LPT_BUCKETS): histogram of the cost keys of the batch, then as many cursors
   int* order;        // [episodes] queue position -> episode of the batch, longest predicted first (k_order)
@@ -77,6 +78,8 @@ struct BBKernelTable {
   int nvars, w, dw, dshift, eshift;
   cudaError_t (*reset)(const BBParams&, const uint8_t* mask, int nwarps, cudaStream_t);
   cudaError_t (*step)(const BBParams&, const int* actions, double* reward, uint8_t* done, int nwarps, cudaStream_t);
+  cudaError_t (*step_obs)(const BBParams&, const int* actions, int action0, double* reward, uint8_t* done, int32_t* obs,
+                          int32_t* lengths, int pmax, int pad, int do_step, int nwarps, cudaStream_t);
   cudaError_t (*select)(const BBParams&, int strategy, int* actions, int nwarps, cudaStream_t);
   cudaError_t (*observe)(const BBParams&, int32_t* obs, int32_t* lengths, int pmax, int nwarps, cudaStream_t);
   cudaError_t (*final_gb)(const BBParams&, int slot, int* ok_out, cudaStream_t);
@@ -173,6 +176,49 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_step(const __grid
   counters_flush(P, sh);
 }
 
+// step() as the reference's binding sees it (wrapped.pyx:23-26: step, then the state matrix and done, in ONE call):
+// one launch does the step of every environment, the auto-reset if enabled, and the observation of the state AFTER it.
+// `actions` may be NULL, then every environment takes `action0` (the single-environment drop-in passes its action by
+// value: no host-to-device copy at all).  The outputs may be device memory or mapped pinned host memory.
+// pad == 0: rows beyond |P| are left untouched (a host caller reads lengths first), else they are -1.
+template <int NV>
+__global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_step_obs(const __grid_constant__ BBParams P,
+                                                                       const int* __restrict__ actions, int action0,
+                                                                       double* __restrict__ reward, uint8_t* __restrict__ done,
+                                                                       int32_t* __restrict__ obs, int32_t* __restrict__ lengths,
+                                                                       int pmax, int pad, int do_step) {
+  __shared__ unsigned long long sh[BB_WARPS][CT_COUNT];
+  unsigned long long* row = counters_row(sh);
+  const int slot = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
+  if (slot < P.num_envs) {
+    Env e; env_load(P, slot, e);
+    Ctr ct; ct.clear();
+    if (do_step) {
+      double r = 0.0;
+      if (e.status == BB_STATUS_RUNNING) {
+        r = step_and_account<NV>(P, slot, e, actions ? actions[slot] : action0, ct, row);
+        env_store(P, slot, e);
+      }
+      if (bb_lane() == 0) {
+        if (reward) reward[slot] = r;
+        if (done) done[slot] = (e.status != BB_STATUS_RUNNING) ? 1 : 0;
+      }
+      if (P.auto_reset && e.status != BB_STATUS_RUNNING) {
+        __syncwarp();
+        warp_reset_slot<NV>(P, slot, slot, (uint32_t)P.st[slot].rng, row);
+        env_load(P, slot, e);
+      }
+    }
+    if (obs) {
+      const int rows = e.nP < pmax ? e.nP : pmax;
+      warp_observe<NV>(P, e, obs + (size_t)slot * pmax * P.cols, pad ? pmax : rows, ct);
+    }
+    if (lengths && bb_lane() == 0) lengths[slot] = e.nP;
+    ct.spill(row);
+  }
+  counters_flush(P, sh);
+}
+
 template <int NV>
 __global__ void __launch_bounds__(BB_THREADS) k_select(const __grid_constant__ BBParams P, int strategy,
                                                        int* __restrict__ actions) {
@@ -240,6 +286,151 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_prepare(const __g
   counters_flush(S, sh);
 }
 
+// The same preparation with ONE THREAD per episode, for the binomial distributions (RandomBinomialIdealGenerator,
+// ideals.cpp:168-201) with at most BB_PREP_S generators: the generator and the s update() calls of reset()
+// (buchberger.cpp:299-315, :52-99) are a few thousand scalar instructions on <= 16 lead monomials and <= 120 pairs, so
+// a warp that spends them on one episode (k_prepare) wastes 31 lanes; here a warp prepares 32 episodes in lockstep
+// out of thread-local arrays and writes each finished state to its staging slot.  Same results, same counters.
+// update() in closed form (see warp_add_basis): with L_i = lcm(LM_i, LM f), (i, m) is emitted iff no L_j strictly divides
+// L_i, no j < i has L_j == L_i, and no j with L_j == L_i is coprime to f.
+#define BB_PREP_S 16
+#define BB_PREP_P (BB_PREP_S * (BB_PREP_S - 1) / 2)
+#define BB_PREP_THREADS 64
+template <int NV>
+__global__ void __launch_bounds__(BB_PREP_THREADS) k_prepare_lanes(const __grid_constant__ BBParams S,
+                                                                    const __grid_constant__ BBRunArgs A) {
+  typedef KL<NV> K;
+  __shared__ unsigned long long sh_up[2];
+  if (threadIdx.x < 2) sh_up[threadIdx.x] = 0ull;
+  __syncthreads();
+  const int b = blockIdx.x * BB_PREP_THREADS + threadIdx.x;
+  unsigned upb = 0u, upp = 0u;
+  if (b < A.episodes) {
+    const BBDist& D = S.dist;
+    const BBField F = S.F;
+    const int ep = A.ep_base + b;
+    const int s = D.s;
+    uint32_t x = rng_seed(A.seeds ? A.seeds[ep] : A.seed_base + ep);
+    uint64_t gk0[BB_PREP_S], gk1[BB_PREP_S];          // generators: lead / second monomial, second coefficient (lead coefficient 1)
+    uint32_t gc1[BB_PREP_S];
+    uint64_t L[BB_PREP_S];                             // update(): key of lcm(LM_i, LM f)
+    uint64_t rl[BB_PREP_S]; uint32_t ri[BB_PREP_S];    // reducer list G_
+    uint32_t prs[BB_PREP_P]; uint64_t plc[BB_PREP_P];  // pair list P with cached lcm keys
+    int nG = 0, nP = 0, status = BB_STATUS_EMPTY, rerolls = 0;
+    for (;;) {
+      bool ok = true;
+      for (int i = 0; i < s && ok; i++) {   // RandomBinomialIdealGenerator::next, as gen_binomial_ideal
+        const uint32_t c = D.pure ? (F.p - 1u) : (uint32_t)rng_uniform(x, 1, (int)F.p - 1);
+        int d1, d2;
+        if (D.homogeneous) d1 = d2 = rng_degree(D, x);
+        else { d1 = rng_degree(D, x); d2 = rng_degree(D, x); }
+        const int o1 = D.basis_off[d1], n1 = D.basis_off[d1 + 1] - o1, o2 = D.basis_off[d2], n2 = D.basis_off[d2 + 1] - o2;
+        ok = false;
+        for (int trials = 0; trials < 1000 && !ok; trials++) {
+          const uint64_t m1 = D.basis[o1 + rng_uniform(x, 0, n1 - 1)];
+          const uint64_t m2 = D.basis[o2 + rng_uniform(x, 0, n2 - 1)];
+          if (m1 != m2) { gk0[i] = m1 < m2 ? m1 : m2; gk1[i] = m1 < m2 ? m2 : m1; gc1[i] = c; ok = true; }
+        }
+      }
+      if (!ok) { nG = nP = 0; status = BB_STATUS_EMPTY; break; }   // the reference throws (ideals.cpp:196-197)
+      if (S.sort_input) {   // ascending lead monomial == descending key, stable (buchberger.cpp:301-302; see warp_load_ideal)
+        for (int i = 1; i < s; i++) {
+          const uint64_t a0 = gk0[i], a1 = gk1[i]; const uint32_t ac = gc1[i];
+          int j = i;
+          while (j > 0 && gk0[j - 1] < a0) { gk0[j] = gk0[j - 1]; gk1[j] = gk1[j - 1]; gc1[j] = gc1[j - 1]; j--; }
+          gk0[j] = a0; gk1[j] = a1; gc1[j] = ac;
+        }
+      }
+      nG = 0; nP = 0; status = BB_STATUS_RUNNING;
+      for (int m = 0; m < s; m++) {   // update(G, P, f) + insertion into G_, generator by generator
+        const uint64_t fk = gk0[m], fe = fk & K::ex_mask;
+        upb += (unsigned)m; upp += (unsigned)nP;
+        int kept = nP;   // old pairs that survive
+        if (S.elimination == BB_ELIM_GEBAUERMOELLER) {
+          bool ovf = false;
+          uint32_t cop = 0u;
+          for (int i = 0; i < m; i++) {
+            const uint64_t le = K::lcm_exps(gk0[i], fk);
+            const uint32_t dg = K::sum_fields(le);
+            ovf |= dg > K::dmax;
+            L[i] = le | ((uint64_t)(K::dmax - dg) << K::dshift);
+            cop |= K::coprime(gk0[i], fk) ? (1u << i) : 0u;
+          }
+          if (ovf) { status = BB_STATUS_OVERFLOW_EXPONENT; break; }
+          int w = 0;
+          for (int q = 0; q < nP; q++) {
+            const uint32_t pr = prs[q]; const uint64_t pl = plc[q];
+            const uint64_t l = pl & K::ex_mask;
+            const bool drop = K::divides(fe, l) && l != (L[pr & 0xffffu] & K::ex_mask) && l != (L[pr >> 16] & K::ex_mask);
+            if (!drop) { prs[w] = pr; plc[w] = pl; w++; }
+          }
+          nP = w; kept = w;
+          for (int i = 0; i < m; i++) {
+            const uint64_t li = L[i] & K::ex_mask;
+            bool emit = true;
+            for (int j = 0; j < m; j++) {
+              const uint64_t lj = L[j] & K::ex_mask;
+              if (lj == li) emit = emit && !(j < i) && !((cop >> j) & 1u);
+              else emit = emit && !((((li | K::ge_mask) - lj) & K::ge_mask) == K::ge_mask);
+            }
+            if (emit) { prs[nP] = ((uint32_t)m << 16) | (uint32_t)i; plc[nP] = L[i]; nP++; }
+          }
+        } else {
+          for (int i = 0; i < m; i++) {
+            if (S.elimination == BB_ELIM_LCM && K::coprime(gk0[i], fk)) continue;
+            prs[nP] = ((uint32_t)m << 16) | (uint32_t)i; plc[nP] = K::key_from_exps(K::lcm_exps(gk0[i], fk)); nP++;
+          }
+        }
+        upp += (unsigned)(nP - kept);   // emitted pairs, counted as warp_load_ideal counts them
+        int pos = m;
+        if (S.sort_reducers) {   // after every element whose lead monomial is <= the new one (key >= new key)
+          pos = 0;
+          while (pos < m && rl[pos] >= fk) pos++;
+          for (int r = m; r > pos; r--) { rl[r] = rl[r - 1]; ri[r] = ri[r - 1]; }
+        }
+        rl[pos] = fk; ri[pos] = (uint32_t)m;
+        nG = m + 1;
+      }
+      if (status != BB_STATUS_RUNNING || nP > 0) break;
+      rerolls++;   // P came out empty: the next ideal of the same stream (buchberger.cpp:313-314)
+    }
+    if (status == BB_STATUS_RUNNING && nP == 0) status = BB_STATUS_DONE;
+    // the finished state goes to the episode's staging slot
+    unsigned char* base = S.arena + (size_t)b * S.slot_stride;
+    GHeadMem* gh = reinterpret_cast<GHeadMem*>(base + S.o_ghead);
+    uint64_t* lm = reinterpret_cast<uint64_t*>(base + S.o_lm);
+    uint64_t* rlm = reinterpret_cast<uint64_t*>(base + S.o_rlm);
+    uint32_t* ridx = reinterpret_cast<uint32_t*>(base + S.o_ridx);
+    uint32_t* pairs = reinterpret_cast<uint32_t*>(base + S.o_pairs);
+    uint64_t* plcm = reinterpret_cast<uint64_t*>(base + S.o_plcm);
+    uint64_t* tk = reinterpret_cast<uint64_t*>(base + S.o_tkey);
+    uint32_t* tc = reinterpret_cast<uint32_t*>(base + S.o_tcoef);
+    uint32_t sd = 0;
+    for (int m = 0; m < nG; m++) {
+      const uint64_t fk = gk0[m], k1 = gk1[m];
+      reinterpret_cast<uint4*>(gh + m)[0] = make_uint4((uint32_t)fk, (uint32_t)(fk >> 32), (uint32_t)k1, (uint32_t)(k1 >> 32));
+      reinterpret_cast<uint4*>(gh + m)[1] = make_uint4(1u | (gc1[m] << 16), K::deg(fk), (uint32_t)(2 * m), 2u);   // 1 / LC = 1
+      lm[m] = fk; rlm[m] = rl[m]; ridx[m] = ri[m];
+      tk[2 * m] = fk; tk[2 * m + 1] = k1; tc[2 * m] = 1u; tc[2 * m + 1] = gc1[m];
+      sd += K::deg(fk);
+    }
+    for (int q = 0; q < nP; q++) { pairs[q] = prs[q]; plcm[q] = plc[q]; }
+    *reinterpret_cast<int4*>(&S.st[b]) = make_int4(nG, nP, 2 * nG, status);
+    S.st[b].rng = x; S.st[b].rerolls = rerolls;
+    uint32_t key = (sd * (BB_LPT_BUCKETS - 1)) / (uint32_t)max(1, D.s * D.d);
+    key = key < BB_LPT_BUCKETS ? key : BB_LPT_BUCKETS - 1;
+    A.cost_key[b] = (uint8_t)key;
+    atomicAdd(&A.queue[BB_LPT_HIST + key], 1);
+  }
+  upb = __reduce_add_sync(BB_FULL, upb); upp = __reduce_add_sync(BB_FULL, upp);
+  if (bb_lane() == 0) { atomicAdd(&sh_up[0], (unsigned long long)upb); atomicAdd(&sh_up[1], (unsigned long long)upp); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (sh_up[0]) atomicAdd(&S.counters[CT_UPB], sh_up[0]);
+    if (sh_up[1]) atomicAdd(&S.counters[CT_UPP], sh_up[1]);
+  }
+}
+
 // Queue order of a batch: episodes sorted by cost bucket, largest first (counting sort).  Every CTA recomputes the
 // bucket starts from the histogram and places a slice of the batch through the global per-bucket cursors.  Within a
 // bucket the order is whatever the atomics produce -- it only decides which worker warp picks an episode up when.
@@ -262,6 +453,7 @@ __global__ void __launch_bounds__(BB_LPT_BUCKETS) k_order(const __grid_constant_
 
 // copy n 32-bit words, lane-strided
 __device__ __forceinline__ void warp_copy_words(uint32_t* __restrict__ d, const uint32_t* __restrict__ s, int n) {
+  d = bb_global(d); s = bb_global(s);
 #pragma unroll 1
   for (int t = bb_lane(); t < n; t += 32) d[t] = s[t];
 }
@@ -319,13 +511,13 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_run(const __grid_
     Ctr ct; ct.clear();
     for (;;) {
       int b = 0;
-      if (lane == 0) { b = atomicAdd(A.queue, 1); b = b < A.episodes ? A.order[b] : -1; }
+      if (lane == 0) { b = atomicAdd(bb_global(A.queue), 1); b = b < A.episodes ? bb_global(A.order)[b] : -1; }
       b = __shfl_sync(BB_FULL, b, 0);
       if (b < 0) break;
       const int ep = A.ep_base + b;
       Env e; env_load(S, b, e);  // the prepared state; e.base still points into the staging arena here
       {
-        unsigned char* db = P.arena + (size_t)slot * P.slot_stride;
+        unsigned char* db = bb_global(P.arena + (size_t)slot * P.slot_stride);
         warp_copy_env(P, db, S, e.base, e);
         e.base = db;
         __syncwarp();
@@ -378,6 +570,7 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_run(const __grid_
 
 // block-strided copy of n 32-bit words
 __device__ __forceinline__ void block_copy_words(uint32_t* __restrict__ d, const uint32_t* __restrict__ s, int n) {
+  d = bb_global(d); s = bb_global(s);
 #pragma unroll 1
   for (int t = threadIdx.x; t < n; t += BBW_THREADS) d[t] = s[t];
 }
@@ -393,17 +586,21 @@ __global__ void __launch_bounds__(BBW_THREADS, BBW_MIN_CTAS) k_run_wide(const __
   __shared__ WideShared ws;
   __shared__ int next_b;
   const int cap = P.max_poly_terms;
+  // two dividend buffers of cap terms + BBW_SENT sentinels, two staging buffers of BBW_BSTAGE terms (bb_wide.cuh)
   uint64_t* hk = reinterpret_cast<uint64_t*>(wide_smem);
-  uint32_t* hc = reinterpret_cast<uint32_t*>(wide_smem + (size_t)16 * cap);
-  uint64_t* sk = reinterpret_cast<uint64_t*>(wide_smem + (size_t)24 * cap);   // staging of a merge's f-side operand
-  uint32_t* sc = reinterpret_cast<uint32_t*>(wide_smem + (size_t)24 * cap + (size_t)8 * BBW_STAGE);
+  uint32_t* hc = reinterpret_cast<uint32_t*>(wide_smem + (size_t)16 * (cap + BBW_SENT));
+  uint64_t* sk = reinterpret_cast<uint64_t*>(wide_smem + (size_t)24 * (cap + BBW_SENT));
+  uint32_t* sc = reinterpret_cast<uint32_t*>(wide_smem + (size_t)24 * (cap + BBW_SENT) + (size_t)16 * BBW_BSTAGE);
   const int tid = threadIdx.x;
   const int slot = blockIdx.x;
   if (tid < CT_COUNT) sh[0][tid] = 0ull;
+  for (int w = tid; w < (int)(sizeof(ws.bits) / 4); w += BBW_THREADS) reinterpret_cast<uint32_t*>(ws.bits)[w] = 0u;
   __syncthreads();
   unsigned long long* row = sh[0];
   Ctr ct; ct.clear();
   int bslot = 0;
+  WidePipe pp;
+  pp.init();
   for (;;) {
     if (tid == 0) { int q = atomicAdd(A.queue, 1); next_b = q < A.episodes ? A.order[q] : -1; }
     __syncthreads();
@@ -431,7 +628,7 @@ __global__ void __launch_bounds__(BBW_THREADS, BBW_MIN_CTAS) k_run_wide(const __
     int4* trace = (A.trace && ep < A.trace_eps) ? reinterpret_cast<int4*>(A.trace) + (size_t)ep * A.trace_cap : nullptr;
     while (e.status == BB_STATUS_RUNNING && (A.max_steps == 0 || steps < A.max_steps)) {
       uint32_t pr;
-      const int a = block_step<NV>(P, e, ws, bslot, hk, hc, cap, sk, sc, A.wide_flags, A.strategy, &acc.sel_rng, pr, ct);
+      const int a = block_step<NV>(P, e, ws, bslot, pp, hk, hc, cap, sk, sc, A.wide_flags, A.strategy, &acc.sel_rng, pr, ct);
       if (tid == 0) {
         const int pi = pr & 0xffffu, pj = pr >> 16;
         acc.th = trace_hash_step(acc.th, pr, a);
@@ -627,6 +824,11 @@ struct BBLaunch {
     k_step<NV><<<grid_for_warps(nwarps), BB_THREADS, 0, s>>>(P, actions, reward, done);
     return cudaGetLastError();
   }
+  static cudaError_t step_obs(const BBParams& P, const int* actions, int action0, double* reward, uint8_t* done, int32_t* obs,
+                              int32_t* lengths, int pmax, int pad, int do_step, int nwarps, cudaStream_t s) {
+    k_step_obs<NV><<<grid_for_warps(nwarps), BB_THREADS, 0, s>>>(P, actions, action0, reward, done, obs, lengths, pmax, pad, do_step);
+    return cudaGetLastError();
+  }
   static cudaError_t select(const BBParams& P, int strategy, int* actions, int nwarps, cudaStream_t s) {
     k_select<NV><<<grid_for_warps(nwarps), BB_THREADS, 0, s>>>(P, strategy, actions);
     return cudaGetLastError();
@@ -640,7 +842,11 @@ struct BBLaunch {
     return cudaGetLastError();
   }
   static cudaError_t prepare(const BBParams& S, const BBRunArgs& A, cudaStream_t s) {
-    k_prepare<NV><<<grid_for_warps(A.episodes), BB_THREADS, 0, s>>>(S, A);
+    // binomial distributions with few generators: one thread per episode; everything else: one warp per episode
+    if (S.dist.enabled && S.dist.kind == 0 && S.dist.s <= BB_PREP_S && !A.prepare_by_warp)
+      k_prepare_lanes<NV><<<(A.episodes + BB_PREP_THREADS - 1) / BB_PREP_THREADS, BB_PREP_THREADS, 0, s>>>(S, A);
+    else
+      k_prepare<NV><<<grid_for_warps(A.episodes), BB_THREADS, 0, s>>>(S, A);
     k_order<NV><<<std::min(64, (A.episodes + 1023) / 1024), BB_LPT_BUCKETS, 0, s>>>(A);
     return cudaGetLastError();
   }
@@ -648,10 +854,10 @@ struct BBLaunch {
     k_run<NV><<<grid_for_warps(nwarps), BB_THREADS, 0, s>>>(P, S, A);
     return cudaGetLastError();
   }
-  static size_t wide_smem(int max_poly_terms) { return (size_t)24 * max_poly_terms + (size_t)12 * BBW_STAGE; }
+  static size_t wide_smem(int max_poly_terms) { return (size_t)24 * (max_poly_terms + BBW_SENT) + (size_t)24 * BBW_BSTAGE; }
   static int wide_ctas_per_sm(int max_poly_terms) {
     const size_t sm = wide_smem(max_poly_terms);
-    if (sm > 200 * 1024) return 0;
+    if (sm > 200 * 1024 || max_poly_terms > BBW_MAXCAP) return 0;
     if (cudaFuncSetAttribute(k_run_wide<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return 0;
     int blocks = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_run_wide<NV>, BBW_THREADS, sm) != cudaSuccess) return 0;
@@ -659,7 +865,7 @@ struct BBLaunch {
   }
   static cudaError_t run_wide(const BBParams& P, const BBParams& S, const BBRunArgs& A, int nctas, cudaStream_t s) {
     const size_t sm = wide_smem(P.max_poly_terms);
-    if (sm > 200 * 1024) return cudaErrorInvalidValue;
+    if (sm > 200 * 1024 || P.max_poly_terms > BBW_MAXCAP) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(k_run_wide<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return e;
     k_run_wide<NV><<<nctas, BBW_THREADS, sm, s>>>(P, S, A);
@@ -719,7 +925,7 @@ struct BBLaunch {
   }
   static const BBKernelTable* table() {
     static const BBKernelTable t = {NV, KL<NV>::w, KL<NV>::dw, KL<NV>::dshift, KL<NV>::eshift,
-                                    &reset, &step, &select, &observe, &final_gb, &prepare, &run, &run_wide, &wide_ctas_per_sm, &value, &policy,
+                                    &reset, &step, &step_obs, &select, &observe, &final_gb, &prepare, &run, &run_wide, &wide_ctas_per_sm, &value, &policy,
                                     &rollout,
                                     &run_blocks_per_sm};
     return &t;

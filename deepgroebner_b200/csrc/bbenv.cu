@@ -97,7 +97,11 @@ struct bb_handle {
   int fork_cap;
   std::vector<void*> fork_allocs;
   unsigned char* fork_arena; BBEnvState* fork_st;
+  // bb_step_host / bb_reset_host: pinned, device-mapped host staging (small batches: the kernel reads and writes it in
+  // place) and a device twin (large batches: one async copy each way)
+  unsigned char* host_stage; unsigned char* dev_stage; size_t stage_bytes;
   int sel_seed_stride;   // bb_run: episode e's Random-selection stream is seeded sel_seed_base + e * stride (default 1)
+  int prepare_by_warp;   // bb_run: 1 = episode preparation by one warp per episode even where the thread-per-episode kernel applies
   int wide_mode;   // bb_run: -1 = one CTA per environment when the capacities ask for long polynomials, 0 = never, 1 = always
   // host mirrors of the distribution tables
   std::vector<double> cp;
@@ -177,6 +181,8 @@ void bb_destroy(bb_handle* h) {
   for (void* p : h->allocs) cudaFree(p);
   for (void* p : h->stage_allocs) cudaFree(p);
   for (void* p : h->fork_allocs) cudaFree(p);
+  if (h->host_stage) cudaFreeHost(h->host_stage);
+  if (h->dev_stage) cudaFree(h->dev_stage);
   delete h;
 }
 
@@ -206,6 +212,8 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
   h->stage_cap = 0; h->stage_arena = nullptr; h->stage_st = nullptr;
   h->fork_cap = 0; h->fork_arena = nullptr; h->fork_st = nullptr;
   h->wide_mode = -1;
+  h->prepare_by_warp = 0;
+  h->host_stage = nullptr; h->dev_stage = nullptr; h->stage_bytes = 0;
   h->sel_seed_stride = 1;
   auto bail = [&](int code) { g_create_err = h->err; bb_destroy(h); return code; };
 #define CKC(call)                                                                                     \
@@ -421,6 +429,88 @@ int bb_step(bb_handle* h, const int32_t* actions_dev, double* reward_dev, uint8_
   return 0;
 }
 
+// ---- the reference binding's calls with HOST buffers (wrapped.pyx:18-26): one launch, one synchronisation
+#define BB_ZERO_COPY_BYTES (256u << 10)
+static int host_call(bb_handle* h, int do_step, const int32_t* actions_host, double* reward_host, uint8_t* done_host,
+                     int32_t* obs_host, int32_t* lengths_host, int pmax, int pad, cudaStream_t s) {
+  const BBParams& P = h->P;
+  const size_t N = (size_t)P.num_envs;
+  if (pmax < 0 || (obs_host && pmax < 1)) return fail(h, "bb_step_host / bb_reset_host: bad pmax");
+  if (do_step && !actions_host) return fail(h, "bb_step_host: null actions");
+  // staging layout: reward f64[N] | obs i32[N * pmax * cols] | lengths i32[N] | actions i32[N] | done u8[N]
+  const size_t o_rew = 0, o_obs = o_rew + 8 * N, o_len = o_obs + (obs_host ? 4 * N * (size_t)pmax * P.cols : 0);
+  const size_t o_act = o_len + 4 * N, o_done = o_act + 4 * N, bytes = (o_done + N + 15) & ~(size_t)15;
+  if (bytes > h->stage_bytes) {
+    CK(cudaStreamSynchronize(s));
+    if (h->host_stage) cudaFreeHost(h->host_stage);
+    if (h->dev_stage) cudaFree(h->dev_stage);
+    h->host_stage = nullptr; h->dev_stage = nullptr; h->stage_bytes = 0;
+    CK(cudaHostAlloc((void**)&h->host_stage, bytes, cudaHostAllocMapped));
+    CK(cudaMalloc((void**)&h->dev_stage, bytes));
+    h->stage_bytes = bytes;
+  }
+  const bool zero_copy = bytes <= BB_ZERO_COPY_BYTES;
+  unsigned char* hs = h->host_stage;
+  unsigned char* ds = zero_copy ? hs : h->dev_stage;   // UVA: mapped pinned memory is addressable from the device as it is
+  const int* d_actions = nullptr;
+  int action0 = 0;
+  if (do_step) {
+    if (N == 1) action0 = actions_host[0];   // by value in the launch parameters
+    else {
+      memcpy(hs + o_act, actions_host, 4 * N);
+      if (!zero_copy) CK(cudaMemcpyAsync(ds + o_act, hs + o_act, 4 * N, cudaMemcpyHostToDevice, s));
+      d_actions = (const int*)(ds + o_act);
+    }
+  }
+  CK(h->K->step_obs(P, d_actions, action0, do_step ? (double*)(ds + o_rew) : nullptr, do_step ? (uint8_t*)(ds + o_done) : nullptr,
+                    obs_host ? (int32_t*)(ds + o_obs) : nullptr, (int32_t*)(ds + o_len), pmax, pad, do_step, P.num_envs, s));
+  if (!zero_copy) {
+    CK(cudaMemcpyAsync(hs, ds, o_act, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(hs + o_done, ds + o_done, N, cudaMemcpyDeviceToHost, s));
+  }
+  CK(cudaStreamSynchronize(s));
+  const int32_t* len = (const int32_t*)(hs + o_len);
+  if (lengths_host) memcpy(lengths_host, len, 4 * N);
+  if (do_step && reward_host) memcpy(reward_host, hs + o_rew, 8 * N);
+  if (do_step && done_host) memcpy(done_host, hs + o_done, N);
+  if (obs_host) {
+    const size_t rowb = 4 * (size_t)P.cols;
+    if (pad) memcpy(obs_host, hs + o_obs, N * (size_t)pmax * rowb);
+    else for (size_t e = 0; e < N; e++)
+      memcpy(obs_host + e * (size_t)pmax * P.cols, hs + o_obs + e * (size_t)pmax * rowb, (size_t)std::min(len[e], pmax) * rowb);
+  }
+  return 0;
+}
+
+int bb_step_observe(bb_handle* h, const int32_t* actions_dev, double* reward_dev, uint8_t* done_dev, int32_t* obs_dev,
+                    int32_t* lengths_dev, int pmax, void* stream) {
+  if (!h) return -1;
+  if (!actions_dev || pmax < 0 || (obs_dev && pmax < 1)) return fail(h, "bb_step_observe: bad argument");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(h->K->step_obs(h->P, actions_dev, 0, reward_dev, done_dev, obs_dev, lengths_dev, pmax, 1, 1, h->P.num_envs, (cudaStream_t)stream));
+  return 0;
+}
+
+int bb_step_host(bb_handle* h, const int32_t* actions_host, double* reward_host, uint8_t* done_host, int32_t* obs_host,
+                 int32_t* lengths_host, int pmax, int pad, void* stream) {
+  if (!h) return -1;
+  CK(cudaSetDevice(h->cfg.device));
+  return host_call(h, 1, actions_host, reward_host, done_host, obs_host, lengths_host, pmax, pad, (cudaStream_t)stream);
+}
+
+int bb_reset_host(bb_handle* h, int32_t* obs_host, int32_t* lengths_host, int pmax, int pad, void* stream) {
+  if (!h) return -1;
+  CK(cudaSetDevice(h->cfg.device));
+  CK(h->K->reset(h->P, nullptr, h->P.num_envs, (cudaStream_t)stream));
+  return host_call(h, 0, nullptr, nullptr, nullptr, obs_host, lengths_host, pmax, pad, (cudaStream_t)stream);
+}
+
+int bb_observe_host(bb_handle* h, int32_t* obs_host, int32_t* lengths_host, int pmax, int pad, void* stream) {
+  if (!h) return -1;
+  CK(cudaSetDevice(h->cfg.device));
+  return host_call(h, 0, nullptr, nullptr, nullptr, obs_host, lengths_host, pmax, pad, (cudaStream_t)stream);
+}
+
 int bb_select(bb_handle* h, int strategy, int32_t* actions_dev, void* stream) {
   if (!h) return -1;
   if ((unsigned)strategy > 8u || !actions_dev) return fail(h, "bb_select: bad argument");
@@ -520,16 +610,16 @@ int bb_run(bb_handle* h, int strategy, int episodes, int seed_base, const int32_
     A.ep_base = base; A.nstaged = h->P.num_envs;
     A.seeds = seeds_dev; A.max_steps = max_steps; A.gamma = gamma; A.compute_gb = compute_gb; A.out = stats_dev;
     A.trace = trace_dev; A.trace_eps = trace_dev ? trace_episodes : 0; A.trace_cap = trace_cap; A.queue = h->d_queue;
-    A.order = h->stage_order; A.cost_key = h->stage_cost_key;
+    A.order = h->stage_order; A.cost_key = h->stage_cost_key; A.prepare_by_warp = h->prepare_by_warp;
     CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int) * (BB_LPT_HIST + 2 * BB_LPT_BUCKETS), s));
     CK(h->K->prepare(S, A, s));
     // long polynomials (general capacities): one CTA per environment, dividend in shared memory (bb_wide.cuh)
     int wide_ctas = 0;
-    A.wide_flags = h->wide_mode == 2 ? BBW_FLAG_RANK_MERGE : (h->wide_mode == 3 ? BBW_FLAG_TWO_WALKS : 0);
+    A.wide_flags = h->wide_mode == 2 ? BBW_FLAG_RANK_MERGE : (h->wide_mode == 3 ? BBW_FLAG_COMPACT : 0);
     if (h->wide_mode != 0 && (h->wide_mode >= 1 || h->P.max_poly_terms >= 256))
       wide_ctas = h->K->wide_ctas_per_sm(h->P.max_poly_terms) * h->sm_count;
     if (h->wide_mode >= 1 && wide_ctas <= 0)
-      return fail(h, "bb_run: the dividend buffers (24 bytes x max_poly_terms) do not fit shared memory");
+      return fail(h, "bb_run: the dividend buffers (24 bytes x max_poly_terms, at most 4096 terms) do not fit shared memory");
     if (wide_ctas > 0) {
       CK(h->K->run_wide(h->P, S, A, std::min(std::min(h->P.num_envs, A.episodes), wide_ctas), s));
     } else {
@@ -621,10 +711,21 @@ int bb_copy_env(bb_handle* dst, int dst_env, bb_handle* src, int src_env, void* 
   return 0;
 }
 
+#ifdef BBW_TIMING   // diagnosis build only, not part of the ABI: per-phase cycle counters of k_run_wide<6> (bb_wide.cuh)
+int bb_debug_read_nv6(unsigned long long* out);
+int bb_debug_read(unsigned long long* out) { return bb_debug_read_nv6(out); }
+#endif
+
 int bb_set_wide(bb_handle* h, int mode) {
   if (!h) return -1;
   if (mode < -1 || mode > 3) return fail(h, "bb_set_wide: mode must be -1 (auto), 0 (off), 1 (on), 2 or 3 (on, merge variants)");
   h->wide_mode = mode;
+  return 0;
+}
+
+int bb_set_prepare_mode(bb_handle* h, int by_warp) {
+  if (!h) return -1;
+  h->prepare_by_warp = by_warp ? 1 : 0;
   return 0;
 }
 

@@ -165,6 +165,23 @@ int bb_reset(bb_handle* h, const uint8_t* mask_dev, void* stream);
  * buchberger.cpp:398-408).  reward_dev double[N] (-(1+steps) or -1), done_dev uint8[N] (|P| == 0).  Environments
  * that are not RUNNING are skipped (reward 0, done 1). */
 int bb_step(bb_handle* h, const int32_t* actions_dev, double* reward_dev, uint8_t* done_dev, void* stream);
+/* bb_step_observe: bb_step followed by bb_observe of the new state (after the auto-reset, if enabled) in ONE launch --
+ * LeadMonomialsEnv::step(int) as a whole (buchberger.cpp:398-408: step, then the state matrix is rebuilt).  Device
+ * buffers as in bb_step / bb_observe (reward_dev, done_dev, obs_dev, lengths_dev may be NULL); rows beyond |P| are -1. */
+int bb_step_observe(bb_handle* h, const int32_t* actions_dev, double* reward_dev, uint8_t* done_dev, int32_t* obs_dev,
+                    int32_t* lengths_dev, int pmax, void* stream);
+/* bb_step_host / bb_reset_host / bb_observe_host: the same calls as the reference's binding makes them -- HOST buffers,
+ * synchronous, step + state matrix + done in ONE call (wrapped.pyx:18-26: `step` returns the matrix copied out of
+ * LeadMonomialsEnv::state).  One kernel launch and one stream synchronisation per call: the kernel does the step (and the
+ * auto-reset, if enabled) and writes the observation of the NEW state; for small batches it reads the actions from and
+ * writes the results to pinned host memory in place (N == 1: the action travels in the launch parameters), for large
+ * ones there is one async copy each way.  actions_host int32[N]; reward_host double[N], done_host uint8[N],
+ * lengths_host int32[N] = |P| after the step, obs_host int32[N, pmax, cols] (any output may be NULL).  pad != 0: rows
+ * beyond |P| are -1 (pg.py:217-226); pad == 0: only the first min(|P|, pmax) rows of each environment are written. */
+int bb_step_host(bb_handle* h, const int32_t* actions_host, double* reward_host, uint8_t* done_host, int32_t* obs_host,
+                 int32_t* lengths_host, int pmax, int pad, void* stream);
+int bb_reset_host(bb_handle* h, int32_t* obs_host, int32_t* lengths_host, int pmax, int pad, void* stream);
+int bb_observe_host(bb_handle* h, int32_t* obs_host, int32_t* lengths_host, int pmax, int pad, void* stream);
 /* bb_select: built-in pair selection (buchberger.cpp:160-241, any BB_SELECT_*): actions_dev int32[N]. */
 int bb_select(bb_handle* h, int strategy, int32_t* actions_dev, void* stream);
 /* bb_observe: obs_dev int32[N, pmax, cols] padded with -1 (pg.py:217-226), lengths_dev int32[N] = |P|
@@ -193,13 +210,19 @@ int bb_run(bb_handle* h, int strategy, int episodes, int seed_base, const int32_
  * does (one `seed` argument for every ideal of the file). */
 int bb_set_selection_seed_stride(bb_handle* h, int stride);
 
+/* bb_set_prepare_mode: how bb_run prepares a batch of episodes (ideal generator + reset(), buchberger.cpp:299-315).
+ * 0 (default): one THREAD per episode where it applies (binomial distributions with at most 16 generators), else one
+ * warp per episode; 1: always one warp per episode.  Both produce bit-identical states and counters; this is a
+ * performance switch that the tests use to compare the two. */
+int bb_set_prepare_mode(bb_handle* h, int by_warp);
+
 /* bb_set_wide: which episode runner bb_run uses.  -1 (default): one warp per environment, except that capacities
  * sized for long polynomials (max_poly_terms >= 256, e.g. cyclic-n) get one CTA per environment with the dividend in
  * shared memory; 0: always one warp per environment; 1: always one CTA per environment (an error if 24 bytes x
- * max_poly_terms exceed shared memory); 2 / 3: as 1 with the block merge forced onto its fallback paths (2: merge by
- * rank, otherwise taken when a reducer outgrows the staging buffer; 3: merge path with two walks, otherwise taken for
- * dividends beyond 1024 terms) so that tests reach them.  Every mode produces bit-identical episodes; this is a
- * performance switch. */
+ * max_poly_terms exceed shared memory or max_poly_terms > 4096); 2 / 3: as 1 with the block's addition forced onto its
+ * fallback paths so that tests reach them (2: merge by rank for every addition, otherwise taken when a reducer has more
+ * than 256 tail terms; 3: the zero-coefficient compaction after every addition, otherwise taken when a coefficient sum
+ * cancelled).  Every mode produces bit-identical episodes; this is a performance switch. */
 int bb_set_wide(bb_handle* h, int mode);
 
 /* bb_value: BuchbergerEnv::value(strategy, gamma) (buchberger.cpp:332-351) for every environment at once:

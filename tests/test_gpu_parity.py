@@ -516,3 +516,32 @@ def test_cta_per_environment_runner_equals_warp_runner(torch_cuda, name, strateg
             assert np.array_equal(s0[f], s1[f]), (mode, f)
         assert np.array_equal(t0, t1), mode
         assert c0 == c1, mode
+
+
+@pytest.mark.parametrize("dist,kw", [
+    ("3-20-10-weighted", {}), ("5-5-10-uniform", {}), ("3-20-10-uniform", dict(elimination="lcm")),
+    ("3-20-10-weighted", dict(elimination="none")), ("4-6-8-maximum-homog", dict(sort_input=True)),
+    ("3-12-6-weighted-pure", dict(sort_reducers=False)), ("2-9-5-uniform-consts", dict(sort_input=True, sort_reducers=False)),
+    ("3-4-16-uniform", {}), ("2-3-3-weighted", {}),
+])
+def test_episode_preparation_by_thread_equals_by_warp(torch_cuda, dist, kw):
+    """bb_set_prepare_mode: the thread-per-episode preparation (generator + reset(), buchberger.cpp:299-315, re-rolls
+    included) leaves exactly the state the warp-per-episode one does -- every episode record and every traffic counter
+    of the runs that start from it are equal -- and both equal the reference."""
+    from deepgroebner_b200.buchberger import BuchbergerEngine
+    episodes = 600
+    eng = BuchbergerEngine(dist, num_envs=256, **kw)
+    out = {}
+    for by_warp in (False, True):
+        eng.set_prepare_mode(by_warp)
+        eng.counters(reset=True)
+        stats, trace = eng.run_episodes("normal", episodes=episodes, seed_base=11, compute_gb=True, trace_episodes=4,
+                                        trace_cap=1024, max_steps=400)
+        out[by_warp] = (stats, trace, eng.counters(reset=True))
+    (s0, t0, c0), (s1, t1, c1) = out[False], out[True]
+    for f in s0.dtype.names:
+        assert np.array_equal(s0[f], s1[f]), f
+    assert np.array_equal(t0, t1) and c0 == c1
+    if not kw.get("sort_input") and kw.get("elimination", "gebauermoeller") != "none":
+        want = ref_oracle().run_records(dist, "normal", episodes, seed0=11, compute_gb=True, max_steps=400, **kw)
+        assert_records_equal(s0, want, dist)

@@ -1,0 +1,6 @@
+# tools/gpu_wide_prof.sh <tag>: the long-polynomial runner -- chain timing of the longest cyclic-6 episodes, then one
+# ncu source-counter capture of a single mid-length episode alone on the GPU (episode 3: ~110 K additions)
+cd $GRAFT_REPO_ROOT; mkdir -p gpurun_out
+timeout 600 python tools/exp_cyclic_chain.py 1024 > gpurun_out/$1_chain.log 2>&1; cat gpurun_out/$1_chain.log
+timeout 900 ncu --section SourceCounters --section WarpStateStats --section SchedulerStats --section LaunchStats --clock-control none --import-source on -k regex:k_run_wide -s 1 -c 1 -o gpurun_out/$1_one python tools/exp_cyclic_one.py 1237 > gpurun_out/$1_one.log 2>&1
+tail -3 gpurun_out/$1_one.log; ls -la gpurun_out/$1_one.ncu-rep
