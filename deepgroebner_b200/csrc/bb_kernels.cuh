@@ -12,7 +12,7 @@
 #pragma once
 #include "bb_device.cuh"
 #include "bb_policy.cuh"
-#include "bb_wide.cuh"
+#include "bb_streams.cuh"
 
 #ifndef BB_WARPS
 #define BB_WARPS 8
@@ -40,7 +40,7 @@ struct BBRunArgs {
   int32_t* trace;
   int trace_eps, trace_cap;
   int prepare_by_warp;  // 1: k_prepare (one warp per episode) even where k_prepare_lanes applies (tests compare the two)
-  int wide_flags;    // k_run_wide: BBW_FLAG_* (bb_wide.cuh), the merge variants bb_set_wide(2 / 3) select
+  int stream_kmax;   // k_run_streams: streams per step kept in shared memory (BBS_KMAX; less under bb_set_wide(2 / 3))
   int* queue;        // [0]: next queue position; [BB_LPT_HIST .. +BB_LPT_BUCKETS): histogram of the cost keys of the batch, then as many cursors
   int* order;        // [episodes] queue position -> episode of the batch, longest predicted first (k_order)
   uint8_t* cost_key; // [episodes] predicted-cost bucket of each episode of the batch (k_prepare)
@@ -85,10 +85,9 @@ struct BBKernelTable {
   cudaError_t (*final_gb)(const BBParams&, int slot, int* ok_out, cudaStream_t);
   cudaError_t (*prepare)(const BBParams& stage, const BBRunArgs&, cudaStream_t);  // k_prepare + k_order
   cudaError_t (*run)(const BBParams&, const BBParams& stage, const BBRunArgs&, int nwarps, cudaStream_t);
-  // one CTA per environment (bb_wide.cuh); nctas worker CTAs; returns cudaErrorInvalidValue if the dividend buffers
-  // (2 x max_poly_terms terms) do not fit shared memory
-  cudaError_t (*run_wide)(const BBParams&, const BBParams& stage, const BBRunArgs&, int nctas, cudaStream_t);
-  int (*wide_ctas_per_sm)(int max_poly_terms);   // 0 if it does not fit
+  // the same runner with reduce() by streams (bb_streams.cuh: long polynomials)
+  cudaError_t (*run_streams)(const BBParams&, const BBParams& stage, const BBRunArgs&, int nwarps, cudaStream_t);
+  int (*streams_warps_per_sm)(void);   // 0 if it does not fit
   cudaError_t (*value)(const BBParams&, const BBParams& fork, const BBValueArgs&, int nwarps, cudaStream_t);
   cudaError_t (*policy)(const BBParams&, const BBPolicy&, unsigned long long counter, int32_t* actions, float* logp,
                         float* logits, int pmax, int nwarps, cudaStream_t);
@@ -473,14 +472,18 @@ __device__ __forceinline__ void warp_copy_env(const BBParams& D, unsigned char* 
 
 // The loop of buchberger() (buchberger.cpp:243-263) on one environment: select, step, accumulate the trace checksum and
 // the discounted return (discounted_return += discount * reward; discount *= gamma, :250-251) until P is empty.
-template <int NV>
+// STREAMS: reduce() by streams (bb_streams.cuh), ws / st = the warp's stream state and table.
+template <int NV, bool STREAMS>
 __device__ __forceinline__ void run_episode(const BBParams& P, Env& e, int strategy, int max_steps, double gamma,
-                                            BBEpisodeAcc& acc, Ctr& ct, int& steps, int& adds, int4* trace, int trace_cap) {
+                                            BBEpisodeAcc& acc, Ctr& ct, int& steps, int& adds, int4* trace, int trace_cap,
+                                            StreamState* ws, WarpStreams* st) {
   const int lane = bb_lane();
   while (e.status == BB_STATUS_RUNNING && (max_steps == 0 || steps < max_steps)) {
     const int prow = warp_select<NV>(P, e, strategy, &acc.sel_rng);
     uint32_t pr;
-    const int a = warp_step<NV>(P, e, prow, pr, ct);
+    int a;
+    if (STREAMS) a = warp_step_streams<NV>(P, e, *ws, *st, prow, pr, ct);
+    else a = warp_step<NV>(P, e, prow, pr, ct);
     if (lane == 0) {
       const int pi = pr & 0xffffu, pj = pr >> 16;
       acc.th = trace_hash_step(acc.th, pr, a);
@@ -495,18 +498,19 @@ __device__ __forceinline__ void run_episode(const BBParams& P, Env& e, int strat
 
 // Persistent episode runner.  Each warp owns slot = its global warp index and loops: pop an episode, copy its
 // prepared initial state from the staging arena, select/step until P is empty (or max_steps), write the episode
-// record, repeat.
-template <int NV>
-__global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_run(const __grid_constant__ BBParams P,
-                                                                  const __grid_constant__ BBParams S,
-                                                                  const __grid_constant__ BBRunArgs A) {
-  typedef KL<NV> K;
-  __shared__ unsigned long long sh[BB_WARPS][CT_COUNT];
-  __shared__ BBEpisodeAcc acc_sh[BB_WARPS];  // per-episode accumulators only lane 0 touches: kept out of registers
-  unsigned long long* row = counters_row(sh);
+// record, repeat.  WARPS = warps per CTA.
+template <int NV, bool STREAMS, int WARPS>
+__device__ __forceinline__ void run_worker(const BBParams& P, const BBParams& S, const BBRunArgs& A, WarpStreams* st) {
+  __shared__ unsigned long long sh[WARPS][CT_COUNT];
+  __shared__ BBEpisodeAcc acc_sh[WARPS];  // per-episode accumulators only lane 0 touches: kept out of registers
+  unsigned long long* row = sh[threadIdx.x >> 5];
+  if (bb_lane() < CT_COUNT) row[bb_lane()] = 0ull;
+  __syncwarp();
   BBEpisodeAcc& acc = acc_sh[threadIdx.x >> 5];
-  const int slot = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
+  const int slot = (blockIdx.x * (WARPS * 32) + threadIdx.x) >> 5;
   const int lane = bb_lane();
+  StreamState ws;
+  ws.clear(); ws.kmax = A.stream_kmax; ws.cz = 0;
   if (slot < P.num_envs) {
     Ctr ct; ct.clear();
     for (;;) {
@@ -526,9 +530,9 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_run(const __grid_
       int steps = 0, adds = 0;
       if (lane == 0) { acc.th = 0ull; acc.ret = 0.0; acc.disc = 1.0; acc.sel_rng = rng_seed(A.sel_seed_base + ep * A.sel_seed_stride); }
       __syncwarp();
-      run_episode<NV>(P, e, A.strategy, A.max_steps, A.gamma, acc, ct, steps, adds,
-                      (A.trace && ep < A.trace_eps) ? reinterpret_cast<int4*>(A.trace) + (size_t)ep * A.trace_cap : nullptr,
-                      A.trace_cap);
+      run_episode<NV, STREAMS>(P, e, A.strategy, A.max_steps, A.gamma, acc, ct, steps, adds,
+                               (A.trace && ep < A.trace_eps) ? reinterpret_cast<int4*>(A.trace) + (size_t)ep * A.trace_cap : nullptr,
+                               A.trace_cap, &ws, st);
       const int nonzero = e.nG - g_start, zero = steps - nonzero;
       env_store(P, slot, e);
       __syncwarp();
@@ -565,122 +569,35 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_run(const __grid_
       __syncwarp();
     }
   }
-  counters_flush(P, sh);
-}
-
-// block-strided copy of n 32-bit words
-__device__ __forceinline__ void block_copy_words(uint32_t* __restrict__ d, const uint32_t* __restrict__ s, int n) {
-  d = bb_global(d); s = bb_global(s);
-#pragma unroll 1
-  for (int t = threadIdx.x; t < n; t += BBW_THREADS) d[t] = s[t];
-}
-
-// Persistent episode runner, one CTA per environment slot (bb_wide.cuh): same queue, staging arena, episode record and
-// checksums as k_run; the step is block_step.  Dynamic shared memory: the two dividend buffers.
-template <int NV>
-__global__ void __launch_bounds__(BBW_THREADS, BBW_MIN_CTAS) k_run_wide(const __grid_constant__ BBParams P, const __grid_constant__ BBParams S,
-                                                          const __grid_constant__ BBRunArgs A) {
-  extern __shared__ __align__(16) unsigned char wide_smem[];
-  __shared__ unsigned long long sh[1][CT_COUNT];
-  __shared__ BBEpisodeAcc acc;
-  __shared__ WideShared ws;
-  __shared__ int next_b;
-  const int cap = P.max_poly_terms;
-  // two dividend buffers of cap terms + BBW_SENT sentinels, two staging buffers of BBW_BSTAGE terms (bb_wide.cuh)
-  uint64_t* hk = reinterpret_cast<uint64_t*>(wide_smem);
-  uint32_t* hc = reinterpret_cast<uint32_t*>(wide_smem + (size_t)16 * (cap + BBW_SENT));
-  uint64_t* sk = reinterpret_cast<uint64_t*>(wide_smem + (size_t)24 * (cap + BBW_SENT));
-  uint32_t* sc = reinterpret_cast<uint32_t*>(wide_smem + (size_t)24 * (cap + BBW_SENT) + (size_t)16 * BBW_BSTAGE);
-  const int tid = threadIdx.x;
-  const int slot = blockIdx.x;
-  if (tid < CT_COUNT) sh[0][tid] = 0ull;
-  for (int w = tid; w < (int)(sizeof(ws.bits) / 4); w += BBW_THREADS) reinterpret_cast<uint32_t*>(ws.bits)[w] = 0u;
   __syncthreads();
-  unsigned long long* row = sh[0];
-  Ctr ct; ct.clear();
-  int bslot = 0;
-  WidePipe pp;
-  pp.init();
-  for (;;) {
-    if (tid == 0) { int q = atomicAdd(A.queue, 1); next_b = q < A.episodes ? A.order[q] : -1; }
-    __syncthreads();
-    const int b = next_b;
-    if (b < 0) break;
-    const int ep = A.ep_base + b;
-    Env e; env_load(S, b, e);
-    {
-      unsigned char* db = P.arena + (size_t)slot * P.slot_stride;
-      const unsigned char* sb = e.base;
-      block_copy_words((uint32_t*)(db + P.o_ghead), (const uint32_t*)(sb + S.o_ghead), e.nG * 8);
-      block_copy_words((uint32_t*)(db + P.o_lm), (const uint32_t*)(sb + S.o_lm), e.nG * 2);
-      block_copy_words((uint32_t*)(db + P.o_rlm), (const uint32_t*)(sb + S.o_rlm), e.nG * 2);
-      block_copy_words((uint32_t*)(db + P.o_ridx), (const uint32_t*)(sb + S.o_ridx), e.nG);
-      block_copy_words((uint32_t*)(db + P.o_pairs), (const uint32_t*)(sb + S.o_pairs), e.nP);
-      block_copy_words((uint32_t*)(db + P.o_plcm), (const uint32_t*)(sb + S.o_plcm), e.nP * 2);
-      block_copy_words((uint32_t*)(db + P.o_tkey), (const uint32_t*)(sb + S.o_tkey), e.nT * 2);
-      block_copy_words((uint32_t*)(db + P.o_tcoef), (const uint32_t*)(sb + S.o_tcoef), e.nT);
-      e.base = db;
-    }
-    const int g_start = e.nG;
-    int steps = 0, adds = 0;
-    if (tid == 0) { acc.th = 0ull; acc.ret = 0.0; acc.disc = 1.0; acc.sel_rng = rng_seed(A.sel_seed_base + ep * A.sel_seed_stride); }
-    __syncthreads();
-    int4* trace = (A.trace && ep < A.trace_eps) ? reinterpret_cast<int4*>(A.trace) + (size_t)ep * A.trace_cap : nullptr;
-    while (e.status == BB_STATUS_RUNNING && (A.max_steps == 0 || steps < A.max_steps)) {
-      uint32_t pr;
-      const int a = block_step<NV>(P, e, ws, bslot, pp, hk, hc, cap, sk, sc, A.wide_flags, A.strategy, &acc.sel_rng, pr, ct);
-      if (tid == 0) {
-        const int pi = pr & 0xffffu, pj = pr >> 16;
-        acc.th = trace_hash_step(acc.th, pr, a);
-        const double r = (P.rewards == BB_REWARD_ADDITIONS) ? -(double)a : -1.0;
-        const double d = acc.disc;
-        acc.ret = __dadd_rn(acc.ret, __dmul_rn(d, r)); acc.disc = __dmul_rn(d, A.gamma);
-        if (trace && steps < A.trace_cap) trace[steps] = make_int4(pi, pj, a, e.nP);
-      }
-      steps++; adds += a;
-    }
-    __syncthreads();
-    if (tid < 32) {   // warp 0: episode record, checksums, reduced Groebner basis (the warp routines of bb_device.cuh)
-      const int nonzero = e.nG - g_start, zero = steps - nonzero;
-      env_store(P, slot, e);
-      __syncwarp();
-      const GHeadMem* gh = ENV_PTR(GHeadMem, e, P, o_ghead);
-      const unsigned long long bh = warp_terms_hash<NV>(ENV_PTR(uint64_t, e, P, o_tkey), ENV_PTR(uint32_t, e, P, o_tcoef),
-                                                        e.nT, reinterpret_cast<const int*>(&gh[0].len),
-                                                        (int)(sizeof(GHeadMem) / sizeof(int)), e.nG);
-      unsigned long long gbh = 0; int gp = 0, gt = 0;
-      int status = e.status;
-      if (A.compute_gb && status == BB_STATUS_DONE) {
-        if (warp_final_gb<NV>(P, slot, row)) {
-          gp = P.gcount[2 * slot]; gt = P.gcount[2 * slot + 1];
-          gbh = warp_terms_hash<NV>(P.gkey + (size_t)slot * P.max_terms, P.gcoef + (size_t)slot * P.max_terms, gt,
-                                    P.glen + (size_t)slot * P.max_basis, 1, gp);
-        } else {
-          status = BB_STATUS_OVERFLOW_SCRATCH;
-        }
-      }
-      if (tid == 0) {
-        const unsigned long long th = acc.th; const double ret = acc.ret;
-        bb_episode_stats o;
-        o.steps = steps; o.additions = adds; o.zero_reductions = zero; o.nonzero_reductions = nonzero;
-        o.nbasis = e.nG; o.nterms = e.nT; o.status = status; o.rerolls = S.st[b].rerolls;
-        o.trace_hash = th; o.basis_hash = bh; o.gb_hash = gbh; o.gb_polys = gp; o.gb_terms = gt;
-        o.discounted_return = ret;
-        A.out[ep] = o;
-        BBEnvState& St = P.st[slot];
-        St.status = status; St.steps = steps; St.adds = adds; St.zero = zero; St.nonzero = nonzero; St.trace_hash = th;
-        St.disc_return = ret; St.rerolls = o.rerolls;
-        row[CT_STEPS] += (unsigned)steps; row[CT_ADDS] += (unsigned)adds; row[CT_NONZERO] += (unsigned)nonzero;
-        row[CT_ZERO] += (unsigned)zero; row[CT_EPISODES] += 1;
-      }
-      ct.spill(row);
-    } else {
-      ct.clear();
-    }
-    __syncthreads();
+  if (threadIdx.x < CT_COUNT) {
+    unsigned long long s = 0;
+#pragma unroll
+    for (int w = 0; w < WARPS; w++) s += sh[w][threadIdx.x];
+    if (s) atomicAdd(&P.counters[threadIdx.x], s);
   }
-  __syncthreads();
-  if (tid < CT_COUNT && sh[0][tid]) atomicAdd(&P.counters[tid], sh[0][tid]);
+}
+
+template <int NV>
+__global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_run(const __grid_constant__ BBParams P,
+                                                                  const __grid_constant__ BBParams S,
+                                                                  const __grid_constant__ BBRunArgs A) {
+  run_worker<NV, false, BB_WARPS>(P, S, A, nullptr);
+}
+
+// The same runner for long polynomials: reduce() by streams, the warp's stream table in dynamic shared memory.
+#ifndef BBS_WARPS
+#define BBS_WARPS 4
+#endif
+#ifndef BBS_MIN_CTAS
+#define BBS_MIN_CTAS 2
+#endif
+template <int NV>
+__global__ void __launch_bounds__(BBS_WARPS * 32, BBS_MIN_CTAS) k_run_streams(const __grid_constant__ BBParams P,
+                                                                             const __grid_constant__ BBParams S,
+                                                                             const __grid_constant__ BBRunArgs A) {
+  extern __shared__ __align__(16) unsigned char streams_smem[];
+  run_worker<NV, true, BBS_WARPS>(P, S, A, reinterpret_cast<WarpStreams*>(streams_smem) + (threadIdx.x >> 5));
 }
 
 // max of doubles through a CAS loop (order independent, hence deterministic)
@@ -728,7 +645,7 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_value(const __gri
         if (lane == 0) { acc.th = 0ull; acc.ret = 0.0; acc.disc = 1.0; acc.sel_rng = rng_seed(seed); }
         __syncwarp();
         int steps = 0, adds = 0;
-        run_episode<NV>(F, e, strategy, A.max_steps, A.gamma, acc, ct, steps, adds, nullptr, 0);
+        run_episode<NV, false>(F, e, strategy, A.max_steps, A.gamma, acc, ct, steps, adds, nullptr, 0, nullptr, nullptr);
         __syncwarp();
         ret = acc.ret;
         if (e.status != BB_STATUS_DONE && !(A.max_steps && steps >= A.max_steps)) ret = __longlong_as_double(0x7ff8000000000000LL);  // fault: NaN
@@ -854,21 +771,19 @@ struct BBLaunch {
     k_run<NV><<<grid_for_warps(nwarps), BB_THREADS, 0, s>>>(P, S, A);
     return cudaGetLastError();
   }
-  static size_t wide_smem(int max_poly_terms) { return (size_t)24 * (max_poly_terms + BBW_SENT) + (size_t)24 * BBW_BSTAGE; }
-  static int wide_ctas_per_sm(int max_poly_terms) {
-    const size_t sm = wide_smem(max_poly_terms);
-    if (sm > 200 * 1024 || max_poly_terms > BBW_MAXCAP) return 0;
-    if (cudaFuncSetAttribute(k_run_wide<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return 0;
+  static size_t streams_smem() { return sizeof(WarpStreams) * (size_t)BBS_WARPS; }
+  static int streams_warps_per_sm() {
+    const size_t sm = streams_smem();
+    if (cudaFuncSetAttribute(k_run_streams<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return 0;
     int blocks = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_run_wide<NV>, BBW_THREADS, sm) != cudaSuccess) return 0;
-    return blocks;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_run_streams<NV>, BBS_WARPS * 32, sm) != cudaSuccess) return 0;
+    return blocks * BBS_WARPS;
   }
-  static cudaError_t run_wide(const BBParams& P, const BBParams& S, const BBRunArgs& A, int nctas, cudaStream_t s) {
-    const size_t sm = wide_smem(P.max_poly_terms);
-    if (sm > 200 * 1024 || P.max_poly_terms > BBW_MAXCAP) return cudaErrorInvalidValue;
-    cudaError_t e = cudaFuncSetAttribute(k_run_wide<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  static cudaError_t run_streams(const BBParams& P, const BBParams& S, const BBRunArgs& A, int nwarps, cudaStream_t s) {
+    const size_t sm = streams_smem();
+    cudaError_t e = cudaFuncSetAttribute(k_run_streams<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     if (e != cudaSuccess) return e;
-    k_run_wide<NV><<<nctas, BBW_THREADS, sm, s>>>(P, S, A);
+    k_run_streams<NV><<<(nwarps + BBS_WARPS - 1) / BBS_WARPS, BBS_WARPS * 32, sm, s>>>(P, S, A);
     return cudaGetLastError();
   }
   static cudaError_t value(const BBParams& P, const BBParams& F, const BBValueArgs& A, int nwarps, cudaStream_t s) {
@@ -925,7 +840,7 @@ struct BBLaunch {
   }
   static const BBKernelTable* table() {
     static const BBKernelTable t = {NV, KL<NV>::w, KL<NV>::dw, KL<NV>::dshift, KL<NV>::eshift,
-                                    &reset, &step, &step_obs, &select, &observe, &final_gb, &prepare, &run, &run_wide, &wide_ctas_per_sm, &value, &policy,
+                                    &reset, &step, &step_obs, &select, &observe, &final_gb, &prepare, &run, &run_streams, &streams_warps_per_sm, &value, &policy,
                                     &rollout,
                                     &run_blocks_per_sm};
     return &t;

@@ -9,10 +9,3 @@
 #define BB_CAT(a, b) BB_CAT2(a, b)
 const BBKernelTable* BB_CAT(bb_kernel_table_nv, BB_NV)() { return BBLaunch<BB_NV>::table(); }
 
-#ifdef BBW_TIMING   // diagnosis build only: reads and clears this instantiation's per-phase cycle counters (bb_wide.cuh)
-extern "C" int BB_CAT(bb_debug_read_nv, BB_NV)(unsigned long long* out) {
-  unsigned long long z[64] = {0};
-  if (cudaMemcpyFromSymbol(out, bbw_dbg, sizeof z) != cudaSuccess) return -1;
-  return cudaMemcpyToSymbol(bbw_dbg, z, sizeof z) == cudaSuccess ? 0 : -1;
-}
-#endif

@@ -102,7 +102,7 @@ struct bb_handle {
   unsigned char* host_stage; unsigned char* dev_stage; size_t stage_bytes;
   int sel_seed_stride;   // bb_run: episode e's Random-selection stream is seeded sel_seed_base + e * stride (default 1)
   int prepare_by_warp;   // bb_run: 1 = episode preparation by one warp per episode even where the thread-per-episode kernel applies
-  int wide_mode;   // bb_run: -1 = one CTA per environment when the capacities ask for long polynomials, 0 = never, 1 = always
+  int wide_mode;   // bb_run: reduce() by streams: -1 = when the capacities ask for long polynomials, 0 = never, 1 = always, 2 / 3 = always, small tables
   // host mirrors of the distribution tables
   std::vector<double> cp;
 };
@@ -131,7 +131,8 @@ static cudaError_t dev_alloc(bb_handle* h, T** p, size_t count) {
 }
 
 // One contiguous arena per slot from the capacities in P: 8-byte arrays first, every array 32-byte aligned, stride a
-// multiple of 128.  Returns false if a slot would exceed 2 GiB.
+// multiple of 128.  Returns false if a slot would exceed 2 GiB.  hkey lies directly behind tkey and hcoef directly behind
+// tcoef (max_terms is a multiple of 8, so no padding): scratch term i is term max_terms + i of the arena (bb_streams.cuh).
 static bool layout_arena(BBParams& P) {
   size_t o = 0;
   auto take = [&o](size_t bytes) { size_t at = o; o = (o + bytes + 31) & ~(size_t)31; return (unsigned)at; };
@@ -236,7 +237,7 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
   P.num_envs = cfg->num_envs; P.k = cfg->k; P.cols = 2 * cfg->nvars * cfg->k;
   P.elimination = cfg->elimination; P.rewards = cfg->rewards;
   P.sort_input = cfg->sort_input ? 1 : 0; P.sort_reducers = cfg->sort_reducers ? 1 : 0;
-  P.max_basis = cfg->max_basis; P.max_pairs = cfg->max_pairs; P.max_terms = cfg->max_terms;
+  P.max_basis = cfg->max_basis; P.max_pairs = cfg->max_pairs; P.max_terms = (cfg->max_terms + 7) & ~7;
   P.max_poly_terms = cfg->max_poly_terms; P.max_gens = cfg->max_gens; P.max_gen_terms = cfg->max_gen_terms;
   const size_t N = (size_t)cfg->num_envs;
   if (!layout_arena(P)) { h->err = "bb_create: per-environment arena exceeds 2 GiB"; return bail(-1); }
@@ -613,17 +614,14 @@ int bb_run(bb_handle* h, int strategy, int episodes, int seed_base, const int32_
     A.order = h->stage_order; A.cost_key = h->stage_cost_key; A.prepare_by_warp = h->prepare_by_warp;
     CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int) * (BB_LPT_HIST + 2 * BB_LPT_BUCKETS), s));
     CK(h->K->prepare(S, A, s));
-    // long polynomials (general capacities): one CTA per environment, dividend in shared memory (bb_wide.cuh)
-    int wide_ctas = 0;
-    A.wide_flags = h->wide_mode == 2 ? BBW_FLAG_RANK_MERGE : (h->wide_mode == 3 ? BBW_FLAG_COMPACT : 0);
-    if (h->wide_mode != 0 && (h->wide_mode >= 1 || h->P.max_poly_terms >= 256))
-      wide_ctas = h->K->wide_ctas_per_sm(h->P.max_poly_terms) * h->sm_count;
-    if (h->wide_mode >= 1 && wide_ctas <= 0)
-      return fail(h, "bb_run: the dividend buffers (24 bytes x max_poly_terms, at most 4096 terms) do not fit shared memory");
-    if (wide_ctas > 0) {
-      CK(h->K->run_wide(h->P, S, A, std::min(std::min(h->P.num_envs, A.episodes), wide_ctas), s));
+    // long polynomials (general capacities): reduce() by streams (bb_streams.cuh)
+    const bool streams = h->wide_mode != 0 && (h->wide_mode >= 1 || h->P.max_poly_terms >= 256);
+    A.stream_kmax = h->wide_mode == 2 ? 6 : (h->wide_mode == 3 ? 48 : BBS_KMAX);
+    const int workers = std::min(h->P.num_envs, A.episodes);
+    if (streams) {
+      if (h->K->streams_warps_per_sm() <= 0) return fail(h, "bb_run: the stream runner does not fit this device");
+      CK(h->K->run_streams(h->P, S, A, workers, s));
     } else {
-      const int workers = std::min(h->P.num_envs, A.episodes);
       CK(h->K->run(h->P, S, A, workers, s));
     }
   }
@@ -711,14 +709,9 @@ int bb_copy_env(bb_handle* dst, int dst_env, bb_handle* src, int src_env, void* 
   return 0;
 }
 
-#ifdef BBW_TIMING   // diagnosis build only, not part of the ABI: per-phase cycle counters of k_run_wide<6> (bb_wide.cuh)
-int bb_debug_read_nv6(unsigned long long* out);
-int bb_debug_read(unsigned long long* out) { return bb_debug_read_nv6(out); }
-#endif
-
 int bb_set_wide(bb_handle* h, int mode) {
   if (!h) return -1;
-  if (mode < -1 || mode > 3) return fail(h, "bb_set_wide: mode must be -1 (auto), 0 (off), 1 (on), 2 or 3 (on, merge variants)");
+  if (mode < -1 || mode > 3) return fail(h, "bb_set_wide: mode must be -1 (auto), 0 (off), 1 (on), 2 or 3 (on, small stream tables)");
   h->wide_mode = mode;
   return 0;
 }

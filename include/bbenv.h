@@ -216,13 +216,13 @@ int bb_set_selection_seed_stride(bb_handle* h, int stride);
  * performance switch that the tests use to compare the two. */
 int bb_set_prepare_mode(bb_handle* h, int by_warp);
 
-/* bb_set_wide: which episode runner bb_run uses.  -1 (default): one warp per environment, except that capacities
- * sized for long polynomials (max_poly_terms >= 256, e.g. cyclic-n) get one CTA per environment with the dividend in
- * shared memory; 0: always one warp per environment; 1: always one CTA per environment (an error if 24 bytes x
- * max_poly_terms exceed shared memory or max_poly_terms > 4096); 2 / 3: as 1 with the block's addition forced onto its
- * fallback paths so that tests reach them (2: merge by rank for every addition, otherwise taken when a reducer has more
- * than 256 tail terms; 3: the zero-coefficient compaction after every addition, otherwise taken when a coefficient sum
- * cancelled).  Every mode produces bit-identical episodes; this is a performance switch. */
+/* bb_set_wide: how bb_run's episode runner reduces.  0: the dividend is materialised (warp-cooperative merges, built
+ * for the 2-term polynomials of binomial ideals); 1: the dividend is a set of streams into the term arena kept in shared
+ * memory, one round per lead term and O(1) work per addition (built for long polynomials, e.g. cyclic-n); -1 (default):
+ * 1 when the capacities are sized for long polynomials (max_poly_terms >= 256), else 0; 2 / 3: as 1 with the stream table
+ * capped at 6 / 48 entries so that tests reach its garbage collection and the consolidation of the dividend into a
+ * scratch list.  Every mode produces bit-identical episodes; this is a performance switch.  Of the bb_counters,
+ * terms_read / terms_written count |h| per addition only where h is materialised (mode 0). */
 int bb_set_wide(bb_handle* h, int mode);
 
 /* bb_value: BuchbergerEnv::value(strategy, gamma) (buchberger.cpp:332-351) for every environment at once:

@@ -495,9 +495,11 @@ def test_sharded_blocks_equal_one_run(torch_cuda):
 @pytest.mark.parametrize("name,strategy", [("cyclic-5", "normal"), ("cyclic-6", "degree"), ("cyclic-6", "random"),
                                            ("3-20-10-weighted", "degree")])
 def test_cta_per_environment_runner_equals_warp_runner(torch_cuda, name, strategy):
-    """bb_set_wide: the one-CTA-per-environment runner (bb_wide.cuh: dividend in shared memory, block-wide divisor
-    search and rank merge) and the one-warp-per-environment runner produce bit-identical episode records -- pair
-    sequence checksum, additions, final basis, reduced Groebner basis, discounted return -- and traffic counters."""
+    """bb_set_wide: reduce() by streams (bb_streams.cuh: the dividend is never materialised, one round per lead term) and
+    the materialising runner (warp_merge / warp_reduce) produce bit-identical episode records -- pair sequence checksum,
+    additions, final basis, reduced Groebner basis, discounted return -- and traffic counters.  Modes 2 / 3 cap the stream
+    table at 6 / 48 entries: garbage collection of exhausted streams and consolidation of the dividend into a scratch
+    list every few additions.  terms_read / terms_written (|h| per addition) exist only where h is materialised."""
     from deepgroebner_b200.buchberger import BuchbergerEngine
     episodes = 12
     eng = BuchbergerEngine(name, num_envs=episodes, **({} if name.startswith("cyclic") else dict(max_poly_terms=256)))
@@ -510,11 +512,12 @@ def test_cta_per_environment_runner_equals_warp_runner(torch_cuda, name, strateg
         out[mode] = (stats, trace, eng.counters(reset=True))
     s0, t0, c0 = out[0]
     assert (s0["status"] == 2).all()
-    for mode in (1, 2, 3):   # 2 / 3: the block merge's fallback paths (rank merge, two-walk merge path)
+    for mode in (1, 2, 3):
         s1, t1, c1 = out[mode]
         for f in s0.dtype.names:
             assert np.array_equal(s0[f], s1[f]), (mode, f)
         assert np.array_equal(t0, t1), mode
+        c1 = dict(c1, terms_read=c0["terms_read"], terms_written=c0["terms_written"])
         assert c0 == c1, mode
 
 
@@ -542,6 +545,6 @@ def test_episode_preparation_by_thread_equals_by_warp(torch_cuda, dist, kw):
     for f in s0.dtype.names:
         assert np.array_equal(s0[f], s1[f]), f
     assert np.array_equal(t0, t1) and c0 == c1
-    if not kw.get("sort_input") and kw.get("elimination", "gebauermoeller") != "none":
+    if not kw.get("sort_input") and kw.get("elimination", "gebauermoeller") == "gebauermoeller":   # lcm / none overflow the binomial pair capacity (flagged, equal in both modes)
         want = ref_oracle().run_records(dist, "normal", episodes, seed0=11, compute_gb=True, max_steps=400, **kw)
         assert_records_equal(s0, want, dist)
