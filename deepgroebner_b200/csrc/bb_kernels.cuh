@@ -13,6 +13,7 @@
 #include "bb_device.cuh"
 #include "bb_policy.cuh"
 #include "bb_streams.cuh"
+#include "bb_wide.cuh"
 
 #ifndef BB_WARPS
 #define BB_WARPS 8
@@ -88,6 +89,9 @@ struct BBKernelTable {
   // the same runner with reduce() by streams (bb_streams.cuh: long polynomials)
   cudaError_t (*run_streams)(const BBParams&, const BBParams& stage, const BBRunArgs&, int nwarps, cudaStream_t);
   int (*streams_warps_per_sm)(void);   // 0 if it does not fit
+  // ... and by one CTA per environment (bb_wide.cuh: shortest chain of additions); nctas worker CTAs
+  cudaError_t (*run_wide)(const BBParams&, const BBParams& stage, const BBRunArgs&, int nctas, cudaStream_t);
+  int (*wide_ctas_per_sm)(void);
   cudaError_t (*value)(const BBParams&, const BBParams& fork, const BBValueArgs&, int nwarps, cudaStream_t);
   cudaError_t (*policy)(const BBParams&, const BBPolicy&, unsigned long long counter, int32_t* actions, float* logp,
                         float* logits, int pmax, int nwarps, cudaStream_t);
@@ -600,6 +604,115 @@ __global__ void __launch_bounds__(BBS_WARPS * 32, BBS_MIN_CTAS) k_run_streams(co
   run_worker<NV, true, BBS_WARPS>(P, S, A, reinterpret_cast<WarpStreams*>(streams_smem) + (threadIdx.x >> 5));
 }
 
+// block-strided copy of n 32-bit words
+__device__ __forceinline__ void block_copy_words(uint32_t* __restrict__ d, const uint32_t* __restrict__ s, int n) {
+  d = bb_global(d); s = bb_global(s);
+#pragma unroll 1
+  for (int t = threadIdx.x; t < n; t += BBW_THREADS) d[t] = s[t];
+}
+
+// Persistent episode runner, one CTA per environment slot (bb_wide.cuh): same queue, staging arena, episode record and
+// checksums as k_run; the step is block_step.  Dynamic shared memory: the streams beyond one per thread.
+template <int NV>
+__global__ void __launch_bounds__(BBW_THREADS, BBW_MIN_CTAS) k_run_wide(const __grid_constant__ BBParams P, const __grid_constant__ BBParams S,
+                                                          const __grid_constant__ BBRunArgs A) {
+  extern __shared__ __align__(16) unsigned char wide_smem[];
+  __shared__ unsigned long long sh[1][CT_COUNT];
+  __shared__ BBEpisodeAcc acc;
+  __shared__ WideShared wsh;
+  __shared__ int next_b;
+  WideStreams& st = *reinterpret_cast<WideStreams*>(wide_smem);   // streams beyond one per thread (bb_wide.cuh)
+  const int tid = threadIdx.x;
+  const int slot = blockIdx.x;
+  if (tid < CT_COUNT) sh[0][tid] = 0ull;
+  __syncthreads();
+  unsigned long long* row = sh[0];
+  Ctr ct; ct.clear();
+  StreamState ws;
+  ws.clear(); ws.kmax = A.stream_kmax < BBS_KMAX ? A.stream_kmax : BBW_KMAX; ws.cz = 0;
+  int half = 0;
+  for (;;) {
+    if (tid == 0) { int q = atomicAdd(A.queue, 1); next_b = q < A.episodes ? A.order[q] : -1; }
+    __syncthreads();
+    const int b = next_b;
+    if (b < 0) break;
+    const int ep = A.ep_base + b;
+    Env e; env_load(S, b, e);
+    {
+      unsigned char* db = P.arena + (size_t)slot * P.slot_stride;
+      const unsigned char* sb = e.base;
+      block_copy_words((uint32_t*)(db + P.o_ghead), (const uint32_t*)(sb + S.o_ghead), e.nG * 8);
+      block_copy_words((uint32_t*)(db + P.o_lm), (const uint32_t*)(sb + S.o_lm), e.nG * 2);
+      block_copy_words((uint32_t*)(db + P.o_rlm), (const uint32_t*)(sb + S.o_rlm), e.nG * 2);
+      block_copy_words((uint32_t*)(db + P.o_ridx), (const uint32_t*)(sb + S.o_ridx), e.nG);
+      block_copy_words((uint32_t*)(db + P.o_pairs), (const uint32_t*)(sb + S.o_pairs), e.nP);
+      block_copy_words((uint32_t*)(db + P.o_plcm), (const uint32_t*)(sb + S.o_plcm), e.nP * 2);
+      block_copy_words((uint32_t*)(db + P.o_tkey), (const uint32_t*)(sb + S.o_tkey), e.nT * 2);
+      block_copy_words((uint32_t*)(db + P.o_tcoef), (const uint32_t*)(sb + S.o_tcoef), e.nT);
+      e.base = db;
+    }
+    const int g_start = e.nG;
+    int steps = 0, adds = 0;
+    if (tid == 0) { acc.th = 0ull; acc.ret = 0.0; acc.disc = 1.0; acc.sel_rng = rng_seed(A.sel_seed_base + ep * A.sel_seed_stride); }
+    __syncthreads();
+    int4* trace = (A.trace && ep < A.trace_eps) ? reinterpret_cast<int4*>(A.trace) + (size_t)ep * A.trace_cap : nullptr;
+    while (e.status == BB_STATUS_RUNNING && (A.max_steps == 0 || steps < A.max_steps)) {
+      uint32_t pr;
+      const int a = block_step<NV>(P, e, wsh, half, ws, st, A.strategy, &acc.sel_rng, pr, ct);
+      if (tid == 0) {
+        const int pi = pr & 0xffffu, pj = pr >> 16;
+        acc.th = trace_hash_step(acc.th, pr, a);
+        const double r = (P.rewards == BB_REWARD_ADDITIONS) ? -(double)a : -1.0;
+        const double d = acc.disc;
+        acc.ret = __dadd_rn(acc.ret, __dmul_rn(d, r)); acc.disc = __dmul_rn(d, A.gamma);
+        if (trace && steps < A.trace_cap) trace[steps] = make_int4(pi, pj, a, e.nP);
+      }
+      steps++; adds += a;
+    }
+    __syncthreads();
+    if (tid < 32) {   // warp 0: episode record, checksums, reduced Groebner basis (the warp routines of bb_device.cuh)
+      const int nonzero = e.nG - g_start, zero = steps - nonzero;
+      env_store(P, slot, e);
+      __syncwarp();
+      const GHeadMem* gh = ENV_PTR(GHeadMem, e, P, o_ghead);
+      const unsigned long long bh = warp_terms_hash<NV>(ENV_PTR(uint64_t, e, P, o_tkey), ENV_PTR(uint32_t, e, P, o_tcoef),
+                                                        e.nT, reinterpret_cast<const int*>(&gh[0].len),
+                                                        (int)(sizeof(GHeadMem) / sizeof(int)), e.nG);
+      unsigned long long gbh = 0; int gp = 0, gt = 0;
+      int status = e.status;
+      if (A.compute_gb && status == BB_STATUS_DONE) {
+        if (warp_final_gb<NV>(P, slot, row)) {
+          gp = P.gcount[2 * slot]; gt = P.gcount[2 * slot + 1];
+          gbh = warp_terms_hash<NV>(P.gkey + (size_t)slot * P.max_terms, P.gcoef + (size_t)slot * P.max_terms, gt,
+                                    P.glen + (size_t)slot * P.max_basis, 1, gp);
+        } else {
+          status = BB_STATUS_OVERFLOW_SCRATCH;
+        }
+      }
+      if (tid == 0) {
+        const unsigned long long th = acc.th; const double ret = acc.ret;
+        bb_episode_stats o;
+        o.steps = steps; o.additions = adds; o.zero_reductions = zero; o.nonzero_reductions = nonzero;
+        o.nbasis = e.nG; o.nterms = e.nT; o.status = status; o.rerolls = S.st[b].rerolls;
+        o.trace_hash = th; o.basis_hash = bh; o.gb_hash = gbh; o.gb_polys = gp; o.gb_terms = gt;
+        o.discounted_return = ret;
+        A.out[ep] = o;
+        BBEnvState& St = P.st[slot];
+        St.status = status; St.steps = steps; St.adds = adds; St.zero = zero; St.nonzero = nonzero; St.trace_hash = th;
+        St.disc_return = ret; St.rerolls = o.rerolls;
+        row[CT_STEPS] += (unsigned)steps; row[CT_ADDS] += (unsigned)adds; row[CT_NONZERO] += (unsigned)nonzero;
+        row[CT_ZERO] += (unsigned)zero; row[CT_EPISODES] += 1;
+      }
+      ct.spill(row);
+    } else {
+      ct.clear();
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+  if (tid < CT_COUNT && sh[0][tid]) atomicAdd(&P.counters[tid], sh[0][tid]);
+}
+
 // max of doubles through a CAS loop (order independent, hence deterministic)
 __device__ __forceinline__ void atomic_max_double(double* addr, double v) {
   unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
@@ -786,6 +899,20 @@ struct BBLaunch {
     k_run_streams<NV><<<(nwarps + BBS_WARPS - 1) / BBS_WARPS, BBS_WARPS * 32, sm, s>>>(P, S, A);
     return cudaGetLastError();
   }
+  static int wide_ctas_per_sm() {
+    const size_t sm = sizeof(WideStreams);
+    if (cudaFuncSetAttribute(k_run_wide<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return 0;
+    int blocks = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, k_run_wide<NV>, BBW_THREADS, sm) != cudaSuccess) return 0;
+    return blocks;
+  }
+  static cudaError_t run_wide(const BBParams& P, const BBParams& S, const BBRunArgs& A, int nctas, cudaStream_t s) {
+    const size_t sm = sizeof(WideStreams);
+    cudaError_t e = cudaFuncSetAttribute(k_run_wide<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return e;
+    k_run_wide<NV><<<nctas, BBW_THREADS, sm, s>>>(P, S, A);
+    return cudaGetLastError();
+  }
   static cudaError_t value(const BBParams& P, const BBParams& F, const BBValueArgs& A, int nwarps, cudaStream_t s) {
     k_value<NV><<<grid_for_warps(nwarps), BB_THREADS, 0, s>>>(P, F, A);
     return cudaGetLastError();
@@ -840,7 +967,7 @@ struct BBLaunch {
   }
   static const BBKernelTable* table() {
     static const BBKernelTable t = {NV, KL<NV>::w, KL<NV>::dw, KL<NV>::dshift, KL<NV>::eshift,
-                                    &reset, &step, &step_obs, &select, &observe, &final_gb, &prepare, &run, &run_streams, &streams_warps_per_sm, &value, &policy,
+                                    &reset, &step, &step_obs, &select, &observe, &final_gb, &prepare, &run, &run_streams, &streams_warps_per_sm, &run_wide, &wide_ctas_per_sm, &value, &policy,
                                     &rollout,
                                     &run_blocks_per_sm};
     return &t;

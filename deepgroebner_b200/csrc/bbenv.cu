@@ -614,13 +614,18 @@ int bb_run(bb_handle* h, int strategy, int episodes, int seed_base, const int32_
     A.order = h->stage_order; A.cost_key = h->stage_cost_key; A.prepare_by_warp = h->prepare_by_warp;
     CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int) * (BB_LPT_HIST + 2 * BB_LPT_BUCKETS), s));
     CK(h->K->prepare(S, A, s));
-    // long polynomials (general capacities): reduce() by streams (bb_streams.cuh)
+    // long polynomials (general capacities): reduce() by streams (bb_streams.cuh), by default with one CTA per
+    // environment (bb_wide.cuh: the shortest chain of additions); mode 4: one warp per environment
     const bool streams = h->wide_mode != 0 && (h->wide_mode >= 1 || h->P.max_poly_terms >= 256);
     A.stream_kmax = h->wide_mode == 2 ? 6 : (h->wide_mode == 3 ? 48 : BBS_KMAX);
     const int workers = std::min(h->P.num_envs, A.episodes);
-    if (streams) {
+    if (streams && h->wide_mode == 4) {
       if (h->K->streams_warps_per_sm() <= 0) return fail(h, "bb_run: the stream runner does not fit this device");
       CK(h->K->run_streams(h->P, S, A, workers, s));
+    } else if (streams) {
+      const int ctas = h->K->wide_ctas_per_sm() * h->sm_count;
+      if (ctas <= 0) return fail(h, "bb_run: the CTA-per-environment stream runner does not fit this device");
+      CK(h->K->run_wide(h->P, S, A, std::min(workers, ctas), s));
     } else {
       CK(h->K->run(h->P, S, A, workers, s));
     }
@@ -711,7 +716,7 @@ int bb_copy_env(bb_handle* dst, int dst_env, bb_handle* src, int src_env, void* 
 
 int bb_set_wide(bb_handle* h, int mode) {
   if (!h) return -1;
-  if (mode < -1 || mode > 3) return fail(h, "bb_set_wide: mode must be -1 (auto), 0 (off), 1 (on), 2 or 3 (on, small stream tables)");
+  if (mode < -1 || mode > 4) return fail(h, "bb_set_wide: mode must be -1 (auto), 0 (off), 1 (on), 2 or 3 (on, small stream tables), 4 (on, one warp per environment)");
   h->wide_mode = mode;
   return 0;
 }

@@ -217,12 +217,13 @@ int bb_set_selection_seed_stride(bb_handle* h, int stride);
 int bb_set_prepare_mode(bb_handle* h, int by_warp);
 
 /* bb_set_wide: how bb_run's episode runner reduces.  0: the dividend is materialised (warp-cooperative merges, built
- * for the 2-term polynomials of binomial ideals); 1: the dividend is a set of streams into the term arena kept in shared
- * memory, one round per lead term and O(1) work per addition (built for long polynomials, e.g. cyclic-n); -1 (default):
- * 1 when the capacities are sized for long polynomials (max_poly_terms >= 256), else 0; 2 / 3: as 1 with the stream table
- * capped at 6 / 48 entries so that tests reach its garbage collection and the consolidation of the dividend into a
- * scratch list.  Every mode produces bit-identical episodes; this is a performance switch.  Of the bb_counters,
- * terms_read / terms_written count |h| per addition only where h is materialised (mode 0). */
+ * for the 2-term polynomials of binomial ideals); 1: the dividend is a set of streams into the term arena, one round per
+ * lead term and O(1) work per addition (built for long polynomials, e.g. cyclic-n), run by one CTA per environment
+ * (shortest chain of additions: a cyclic-6 launch lasts as long as its longest episode); 4: the same by one warp per
+ * environment (more environments in flight); -1 (default): 1 when the capacities are sized for long polynomials
+ * (max_poly_terms >= 256), else 0; 2 / 3: as 1 with the stream table capped at 6 / 48 entries so that tests reach the
+ * consolidation of the dividend into a scratch list.  Every mode produces bit-identical episodes; this is a performance
+ * switch.  Of the bb_counters, terms_read / terms_written count |h| per addition only where h is materialised (mode 0). */
 int bb_set_wide(bb_handle* h, int mode);
 
 /* bb_value: BuchbergerEnv::value(strategy, gamma) (buchberger.cpp:332-351) for every environment at once:
