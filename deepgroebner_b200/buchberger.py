@@ -259,27 +259,45 @@ class BuchbergerEngine:
 
     # ---- whole episodes
     def run_episodes(self, strategy="degree", episodes=None, seed_base=0, seeds=None, max_steps=0, gamma=0.99,
-                     compute_gb=False, trace_episodes=0, trace_cap=0, to_host=True, selection_seed=0):
+                     compute_gb=False, trace_episodes=0, trace_cap=0, to_host=True, selection_seed=0, out_host=None):
         """Runs `episodes` episodes to completion with on-device selection (bb_run).  Returns (stats, trace):
         stats is a structured array of bb_episode_stats (numpy if to_host else a uint8 cuda tensor), trace an
-        int32 [trace_episodes, trace_cap, 4] array of (i, j, additions, |P| after), -1 padded."""
+        int32 [trace_episodes, trace_cap, 4] array of (i, j, additions, |P| after), -1 padded.
+        seeds: per-episode ideal-stream seeds, a numpy array or an int32 torch tensor (pinned host memory is copied
+        asynchronously); out_host: a pinned uint8 host tensor of episodes * 72 bytes that receives the records (the
+        returned array is a view of it)."""
         episodes = self.num_envs if episodes is None else int(episodes)
         with torch.cuda.device(self.device):
-            buf = torch.empty(max(episodes, 1) * C.sizeof(_lib.BBEpisodeStats), dtype=torch.uint8, device=self.device)
+            nbytes = max(episodes, 1) * C.sizeof(_lib.BBEpisodeStats)
+            buf = getattr(self, "_run_buf", None)
+            if buf is None or buf.numel() < nbytes:
+                buf = self._run_buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             trace = None
             if trace_episodes > 0 and trace_cap > 0:
                 trace = torch.full((trace_episodes, trace_cap, 4), -1, dtype=torch.int32, device=self.device)
             d_seeds = None
             if seeds is not None:
-                d_seeds = torch.as_tensor(np.ascontiguousarray(seeds, np.int32), device=self.device)
-                assert d_seeds.numel() == episodes
+                if torch.is_tensor(seeds):
+                    assert seeds.dtype == torch.int32 and seeds.numel() == episodes
+                    d_seeds = getattr(self, "_run_seeds", None)
+                    if d_seeds is None or d_seeds.numel() != episodes:
+                        d_seeds = self._run_seeds = torch.empty(episodes, dtype=torch.int32, device=self.device)
+                    d_seeds.copy_(seeds, non_blocking=True)
+                else:
+                    d_seeds = torch.as_tensor(np.ascontiguousarray(seeds, np.int32), device=self.device)
+                    assert d_seeds.numel() == episodes
             self._ck(self.lib.bb_run(self.h, _lib.SELECTION[strategy], episodes, int(seed_base), _ptr(d_seeds),
                                      int(selection_seed), int(max_steps), float(gamma), int(bool(compute_gb)),
                                      _ptr(buf), _ptr(trace),
                                      int(trace_episodes), int(trace_cap), _stream()), "bb_run")
             if not to_host:
-                return buf, trace
-            stats = buf.cpu().numpy().view(np.dtype(_lib.STATS_DTYPE))[:episodes]
+                return buf[:nbytes], trace
+            if out_host is not None:
+                out_host[:nbytes].copy_(buf[:nbytes], non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                stats = out_host.numpy().view(np.dtype(_lib.STATS_DTYPE))[:episodes]
+            else:
+                stats = buf[:nbytes].cpu().numpy().view(np.dtype(_lib.STATS_DTYPE))[:episodes]
             return stats, (trace.cpu().numpy() if trace is not None else None)
 
     def value(self, strategy="degree", gamma=0.99, rollouts=1, selection_seed=0, max_steps=0, out=None):
