@@ -4,14 +4,23 @@ reference's own CPU environment.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            this repo's CUDA path
   python bench.py --impl reference [--steps K] [--warmup W]      the unmodified reference on the host cores
+  BB_BENCH_WORKLOAD=u3|u5|cyclic6|rollout python bench.py ...    another BASELINE config (same as --workload)
 
 Workload (BASELINE.json configs[1]): 3-20-10-weighted, 16384 episodes per GPU run to completion under Degree
 selection; episode e draws its ideal from the reference generator stream seed(e).  One bench "step" = one pass of
-the hot path over that batch = one launch of the persistent episode kernel (reset + select + spoly + reduce +
-update for every step of every episode).  `value` = env steps / device time with the inputs (seeds) resident in
-HBM; `e2e` = the same through BuchbergerEngine.run_episodes with HOST buffers (pinned seeds H2D, episode records
-D2H, inside the timed region).  The oracle / reference is only ever used here as the cpu_baseline leg, the
-`--impl reference` arm and a post-run spot check -- never inside a timed GPU region.
+the hot path over that batch: episode preparation (ideal generator + reset, k_prepare_lanes + k_order) and the
+persistent episode runner (k_run: select + spoly + reduce + update for every step of every episode).  Steps are
+pipelined the way a job of many batches runs: the batch of step i + 1 is prepared on a side stream while the runner
+works through batch i (bb_prepare, two staging sets); both lie inside the CUDA-event pair of step i.
+`value` = env steps / device time with the inputs (seeds) resident in HBM; `e2e` = the same through
+BuchbergerEngine.prepare_episodes / run_episodes with HOST buffers (pinned seeds H2D, episode records D2H and a
+stream synchronisation per step, inside the timed region).
+
+Parity gate: EVERY episode record of the timed output (and of one extra launch with the reduced Groebner basis,
+outside the timed region) is compared with the unmodified reference (oracle/_ref, ref_run_records) -- pair sequence and
+per-step rewards (rolling checksum), length, additions, final basis, reduced basis, discounted return.  A mismatch
+aborts the run: no `value` is printed.  The oracle / reference is used as the checker, the cpu_baseline leg and the
+`--impl reference` arm only -- never inside a timed GPU region.
 """
 import argparse
 import json
@@ -51,6 +60,12 @@ SCALING, CONFIG_ID, DATA_NOTE = "weak", "configs[1]", ""
 SEL_SEED = 1234  # Random selection: episode e draws choice() from minstd_rand0 seeded SEL_SEED + e
 
 
+def workload_string():
+    """config.workload: the same string in both arms (the driver compares them)."""
+    return "%s, %d episodes %s to completion, %s selection (BASELINE %s)" % (
+        DIST, EPISODES, "per GPU" if SCALING == "weak" else "in total, sharded", STRATEGY, CONFIG_ID)
+
+
 def algorithmic_bytes(c):
     """12 B per term read/written by an addition, 8 B per reducer lead monomial examined,
     24 B per lead term moved to the remainder, 8 B per basis / pair entry touched by update()."""
@@ -78,28 +93,38 @@ def ncu_capture():
     return {}
 
 
-def ncu_traffic():
-    """DRAM bytes per launch of k_run from the committed ncu --set full capture, if any."""
-    return ncu_capture().get("k_run_dram_bytes_per_launch")
+def ncu_traffic(kernel):
+    """DRAM bytes per launch of the workload's dominant kernel from a committed ncu --set full capture of the same
+    command, or None when no capture of that kernel / workload is committed."""
+    return ncu_capture().get(kernel + "_dram_bytes_per_launch")
 
 
-def int_pipe(launch_s, sm_mhz, sm_count):
-    """The secondary roofline BASELINE.json allows for this path (instruction issue / integer pipe):
-    warp instructions per launch of k_run (a property of the kernel + workload, from the committed ncu capture of the
-    same command) over the LIVE launch time, against the issue peak = SMs x 4 schedulers x SM clock sampled during
-    the timed region.  The pipe percentages are the capture's."""
-    c = ncu_capture()
-    inst = c.get("k_run_warp_instructions_per_launch")
-    if not inst or not sm_mhz:
+def int_pipe(kernel, kernel_s, sm_mhz, sm_count, counters):
+    """The secondary roofline BASELINE.json allows for this path, both ways of counting it:
+    `issue`: warp instructions per launch of the kernel (a property of kernel + workload, from the committed ncu
+    capture of the same command) over the kernel's OWN live launch time, against SMs x 4 schedulers x SM clock;
+    `algorithmic`: SURVEY 8(d)'s integer-op model -- 10 thread-int-ops per merged output term, 5 per reducer lead
+    monomial examined -- against SMs x 4 sub-partitions x 16 INT32 lanes x SM clock."""
+    if not sm_mhz or not kernel_s:
         return None
-    peak = sm_count * 4 * sm_mhz * 1e6
-    ach = inst / launch_s
-    return {"bound": "issue", "achieved": ach / 1e9, "peak": peak / 1e9, "unit": "G warp-inst/s", "frac": ach / peak,
-            "warp_instructions_per_launch": inst, "sm_mhz": sm_mhz,
-            "alu_pipe_pct_of_peak_while_active": c.get("k_run_alu_pipe_pct_active"),
-            "issue_slots_busy_pct": c.get("k_run_issue_active_pct"),
-            "threads_per_warp_instruction": c.get("k_run_threads_per_warp_instruction"),
-            "source": c.get("source")}
+    c = ncu_capture()
+    clk = sm_mhz * 1e6
+    ops = 10.0 * counters["terms_written"] + 5.0 * counters["lms_scanned"]
+    peak_ops = sm_count * 4 * 16 * clk
+    out = {"kernel": kernel, "kernel_ms": kernel_s * 1e3, "sm_mhz": sm_mhz,
+           "algorithmic": {"int_ops_per_launch": ops, "achieved": ops / kernel_s / 1e12, "peak": peak_ops / 1e12,
+                           "unit": "T thread-int-op/s", "frac": ops / kernel_s / peak_ops,
+                           "model": "10 per output term + 5 per lead monomial scanned (SURVEY 8(d)); peak = SMs x 4 x 16 x clock"}}
+    inst = c.get(kernel + "_warp_instructions_per_launch")
+    if inst:
+        peak = sm_count * 4 * clk
+        out["issue"] = {"achieved": inst / kernel_s / 1e9, "peak": peak / 1e9, "unit": "G warp-inst/s",
+                        "frac": inst / kernel_s / peak, "warp_instructions_per_launch": inst,
+                        "alu_pipe_pct_of_peak_while_active": c.get(kernel + "_alu_pipe_pct_active"),
+                        "issue_slots_busy_pct": c.get(kernel + "_issue_active_pct"),
+                        "threads_per_warp_instruction": c.get(kernel + "_threads_per_warp_instruction"),
+                        "source": c.get(kernel + "_source") or c.get("source")}
+    return out
 
 
 class ClockSampler:
@@ -228,9 +253,8 @@ def reference_arm(args):
         "warmup": args.warmup, "ms_per_step": 1000.0 * secs / args.steps, "higher_is_better": True,
         "scaling": SCALING, "vs_baseline": None, "dtype": "int32 (GF(32003) coefficients, int exponent vectors)",
         "data": DATA_NOTE.replace("on-device restatement of the reference", "reference"),
-        "config": {"workload": "%s, %s selection, episodes to completion; bounded sample: episodes 0..%d of %d per step"
-                               % (DIST, STRATEGY, count - 1, EPISODES), "episodes_per_step": count,
-                   "host_threads": threads},
+        "config": {"workload": workload_string(), "sample": "bounded sample: episodes 0..%d of %d per step" % (count - 1, EPISODES),
+                   "episodes_per_step": count, "host_threads": threads},
         "additions_per_sec": adds / secs,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind,
                          "sample": "%d episodes (seeds 0..%d) x %d steps, one BuchbergerEnv per thread, "
@@ -241,6 +265,177 @@ def reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
+
+
+RECORD_FIELDS = ("steps", "additions", "zero_reductions", "nonzero_reductions", "nbasis", "nterms", "status", "rerolls",
+                 "trace_hash", "basis_hash", "discounted_return")
+GB_FIELDS = ("gb_hash", "gb_polys", "gb_terms")
+
+
+def parity_gate(orc, kind, timed, with_gb, ep_first, limit):
+    """Every episode record of the timed output (`timed`, compute_gb = 0) and of the extra launch with the reduced
+    Groebner basis (`with_gb`) against the unmodified reference on the host threads.  Returns the `parity` object;
+    raises SystemExit on any mismatch (no value is printed then)."""
+    if kind != "reference":
+        raise SystemExit("bench.py: the parity gate needs oracle/_ref (the unmodified reference compiled by oracle/Makefile)")
+    n = len(timed) if not limit else min(limit, len(timed))
+    t0 = time.perf_counter()
+    want = orc.run_records(DIST, STRATEGY, n, seed0=ep_first, sel_seed0=SEL_SEED + ep_first, gamma=0.99, compute_gb=True)
+    secs = time.perf_counter() - t0
+    bad = {}
+    for f in RECORD_FIELDS:
+        for name, got in (("timed", timed), ("with_gb", with_gb)):
+            m = int((got[f][:n] != want[f]).sum())
+            if m:
+                bad["%s.%s" % (name, f)] = m
+    for f in GB_FIELDS:
+        m = int((with_gb[f][:n] != want[f]).sum())
+        if m:
+            bad["with_gb.%s" % f] = m
+    mism = int(sum(bad.values()))
+    out = {"episodes_checked": n, "episodes_in_launch": len(timed), "mismatches": mism,
+           "fields": list(RECORD_FIELDS) + list(GB_FIELDS),
+           "against": "unmodified reference (oracle/_ref: BuchbergerEnv seed/reset/step + interreduce(minimalize(G)), "
+                      "buchberger.cpp:299-329, 102-122), %.1f s on the host threads" % secs}
+    if mism:
+        raise SystemExit("bench.py: PARITY FAILURE, no value reported: %r" % (bad,))
+    return out
+
+
+def time_launches(torch, fn, steps, flush):
+    """Device time of `steps` calls of fn(), L2 flushed before each: (total ms, [ms])."""
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        flush.fill_(1)
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    ms = [a.elapsed_time(b) for a, b in ev]
+    return sum(ms), ms
+
+
+def extra_step_api(torch, dev, local, flush):
+    """The step API that IS the drop-in for a vectorised trainer: per call one bb_select (Degree) + one bb_step_observe
+    (step, auto-reset, state matrix of pmax = 64 rows, |P|, reward, done) for 16384 LeadMonomialsEnv(k=2) environments,
+    16 calls captured in one CUDA graph.  env steps = environments x calls (auto-reset keeps every environment running)."""
+    from deepgroebner_b200 import LeadMonomialsEnv
+    N, PMAX, G = 16384, 64, 16
+    env = LeadMonomialsEnv(DIST, k=2, num_envs=N, device="cuda:%d" % local, pmax=PMAX)
+    eng = env.engine
+    eng.seed(0)
+    eng.set_auto_reset(True)
+    eng.reset()
+    acts = torch.empty(N, dtype=torch.int32, device=dev)
+    obs = torch.empty((N, PMAX, eng.cols), dtype=torch.int32, device=dev)
+    lens = torch.empty(N, dtype=torch.int32, device=dev)
+    rew = torch.empty(N, dtype=torch.float64, device=dev)
+    done = torch.empty(N, dtype=torch.uint8, device=dev)
+
+    def one():
+        eng.select(STRATEGY, out=acts)
+        eng.step_observe(acts, PMAX, reward=rew, done=done, obs=obs, lengths=lens)
+
+    for _ in range(8):
+        one()
+    torch.cuda.synchronize()
+    eng.counters(reset=True)
+    tot, _ = time_launches(torch, lambda: [one() for _ in range(G)], 5, flush)
+    eager = N * G * 5 / (tot / 1e3)
+    graph = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        one()
+        torch.cuda.synchronize()
+        with torch.cuda.graph(graph, stream=s):
+            for _ in range(G):
+                one()
+    torch.cuda.synchronize()
+    graph.replay()
+    torch.cuda.synchronize()
+    eng.counters(reset=True)
+    tot, _ = time_launches(torch, graph.replay, 10, flush)
+    c = eng.counters(reset=True)
+    assert c["env_steps"] == N * G * 10, (c["env_steps"], N * G * 10)
+    return {"value": N * G * 10 / (tot / 1e3), "unit": UNIT, "eager_launches": eager, "environments": N, "pmax": PMAX,
+            "calls_per_graph": G, "kernels_per_call": 2, "obs_bytes_per_call": int(obs.numel() * 4),
+            "what": "bb_select(degree) + bb_step_observe (step + auto-reset + state matrix + |P| + reward + done) per call, "
+                    "device-timed, L2 flushed between graph replays"}
+
+
+def extra_dropin_n1(seconds=2.0):
+    """LeadMonomialsEnv(num_envs=1) driven exactly like the reference's scripts/random_episodes.py:30-41 drives
+    CLeadMonomialsEnv (reset, uniform-random row, step until done), host call by host call -- the class INTEGRATION.md
+    tells a maintainer to switch to -- beside the reference's own Cython binding timed on this box (oracle/_ref)."""
+    import numpy as np
+    from deepgroebner_b200 import LeadMonomialsEnv
+
+    def drive(env, secs):
+        rng = np.random.default_rng(0)
+        n = eps = 0
+        t0 = time.perf_counter()
+        while time.perf_counter() - t0 < secs:
+            s = env.reset()
+            done = False
+            while not done:
+                s, r, done, _ = env.step(int(rng.integers(len(s))))
+                n += 1
+            eps += 1
+        return n / (time.perf_counter() - t0), eps
+
+    env = LeadMonomialsEnv(DIST, k=2, num_envs=1, pmax=256)
+    env.seed(0)
+    drive(env, 0.3)
+    ours, eps = drive(env, seconds)
+    out = {"value": ours, "unit": UNIT, "episodes": eps,
+           "what": "LeadMonomialsEnv(k=2, num_envs=1): one kernel launch + one stream synchronisation per reset()/step(), "
+                   "state matrix returned as a numpy array (bb_reset_host / bb_step_host)"}
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
+        from deepgroebner_ref.wrapped import CLeadMonomialsEnv
+        ref = CLeadMonomialsEnv(DIST, k=2)
+        ref.seed(0)
+        drive(ref, 0.2)
+        r, _ = drive(ref, seconds)
+        out["reference_cython"] = {"value": r, "unit": UNIT, "cores": 1,
+                                   "what": "the reference's own CLeadMonomialsEnv (wrapped.pyx:11-38) built unmodified by "
+                                           "oracle/build_cython_ref.sh, same loop, one host thread"}
+    except Exception as ex:  # the Cython build does not exist on this box: say so instead of inventing a number
+        out["reference_cython"] = {"unavailable": repr(ex)[:200]}
+    return out
+
+
+def extra_cyclic6(torch, local, orc, kind):
+    """BASELINE configs[4] beside the headline: cyclic-6, seeded Random selection, one launch of 1024 and one of 8192
+    episodes (the launch lasts at least as long as its longest episode, so the larger batch is the steady-state figure);
+    the first 256 records of the 1024-episode launch are checked against the reference."""
+    import numpy as np
+    from deepgroebner_b200 import _lib
+    from deepgroebner_b200.buchberger import BuchbergerEngine
+    eng = BuchbergerEngine("cyclic-6", num_envs=1024, device="cuda:%d" % local)
+    out = {"what": "cyclic-6 over GF(32003), seeded Random selection (episode e: minstd_rand0 seeded %d + e), k_run_wide "
+                   "(one CTA per environment, dividend as streams)" % SEL_SEED}
+    eng.run_episodes("random", episodes=64, selection_seed=SEL_SEED)
+    for n in (1024, 8192):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        buf, _ = eng.run_episodes("random", episodes=n, selection_seed=SEL_SEED, to_host=False)
+        b.record()
+        torch.cuda.synchronize()
+        st = buf.cpu().numpy().view(np.dtype(_lib.STATS_DTYPE))[:n]
+        assert (st["status"] == 2).all()
+        ms = a.elapsed_time(b)
+        out["episodes_%d" % n] = {"ms": ms, "additions_per_sec": float(st["additions"].sum()) / (ms / 1e3),
+                                  "env_steps_per_sec": float(st["steps"].sum()) / (ms / 1e3),
+                                  "additions": int(st["additions"].sum()), "env_steps": int(st["steps"].sum())}
+        if n == 1024 and kind == "reference":
+            want = orc.run_records("cyclic-6", "random", 256, sel_seed0=SEL_SEED, gamma=0.99, compute_gb=False)
+            bad = sum(int((st[f][:256] != want[f]).sum()) for f in RECORD_FIELDS)
+            if bad:
+                raise SystemExit("bench.py: PARITY FAILURE on cyclic-6 (%d field mismatches)" % bad)
+            out["parity"] = {"episodes_checked": 256, "mismatches": 0}
+    return out
 
 
 def gpu_arm(args):
@@ -263,81 +458,130 @@ def gpu_arm(args):
     from deepgroebner_b200 import sharding
     from deepgroebner_b200.ideals import FixedIdealGenerator, parse_ideal_dist
     spec = parse_ideal_dist(DIST, 32003)
-    nvars = spec.nvars() if isinstance(spec, FixedIdealGenerator) else spec.n
+    fixed = isinstance(spec, FixedIdealGenerator)
+    nvars = spec.nvars() if fixed else spec.n
     if SCALING == "weak":   # every rank runs its own EPISODES episodes, disjoint seeds
         ep_first, ep_local = rank * EPISODES, EPISODES
     else:                   # EPISODES in total, contiguous blocks (deepgroebner_b200/sharding.py)
         ep_first, ep_local = sharding.shard_range(EPISODES, rank, world)
     slots = args.slots or min(resident_envs(local, nvars), ep_local)
     eng = BuchbergerEngine(DIST, num_envs=slots, device="cuda:%d" % local)
+    eng.set_episode_offset(ep_first)   # selection seeds (and staged ideals) follow the global episode index
+    kernel = "k_run_wide" if fixed else "k_run"
     seeds_host = torch.arange(ep_first, ep_first + ep_local, dtype=torch.int32).pin_memory()
     seeds_dev = seeds_host.to(dev)
     stats_bytes = ep_local * 72
-    stats_dev = torch.empty(stats_bytes, dtype=torch.uint8, device=dev)
     stats_host = torch.empty(stats_bytes, dtype=torch.uint8).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    main, side = torch.cuda.current_stream(), torch.cuda.Stream()
+    pipelined = ep_local <= 65536 and not args.no_pipeline
 
-    import ctypes as C
-    lib = eng.lib
+    def prepare(seeds):
+        with torch.cuda.stream(side):
+            return eng.prepare_episodes(ep_local, seeds=seeds)
 
-    def launch(gb):
-        rc = lib.bb_run(eng.h, _lib.SELECTION[STRATEGY], ep_local, 0, C.c_void_p(seeds_dev.data_ptr()), SEL_SEED + ep_first,
-                        0, 0.99, gb, C.c_void_p(stats_dev.data_ptr()), None, 0, 0,
-                        C.c_void_p(torch.cuda.current_stream().cuda_stream))
-        if rc < 0:
-            raise RuntimeError(lib.bb_last_error(eng.h))
+    def run(seeds, gb=False, **kw):
+        return eng.run_episodes(STRATEGY, episodes=ep_local, seeds=seeds, selection_seed=SEL_SEED, gamma=0.99,
+                                compute_gb=gb, **kw)
 
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
 
-    for _ in range(max(args.warmup, 3)):
-        flush.fill_(1)
-        launch(0)
-    torch.cuda.synchronize()
+    def device_steps(n, timed):
+        """n steps; step i: [event a] prepare(batch i + 1) on the side stream || runner(batch i) [event b]."""
+        ev = []
+        if pipelined:
+            side.wait_stream(main)
+            prepare(seeds_dev)
+        for _ in range(n):
+            flush.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            if pipelined:
+                side.wait_event(a)            # the next batch's preparation starts inside this step's timed interval ...
+                prepare(seeds_dev)
+                pe = torch.cuda.Event()
+                pe.record(side)
+            buf, _ = run(seeds_dev, to_host=False)
+            if pipelined:
+                main.wait_event(pe)           # ... and ends inside it
+            b.record()
+            ev.append((a, b))
+        return ev, buf
+
+    device_steps(max(args.warmup, 3), False)
+    barrier()
     eng.counters(reset=True)
 
-    # ---- device-timed region: K launches, L2 flushed between them (flush outside the event pairs)
+    # ---- device-timed region: K steps, L2 flushed between them (flush outside the event pairs)
     sampler = ClockSampler(local) if rank == 0 else None
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
     wall0 = time.perf_counter()
-    for a, b in ev:
-        flush.fill_(1)
-        a.record()
-        launch(0)
-        b.record()
+    ev, buf = device_steps(args.steps, True)
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop() if sampler else None
     dev_ms = sum(a.elapsed_time(b) for a, b in ev)
     counters = eng.counters(reset=True)
-    stats = stats_dev.cpu().numpy().view(np.dtype(_lib.STATS_DTYPE))
+    stats = buf.cpu().numpy().view(np.dtype(_lib.STATS_DTYPE))[:ep_local].copy()
     assert (stats["status"] == 2).all(), "not every episode finished: status histogram %r" % (
         dict(zip(*[x.tolist() for x in np.unique(stats["status"], return_counts=True)])),)
     steps_per_launch = int(stats["steps"].sum())
     adds_per_launch = int(stats["additions"].sum())
     assert counters["env_steps"] == steps_per_launch * args.steps
 
-    # ---- end-to-end through the public API with host buffers
+    # ---- end to end through the public API with host buffers: pinned seeds H2D (side stream, with the preparation),
+    # runner, records D2H, one stream synchronisation per step
     barrier()
     t0 = time.perf_counter()
+    cur = prepare(seeds_host) if pipelined else None
     for _ in range(args.steps):
-        seeds_dev.copy_(seeds_host, non_blocking=True)
-        launch(0)
-        stats_host.copy_(stats_dev, non_blocking=True)
-        torch.cuda.synchronize()
+        if pipelined:
+            side.wait_stream(main)
+            nxt = prepare(seeds_host)
+            e2e_stats, _ = run(cur, out_host=stats_host)
+            cur = nxt
+        else:
+            e2e_stats, _ = run(seeds_host, out_host=stats_host)
     barrier()
     e2e_s = time.perf_counter() - t0
+    assert int(e2e_stats["steps"].sum()) == steps_per_launch
+    eng.counters(reset=True)
+
+    # ---- the kernels on their own (outside the timed regions): unpipelined launches with events inside bb_run
+    eng.set_timing(True)
+    kprep, krun = [], []
+    for _ in range(5):
+        flush.fill_(1)
+        run(seeds_dev, to_host=False)
+        p_ms, r_ms = eng.last_run_ms()
+        kprep.append(p_ms); krun.append(r_ms)
+    eng.set_timing(False)
+    kernel_counters = eng.counters(reset=True)
+    kprep_ms, krun_ms = float(np.median(kprep)), float(np.median(krun))
+
+    # ---- one launch with the reduced Groebner basis (outside the timed regions), timed for `with_gb`
+    gb_tot, _ = time_launches(torch, lambda: run(seeds_dev, gb=True, to_host=False), 3, flush)
+    gb_buf, _ = run(seeds_dev, gb=True, to_host=False)
+    gb_stats = gb_buf.cpu().numpy().view(np.dtype(_lib.STATS_DTYPE))[:ep_local].copy()
+    eng.counters(reset=True)
+
+    # ---- parity gate: every rank checks every episode of its own shard
+    orc, kind = load_cpu_oracle()
+    limit = args.parity_episodes or (1024 if fixed else 0)
+    parity = parity_gate(orc, kind, stats, gb_stats, ep_first, limit)
 
     t = torch.tensor([dev_ms, e2e_s * 1000.0], dtype=torch.float64, device=dev)
-    tot = torch.tensor([float(steps_per_launch), float(adds_per_launch)], dtype=torch.float64, device=dev)
+    tot = torch.tensor([float(steps_per_launch), float(adds_per_launch), float(parity["episodes_checked"]),
+                        float(parity["mismatches"])], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     dev_ms_max, e2e_ms_max = float(t[0]), float(t[1])
     total_steps, total_adds = float(tot[0]), float(tot[1])
+    parity["episodes_checked"], parity["mismatches"] = int(tot[2]), int(tot[3])
     per_rank = None
     if world > 1:   # diagnosis of the scaling figure: every rank's own device time, fastest single launch and work
         mine = torch.tensor([dev_ms / args.steps, min(a.elapsed_time(b) for a, b in ev), float(steps_per_launch)],
@@ -348,28 +592,11 @@ def gpu_arm(args):
                     "env_steps_per_launch": [int(x[2]) for x in allr]}
 
     if rank == 0:
-        # spot check (outside every timed region): a sample of the timed output against the CPU oracle
-        orc, kind = load_cpu_oracle()
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        from hashing import trace_hash
-        env = orc.env(DIST)
-        for e in range(0, ep_local, max(1, ep_local // (4 if STRATEGY == "random" else 16))):
-            env.seed(ep_first + e)
-            F, _ = env.reset()
-            if STRATEGY == "random":   # the reference's own buchberger() loop with the episode's selection seed
-                _, st = orc.buchberger(F, selection="random", gamma=0.99, seed=SEL_SEED + ep_first + e)
-                ok = (stats["steps"][e] == st["zero_reductions"] + st["nonzero_reductions"]
-                      and stats["additions"][e] == st["polynomial_additions"]
-                      and stats["discounted_return"][e] == st["discounted_return"])
-            else:
-                tr = env.run(selection=STRATEGY)
-                ok = stats["steps"][e] == len(tr) and int(stats["trace_hash"][e]) == trace_hash(tr)
-            assert ok, "GPU episode %d differs from the %s oracle" % (ep_first + e, kind)
-
         peak, peak_src = measured_peak()
-        abytes = algorithmic_bytes(counters) / args.steps
-        launch_s = dev_ms / 1000.0 / args.steps
-        achieved = abytes / launch_s / 1e9
+        per_launch = {k: v / 5.0 for k, v in kernel_counters.items()}   # the 5 unpipelined launches above
+        abytes = algorithmic_bytes(per_launch)
+        kernel_s = krun_ms / 1000.0
+        achieved = abytes / kernel_s / 1e9
         value = total_steps * args.steps / (dev_ms_max / 1000.0)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -377,29 +604,39 @@ def gpu_arm(args):
             "scaling": SCALING, "vs_baseline": None,
             "dtype": "u64 packed monomials + u32 GF(32003) coefficients (integer)",
             "data": DATA_NOTE,
-            "config": {"workload": "%s, %d episodes %s to completion, %s selection (BASELINE %s)"
-                                   % (DIST, EPISODES, "per GPU" if SCALING == "weak" else "in total, sharded", STRATEGY,
-                                      CONFIG_ID),
+            "config": {"workload": workload_string(),
                        "episodes_per_gpu": ep_local, "env_steps_per_launch": steps_per_launch, "slots": slots,
                        "parallelism": "episodes sharded across GPUs, no collective on the step path",
-                       "l2": "256 MiB flush write between timed launches"},
+                       "pipeline": ("batch i + 1 is prepared (k_prepare_lanes + k_order, side stream) while the runner works "
+                                    "through batch i; both inside the event pair of step i") if pipelined else "none",
+                       "l2": "256 MiB flush write between timed steps"},
             "additions_per_sec": total_adds * args.steps / (dev_ms_max / 1000.0),
             "spair_reductions_per_sec": value,
-            # per step: k_prepare + k_order + k_run (bb_run, one batch) -- the L2 flush fill and the queue memset are not ours
+            # per step: k_prepare(_lanes) + k_order + the runner (one batch) -- the L2 flush fill and the queue memset are not ours
             "gpu_launches": 3 * args.steps * ((ep_local + 65535) // 65536),
             "wall_s_timed_region": wall,
             "clocks": clocks,
+            "parity": parity,
             "e2e": {"value": total_steps * args.steps / (e2e_ms_max / 1000.0), "unit": UNIT,
-                    "h2d_bytes_per_step": ep_local * 4, "d2h_bytes_per_step": stats_bytes},
+                    "h2d_bytes_per_step": ep_local * 4, "d2h_bytes_per_step": stats_bytes,
+                    "api": "BuchbergerEngine.prepare_episodes(seeds=pinned host) + run_episodes(out_host=pinned host)"},
+            "kernel_ms": {"prepare+order": kprep_ms, kernel: krun_ms,
+                          "how": "CUDA events inside bb_run (bb_set_timing), median of 5 unpipelined launches, L2 flushed"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "k_run",
+                         "traffic": ncu_traffic(kernel) if args.workload == "episodes" or fixed else None,
+                         "peak_source": peak_src, "kernel": kernel, "kernel_ms": krun_ms,
                          "algorithmic_bytes_per_launch": abytes,
-                         "note": "latency/integer bound at binomial sizes (working set lives in L1/L2); see DESIGN.md"},
-            "counters_per_launch": {k: v / args.steps for k, v in counters.items()},
+                         "note": ("terms_read / terms_written count the reducers only: the dividend is never materialised "
+                                  "(bb_streams.cuh)") if fixed else
+                                 "latency/integer bound at binomial sizes (working set lives in L1/L2); see DESIGN.md"},
+            "with_gb": {"value": steps_per_launch * 3 / (gb_tot / 1000.0), "unit": UNIT, "n_gpus": 1,
+                        "what": "the same launch with compute_gb = 1 (interreduce(minimalize(G)) + checksum per episode), "
+                                "rank 0, unpipelined, 3 launches"},
+            "counters_per_launch": per_launch,
         }
         if per_rank:
             line["per_rank"] = per_rank
-        ip = int_pipe(launch_s, (clocks or {}).get("sm_mhz"), eng.sm_count) if args.workload == "episodes" else None
+        ip = int_pipe(kernel, kernel_s, (clocks or {}).get("sm_mhz"), eng.sm_count, per_launch)
         if ip:
             line["int_pipe"] = ip
         if world == 1 and not args.no_cpu:
@@ -409,6 +646,12 @@ def gpu_arm(args):
                 "value": r["steps"] / r["seconds"], "unit": UNIT, "cores": threads, "kind": kind,
                 "sample": "%d episodes (seeds 0..%d) of the same workload x %d passes, one reference BuchbergerEnv per "
                           "host thread, %.1f s" % (count, count - 1, r.get("reps", 1), r["seconds"])}
+        if world == 1 and not args.no_extras and args.workload == "episodes":
+            del eng
+            torch.cuda.empty_cache()
+            line["step_api"] = extra_step_api(torch, dev, local, flush)
+            line["dropin_n1"] = extra_dropin_n1()
+            line["cyclic6"] = extra_cyclic6(torch, local, orc, kind)
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -520,7 +763,7 @@ def rollout_arm(args):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--workload", default="episodes", choices=sorted(WORKLOADS) + ["rollout"],
+    ap.add_argument("--workload", default=os.environ.get("BB_BENCH_WORKLOAD", "episodes"), choices=sorted(WORKLOADS) + ["rollout"],
                     help="episodes = BASELINE configs[1] (the headline); u3/u5 = configs[2]; cyclic6 = configs[4]; "
                          "rollout = configs[3]")
     ap.add_argument("--episodes", type=int, default=0, help="override the workload's episode count")
@@ -533,6 +776,10 @@ def main():
     ap.add_argument("--slots", type=int, default=0, help="environment slots (0 = one resident wave)")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the step_api / dropin_n1 / cyclic6 sub-objects")
+    ap.add_argument("--no-pipeline", action="store_true", help="prepare every batch on the runner's stream (A/B)")
+    ap.add_argument("--parity-episodes", type=int, default=0,
+                    help="episodes of the launch checked against the reference (0 = all; cyclic-6: 1024)")
     args = ap.parse_args()
     global DIST, STRATEGY, EPISODES, SCALING, CONFIG_ID, DATA_NOTE
     DIST, STRATEGY, EPISODES, SCALING, CONFIG_ID = WORKLOADS.get(args.workload, WORKLOADS["episodes"])

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # BBENV_LIB selects another build of the SAME library (A/B runs of kernel variants); it is never a fallback.
 LIB_PATH = os.environ.get("BBENV_LIB") or os.path.join(HERE, "libbbenv.so")
 
-BB_ABI_VERSION = 2
+BB_ABI_VERSION = 3
 
 ELIMINATION = {"gebauermoeller": 0, "lcm": 1, "none": 2}
 REWARDS = {"additions": 0, "reductions": 1}
@@ -20,7 +20,8 @@ VALUE_SAMPLE = 100  # bb_value only: value("sample")
 DISTRIBUTION = {"uniform": 0, "weighted": 1, "maximum": 2}
 
 STATUS_NAMES = {0: "empty", 1: "running", 2: "done", 3: "bad_action", 4: "overflow_basis", 5: "overflow_pairs",
-                6: "overflow_terms", 7: "overflow_exponent", 8: "overflow_scratch"}
+                6: "overflow_terms", 7: "overflow_exponent", 8: "overflow_scratch", 9: "truncated"}
+STATUS_COUNT = 10
 
 
 class BBConfig(C.Structure):
@@ -57,6 +58,8 @@ EXPORTS = [
     "bb_set_distribution", "bb_set_distribution_poly", "bb_seed", "bb_set_ideals", "bb_reset", "bb_step", "bb_select", "bb_observe", "bb_pairs",
     "bb_status", "bb_stats", "bb_run", "bb_download_basis", "bb_final_gb", "bb_counters_read", "bb_hash_item",
     "bb_seed_selection", "bb_value", "bb_copy_env", "bb_set_auto_reset", "bb_step_observe", "bb_step_host", "bb_reset_host", "bb_observe_host", "bb_set_wide", "bb_set_prepare_mode", "bb_set_selection_seed_stride", "bb_policy_pmlp", "bb_rollout",
+    "bb_seed_on", "bb_prepare", "bb_set_episode_offset", "bb_set_timing", "bb_last_run_ms", "bb_set_max_episode_length",
+    "bb_set_compaction", "bb_compact", "bb_status_summary", "bb_set_obs_nvars", "bb_discount",
 ]
 
 _lib = None
@@ -134,6 +137,21 @@ def load():
     lib.bb_set_prepare_mode.argtypes = [vp, i]
     lib.bb_set_selection_seed_stride.restype = i
     lib.bb_set_selection_seed_stride.argtypes = [vp, i]
+    lib.bb_seed_on.restype = i
+    lib.bb_seed_on.argtypes = [vp, ip, i, i, vp]
+    lib.bb_prepare.restype = i
+    lib.bb_prepare.argtypes = [vp, i, i, vp, vp]
+    for n in ("bb_set_episode_offset", "bb_set_timing", "bb_set_max_episode_length", "bb_set_compaction", "bb_set_obs_nvars"):
+        getattr(lib, n).restype = i
+        getattr(lib, n).argtypes = [vp, i]
+    lib.bb_last_run_ms.restype = i
+    lib.bb_last_run_ms.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+    lib.bb_compact.restype = i
+    lib.bb_compact.argtypes = [vp, vp, vp]
+    lib.bb_status_summary.restype = i
+    lib.bb_status_summary.argtypes = [vp, ip, vp]
+    lib.bb_discount.restype = i
+    lib.bb_discount.argtypes = [vp, i, i, vp, vp, C.c_double, vp, vp]
     u64 = C.c_uint64
     lib.bb_policy_pmlp.restype = i
     lib.bb_policy_pmlp.argtypes = [vp, i, vp, vp, vp, vp, u64, u64, i, vp, vp, vp, i, vp]

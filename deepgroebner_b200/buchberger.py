@@ -111,21 +111,23 @@ class BuchbergerEngine:
         seed(sequence): explicit per-environment seeds."""
         if seed is None:
             return
-        if np.ndim(seed) == 0:
-            self._ck(self.lib.bb_seed(self.h, None, int(seed)), "bb_seed")
-        else:
-            a = np.ascontiguousarray(seed, dtype=np.int32)
-            assert a.shape == (self.num_envs,)
-            self._ck(self.lib.bb_seed(self.h, a.ctypes.data_as(C.POINTER(C.c_int32)), 0), "bb_seed")
+        self._seed(seed, 0)
+
+    def _seed(self, seed, selection):
+        # bb_seed_on: one kernel on the current stream, no allocation, no synchronisation (the reference pattern
+        # re-seeds before every episode, randomized_agent.py:141-142)
+        with torch.cuda.device(self.device):
+            if np.ndim(seed) == 0:
+                self._ck(self.lib.bb_seed_on(self.h, None, int(seed), selection, _stream()), "bb_seed_on")
+            else:
+                a = np.ascontiguousarray(seed, dtype=np.int32)
+                assert a.shape == (self.num_envs,)
+                self._ck(self.lib.bb_seed_on(self.h, a.ctypes.data_as(C.POINTER(C.c_int32)), 0, selection, _stream()),
+                         "bb_seed_on")
 
     def seed_selection(self, seed=0):
         """Seeds the per-environment stream that 'random' selection draws from (buchberger(..., seed))."""
-        if np.ndim(seed) == 0:
-            self._ck(self.lib.bb_seed_selection(self.h, None, int(seed)), "bb_seed_selection")
-        else:
-            a = np.ascontiguousarray(seed, dtype=np.int32)
-            assert a.shape == (self.num_envs,)
-            self._ck(self.lib.bb_seed_selection(self.h, a.ctypes.data_as(C.POINTER(C.c_int32)), 0), "bb_seed_selection")
+        self._seed(seed, 1)
 
     def set_ideals(self, ideals, env_ids=None):
         """ideals: list (one per environment) of lists of polynomials [(coef, exps), ...]."""
@@ -257,7 +259,74 @@ class BuchbergerEngine:
             self._ck(self.lib.bb_stats(self.h, _ptr(buf), _stream()), "bb_stats")
             return buf.cpu().numpy().view(np.dtype(_lib.STATS_DTYPE))
 
+    # ---- batch management (SURVEY north_star: finished / diverged episodes are compacted)
+    def compact(self, out=None):
+        """int32 cuda tensor [N + 1]: the number of RUNNING environments, then every slot with the RUNNING ones first
+        (bb_compact).  step() / step_observe() do this themselves when auto-reset is off."""
+        with torch.cuda.device(self.device):
+            if out is None:
+                out = torch.empty(self.num_envs + 1, dtype=torch.int32, device=self.device)
+            self._ck(self.lib.bb_compact(self.h, _ptr(out), _stream()), "bb_compact")
+        return out
+
+    def set_compaction(self, on=True):
+        self._ck(self.lib.bb_set_compaction(self.h, int(bool(on))), "bb_set_compaction")
+
+    def status_summary(self):
+        """{status name: number of environments} (bb_status_summary; synchronises).  'diverged' sums the faults."""
+        counts = np.zeros(_lib.STATUS_COUNT, np.int32)
+        with torch.cuda.device(self.device):
+            self._ck(self.lib.bb_status_summary(self.h, counts.ctypes.data_as(C.POINTER(C.c_int32)), _stream()),
+                     "bb_status_summary")
+        out = {_lib.STATUS_NAMES[i]: int(counts[i]) for i in range(_lib.STATUS_COUNT)}
+        out["diverged"] = int(counts[3:9].sum())
+        return out
+
+    def set_max_episode_length(self, max_steps=0):
+        """Episodes of step() / rollout() are cut once they have MORE than max_steps steps (pg.py:470-471); 0 = never."""
+        self._ck(self.lib.bb_set_max_episode_length(self.h, int(max_steps or 0)), "bb_set_max_episode_length")
+
+    def set_obs_nvars(self, n_obs):
+        """State matrices show the first n_obs variables only (bb_set_obs_nvars: the C++ FixedIdealGenerator quirk)."""
+        self._ck(self.lib.bb_set_obs_nvars(self.h, int(n_obs)), "bb_set_obs_nvars")
+        self.cols = self.lib.bb_cols(self.h)
+
     # ---- whole episodes
+    def prepare_episodes(self, episodes=None, seed_base=0, seeds=None):
+        """The preparation half of the NEXT run_episodes call (bb_prepare) on the current stream -- call it under
+        `torch.cuda.stream(side)` to overlap it with a runner at work on another stream.  `seeds`: None for
+        seed_base + e, an int32 cuda tensor, or an int32 HOST tensor (pinned: copied asynchronously into one of two
+        device buffers of the engine, on the current stream).  Returns the device seeds tensor (or None): pass THAT
+        object as `seeds` to the run_episodes call this preparation is for."""
+        episodes = self.num_envs if episodes is None else int(episodes)
+        with torch.cuda.device(self.device):
+            if seeds is not None:
+                assert torch.is_tensor(seeds) and seeds.dtype == torch.int32 and seeds.numel() == episodes
+                if not seeds.is_cuda:
+                    ring = getattr(self, "_seed_ring", None)
+                    if ring is None or ring[0].numel() != episodes:
+                        ring = self._seed_ring = [torch.empty(episodes, dtype=torch.int32, device=self.device) for _ in range(2)]
+                        self._seed_turn = 0
+                    dev = ring[self._seed_turn]
+                    self._seed_turn ^= 1
+                    dev.copy_(seeds, non_blocking=True)
+                    seeds = dev
+            self._ck(self.lib.bb_prepare(self.h, episodes, int(seed_base), _ptr(seeds), _stream()), "bb_prepare")
+        return seeds
+
+    def set_episode_offset(self, offset=0):
+        """Global index of episode 0 of the following run_episodes calls (bb_set_episode_offset; sharding.py)."""
+        self._ck(self.lib.bb_set_episode_offset(self.h, int(offset)), "bb_set_episode_offset")
+
+    def set_timing(self, on=True):
+        self._ck(self.lib.bb_set_timing(self.h, int(bool(on))), "bb_set_timing")
+
+    def last_run_ms(self):
+        """(preparation ms, runner ms) of the last run_episodes call (first batch); needs set_timing(True)."""
+        a, b = C.c_float(0), C.c_float(0)
+        self._ck(self.lib.bb_last_run_ms(self.h, C.byref(a), C.byref(b)), "bb_last_run_ms")
+        return float(a.value), float(b.value)
+
     def run_episodes(self, strategy="degree", episodes=None, seed_base=0, seeds=None, max_steps=0, gamma=0.99,
                      compute_gb=False, trace_episodes=0, trace_cap=0, to_host=True, selection_seed=0, out_host=None):
         """Runs `episodes` episodes to completion with on-device selection (bb_run).  Returns (stats, trace):
@@ -277,7 +346,10 @@ class BuchbergerEngine:
                 trace = torch.full((trace_episodes, trace_cap, 4), -1, dtype=torch.int32, device=self.device)
             d_seeds = None
             if seeds is not None:
-                if torch.is_tensor(seeds):
+                if torch.is_tensor(seeds) and seeds.is_cuda:
+                    assert seeds.dtype == torch.int32 and seeds.numel() == episodes
+                    d_seeds = seeds
+                elif torch.is_tensor(seeds):
                     assert seeds.dtype == torch.int32 and seeds.numel() == episodes
                     d_seeds = getattr(self, "_run_seeds", None)
                     if d_seeds is None or d_seeds.numel() != episodes:
@@ -300,10 +372,13 @@ class BuchbergerEngine:
                 stats = buf[:nbytes].cpu().numpy().view(np.dtype(_lib.STATS_DTYPE))[:episodes]
             return stats, (trace.cpu().numpy() if trace is not None else None)
 
-    def value(self, strategy="degree", gamma=0.99, rollouts=1, selection_seed=0, max_steps=0, out=None):
+    def value(self, strategy="degree", gamma=0.99, rollouts=None, selection_seed=0, max_steps=0, out=None):
         """BuchbergerEnv.value for every environment (bb_value): float64 cuda tensor [N].  strategy is a selection
-        name or 'sample' (1 Degree + 100 Random rollouts, best kept)."""
+        name or 'sample' (1 Degree + 100 Random rollouts, best kept, buchberger.cpp:333-341).  rollouts: None = the
+        reference's count (101 for 'sample', 1 otherwise); for 'sample' it includes the Degree rollout."""
         code = _lib.VALUE_SAMPLE if strategy == "sample" else _lib.SELECTION[strategy]
+        if rollouts is None:
+            rollouts = 0 if strategy == "sample" else 1   # bb_value: 0 -> 101 for BB_VALUE_SAMPLE
         with torch.cuda.device(self.device):
             if out is None:
                 out = torch.empty(self.num_envs, dtype=torch.float64, device=self.device)
@@ -425,9 +500,15 @@ class LeadMonomialsEnv:
 
     def __init__(self, ideal_dist="3-20-10-uniform", elimination="gebauermoeller", rewards="additions",
                  sort_input=False, sort_reducers=True, k=1, dtype=np.int32, num_envs=1, device="cuda:0", pmax=None,
-                 **engine_kwargs):
+                 compat_cxx_nvars=False, max_episode_length=None, **engine_kwargs):
         self.engine = BuchbergerEngine(ideal_dist, elimination, rewards, sort_input, sort_reducers, k, num_envs,
                                        device, **engine_kwargs)
+        if compat_cxx_nvars and isinstance(self.engine.spec, FixedIdealGenerator):
+            # the C++ / Cython env shows max(variable index in use) variables for a fixed ideal (ideals.cpp:146-154)
+            used = [v for f in self.engine.spec.F for _, e in f for v, x in enumerate(e) if x]
+            self.engine.set_obs_nvars(max(1, max(used) if used else 1))
+        if max_episode_length:
+            self.engine.set_max_episode_length(max_episode_length)
         self.k, self.dtype, self.num_envs = k, dtype, num_envs
         self.pmax = int(pmax) if pmax else self.engine.caps["max_pairs"]
 
@@ -535,4 +616,11 @@ class BuchbergerAgent:
         self.strategy = selection
 
     def act(self, env):
-        return env.engine.select(self.strategy)
+        """LeadMonomialsEnv: row indices [N] (an int for num_envs == 1); BuchbergerEnv: pairs [N, 2] (a tuple (i, j)
+        for num_envs == 1), as buchberger.py:397-439 returns them."""
+        rows = env.engine.select(self.strategy)
+        if isinstance(env, BuchbergerEnv):
+            pairs, _ = env.engine.pairs(env.pmax)
+            picked = pairs[torch.arange(env.num_envs, device=pairs.device), rows.long().clamp(0, env.pmax - 1)]
+            return tuple(int(x) for x in picked[0].cpu()) if env.num_envs == 1 else picked
+        return int(rows.item()) if env.num_envs == 1 else rows

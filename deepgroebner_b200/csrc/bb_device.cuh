@@ -89,6 +89,9 @@ struct BBParams {
   unsigned o_hcoef;   // u32     [2][max_poly_terms]
   unsigned o_logit;   // f32     [max_pairs]          policy head scratch: one logit per pair row
   int auto_reset;     // k_step / k_rollout: a finished environment is reset in the same call (vector-env semantics)
+  int max_episode_length;  // k_step / k_rollout: 0 = unlimited; else an episode is cut (BB_STATUS_TRUNCATED, done = 1) once it
+                           // has MORE than this many steps -- `episode_length > max_episode_length: break`, pg.py:470-471
+  int obs_nv;         // variables shown per monomial in the state matrix (= nvars; less only under bb_set_obs_nvars)
   BBEnvState* st;
   // staged input ideals, one per slot
   uint64_t* in_key; uint32_t* in_coef;  // [num_envs][max_gen_terms], each polynomial sorted descending
@@ -419,6 +422,36 @@ __device__ __forceinline__ int warp_reduce(const BBParams& P, Env& e, Dividend& 
 }
 
 // ---------------------------------------------------------------------------------------------------- update
+// The fields of BBParams that update() reads.  warp_add_basis is one out-of-line copy, so `P` reaches it as a generic
+// pointer into the kernel's parameter bank and every P.field would be a generic load (15 of them per call,
+// profiles/README.md r2); every kernel that can reach it copies them to this block-shared record first (hot_init) and the
+// function reads them with LDS at constant addresses.  -DBB_HOT_SHARED=0 reads P instead (A/B).
+struct BBHot {
+  int max_basis, max_pairs, elimination, sort_reducers;
+  unsigned o_tkey, o_tcoef, o_lm, o_lscr, o_plcm, o_pairs, o_rlm, o_ridx, o_ghead, pad;
+  const uint16_t* invtab;
+};
+#ifndef BB_HOT_SHARED
+#define BB_HOT_SHARED 1
+#endif
+#if BB_HOT_SHARED
+static __shared__ BBHot g_hot;
+#define BB_HOT(P) g_hot
+// every thread of the CTA, before anything else (contains a block barrier)
+__device__ __forceinline__ void hot_init(const BBParams& P) {
+  if (threadIdx.x == 0) {
+    g_hot.max_basis = P.max_basis; g_hot.max_pairs = P.max_pairs; g_hot.elimination = P.elimination;
+    g_hot.sort_reducers = P.sort_reducers; g_hot.o_tkey = P.o_tkey; g_hot.o_tcoef = P.o_tcoef; g_hot.o_lm = P.o_lm;
+    g_hot.o_lscr = P.o_lscr; g_hot.o_plcm = P.o_plcm; g_hot.o_pairs = P.o_pairs; g_hot.o_rlm = P.o_rlm;
+    g_hot.o_ridx = P.o_ridx; g_hot.o_ghead = P.o_ghead; g_hot.pad = 0u; g_hot.invtab = P.invtab;
+  }
+  __syncthreads();
+}
+#else
+#define BB_HOT(P) (P)
+__device__ __forceinline__ void hot_init(const BBParams&) {}
+#endif
+
 // Registers the polynomial stored at arena[off, off+len) (first two terms given in registers) as basis element
 // m and runs update(G, P, f, elimination), buchberger.cpp:52-99, then the reducer-list insertion
 // (upper_bound by lead monomial when sort_reducers: after every element whose lead monomial is <= the new one,
@@ -436,19 +469,20 @@ template <int NV>
 __device__ BB_ADD_BASIS_INLINE long long warp_add_basis(const BBParams& P, unsigned char* base, int m, int nP, int off, int len,
                                                  int sug) {
   typedef KL<NV> K;
+  const auto& H = BB_HOT(P);
   const int lane = bb_lane();
   const uint32_t ltm = bb_lt_mask();
-  if (m >= P.max_basis) return -2;
+  if (m >= H.max_basis) return -2;
   base = bb_global(base);
-  const uint64_t* tk = reinterpret_cast<const uint64_t*>(base + P.o_tkey) + off;
-  const uint32_t* tc = reinterpret_cast<const uint32_t*>(base + P.o_tcoef) + off;
+  const uint64_t* tk = reinterpret_cast<const uint64_t*>(base + H.o_tkey) + off;
+  const uint32_t* tc = reinterpret_cast<const uint32_t*>(base + H.o_tcoef) + off;
   const uint64_t fk = tk[0];
-  uint64_t* lm = reinterpret_cast<uint64_t*>(base + P.o_lm);
-  uint64_t* lscr = reinterpret_cast<uint64_t*>(base + P.o_lscr);
-  uint64_t* plcm = reinterpret_cast<uint64_t*>(base + P.o_plcm);
-  uint32_t* pairs = reinterpret_cast<uint32_t*>(base + P.o_pairs);
+  uint64_t* lm = reinterpret_cast<uint64_t*>(base + H.o_lm);
+  uint64_t* lscr = reinterpret_cast<uint64_t*>(base + H.o_lscr);
+  uint64_t* plcm = reinterpret_cast<uint64_t*>(base + H.o_plcm);
+  uint32_t* pairs = reinterpret_cast<uint32_t*>(base + H.o_pairs);
   int emitted = 0;
-  if (P.elimination == BB_ELIM_GEBAUERMOELLER && m <= 64) {
+  if (H.elimination == BB_ELIM_GEBAUERMOELLER && m <= 64) {
     // The common case (profiles/r01_v6: the sweep loop below was the largest single consumer of issue slots): with at
     // most 64 basis elements every lane keeps L_lane and L_{lane+32} in registers, so the peeling needs no memory at
     // all -- one candidate reduction and one two-register sweep per kept lcm.  Same algorithm as the general path.
@@ -534,11 +568,11 @@ __device__ BB_ADD_BASIS_INLINE long long warp_add_basis(const BBParams& P, unsig
     }
     const uint32_t km0 = __ballot_sync(BB_FULL, k0), km1 = two ? __ballot_sync(BB_FULL, k1) : 0u;
     const int cnt0 = __popc(km0), cnt1 = __popc(km1);
-    if (nP + cnt0 + cnt1 > P.max_pairs) return -1;
+    if (nP + cnt0 + cnt1 > H.max_pairs) return -1;
     if (k0) { const int pos = nP + __popc(km0 & ltm); pairs[pos] = ((uint32_t)m << 16) | (uint32_t)i0; plcm[pos] = v0; }
     if (two && k1) { const int pos = nP + cnt0 + __popc(km1 & ltm); pairs[pos] = ((uint32_t)m << 16) | (uint32_t)i1; plcm[pos] = v1; }
     nP += cnt0 + cnt1; emitted = cnt0 + cnt1;
-  } else if (P.elimination == BB_ELIM_GEBAUERMOELLER) {
+  } else if (H.elimination == BB_ELIM_GEBAUERMOELLER) {
     // lscr[i] = key of L_i = lcm(LM_i, LM f), for every basis element (the old-pair filter gathers from it)
     bool ovf = false;  // deg(L_i) must fit the degree field: bit 63 is a tag below, never a silently wrapped degree
 #pragma unroll 1
@@ -619,7 +653,7 @@ __device__ BB_ADD_BASIS_INLINE long long warp_add_basis(const BBParams& P, unsig
       const bool keep = (long long)v < 0;
       const uint32_t km = __ballot_sync(BB_FULL, keep);
       const int cnt = __popc(km);
-      if (nP + cnt > P.max_pairs) return -1;
+      if (nP + cnt > H.max_pairs) return -1;
       if (keep) {
         const int pos = nP + __popc(km & ltm);
         pairs[pos] = ((uint32_t)m << 16) | (uint32_t)i;
@@ -633,10 +667,10 @@ __device__ BB_ADD_BASIS_INLINE long long warp_add_basis(const BBParams& P, unsig
       const int i = b0 + lane;
       bool keep = i < m;
       const uint64_t li = keep ? lm[i] : 0ull;
-      if (keep && P.elimination == BB_ELIM_LCM) keep = !K::coprime(li, fk);  // :58-62
+      if (keep && H.elimination == BB_ELIM_LCM) keep = !K::coprime(li, fk);  // :58-62
       const uint32_t km = __ballot_sync(BB_FULL, keep);
       const int cnt = __popc(km);
-      if (nP + cnt > P.max_pairs) return -1;
+      if (nP + cnt > H.max_pairs) return -1;
       if (keep) {
         const int pos = nP + __popc(km & ltm);
         pairs[pos] = ((uint32_t)m << 16) | (uint32_t)i;
@@ -646,10 +680,10 @@ __device__ BB_ADD_BASIS_INLINE long long warp_add_basis(const BBParams& P, unsig
     }
   }
   // reducer list
-  uint64_t* rlm = reinterpret_cast<uint64_t*>(base + P.o_rlm);
-  uint32_t* ridx = reinterpret_cast<uint32_t*>(base + P.o_ridx);
+  uint64_t* rlm = reinterpret_cast<uint64_t*>(base + H.o_rlm);
+  uint32_t* ridx = reinterpret_cast<uint32_t*>(base + H.o_ridx);
   int pos = m;
-  if (P.sort_reducers && m <= 64) {   // both halves of the list in registers: count, then shift by one, no read-after-write hazard
+  if (H.sort_reducers && m <= 64) {   // both halves of the list in registers: count, then shift by one, no read-after-write hazard
     const int i0 = lane, i1 = lane + 32;
     uint64_t r0 = 0ull, r1 = 0ull; uint32_t x0 = 0u, x1 = 0u;
     const bool two = m > 32;
@@ -662,7 +696,7 @@ __device__ BB_ADD_BASIS_INLINE long long warp_add_basis(const BBParams& P, unsig
     if (i0 < m && i0 >= pos) { rlm[i0 + 1] = r0; ridx[i0 + 1] = x0; }
     if (two && i1 < m && i1 >= pos) { rlm[i1 + 1] = r1; ridx[i1 + 1] = x1; }
     __syncwarp();
-  } else if (P.sort_reducers) {
+  } else if (H.sort_reducers) {
     int cnt = 0;  // reducers with LM <= new LM  <=>  key >= new key
 #pragma unroll 1
     for (int b0 = 0; b0 < m; b0 += 32) {
@@ -685,8 +719,8 @@ __device__ BB_ADD_BASIS_INLINE long long warp_add_basis(const BBParams& P, unsig
   if (lane == 0) {
     rlm[pos] = fk; ridx[pos] = (uint32_t)m;
     lm[m] = fk;
-    GHeadMem* g = reinterpret_cast<GHeadMem*>(base + P.o_ghead) + m;
-    const uint32_t inv = bb_global(P.invtab)[tc[0]];  // 1/LC: one table load instead of a 15-step power ladder
+    GHeadMem* g = reinterpret_cast<GHeadMem*>(base + H.o_ghead) + m;
+    const uint32_t inv = bb_global(H.invtab)[tc[0]];  // 1/LC: one table load instead of a 15-step power ladder
     const uint64_t k1 = len > 1 ? tk[1] : 0ull;
     const uint32_t c1 = len > 1 ? tc[1] : 0u;
     reinterpret_cast<uint4*>(g)[0] = make_uint4((uint32_t)fk, (uint32_t)(fk >> 32), (uint32_t)k1, (uint32_t)(k1 >> 32));
@@ -905,7 +939,8 @@ template <int NV>
 __device__ __forceinline__ void warp_observe(const BBParams& P, const Env& e, int32_t* obs, int pmax, Ctr& ct) {
   typedef KL<NV> K;
   const int lane = bb_lane();
-  const int cols = P.cols, half = NV * P.k;
+  const int nv = P.obs_nv;   // == NV except under bb_set_obs_nvars (the C++ FixedIdealGenerator::nvars quirk, ideals.cpp:146-154)
+  const int cols = P.cols, half = nv * P.k;
   const int rows = e.nP < pmax ? e.nP : pmax;
   const int live = rows * cols, total = pmax * cols;
   const uint32_t* pairs = ENV_PTR(uint32_t, e, P, o_pairs);
@@ -916,7 +951,7 @@ __device__ __forceinline__ void warp_observe(const BBParams& P, const Env& e, in
     const uint32_t pr = pairs[row];
     const int side = c >= half;
     const int cc = c - side * half;
-    const int t = cc / NV, v = cc - t * NV;
+    const int t = cc / nv, v = cc - t * nv;
     const GHeadMem* g = gh + (side ? (pr >> 16) : (pr & 0xffffu));
     int32_t val = 0;
     if (t < (int)g->len) val = (int32_t)K::exp(t == 0 ? g->lm : (t == 1 ? g->k1 : tk[g->off + t]), v);

@@ -32,7 +32,9 @@ struct BBRunArgs {
   int sel_seed_base;  // Random selection: episode e draws choice() from minstd_rand0 seeded sel_seed_base + e * sel_seed_stride
   int sel_seed_stride;
   int ep_base;      // first episode of this batch: episode ids are ep_base .. ep_base + episodes - 1
-  int nstaged;      // fixed ideals: number of staged ideals (episode e replays ideal e mod nstaged)
+  int ep_offset;    // global index of the call's episode 0 (bb_set_episode_offset): selection seeds and the staged ideal
+                    // an episode replays follow the GLOBAL index, so a shard of a job behaves like its slice of the whole
+  int nstaged;      // fixed ideals: number of staged ideals (global episode g replays ideal g mod nstaged)
   const int* seeds;
   int max_steps;
   double gamma;
@@ -78,9 +80,10 @@ struct BBRolloutArgs {
 struct BBKernelTable {
   int nvars, w, dw, dshift, eshift;
   cudaError_t (*reset)(const BBParams&, const uint8_t* mask, int nwarps, cudaStream_t);
-  cudaError_t (*step)(const BBParams&, const int* actions, double* reward, uint8_t* done, int nwarps, cudaStream_t);
+  cudaError_t (*step)(const BBParams&, const int* actions, double* reward, uint8_t* done, const int* active, int nwarps,
+                      cudaStream_t);
   cudaError_t (*step_obs)(const BBParams&, const int* actions, int action0, double* reward, uint8_t* done, int32_t* obs,
-                          int32_t* lengths, int pmax, int pad, int do_step, int nwarps, cudaStream_t);
+                          int32_t* lengths, int pmax, int pad, int do_step, const int* active, int nwarps, cudaStream_t);
   cudaError_t (*select)(const BBParams&, int strategy, int* actions, int nwarps, cudaStream_t);
   cudaError_t (*observe)(const BBParams&, int32_t* obs, int32_t* lengths, int pmax, int nwarps, cudaStream_t);
   cudaError_t (*final_gb)(const BBParams&, int slot, int* ok_out, cudaStream_t);
@@ -123,6 +126,7 @@ __device__ __forceinline__ unsigned long long* counters_row(unsigned long long (
 template <int NV>
 __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_reset(const __grid_constant__ BBParams P, const uint8_t* mask) {
   __shared__ unsigned long long sh[BB_WARPS][CT_COUNT];
+  hot_init(P);
   unsigned long long* row = counters_row(sh);
   const int slot = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
   if (slot < P.num_envs && (!mask || mask[slot])) warp_reset_slot<NV>(P, slot, slot, (uint32_t)P.st[slot].rng, row);
@@ -148,16 +152,30 @@ __device__ __forceinline__ double step_and_account(const BBParams& P, int slot, 
     row[e.nG > g0 ? CT_NONZERO : CT_ZERO] += 1;
     if (e.status == BB_STATUS_DONE) row[CT_EPISODES] += 1;
   }
+  if (P.max_episode_length > 0 && e.status == BB_STATUS_RUNNING) {   // pg.py:470-471: cut once episode_length > max
+    int n = 0;
+    if (bb_lane() == 0) n = P.st[slot].steps;
+    n = __shfl_sync(BB_FULL, n, 0);
+    if (n > P.max_episode_length) {
+      e.status = BB_STATUS_TRUNCATED;
+      if (bb_lane() == 0) { P.st[slot].truncated = 1; row[CT_EPISODES] += 1; }
+    }
+  }
   return (P.rewards == BB_REWARD_ADDITIONS) ? -(double)adds : -1.0;
 }
 
 template <int NV>
 __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_step(const __grid_constant__ BBParams P,
                                                                    const int* __restrict__ actions,
-                                                                   double* __restrict__ reward, uint8_t* __restrict__ done) {
+                                                                   double* __restrict__ reward, uint8_t* __restrict__ done,
+                                                                   const int* __restrict__ active) {
   __shared__ unsigned long long sh[BB_WARPS][CT_COUNT];
+  hot_init(P);
   unsigned long long* row = counters_row(sh);
-  const int slot = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
+  const int w = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
+  // active (k_compact): warp w takes the w-th environment of the RUNNING-first order, so the stepping warps fill whole
+  // CTAs and the CTAs behind them hold idle environments only
+  const int slot = (active && w < P.num_envs) ? active[1 + w] : w;
   if (slot < P.num_envs) {
     Env e; env_load(P, slot, e);
     Ctr ct; ct.clear();
@@ -189,10 +207,13 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_step_obs(const __
                                                                        const int* __restrict__ actions, int action0,
                                                                        double* __restrict__ reward, uint8_t* __restrict__ done,
                                                                        int32_t* __restrict__ obs, int32_t* __restrict__ lengths,
-                                                                       int pmax, int pad, int do_step) {
+                                                                       int pmax, int pad, int do_step,
+                                                                       const int* __restrict__ active) {
   __shared__ unsigned long long sh[BB_WARPS][CT_COUNT];
+  hot_init(P);
   unsigned long long* row = counters_row(sh);
-  const int slot = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
+  const int w = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
+  const int slot = (active && w < P.num_envs) ? active[1 + w] : w;   // as k_step
   if (slot < P.num_envs) {
     Env e; env_load(P, slot, e);
     Ctr ct; ct.clear();
@@ -265,11 +286,12 @@ template <int NV>
 __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_prepare(const __grid_constant__ BBParams S,
                                                                       const __grid_constant__ BBRunArgs A) {
   __shared__ unsigned long long sh[BB_WARPS][CT_COUNT];
+  hot_init(S);
   unsigned long long* row = counters_row(sh);
   const int b = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
   if (b < A.episodes) {
     const int ep = A.ep_base + b;
-    warp_reset_slot<NV>(S, b, S.dist.enabled ? b : ep % A.nstaged, rng_seed(A.seeds ? A.seeds[ep] : A.seed_base + ep), row);
+    warp_reset_slot<NV>(S, b, S.dist.enabled ? b : (A.ep_offset + ep) % A.nstaged, rng_seed(A.seeds ? A.seeds[ep] : A.seed_base + ep), row);
     // Predicted cost of the episode, for the longest-first queue order: the summed degree of the generators' lead
     // monomials (rank correlation with the episode length ~0.5 on the binomial distributions), scaled to a bucket.
     // Only the ORDER in which episodes start depends on it, never a result.
@@ -507,6 +529,7 @@ template <int NV, bool STREAMS, int WARPS>
 __device__ __forceinline__ void run_worker(const BBParams& P, const BBParams& S, const BBRunArgs& A, WarpStreams* st) {
   __shared__ unsigned long long sh[WARPS][CT_COUNT];
   __shared__ BBEpisodeAcc acc_sh[WARPS];  // per-episode accumulators only lane 0 touches: kept out of registers
+  hot_init(P);
   unsigned long long* row = sh[threadIdx.x >> 5];
   if (bb_lane() < CT_COUNT) row[bb_lane()] = 0ull;
   __syncwarp();
@@ -532,7 +555,7 @@ __device__ __forceinline__ void run_worker(const BBParams& P, const BBParams& S,
       }
       const int g_start = e.nG;
       int steps = 0, adds = 0;
-      if (lane == 0) { acc.th = 0ull; acc.ret = 0.0; acc.disc = 1.0; acc.sel_rng = rng_seed(A.sel_seed_base + ep * A.sel_seed_stride); }
+      if (lane == 0) { acc.th = 0ull; acc.ret = 0.0; acc.disc = 1.0; acc.sel_rng = rng_seed(A.sel_seed_base + (A.ep_offset + ep) * A.sel_seed_stride); }
       __syncwarp();
       run_episode<NV, STREAMS>(P, e, A.strategy, A.max_steps, A.gamma, acc, ct, steps, adds,
                                (A.trace && ep < A.trace_eps) ? reinterpret_cast<int4*>(A.trace) + (size_t)ep * A.trace_cap : nullptr,
@@ -624,6 +647,7 @@ __global__ void __launch_bounds__(BBW_THREADS, BBW_MIN_CTAS) k_run_wide(const __
   WideStreams& st = *reinterpret_cast<WideStreams*>(wide_smem);   // streams beyond one per thread (bb_wide.cuh)
   const int tid = threadIdx.x;
   const int slot = blockIdx.x;
+  hot_init(P);
   if (tid < CT_COUNT) sh[0][tid] = 0ull;
   __syncthreads();
   unsigned long long* row = sh[0];
@@ -653,7 +677,7 @@ __global__ void __launch_bounds__(BBW_THREADS, BBW_MIN_CTAS) k_run_wide(const __
     }
     const int g_start = e.nG;
     int steps = 0, adds = 0;
-    if (tid == 0) { acc.th = 0ull; acc.ret = 0.0; acc.disc = 1.0; acc.sel_rng = rng_seed(A.sel_seed_base + ep * A.sel_seed_stride); }
+    if (tid == 0) { acc.th = 0ull; acc.ret = 0.0; acc.disc = 1.0; acc.sel_rng = rng_seed(A.sel_seed_base + (A.ep_offset + ep) * A.sel_seed_stride); }
     __syncthreads();
     int4* trace = (A.trace && ep < A.trace_eps) ? reinterpret_cast<int4*>(A.trace) + (size_t)ep * A.trace_cap : nullptr;
     while (e.status == BB_STATUS_RUNNING && (A.max_steps == 0 || steps < A.max_steps)) {
@@ -734,6 +758,7 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_value(const __gri
                                                                     const __grid_constant__ BBValueArgs A) {
   __shared__ unsigned long long sh[BB_WARPS][CT_COUNT];
   __shared__ BBEpisodeAcc acc_sh[BB_WARPS];
+  hot_init(F);
   unsigned long long* row = counters_row(sh);
   BBEpisodeAcc& acc = acc_sh[threadIdx.x >> 5];
   const int w = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
@@ -799,6 +824,7 @@ __global__ void __launch_bounds__(BB_THREADS, BB_ROLLOUT_MIN_BLOCKS) k_rollout(c
                                                            const __grid_constant__ BBRolloutArgs A) {
   extern __shared__ float wsm[];
   __shared__ unsigned long long sh[BB_WARPS][CT_COUNT];
+  hot_init(P);
   policy_load_weights(A.W, P.cols, wsm);
   unsigned long long* row = counters_row(sh);
   const int slot = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
@@ -850,13 +876,15 @@ struct BBLaunch {
     k_reset<NV><<<grid_for_warps(nwarps), BB_THREADS, 0, s>>>(P, mask);
     return cudaGetLastError();
   }
-  static cudaError_t step(const BBParams& P, const int* actions, double* reward, uint8_t* done, int nwarps, cudaStream_t s) {
-    k_step<NV><<<grid_for_warps(nwarps), BB_THREADS, 0, s>>>(P, actions, reward, done);
+  static cudaError_t step(const BBParams& P, const int* actions, double* reward, uint8_t* done, const int* active, int nwarps,
+                          cudaStream_t s) {
+    k_step<NV><<<grid_for_warps(nwarps), BB_THREADS, 0, s>>>(P, actions, reward, done, active);
     return cudaGetLastError();
   }
   static cudaError_t step_obs(const BBParams& P, const int* actions, int action0, double* reward, uint8_t* done, int32_t* obs,
-                              int32_t* lengths, int pmax, int pad, int do_step, int nwarps, cudaStream_t s) {
-    k_step_obs<NV><<<grid_for_warps(nwarps), BB_THREADS, 0, s>>>(P, actions, action0, reward, done, obs, lengths, pmax, pad, do_step);
+                              int32_t* lengths, int pmax, int pad, int do_step, const int* active, int nwarps, cudaStream_t s) {
+    k_step_obs<NV><<<grid_for_warps(nwarps), BB_THREADS, 0, s>>>(P, actions, action0, reward, done, obs, lengths, pmax, pad, do_step,
+                                                                active);
     return cudaGetLastError();
   }
   static cudaError_t select(const BBParams& P, int strategy, int* actions, int nwarps, cudaStream_t s) {

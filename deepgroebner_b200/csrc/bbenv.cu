@@ -60,6 +60,64 @@ __global__ void __launch_bounds__(BB_THREADS) k_status(BBParams P, int32_t* stat
   }
 }
 
+// Stream compaction of the environment list (north_star "batch management"): out[0] = number of RUNNING environments,
+// out[1 ..] = every slot, RUNNING ones first, both groups in ascending order (a stable partition).  One CTA walks the
+// status words in chunks of 1024: ballot + per-warp totals give each slot its rank inside the chunk.
+__global__ void __launch_bounds__(1024) k_compact(BBParams P, int* __restrict__ out) {
+  __shared__ int wsum[32];
+  __shared__ int total;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int N = P.num_envs;
+  int running = 0;
+  for (int i = tid; i < N; i += 1024) running += P.st[i].status == BB_STATUS_RUNNING;
+  running = __reduce_add_sync(0xffffffffu, running);
+  if (lane == 0) wsum[wid] = running;
+  __syncthreads();
+  if (wid == 0) {
+    const int t = __reduce_add_sync(0xffffffffu, wsum[lane]);
+    if (lane == 0) { total = t; out[0] = t; }
+  }
+  __syncthreads();
+  const int R = total;
+  int before = 0;   // RUNNING environments in the chunks already placed
+  for (int c0 = 0; c0 < N; c0 += 1024) {
+    const int i = c0 + tid;
+    const bool run = i < N && P.st[i].status == BB_STATUS_RUNNING;
+    const unsigned m = __ballot_sync(0xffffffffu, run);
+    __syncthreads();   // wsum of the previous chunk has been read
+    if (lane == 0) wsum[wid] = __popc(m);
+    __syncthreads();
+    int wbefore = 0, chunk = 0;
+    for (int w = 0; w < 32; w++) { const int v = wsum[w]; chunk += v; if (w < wid) wbefore += v; }
+    const int rb = before + wbefore + __popc(m & ((1u << lane) - 1u));   // RUNNING environments before slot i
+    if (i < N) out[1 + (run ? rb : R + i - rb)] = i;
+    before += chunk;
+  }
+}
+
+__global__ void __launch_bounds__(BB_THREADS) k_status_hist(BBParams P, int* __restrict__ hist) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= P.num_envs) return;
+  const int st = P.st[e].status;
+  atomicAdd(&hist[(unsigned)st < BB_STATUS_COUNT ? st : 0], 1);
+}
+
+// Discounted suffix sums inside episode segments (pg.discount_rewards, pg.py:18-39, on [N, T] trajectories):
+// out[n][t] = x[n][t] + (done[n][t] ? 0 : gam * out[n][t+1]), one thread per trajectory walking backwards in fp64.
+__global__ void __launch_bounds__(BB_THREADS) k_discount(int N, int T, const double* __restrict__ x,
+                                                         const uint8_t* __restrict__ done, double gam, double* __restrict__ out) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const double* xr = x + (size_t)n * T;
+  const uint8_t* dr = done + (size_t)n * T;
+  double* o = out + (size_t)n * T;
+  double run = 0.0;
+  for (int t = T - 1; t >= 0; t--) {
+    run = dr[t] ? xr[t] : __dadd_rn(xr[t], __dmul_rn(gam, run));
+    o[t] = run;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ kernel tables
 const BBKernelTable* bb_kernel_table_nv1(); const BBKernelTable* bb_kernel_table_nv2();
 const BBKernelTable* bb_kernel_table_nv3(); const BBKernelTable* bb_kernel_table_nv4();
@@ -85,14 +143,29 @@ struct bb_handle {
   int sm_count;
   std::vector<void*> allocs;
   std::string err;
-  int* d_queue;
+  int* d_queue;             // bb_value's task counter
   int* d_ok;
-  // staging arena of bb_run: one compact slot per episode of a batch, holding the state right after reset()
-  int stage_cap;                    // episodes it can hold (0 = not allocated yet)
-  std::vector<void*> stage_allocs;
-  unsigned char* stage_arena; BBEnvState* stage_st;
-  uint64_t* stage_in_key; uint32_t* stage_in_coef; int* stage_in_off; int* stage_in_np;
-  int* stage_order; uint8_t* stage_cost_key;   // longest-predicted-first queue order of the batch (k_order)
+  // Staging of bb_run, TWO sets (double buffering): one compact slot per episode of a batch, holding the state right
+  // after reset(), plus the batch's queue words and longest-predicted-first order.  While the runner works through
+  // set b, the next batch is prepared into set b ^ 1 on another stream (bb_prepare, or bb_run's own side stream when a
+  // call spans several batches).
+  struct Stage {
+    int cap;                        // episodes it can hold (0 = not allocated yet)
+    std::vector<void*> allocs;
+    unsigned char* arena; BBEnvState* st;
+    uint64_t* in_key; uint32_t* in_coef; int* in_off; int* in_np;
+    int* order; uint8_t* cost_key;  // longest-predicted-first queue order of the batch (k_order)
+    int* queue;                     // [BB_LPT_HIST + 2 * BB_LPT_BUCKETS] queue position, cost histogram, cursors
+    cudaEvent_t prepared;           // recorded after k_prepare + k_order of the batch it holds
+    cudaEvent_t consumed;           // recorded after the k_run that read it
+    // the batch a bb_prepare call left here, waiting for its bb_run (episodes == 0: none)
+    int episodes, seed_base; const int32_t* seeds;
+  } stage[2];
+  int stage_next;                   // set the next batch goes to
+  cudaStream_t side;                // bb_run's own prepare stream (calls that span several batches)
+  cudaEvent_t ev_entry;
+  // bb_set_timing: events around the preparation and the runner of the LAST bb_run call (first batch)
+  int timing; cudaEvent_t ev_t[3];
   // fork arena of bb_value: one full-size slot per worker warp
   int fork_cap;
   std::vector<void*> fork_allocs;
@@ -101,10 +174,16 @@ struct bb_handle {
   // place) and a device twin (large batches: one async copy each way)
   unsigned char* host_stage; unsigned char* dev_stage; size_t stage_bytes;
   int sel_seed_stride;   // bb_run: episode e's Random-selection stream is seeded sel_seed_base + e * stride (default 1)
+  int episode_offset;    // bb_run: global index of episode 0 of a call (bb_set_episode_offset: shards of one job)
+  int nstaged;           // fixed ideals: environments 0 .. nstaged - 1 hold a staged ideal (bb_set_ideals)
+  int* d_seeds; int* h_seeds; cudaEvent_t ev_seeds;   // bb_seed: device / pinned staging of explicit seeds
+  int* d_active;         // [num_envs + 1] slots of the RUNNING environments in ascending order, count in front (k_compact)
+  int compaction;        // bb_set_compaction
   int prepare_by_warp;   // bb_run: 1 = episode preparation by one warp per episode even where the thread-per-episode kernel applies
   int wide_mode;   // bb_run: reduce() by streams: -1 = when the capacities ask for long polynomials, 0 = never, 1 = always, 2 / 3 = always, small tables
   // host mirrors of the distribution tables
   std::vector<double> cp;
+  std::vector<char> staged;   // bb_set_ideals: which environments hold a staged ideal
 };
 
 static thread_local std::string g_create_err;
@@ -180,7 +259,16 @@ void bb_destroy(bb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
   for (void* p : h->allocs) cudaFree(p);
-  for (void* p : h->stage_allocs) cudaFree(p);
+  for (int b = 0; b < 2; b++) {
+    for (void* p : h->stage[b].allocs) cudaFree(p);
+    if (h->stage[b].prepared) cudaEventDestroy(h->stage[b].prepared);
+    if (h->stage[b].consumed) cudaEventDestroy(h->stage[b].consumed);
+  }
+  if (h->side) cudaStreamDestroy(h->side);
+  if (h->ev_entry) cudaEventDestroy(h->ev_entry);
+  if (h->ev_seeds) cudaEventDestroy(h->ev_seeds);
+  for (int t = 0; t < 3; t++) if (h->ev_t[t]) cudaEventDestroy(h->ev_t[t]);
+  if (h->h_seeds) cudaFreeHost(h->h_seeds);
   for (void* p : h->fork_allocs) cudaFree(p);
   if (h->host_stage) cudaFreeHost(h->host_stage);
   if (h->dev_stage) cudaFree(h->dev_stage);
@@ -210,7 +298,16 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
   h = new bb_handle();
   h->cfg = *cfg;
   h->d_queue = nullptr; h->d_ok = nullptr;
-  h->stage_cap = 0; h->stage_arena = nullptr; h->stage_st = nullptr;
+  for (int b = 0; b < 2; b++) {
+    bb_handle::Stage& T = h->stage[b];
+    T.cap = 0; T.arena = nullptr; T.st = nullptr; T.in_key = nullptr; T.in_coef = nullptr; T.in_off = nullptr; T.in_np = nullptr;
+    T.order = nullptr; T.cost_key = nullptr; T.queue = nullptr; T.prepared = nullptr; T.consumed = nullptr;
+    T.episodes = 0; T.seed_base = 0; T.seeds = nullptr;
+  }
+  h->stage_next = 0; h->side = nullptr; h->ev_entry = nullptr; h->timing = 0;
+  h->ev_t[0] = h->ev_t[1] = h->ev_t[2] = nullptr;
+  h->episode_offset = 0; h->nstaged = 0; h->d_seeds = nullptr; h->h_seeds = nullptr; h->ev_seeds = nullptr;
+  h->d_active = nullptr; h->compaction = 1;
   h->fork_cap = 0; h->fork_arena = nullptr; h->fork_st = nullptr;
   h->wide_mode = -1;
   h->prepare_by_warp = 0;
@@ -239,6 +336,7 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
   P.sort_input = cfg->sort_input ? 1 : 0; P.sort_reducers = cfg->sort_reducers ? 1 : 0;
   P.max_basis = cfg->max_basis; P.max_pairs = cfg->max_pairs; P.max_terms = (cfg->max_terms + 7) & ~7;
   P.max_poly_terms = cfg->max_poly_terms; P.max_gens = cfg->max_gens; P.max_gen_terms = cfg->max_gen_terms;
+  P.obs_nv = cfg->nvars; P.max_episode_length = 0;
   const size_t N = (size_t)cfg->num_envs;
   if (!layout_arena(P)) { h->err = "bb_create: per-environment arena exceeds 2 GiB"; return bail(-1); }
   CKC(dev_alloc(h, &P.arena, N * P.slot_stride));
@@ -262,8 +360,20 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
     CKC(cudaGetLastError());
     P.invtab = tab;
   }
-  CKC(dev_alloc(h, &h->d_queue, (size_t)(BB_LPT_HIST + 2 * BB_LPT_BUCKETS)));
+  CKC(dev_alloc(h, &h->d_queue, (size_t)4));
   CKC(dev_alloc(h, &h->d_ok, (size_t)4));
+  CKC(dev_alloc(h, &h->d_seeds, N));
+  CKC(dev_alloc(h, &h->d_active, std::max(N + 1, (size_t)16)));
+  CKC(cudaHostAlloc((void**)&h->h_seeds, sizeof(int) * N, cudaHostAllocDefault));
+  CKC(cudaEventCreateWithFlags(&h->ev_seeds, cudaEventDisableTiming));
+  CKC(cudaEventCreateWithFlags(&h->ev_entry, cudaEventDisableTiming));
+  CKC(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+  for (int b = 0; b < 2; b++) {
+    CKC(dev_alloc(h, &h->stage[b].queue, (size_t)(BB_LPT_HIST + 2 * BB_LPT_BUCKETS)));
+    CKC(cudaEventCreateWithFlags(&h->stage[b].prepared, cudaEventDisableTiming));
+    CKC(cudaEventCreateWithFlags(&h->stage[b].consumed, cudaEventDisableTiming));
+  }
+  for (int t = 0; t < 3; t++) CKC(cudaEventCreate(&h->ev_t[t]));
   k_seed<<<(cfg->num_envs + BB_THREADS - 1) / BB_THREADS, BB_THREADS>>>(P, nullptr, 0, 0);
   k_seed<<<(cfg->num_envs + BB_THREADS - 1) / BB_THREADS, BB_THREADS>>>(P, nullptr, 0, 1);
   CKC(cudaGetLastError());
@@ -345,22 +455,28 @@ int bb_set_distribution_poly(bb_handle* h, int d, int s, double lam, int dist, i
   return set_distribution_impl(h, 1, d, s, lam, dist, constants, homogeneous, 0);
 }
 
-static int seed_impl(bb_handle* h, const int32_t* seeds, int base, int selection) {
+// Seeds on `s`: explicit seeds travel through the handle's pinned staging (one async copy, no allocation, no device
+// synchronisation; a second call waits for the first one's copy only if it is still in flight).
+static int seed_impl(bb_handle* h, const int32_t* seeds, int base, int selection, cudaStream_t s) {
   if (!h) return -1;
   CK(cudaSetDevice(h->cfg.device));
-  int* d_seeds = nullptr;
+  const int* d_seeds = nullptr;
   if (seeds) {
-    CK(cudaMalloc(&d_seeds, sizeof(int) * (size_t)h->P.num_envs));
-    CK(cudaMemcpy(d_seeds, seeds, sizeof(int) * (size_t)h->P.num_envs, cudaMemcpyHostToDevice));
+    CK(cudaEventSynchronize(h->ev_seeds));
+    memcpy(h->h_seeds, seeds, sizeof(int) * (size_t)h->P.num_envs);
+    CK(cudaMemcpyAsync(h->d_seeds, h->h_seeds, sizeof(int) * (size_t)h->P.num_envs, cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(h->ev_seeds, s));
+    d_seeds = h->d_seeds;
   }
-  k_seed<<<(h->P.num_envs + BB_THREADS - 1) / BB_THREADS, BB_THREADS>>>(h->P, d_seeds, base, selection);
-  cudaError_t e1 = cudaGetLastError(), e2 = cudaDeviceSynchronize();
-  if (d_seeds) cudaFree(d_seeds);
-  CK(e1); CK(e2);
+  k_seed<<<(h->P.num_envs + BB_THREADS - 1) / BB_THREADS, BB_THREADS, 0, s>>>(h->P, d_seeds, base, selection);
+  CK(cudaGetLastError());
   return 0;
 }
-int bb_seed(bb_handle* h, const int32_t* seeds, int base) { return seed_impl(h, seeds, base, 0); }
-int bb_seed_selection(bb_handle* h, const int32_t* seeds, int base) { return seed_impl(h, seeds, base, 1); }
+int bb_seed(bb_handle* h, const int32_t* seeds, int base) { return seed_impl(h, seeds, base, 0, (cudaStream_t)0); }
+int bb_seed_selection(bb_handle* h, const int32_t* seeds, int base) { return seed_impl(h, seeds, base, 1, (cudaStream_t)0); }
+int bb_seed_on(bb_handle* h, const int32_t* seeds, int base, int selection, void* stream) {
+  return seed_impl(h, seeds, base, selection ? 1 : 0, (cudaStream_t)stream);
+}
 
 int bb_set_ideals(bb_handle* h, const int32_t* env_ids, int count, const int32_t* ideal_offsets,
                   const int32_t* poly_offsets, const int32_t* exps, const int32_t* coefs) {
@@ -410,8 +526,13 @@ int bb_set_ideals(bb_handle* h, const int32_t* env_ids, int count, const int32_t
     CK(cudaMemcpy(P.in_coef + (size_t)env * P.max_gen_terms, cf.data(), sizeof(uint32_t) * nt, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(P.in_off + (size_t)env * (P.max_gens + 1), off.data(), sizeof(int) * (np + 1), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(P.in_np + env, &np, sizeof(int), cudaMemcpyHostToDevice));
+    if (h->staged.empty()) h->staged.assign((size_t)P.num_envs, 0);
+    h->staged[(size_t)env] = 1;
   }
   P.dist.enabled = 0;
+  // bb_run replays staged ideal (e mod nstaged): the staged environments must be a prefix 0 .. nstaged - 1
+  h->nstaged = 0;
+  while (h->nstaged < P.num_envs && !h->staged.empty() && h->staged[(size_t)h->nstaged]) h->nstaged++;
   return 0;
 }
 
@@ -422,11 +543,26 @@ int bb_reset(bb_handle* h, const uint8_t* mask_dev, void* stream) {
   return 0;
 }
 
+// Without auto-reset finished and faulted environments pile up over a batch of episodes: the step kernels then take the
+// environments in RUNNING-first order (k_compact), so that the stepping warps sit in full CTAs.  With auto-reset every
+// environment is RUNNING after every call and the list would be the identity.
+static int compact_for_step(bb_handle* h, cudaStream_t s, const int** active) {
+  *active = nullptr;
+  if (!h->compaction || h->P.auto_reset || h->P.num_envs < 2 * BB_WARPS) return 0;
+  k_compact<<<1, 1024, 0, s>>>(h->P, h->d_active);
+  CK(cudaGetLastError());
+  *active = h->d_active;
+  return 0;
+}
+
 int bb_step(bb_handle* h, const int32_t* actions_dev, double* reward_dev, uint8_t* done_dev, void* stream) {
   if (!h) return -1;
   if (!actions_dev) return fail(h, "bb_step: null actions");
   CK(cudaSetDevice(h->cfg.device));
-  CK(h->K->step(h->P, actions_dev, reward_dev, done_dev, h->P.num_envs, (cudaStream_t)stream));
+  const int* active = nullptr;
+  int rc = compact_for_step(h, (cudaStream_t)stream, &active);
+  if (rc < 0) return rc;
+  CK(h->K->step(h->P, actions_dev, reward_dev, done_dev, active, h->P.num_envs, (cudaStream_t)stream));
   return 0;
 }
 
@@ -463,8 +599,10 @@ static int host_call(bb_handle* h, int do_step, const int32_t* actions_host, dou
       d_actions = (const int*)(ds + o_act);
     }
   }
+  const int* active = nullptr;
+  if (do_step) { int rc = compact_for_step(h, s, &active); if (rc < 0) return rc; }
   CK(h->K->step_obs(P, d_actions, action0, do_step ? (double*)(ds + o_rew) : nullptr, do_step ? (uint8_t*)(ds + o_done) : nullptr,
-                    obs_host ? (int32_t*)(ds + o_obs) : nullptr, (int32_t*)(ds + o_len), pmax, pad, do_step, P.num_envs, s));
+                    obs_host ? (int32_t*)(ds + o_obs) : nullptr, (int32_t*)(ds + o_len), pmax, pad, do_step, active, P.num_envs, s));
   if (!zero_copy) {
     CK(cudaMemcpyAsync(hs, ds, o_act, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(hs + o_done, ds + o_done, N, cudaMemcpyDeviceToHost, s));
@@ -488,7 +626,11 @@ int bb_step_observe(bb_handle* h, const int32_t* actions_dev, double* reward_dev
   if (!h) return -1;
   if (!actions_dev || pmax < 0 || (obs_dev && pmax < 1)) return fail(h, "bb_step_observe: bad argument");
   CK(cudaSetDevice(h->cfg.device));
-  CK(h->K->step_obs(h->P, actions_dev, 0, reward_dev, done_dev, obs_dev, lengths_dev, pmax, 1, 1, h->P.num_envs, (cudaStream_t)stream));
+  const int* active = nullptr;
+  int rc = compact_for_step(h, (cudaStream_t)stream, &active);
+  if (rc < 0) return rc;
+  CK(h->K->step_obs(h->P, actions_dev, 0, reward_dev, done_dev, obs_dev, lengths_dev, pmax, 1, 1, active, h->P.num_envs,
+                    (cudaStream_t)stream));
   return 0;
 }
 
@@ -553,41 +695,91 @@ int bb_stats(bb_handle* h, bb_episode_stats* stats_dev, void* stream) {
   return 0;
 }
 
-// Staging parameters for a batch: a copy of P whose arena is the compact per-episode one (capacity: the input
-// ideal only -- max_gens polynomials, all their pairs, max_gen_terms terms).
+// Staging parameters for a batch in set `which`: a copy of P whose arena is the compact per-episode one (capacity: the
+// input ideal only -- max_gens polynomials, all their pairs, max_gen_terms terms).
 #define BB_RUN_BATCH 65536
-static int stage_params(bb_handle* h, int batch, BBParams& S) {
+static int stage_params(bb_handle* h, int which, int batch, BBParams& S) {
   const BBParams& P = h->P;
+  bb_handle::Stage& T = h->stage[which];
   S = P;
   S.max_basis = P.max_gens;
   S.max_pairs = std::max(1, P.max_gens * (P.max_gens - 1) / 2);
   S.max_terms = P.max_gen_terms;
   S.max_poly_terms = 1;
   if (!layout_arena(S)) return fail(h, "bb_run: staging slot too large");
-  if (batch > h->stage_cap) {
-    for (void* p : h->stage_allocs) cudaFree(p);
-    h->stage_allocs.clear();
-    h->stage_cap = 0;
+  if (batch > T.cap) {
+    CK(cudaDeviceSynchronize());   // the set is about to be replaced (first call, or a larger batch than ever before)
+    for (void* p : T.allocs) cudaFree(p);
+    T.allocs.clear();
+    T.cap = 0;
     const size_t n = (size_t)batch;
     auto alloc = [&](void** out, size_t bytes) {
       cudaError_t e = cudaMalloc(out, bytes + 16);
-      if (e == cudaSuccess) { h->stage_allocs.push_back(*out); e = cudaMemset(*out, 0, bytes + 16); }
+      if (e == cudaSuccess) { T.allocs.push_back(*out); e = cudaMemset(*out, 0, bytes + 16); }
       return e;
     };
-    CK(alloc((void**)&h->stage_arena, n * S.slot_stride));
-    CK(alloc((void**)&h->stage_st, n * sizeof(BBEnvState)));
-    CK(alloc((void**)&h->stage_in_key, n * P.max_gen_terms * sizeof(uint64_t)));
-    CK(alloc((void**)&h->stage_in_coef, n * P.max_gen_terms * sizeof(uint32_t)));
-    CK(alloc((void**)&h->stage_in_off, n * (P.max_gens + 1) * sizeof(int)));
-    CK(alloc((void**)&h->stage_in_np, n * sizeof(int)));
-    CK(alloc((void**)&h->stage_order, n * sizeof(int)));
-    CK(alloc((void**)&h->stage_cost_key, n));
-    h->stage_cap = batch;
+    CK(alloc((void**)&T.arena, n * S.slot_stride));
+    CK(alloc((void**)&T.st, n * sizeof(BBEnvState)));
+    CK(alloc((void**)&T.in_key, n * P.max_gen_terms * sizeof(uint64_t)));
+    CK(alloc((void**)&T.in_coef, n * P.max_gen_terms * sizeof(uint32_t)));
+    CK(alloc((void**)&T.in_off, n * (P.max_gens + 1) * sizeof(int)));
+    CK(alloc((void**)&T.in_np, n * sizeof(int)));
+    CK(alloc((void**)&T.order, n * sizeof(int)));
+    CK(alloc((void**)&T.cost_key, n));
+    CK(cudaDeviceSynchronize());
+    T.cap = batch;
   }
-  S.arena = h->stage_arena; S.st = h->stage_st; S.num_envs = batch;
+  S.arena = T.arena; S.st = T.st; S.num_envs = batch;
   if (P.dist.enabled) {  // generated ideals are staged per episode; fixed ideals are read in place from the handle
-    S.in_key = h->stage_in_key; S.in_coef = h->stage_in_coef; S.in_off = h->stage_in_off; S.in_np = h->stage_in_np;
+    S.in_key = T.in_key; S.in_coef = T.in_coef; S.in_off = T.in_off; S.in_np = T.in_np;
   }
+  return 0;
+}
+
+// The part of BBRunArgs the preparation reads, for episodes [base, base + count) of a call
+static void prepare_args(bb_handle* h, int which, int base, int count, int seed_base, const int32_t* seeds_dev, BBRunArgs& A) {
+  memset(&A, 0, sizeof A);
+  const bb_handle::Stage& T = h->stage[which];
+  A.episodes = count; A.seed_base = seed_base; A.seeds = seeds_dev; A.ep_base = base;
+  A.ep_offset = h->episode_offset; A.nstaged = std::max(1, h->nstaged);
+  A.queue = T.queue; A.order = T.order; A.cost_key = T.cost_key; A.prepare_by_warp = h->prepare_by_warp;
+}
+
+// k_prepare + k_order of one batch into set `which` on stream ps; the set's previous reader must have finished.
+static int enqueue_prepare(bb_handle* h, int which, int base, int count, int seed_base, const int32_t* seeds_dev, cudaStream_t ps) {
+  BBParams S;
+  int rc = stage_params(h, which, std::max(count, h->stage[which].cap), S);
+  if (rc < 0) return rc;
+  bb_handle::Stage& T = h->stage[which];
+  BBRunArgs A;
+  prepare_args(h, which, base, count, seed_base, seeds_dev, A);
+  CK(cudaStreamWaitEvent(ps, T.consumed, 0));
+  CK(cudaStreamWaitEvent(ps, T.prepared, 0));   // a bb_prepare whose batch was never run may still be writing the set
+  CK(cudaMemsetAsync(T.queue, 0, sizeof(int) * (BB_LPT_HIST + 2 * BB_LPT_BUCKETS), ps));
+  CK(h->K->prepare(S, A, ps));
+  CK(cudaEventRecord(T.prepared, ps));
+  return 0;
+}
+
+static int check_staged(bb_handle* h, const char* who) {
+  if (!h->P.dist.enabled && h->nstaged < 1)
+    return fail(h, std::string(who) + ": no ideal distribution set and no ideal staged in environment 0 (bb_set_ideals)");
+  return 0;
+}
+
+int bb_prepare(bb_handle* h, int episodes, int seed_base, const int32_t* seeds_dev, void* stream) {
+  if (!h) return -1;
+  if (episodes < 1 || episodes > BB_RUN_BATCH) return fail(h, "bb_prepare: episodes must be in 1..65536 (one batch)");
+  CK(cudaSetDevice(h->cfg.device));
+  int rc = check_staged(h, "bb_prepare");
+  if (rc < 0) return rc;
+  // the set the next runner would take, unless a prepared batch is already waiting there
+  const int which = h->stage[h->stage_next].episodes == 0 ? h->stage_next : h->stage_next ^ 1;
+  h->stage[which].episodes = 0;
+  rc = enqueue_prepare(h, which, 0, episodes, seed_base, seeds_dev, (cudaStream_t)stream);
+  if (rc < 0) return rc;
+  bb_handle::Stage& T = h->stage[which];
+  T.episodes = episodes; T.seed_base = seed_base; T.seeds = seeds_dev;
   return 0;
 }
 
@@ -599,37 +791,96 @@ int bb_run(bb_handle* h, int strategy, int episodes, int seed_base, const int32_
   CK(cudaSetDevice(h->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
   if (episodes == 0) return 0;
-  const int batch_cap = std::min(episodes, BB_RUN_BATCH);
-  BBParams S;
-  if (batch_cap > h->stage_cap) CK(cudaStreamSynchronize(s));  // the staging arena is about to be replaced
-  int rc = stage_params(h, std::max(batch_cap, h->stage_cap), S);
+  int rc = check_staged(h, "bb_run");
   if (rc < 0) return rc;
-  for (int base = 0; base < episodes; base += BB_RUN_BATCH) {
-    BBRunArgs A;
-    A.strategy = strategy; A.episodes = std::min(BB_RUN_BATCH, episodes - base); A.seed_base = seed_base;
-    A.sel_seed_base = sel_seed_base; A.sel_seed_stride = h->sel_seed_stride;
-    A.ep_base = base; A.nstaged = h->P.num_envs;
-    A.seeds = seeds_dev; A.max_steps = max_steps; A.gamma = gamma; A.compute_gb = compute_gb; A.out = stats_dev;
-    A.trace = trace_dev; A.trace_eps = trace_dev ? trace_episodes : 0; A.trace_cap = trace_cap; A.queue = h->d_queue;
-    A.order = h->stage_order; A.cost_key = h->stage_cost_key; A.prepare_by_warp = h->prepare_by_warp;
-    CK(cudaMemsetAsync(h->d_queue, 0, sizeof(int) * (BB_LPT_HIST + 2 * BB_LPT_BUCKETS), s));
-    CK(h->K->prepare(S, A, s));
-    // long polynomials (general capacities): reduce() by streams (bb_streams.cuh), by default with one CTA per
-    // environment (bb_wide.cuh: the shortest chain of additions); mode 4: one warp per environment
-    const bool streams = h->wide_mode != 0 && (h->wide_mode >= 1 || h->P.max_poly_terms >= 256);
-    A.stream_kmax = h->wide_mode == 2 ? 6 : (h->wide_mode == 3 ? 48 : BBS_KMAX);
-    const int workers = std::min(h->P.num_envs, A.episodes);
-    if (streams && h->wide_mode == 4) {
-      if (h->K->streams_warps_per_sm() <= 0) return fail(h, "bb_run: the stream runner does not fit this device");
-      CK(h->K->run_streams(h->P, S, A, workers, s));
-    } else if (streams) {
-      const int ctas = h->K->wide_ctas_per_sm() * h->sm_count;
-      if (ctas <= 0) return fail(h, "bb_run: the CTA-per-environment stream runner does not fit this device");
-      CK(h->K->run_wide(h->P, S, A, std::min(workers, ctas), s));
-    } else {
-      CK(h->K->run(h->P, S, A, workers, s));
-    }
+  // long polynomials (general capacities): reduce() by streams (bb_streams.cuh), by default with one CTA per
+  // environment (bb_wide.cuh: the shortest chain of additions); mode 4: one warp per environment
+  const bool streams = h->wide_mode != 0 && (h->wide_mode >= 1 || h->P.max_poly_terms >= 256);
+  int wide_ctas = 0;
+  if (streams && h->wide_mode == 4) {
+    if (h->K->streams_warps_per_sm() <= 0) return fail(h, "bb_run: the stream runner does not fit this device");
+  } else if (streams) {
+    wide_ctas = h->K->wide_ctas_per_sm() * h->sm_count;
+    if (wide_ctas <= 0) return fail(h, "bb_run: the CTA-per-environment stream runner does not fit this device");
   }
+  const int nbatch = (episodes + BB_RUN_BATCH - 1) / BB_RUN_BATCH;
+  // Batch 0: already prepared by a matching bb_prepare, or prepared here on the caller's stream.  Batches 1.. of the
+  // same call are prepared on the handle's side stream while the runner works through their predecessor.
+  int which = h->stage_next;
+  {
+    const int count0 = std::min(BB_RUN_BATCH, episodes);
+    auto matches = [&](int b) {
+      const bb_handle::Stage& T = h->stage[b];
+      return T.episodes == count0 && nbatch == 1 && T.seed_base == seed_base && T.seeds == seeds_dev;
+    };
+    bool ready = matches(which);
+    if (!ready && matches(which ^ 1)) { which ^= 1; ready = true; }
+    if (!ready && h->stage[which].episodes != 0 && h->stage[which ^ 1].episodes == 0) which ^= 1;   // leave the waiting batch alone
+    bb_handle::Stage& T = h->stage[which];
+    if (h->timing) CK(cudaEventRecord(h->ev_t[0], s));
+    if (ready) CK(cudaStreamWaitEvent(s, T.prepared, 0));
+    else {
+      rc = enqueue_prepare(h, which, 0, count0, seed_base, seeds_dev, s);
+      if (rc < 0) return rc;
+    }
+    T.episodes = 0;
+    if (h->timing) CK(cudaEventRecord(h->ev_t[1], s));
+  }
+  if (nbatch > 1) CK(cudaEventRecord(h->ev_entry, s));   // seeds_dev and the ideals are valid on the side stream from here on
+  for (int bi = 0; bi < nbatch; bi++) {
+    const int base = bi * BB_RUN_BATCH, count = std::min(BB_RUN_BATCH, episodes - base);
+    if (bi + 1 < nbatch) {   // the next batch into the other set, concurrently with this batch's runner
+      const int nbase = base + BB_RUN_BATCH;
+      if (bi == 0) CK(cudaStreamWaitEvent(h->side, h->ev_entry, 0));
+      h->stage[which ^ 1].episodes = 0;
+      rc = enqueue_prepare(h, which ^ 1, nbase, std::min(BB_RUN_BATCH, episodes - nbase), seed_base, seeds_dev, h->side);
+      if (rc < 0) return rc;
+    }
+    BBParams S;
+    rc = stage_params(h, which, h->stage[which].cap, S);
+    if (rc < 0) return rc;
+    BBRunArgs A;
+    prepare_args(h, which, base, count, seed_base, seeds_dev, A);
+    A.strategy = strategy; A.sel_seed_base = sel_seed_base; A.sel_seed_stride = h->sel_seed_stride;
+    A.max_steps = max_steps; A.gamma = gamma; A.compute_gb = compute_gb; A.out = stats_dev;
+    A.trace = trace_dev; A.trace_eps = trace_dev ? trace_episodes : 0; A.trace_cap = trace_cap;
+    A.stream_kmax = h->wide_mode == 2 ? 6 : (h->wide_mode == 3 ? 48 : BBS_KMAX);
+    if (bi > 0) CK(cudaStreamWaitEvent(s, h->stage[which].prepared, 0));
+    const int workers = std::min(h->P.num_envs, count);
+    if (streams && h->wide_mode == 4) CK(h->K->run_streams(h->P, S, A, workers, s));
+    else if (streams) CK(h->K->run_wide(h->P, S, A, std::min(workers, wide_ctas), s));
+    else CK(h->K->run(h->P, S, A, workers, s));
+    CK(cudaEventRecord(h->stage[which].consumed, s));
+    if (h->timing && bi == 0) CK(cudaEventRecord(h->ev_t[2], s));
+    which ^= 1;
+  }
+  h->stage_next = which;
+  return 0;
+}
+
+int bb_set_timing(bb_handle* h, int on) {
+  if (!h) return -1;
+  h->timing = on ? 1 : 0;
+  return 0;
+}
+
+int bb_last_run_ms(bb_handle* h, float* prepare_ms, float* run_ms) {
+  if (!h) return -1;
+  if (!h->timing) return fail(h, "bb_last_run_ms: timing is off (bb_set_timing)");
+  CK(cudaSetDevice(h->cfg.device));
+  CK(cudaEventSynchronize(h->ev_t[2]));
+  float a = 0.f, b = 0.f;
+  CK(cudaEventElapsedTime(&a, h->ev_t[0], h->ev_t[1]));
+  CK(cudaEventElapsedTime(&b, h->ev_t[1], h->ev_t[2]));
+  if (prepare_ms) *prepare_ms = a;
+  if (run_ms) *run_ms = b;
+  return 0;
+}
+
+int bb_set_episode_offset(bb_handle* h, int offset) {
+  if (!h) return -1;
+  if (offset < 0) return fail(h, "bb_set_episode_offset: negative offset");
+  h->episode_offset = offset;
   return 0;
 }
 
@@ -714,6 +965,60 @@ int bb_copy_env(bb_handle* dst, int dst_env, bb_handle* src, int src_env, void* 
   return 0;
 }
 
+int bb_discount(bb_handle* h, int N, int T, const double* x_dev, const uint8_t* done_dev, double gam, double* out_dev,
+                void* stream) {
+  if (!h) return -1;
+  if (N < 0 || T < 0 || !x_dev || !done_dev || !out_dev) return fail(h, "bb_discount: bad argument");
+  if (N == 0 || T == 0) return 0;
+  CK(cudaSetDevice(h->cfg.device));
+  k_discount<<<(N + BB_THREADS - 1) / BB_THREADS, BB_THREADS, 0, (cudaStream_t)stream>>>(N, T, x_dev, done_dev, gam, out_dev);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int bb_set_compaction(bb_handle* h, int on) {
+  if (!h) return -1;
+  h->compaction = on ? 1 : 0;
+  return 0;
+}
+
+int bb_compact(bb_handle* h, int32_t* active_dev, void* stream) {
+  if (!h) return -1;
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  k_compact<<<1, 1024, 0, s>>>(h->P, active_dev ? active_dev : h->d_active);
+  CK(cudaGetLastError());
+  return 0;
+}
+
+int bb_status_summary(bb_handle* h, int32_t* counts_host, void* stream) {
+  if (!h || !counts_host) return -1;
+  CK(cudaSetDevice(h->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  int* hist = h->d_active;   // the list is rebuilt by every call that uses it
+  CK(cudaMemsetAsync(hist, 0, sizeof(int) * BB_STATUS_COUNT, s));
+  k_status_hist<<<(h->P.num_envs + BB_THREADS - 1) / BB_THREADS, BB_THREADS, 0, s>>>(h->P, hist);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(counts_host, hist, sizeof(int) * BB_STATUS_COUNT, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int bb_set_max_episode_length(bb_handle* h, int max_steps) {
+  if (!h) return -1;
+  if (max_steps < 0) return fail(h, "bb_set_max_episode_length: negative length");
+  h->P.max_episode_length = max_steps;
+  return 0;
+}
+
+int bb_set_obs_nvars(bb_handle* h, int n_obs) {
+  if (!h) return -1;
+  if (n_obs < 1 || n_obs > h->cfg.nvars) return fail(h, "bb_set_obs_nvars: must be in 1..nvars");
+  h->P.obs_nv = n_obs;
+  h->P.cols = 2 * n_obs * h->P.k;
+  return 0;
+}
+
 int bb_set_wide(bb_handle* h, int mode) {
   if (!h) return -1;
   if (mode < -1 || mode > 4) return fail(h, "bb_set_wide: mode must be -1 (auto), 0 (off), 1 (on), 2 or 3 (on, small stream tables), 4 (on, one warp per environment)");
@@ -743,6 +1048,7 @@ static int check_policy(bb_handle* h, int hidden, const float* W1, const float* 
   if (!W1 || !b1 || !w2 || !b2) return fail(h, "policy: null weight pointer");
   if (hidden != 32 && hidden != 64 && hidden != 128 && hidden != 256) return fail(h, "policy: hidden must be 32, 64, 128 or 256");
   if (h->P.cols > BB_POLICY_MAX_COLS) return fail(h, "policy: more than 64 state columns");
+  if (h->P.obs_nv != h->P.nvars) return fail(h, "policy: not available under bb_set_obs_nvars (comparison mode of the state matrix)");
   return 0;
 }
 

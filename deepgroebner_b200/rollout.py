@@ -58,19 +58,34 @@ class PairsPolicy:
         return torch.log_softmax(z, dim=-1)
 
 
-def collect(env, net, T, counter0=0, greedy=False, store_obs=True, pmax=64):
+def collect(env, net, T, counter0=0, greedy=False, store_obs=True, pmax=64, max_episode_length=None):
     """Runs T steps of every environment of a LeadMonomialsEnv under policy `net` and returns a TrajectoryBatch.
-    The environments must have been reset; auto-reset keeps every slot busy."""
+    The environments must have been reset; auto-reset keeps every slot busy.  max_episode_length cuts episodes as
+    pg.Agent.run_episode does (pg.py:470-471; train.py's default is 500).  States with more than pmax rows keep their
+    action and log-probability but cannot be stored: TrajectoryBatch.get() leaves them out (and counts them)."""
     eng = env.engine
     eng.set_auto_reset(True)
+    if max_episode_length is not None:
+        eng.set_max_episode_length(max_episode_length)
     out = eng.rollout(net, T, counter0=counter0, greedy=greedy, store_obs=store_obs, pmax=pmax)
-    return TrajectoryBatch(out)
+    return TrajectoryBatch(out, engine=eng)
 
 
-def discount_rewards(rewards, done, gam):
+def discount_rewards(rewards, done, gam, engine=None):
     """Rewards-to-go within each episode segment: pg.discount_rewards (pg.py:18-39) along the T axis of [N, T]
-    tensors, restarting after every done."""
+    tensors, restarting after every done.  With `engine` (cuda tensors) this is ONE kernel (bb_discount); without it,
+    a host-side restatement in torch ops used by the CPU tests."""
     N, T = rewards.shape
+    if engine is not None and rewards.is_cuda:
+        import ctypes as C
+        x = rewards.to(torch.float64).contiguous()
+        d = done.to(torch.uint8).contiguous()
+        out = torch.empty_like(x)
+        with torch.cuda.device(x.device):
+            engine._ck(engine.lib.bb_discount(engine.h, N, T, C.c_void_p(x.data_ptr()), C.c_void_p(d.data_ptr()), float(gam),
+                                              C.c_void_p(out.data_ptr()),
+                                              C.c_void_p(torch.cuda.current_stream().cuda_stream)), "bb_discount")
+        return out
     out = torch.empty_like(rewards, dtype=torch.float64)
     run = torch.zeros(N, dtype=torch.float64, device=rewards.device)
     for t in range(T - 1, -1, -1):
@@ -79,7 +94,7 @@ def discount_rewards(rewards, done, gam):
     return out
 
 
-def compute_advantages(rewards, values, done, gam, lam):
+def compute_advantages(rewards, values, done, gam, lam, engine=None):
     """Generalised advantage estimates, pg.compute_advantages (pg.py:42-78): delta_t = r_t - v_t + gam * v_{t+1}
     (v after the last step of an episode is 0), discounted by gam * lam within each episode segment."""
     r = rewards.to(torch.float64)
@@ -87,13 +102,15 @@ def compute_advantages(rewards, values, done, gam, lam):
     nxt = torch.zeros_like(v)
     nxt[:, :-1] = v[:, 1:]
     nxt = nxt * (~done).to(torch.float64)
-    return discount_rewards(r - v + gam * nxt, done, gam * lam)
+    return discount_rewards(r - v + gam * nxt, done, gam * lam, engine)
 
 
 class TrajectoryBatch:
     """[N, T] trajectories on device with the TrajectoryBuffer post-processing of the reference."""
 
-    def __init__(self, out):
+    def __init__(self, out, engine=None):
+        self.engine = engine   # with it, the discounted sums run as one kernel each (bb_discount)
+        self.dropped_wide = 0  # get(): samples left out because their state had more rows than the stored matrices
         self.actions, self.logp = out["actions"], out["logp"]
         self.reward, self.lengths = out["reward"], out["lengths"]
         self.done = out["done"].bool()
@@ -110,23 +127,23 @@ class TrajectoryBatch:
         steps = torch.cumsum(self.finished.to(torch.int64), dim=1)
         idx = self.done & self.finished
         ends_r, ends_s = csum[idx], steps[idx]
-        # subtract the cumulative value at the previous episode end of the same environment
-        prev_r = torch.zeros_like(csum)
-        prev_s = torch.zeros_like(steps)
+        # subtract the cumulative value at the previous episode end of the same environment: position of the last
+        # episode end strictly before t, by a running maximum over the end positions
         N, T = self.reward.shape
-        last_r = torch.zeros(N, dtype=torch.float64, device=r.device)
-        last_s = torch.zeros(N, dtype=torch.int64, device=r.device)
-        for t in range(T):
-            prev_r[:, t], prev_s[:, t] = last_r, last_s
-            d = idx[:, t]
-            last_r = torch.where(d, csum[:, t], last_r)
-            last_s = torch.where(d, steps[:, t], last_s)
+        pos = torch.where(idx, torch.arange(T, device=r.device).expand(N, T), torch.full((N, T), -1, device=r.device))
+        last = torch.cummax(pos, dim=1).values
+        prev = torch.cat([torch.full((N, 1), -1, device=r.device, dtype=last.dtype), last[:, :-1]], dim=1)
+        has = prev >= 0
+        at = prev.clamp(min=0)
+        prev_r = torch.where(has, torch.gather(csum, 1, at), torch.zeros_like(csum))
+        prev_s = torch.where(has, torch.gather(steps, 1, at), torch.zeros_like(steps))
         return ends_r - prev_r[idx], ends_s - prev_s[idx]
 
     def finish(self, gam=0.99, lam=0.97, values=None):
         """TrajectoryBuffer.finish for every episode segment: returns (rewards_to_go, advantages), float64 [N, T]."""
         v = torch.zeros_like(self.reward) if values is None else values
-        return discount_rewards(self.reward, self.done, gam), compute_advantages(self.reward, v, self.done, gam, lam)
+        return (discount_rewards(self.reward, self.done, gam, self.engine),
+                compute_advantages(self.reward, v, self.done, gam, lam, self.engine))
 
     def get(self, gam=0.99, lam=0.97, values=None, normalize_advantages=True):
         """The flat training set of TrajectoryBuffer.get (pg.py:183-226): steps of finished trajectories whose state
@@ -137,5 +154,9 @@ class TrajectoryBatch:
         if normalize_advantages and a.numel() > 1:
             a = (a - a.mean()) / a.std(unbiased=False)
         multi = self.lengths[keep] != 1
+        if self.obs is not None:   # a state with more rows than were stored cannot be a training sample
+            fits = self.lengths[keep] <= self.obs.shape[2]
+            self.dropped_wide = int((multi & ~fits).sum())
+            multi = multi & fits
         obs = self.obs[keep][multi] if self.obs is not None else None
         return obs, self.actions[keep][multi], self.logp[keep][multi], a[multi], rtg[keep][multi].to(torch.float32)

@@ -82,7 +82,12 @@ def run_sharded(engine, strategy, total, seed_base=0, gather=True, group=None, *
     else:
         rank, ws = 0, 1
     first, count = shard_range(total, rank, ws)
-    buf, _ = engine.run_episodes(strategy, episodes=count, seed_base=seed_base + first, to_host=False, **run_kwargs)
+    # the selection seed of 'random' and the staged ideal an episode replays follow the GLOBAL episode index
+    engine.set_episode_offset(first)
+    try:
+        buf, _ = engine.run_episodes(strategy, episodes=count, seed_base=seed_base + first, to_host=False, **run_kwargs)
+    finally:
+        engine.set_episode_offset(0)
     buf = buf[:count * RECORD_BYTES]
     if not gather:
         return buf.cpu().numpy().view(np.dtype(_lib.STATS_DTYPE))

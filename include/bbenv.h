@@ -8,7 +8,7 @@
  *   ------------------------------------------------------  -----------------------------------------
  *   LeadMonomialsEnv(string,bint,bint,int) pxd:11           bb_create(cfg)  (+ bb_set_distribution)
  *   ~LeadMonomialsEnv                                       bb_destroy
- *   void seed(int)                       pxd:15             bb_seed
+ *   void seed(int)                       pxd:15             bb_seed / bb_seed_on
  *   void reset()                         pxd:13             bb_reset / bb_set_ideals
  *   double step(int)                     pxd:14             bb_step
  *   vector[int] state, int cols          pxd:17-18          bb_observe, bb_cols
@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define BB_ABI_VERSION 2
+#define BB_ABI_VERSION 3
 
 /* EliminationType, buchberger.h:58 */
 enum { BB_ELIM_GEBAUERMOELLER = 0, BB_ELIM_LCM = 1, BB_ELIM_NONE = 2 };
@@ -61,8 +61,10 @@ enum {
   BB_STATUS_OVERFLOW_PAIRS = 5,
   BB_STATUS_OVERFLOW_TERMS = 6,
   BB_STATUS_OVERFLOW_EXPONENT = 7, /* a packed exponent/degree field would wrap: never silently wrong */
-  BB_STATUS_OVERFLOW_SCRATCH = 8
+  BB_STATUS_OVERFLOW_SCRATCH = 8,
+  BB_STATUS_TRUNCATED = 9   /* cut by bb_set_max_episode_length (pg.py:470-471): done, not finished */
 };
+#define BB_STATUS_COUNT 10
 
 typedef struct bb_config {
   int abi_version;    /* BB_ABI_VERSION */
@@ -144,6 +146,10 @@ int bb_set_distribution(bb_handle* h, int d, int s, int dist, int constants, int
  * ideal: an ideal that does not fit leaves its environment in BB_STATUS_OVERFLOW_TERMS. */
 int bb_set_distribution_poly(bb_handle* h, int d, int s, double lam, int dist, int constants, int homogeneous);
 int bb_seed(bb_handle* h, const int32_t* seeds, int base);
+/* bb_seed_on: bb_seed (selection == 0) / bb_seed_selection (selection != 0) enqueued on `stream`.  No allocation and no
+ * device synchronisation: the reference pattern re-seeds before every episode (randomized_agent.py:141-142).  bb_seed and
+ * bb_seed_selection are the same on the legacy default stream. */
+int bb_seed_on(bb_handle* h, const int32_t* seeds, int base, int selection, void* stream);
 /* bb_seed_selection: the same for the per-environment stream BB_SELECT_RANDOM draws from in bb_select (the `seed`
  * argument of buchberger(), buchberger.cpp:190-197).  Both streams are seeded with base + e at bb_create. */
 int bb_seed_selection(bb_handle* h, const int32_t* seeds, int base);
@@ -197,13 +203,34 @@ int bb_stats(bb_handle* h, bb_episode_stats* stats_dev, void* stream);
  * bb_run: runs `episodes` episodes to completion with on-device selection.  The handle's N slots act as workers that
  * pull episode e = 0..episodes-1 from a queue (finished slots are refilled at once, so warps stay full); episode e
  * draws its ideal from stream seed = seed_base + e (or seeds_dev[e]) when a distribution is set, or replays staged
- * ideal (e mod staged count).  stats_dev bb_episode_stats[episodes].  trace_dev (optional) int32[trace_episodes,
+ * ideal (e mod staged count; the staged environments must be a prefix 0 .. count-1 of the handle, else the call fails).
+ * Calls of more than 65536 episodes go batch by batch, the next batch being prepared on a side stream of the handle
+ * while the runner works through the current one.  stats_dev bb_episode_stats[episodes].  trace_dev (optional) int32[trace_episodes,
  * trace_cap, 4] = (i, j, additions, |P| after) for the first trace_episodes episodes, -1 padded.
  * max_steps truncates an episode (0 = unlimited); gamma feeds discounted_return.  With BB_SELECT_RANDOM episode e
  * draws its choices from a minstd_rand0 stream seeded sel_seed_base + e (buchberger(..., seed), buchberger.cpp:190-197). */
 int bb_run(bb_handle* h, int strategy, int episodes, int seed_base, const int32_t* seeds_dev, int sel_seed_base,
            int max_steps, double gamma, int compute_gb, bb_episode_stats* stats_dev, int32_t* trace_dev,
            int trace_episodes, int trace_cap, void* stream);
+
+/* bb_prepare: the preparation half of the NEXT bb_run call (ideal generator + reset() of every episode of the batch,
+ * buchberger.cpp:299-315) enqueued on `stream`, which may be a different stream than the one the runner uses: the handle
+ * keeps two staging sets, so the batch of call i + 1 is prepared while the runner of call i is still at work.  A later
+ * bb_run with the same (episodes, seed_base, seeds_dev) waits for it instead of preparing; any other bb_run ignores it.
+ * episodes <= 65536 (one batch).  Results are those of bb_run alone. */
+int bb_prepare(bb_handle* h, int episodes, int seed_base, const int32_t* seeds_dev, void* stream);
+
+/* bb_set_episode_offset: global index of episode 0 of the following bb_run calls (default 0).  Episode e of a call then
+ * seeds its Random-selection stream with sel_seed_base + (offset + e) * stride and replays staged ideal
+ * (offset + e) mod staged count -- a rank that runs episodes [first, first + count) of a job gets the records of that
+ * slice of the whole job (sharding.py).  The ideal stream is still seeded seed_base + e (or seeds_dev[e]). */
+int bb_set_episode_offset(bb_handle* h, int offset);
+
+/* bb_set_timing / bb_last_run_ms: with timing on, bb_run records CUDA events on its stream around the preparation and
+ * around the episode runner of its first batch; bb_last_run_ms synchronises on them and returns both durations (bench.py:
+ * the roofline of the runner kernel on its own launch time). */
+int bb_set_timing(bb_handle* h, int on);
+int bb_last_run_ms(bb_handle* h, float* prepare_ms, float* run_ms);
 
 /* bb_set_selection_seed_stride: bb_run seeds episode e's BB_SELECT_RANDOM stream with sel_seed_base + e * stride.
  * Default 1 (every episode its own stream); 0 gives every episode the SAME seed, which is what scripts/make_strat.cpp:66
@@ -248,6 +275,30 @@ int bb_copy_env(bb_handle* dst, int dst_env, bb_handle* src, int src_env, void* 
  * round trip, and no idle slots. */
 int bb_set_auto_reset(bb_handle* h, int on);
 
+/* bb_set_max_episode_length: bb_step / bb_step_observe / bb_step_host / bb_rollout cut an episode once it has MORE than
+ * `max_steps` steps (the loop of pg.Agent.run_episode, pg.py:470-471: `if episode_length > max_episode_length: break`;
+ * train.py's default is 500): the environment goes to BB_STATUS_TRUNCATED, reports done = 1 and is reset by auto-reset
+ * like a finished one.  0 (default) = unlimited. */
+int bb_set_max_episode_length(bb_handle* h, int max_steps);
+
+/* ---- batch management (north_star: "finished or diverged episodes are compacted by stream compaction")
+ * bb_compact: active_dev int32[N + 1] <- (number of RUNNING environments, then every slot with the RUNNING ones first,
+ * both groups ascending); active_dev == NULL refreshes the handle's own list only.  bb_step / bb_step_observe /
+ * bb_step_host run it themselves when auto-reset is off (bb_set_compaction(0) turns that off) and take the environments
+ * in that order, so stepping warps fill whole CTAs; results are identical either way.
+ * bb_status_summary: counts_host int32[BB_STATUS_COUNT] <- number of environments per BB_STATUS_* word (finished,
+ * truncated and diverged = every BB_STATUS_OVERFLOW_* / BAD_ACTION); synchronises the stream. */
+int bb_set_compaction(bb_handle* h, int on);
+int bb_compact(bb_handle* h, int32_t* active_dev, void* stream);
+int bb_status_summary(bb_handle* h, int32_t* counts_host, void* stream);
+
+/* bb_set_obs_nvars: state matrices show only the first n_obs variables of every monomial (cols = 2 * n_obs * k).  This
+ * exists for byte-level comparison with the reference's C++ / Cython LeadMonomialsEnv on FIXED ideals, whose
+ * FixedIdealGenerator::nvars is the largest variable INDEX in use, i.e. one less than the number of variables
+ * (ideals.cpp:146-154): cyclic-6 is observed with n = 5, 20 columns.  The default follows the Python environment
+ * (ring.ngens, buchberger.py:537).  Episodes are not affected; the policy head is not available in this mode. */
+int bb_set_obs_nvars(bb_handle* h, int n_obs);
+
 /* ---- the pairs policy head on device
  * bb_policy_pmlp: ParallelMultilayerPerceptron([hidden]) (networks.py:522-571) evaluated on every environment's
  * current state matrix, then tf.random.categorical (pg.py:323-326):
@@ -271,6 +322,12 @@ int bb_policy_pmlp(bb_handle* h, int hidden, const float* W1_dev, const float* b
 int bb_rollout(bb_handle* h, int hidden, const float* W1_dev, const float* b1_dev, const float* w2_dev, const float* b2_dev,
                uint64_t seed, uint64_t counter0, int greedy, int T, int32_t* actions_dev, float* logprob_dev,
                float* reward_dev, uint8_t* done_dev, int32_t* lengths_dev, int32_t* obs_dev, int pmax, void* stream);
+
+/* bb_discount: discounted suffix sums inside episode segments, the primitive of pg.discount_rewards (pg.py:18-39) and
+ * of the generalised advantage estimates (pg.compute_advantages, pg.py:42-78) on the [N, T] trajectories bb_rollout
+ * writes:  out[n][t] = x[n][t] + (done[n][t] ? 0 : gam * out[n][t+1]),  out[n][T] = 0, in fp64 (mul then add, no fma). */
+int bb_discount(bb_handle* h, int N, int T, const double* x_dev, const uint8_t* done_dev, double gam, double* out_dev,
+                void* stream);
 
 /* ---- host views (synchronising)
  * bb_download_basis: basis G of environment env in insertion order: lens[npoly], exps[nterms*n], coefs[nterms].

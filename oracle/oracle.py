@@ -406,9 +406,12 @@ class Env:
     def value(self, strategy="degree", gamma=0.99):
         return self.o.c_env_value(self.h, strategy.encode(), gamma)
 
-    def value_seeded(self, strategy="degree", gamma=0.99, seed=0, rollouts=1):
-        """value() with explicit seeds for the random strategies; strategy may be 'sample'."""
+    def value_seeded(self, strategy="degree", gamma=0.99, seed=0, rollouts=None):
+        """value() with explicit seeds for the random strategies; strategy may be 'sample'.  rollouts None = the
+        reference's count: 1 Degree + 100 Random for 'sample' (buchberger.cpp:333-341), 1 otherwise."""
         code = 100 if strategy == "sample" else SELECT[strategy]
+        if rollouts is None:
+            rollouts = 0 if strategy == "sample" else 1
         return self.o.c_env_value_seeded(self.h, code, gamma, seed, rollouts)
 
     def select(self, selection):

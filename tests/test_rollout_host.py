@@ -55,7 +55,7 @@ def test_segments_restart_after_done():
 def test_trajectory_batch_keeps_only_finished_multi_row_steps():
     N, T = 3, 6
     out = dict(actions=torch.zeros((N, T), dtype=torch.int32), logp=torch.zeros((N, T)),
-               reward=-torch.ones((N, T)), lengths=torch.full((N, T), 4, dtype=torch.int32),
+               reward=-torch.ones((N, T)), lengths=torch.full((N, T), 2, dtype=torch.int32),
                done=torch.zeros((N, T), dtype=torch.uint8),
                obs=torch.arange(N * T * 2 * 2, dtype=torch.int32).reshape(N, T, 2, 2))
     out["done"][0, 2] = 1            # env 0: episode of 3 steps, then an unfinished tail
@@ -68,6 +68,13 @@ def test_trajectory_batch_keeps_only_finished_multi_row_steps():
     obs, actions, logp, adv, rtg = tb.get(gam=1.0, lam=1.0, normalize_advantages=False)
     assert obs.shape == (8, 2, 2) and actions.shape == (8,)
     assert sorted(rtg.tolist()) == sorted([-3.0, -2.0, -1.0] + [-6.0, -5.0, -4.0, -2.0, -1.0])
+    assert tb.dropped_wide == 0
+    # a state with more rows than the stored matrices hold (rollout(pmax=...)) cannot be a training sample
+    out["lengths"][0, 1] = 4
+    tb = TrajectoryBatch(out)
+    obs, actions, logp, adv, rtg = tb.get(gam=1.0, lam=1.0, normalize_advantages=False)
+    assert obs.shape == (7, 2, 2) and tb.dropped_wide == 1
+    assert sorted(rtg.tolist()) == sorted([-3.0, -1.0] + [-6.0, -5.0, -4.0, -2.0, -1.0])
 
 
 def test_pairs_policy_reference_forward_masks_padding():

@@ -38,6 +38,10 @@ class StubEngine:
 
     def __init__(self):
         self.ran = []
+        self.offsets = []
+
+    def set_episode_offset(self, offset=0):
+        self.offsets.append(offset)
 
     def run_episodes(self, strategy, episodes, seed_base, to_host, **kw):
         assert to_host is False
