@@ -471,9 +471,10 @@ def gpu_arm(args):
     seeds_host = torch.arange(ep_first, ep_first + ep_local, dtype=torch.int32).pin_memory()
     seeds_dev = seeds_host.to(dev)
     stats_bytes = ep_local * 72
-    stats_host = torch.empty(stats_bytes, dtype=torch.uint8).pin_memory()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    main, side = torch.cuda.current_stream(), torch.cuda.Stream()
+    flush = torch.empty(160 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    main, alt, side = torch.cuda.current_stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    runners = [main, alt]
+    outs = [torch.empty(stats_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
     pipelined = ep_local <= 65536 and not args.no_pipeline
 
     def prepare(seeds):
@@ -489,42 +490,63 @@ def gpu_arm(args):
         if world > 1:
             dist.barrier()
 
-    def device_steps(n, timed):
-        """n steps; step i: [event a] prepare(batch i + 1) on the side stream || runner(batch i) [event b]."""
+    def device_steps(n):
+        """n steps.  Pipelined (the default): the runner of step i goes to stream i % 2, so the CTAs of batch i + 1 move in
+        while batch i drains (an episode runner ends with its longest episodes on a mostly idle GPU), and the preparation
+        runs two batches ahead on a third stream; the L2 flush write of a step sits on that step's stream in front of its
+        runner.  The timed span is first event -> everything finished, divided by n.  Otherwise: one stream, prepare then
+        run, L2 flushed between steps outside the event pairs.  Returns (ms, per-step event pairs, last output buffer)."""
         ev = []
-        if pipelined:
-            side.wait_stream(main)
+        torch.cuda.synchronize()
+        if not pipelined:
+            for i in range(n):
+                flush.fill_(1)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                buf, _ = run(seeds_dev, to_host=False, out=outs[0])
+                b.record()
+                ev.append((a, b))
+            torch.cuda.synchronize()
+            return sum(a.elapsed_time(b) for a, b in ev), ev, buf, eng.counters(reset=True)
+        prepare(seeds_dev)            # batches 0 and 1 (K preparations lie inside the span: those of batches 2 .. K + 1)
+        prepare(seeds_dev)
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record(main)
+        alt.wait_event(t0)
+        side.wait_event(t0)
+        for i in range(n):
+            with torch.cuda.stream(runners[i % 2]):
+                flush.fill_(1)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                buf, _ = run(seeds_dev, to_host=False, out=outs[i % 2])
+                b.record()
+                ev.append((a, b))
             prepare(seeds_dev)
-        for _ in range(n):
-            flush.fill_(1)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            if pipelined:
-                side.wait_event(a)            # the next batch's preparation starts inside this step's timed interval ...
-                prepare(seeds_dev)
-                pe = torch.cuda.Event()
-                pe.record(side)
-            buf, _ = run(seeds_dev, to_host=False)
-            if pipelined:
-                main.wait_event(pe)           # ... and ends inside it
-            b.record()
-            ev.append((a, b))
-        return ev, buf
+        main.wait_stream(alt)
+        main.wait_stream(side)
+        t1.record(main)
+        torch.cuda.synchronize()
+        c = eng.counters(reset=True)
+        for _ in range(2):   # the two batches prepared ahead at the end of the span: run them off (untimed)
+            run(seeds_dev, to_host=False)
+        torch.cuda.synchronize()
+        eng.counters(reset=True)
+        return t0.elapsed_time(t1), ev, buf, c
 
-    device_steps(max(args.warmup, 3), False)
+    device_steps(max(args.warmup, 3))
     barrier()
     eng.counters(reset=True)
 
-    # ---- device-timed region: K steps, L2 flushed between them (flush outside the event pairs)
+    # ---- device-timed region: K steps
     sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     wall0 = time.perf_counter()
-    ev, buf = device_steps(args.steps, True)
+    dev_ms, ev, buf, counters = device_steps(args.steps)
     barrier()
     wall = time.perf_counter() - wall0
     clocks = sampler.stop() if sampler else None
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    counters = eng.counters(reset=True)
     stats = buf.cpu().numpy().view(np.dtype(_lib.STATS_DTYPE))[:ep_local].copy()
     assert (stats["status"] == 2).all(), "not every episode finished: status histogram %r" % (
         dict(zip(*[x.tolist() for x in np.unique(stats["status"], return_counts=True)])),)
@@ -532,22 +554,48 @@ def gpu_arm(args):
     adds_per_launch = int(stats["additions"].sum())
     assert counters["env_steps"] == steps_per_launch * args.steps
 
-    # ---- end to end through the public API with host buffers: pinned seeds H2D (side stream, with the preparation),
-    # runner, records D2H, one stream synchronisation per step
-    barrier()
-    t0 = time.perf_counter()
-    cur = prepare(seeds_host) if pipelined else None
-    for _ in range(args.steps):
+    # ---- end to end through the public API with host buffers.  Per step: pinned seeds H2D (with the preparation, two
+    # batches ahead), runner, episode records D2H into pinned memory; the host waits for and reads the records of step
+    # i - 1 while step i is in flight.
+    host_out = [torch.empty(stats_bytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+
+    def e2e_steps(n):
+        """Seconds of n end-to-end steps (host clock, barrier on both sides) and the env steps the host read back."""
+        barrier()
+        t0 = time.perf_counter()
+        seen = 0
         if pipelined:
-            side.wait_stream(main)
-            nxt = prepare(seeds_host)
-            e2e_stats, _ = run(cur, out_host=stats_host)
-            cur = nxt
+            ahead = [prepare(seeds_host), prepare(seeds_host)]
+            done = []
+            for i in range(n):
+                with torch.cuda.stream(runners[i % 2]):
+                    b_, _ = run(ahead[i], to_host=False, out=outs[i % 2])
+                    host_out[i % 2].copy_(b_, non_blocking=True)
+                    e_ = torch.cuda.Event()
+                    e_.record()
+                    done.append(e_)
+                ahead.append(prepare(seeds_host))
+                if i >= 1:
+                    done[i - 1].synchronize()
+                    seen += int(host_out[(i - 1) % 2].numpy().view(np.dtype(_lib.STATS_DTYPE))["steps"][:ep_local].sum())
+            done[-1].synchronize()
+            seen += int(host_out[(n - 1) % 2].numpy().view(np.dtype(_lib.STATS_DTYPE))["steps"][:ep_local].sum())
+            barrier()
+            secs = time.perf_counter() - t0
+            for _ in range(2):   # run off the batches prepared ahead (untimed)
+                run(seeds_dev, to_host=False)
+            torch.cuda.synchronize()
         else:
-            e2e_stats, _ = run(seeds_host, out_host=stats_host)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    assert int(e2e_stats["steps"].sum()) == steps_per_launch
+            for _ in range(n):
+                st_, _ = run(seeds_host, out_host=host_out[0])
+                seen += int(st_["steps"].sum())
+            barrier()
+            secs = time.perf_counter() - t0
+        return secs, seen
+
+    e2e_steps(3)   # first use allocates the seed ring and pins nothing new afterwards
+    e2e_s, seen = e2e_steps(args.steps)
+    assert seen == steps_per_launch * args.steps, (seen, steps_per_launch * args.steps)
     eng.counters(reset=True)
 
     # ---- the kernels on their own (outside the timed regions): unpipelined launches with events inside bb_run
@@ -607,19 +655,23 @@ def gpu_arm(args):
             "config": {"workload": workload_string(),
                        "episodes_per_gpu": ep_local, "env_steps_per_launch": steps_per_launch, "slots": slots,
                        "parallelism": "episodes sharded across GPUs, no collective on the step path",
-                       "pipeline": ("batch i + 1 is prepared (k_prepare_lanes + k_order, side stream) while the runner works "
-                                    "through batch i; both inside the event pair of step i") if pipelined else "none",
-                       "l2": "256 MiB flush write between timed steps"},
+                       "pipeline": ("steps are pipelined like the batches of one job: the runner of step i on stream i % 2 (the CTAs "
+                                    "of batch i + 1 move in while batch i drains), preparation (k_prepare_lanes + k_order) two "
+                                    "batches ahead on a third stream; timed span = first event to all streams idle, / steps")
+                                   if pipelined else "none: prepare, then run, on one stream; sum of the steps' event pairs",
+                       "l2": "160 MiB flush write (L2: 126 MB) in front of every step's runner" + (" (inside the timed span)" if pipelined else "")},
             "additions_per_sec": total_adds * args.steps / (dev_ms_max / 1000.0),
             "spair_reductions_per_sec": value,
             # per step: k_prepare(_lanes) + k_order + the runner (one batch) -- the L2 flush fill and the queue memset are not ours
             "gpu_launches": 3 * args.steps * ((ep_local + 65535) // 65536),
             "wall_s_timed_region": wall,
+            "step_ms": [round(a.elapsed_time(b), 4) for a, b in ev[:8]],
             "clocks": clocks,
             "parity": parity,
             "e2e": {"value": total_steps * args.steps / (e2e_ms_max / 1000.0), "unit": UNIT,
                     "h2d_bytes_per_step": ep_local * 4, "d2h_bytes_per_step": stats_bytes,
-                    "api": "BuchbergerEngine.prepare_episodes(seeds=pinned host) + run_episodes(out_host=pinned host)"},
+                    "api": "BuchbergerEngine.prepare_episodes(seeds=pinned host) + run_episodes + records copied to pinned host "
+                           "memory and read by the host, one step behind the step in flight"},
             "kernel_ms": {"prepare+order": kprep_ms, kernel: krun_ms,
                           "how": "CUDA events inside bb_run (bb_set_timing), median of 5 unpipelined launches, L2 flushed"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -684,7 +736,7 @@ def rollout_arm(args):
     out = env.engine.rollout(net, T)
     host = {k: torch.empty_like(out[k], device="cpu").pin_memory() for k in ("reward", "done")}
     w_host = [t.cpu().pin_memory() for t in net.parameters()]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush = torch.empty(160 << 20, dtype=torch.uint8, device=dev)
 
     def barrier():
         torch.cuda.synchronize()
@@ -739,7 +791,7 @@ def rollout_arm(args):
             "data": "synthetic (device generator, env e = stream seed e; PMLP(128) Glorot-initialised, torch seed 0)",
             "config": {"workload": "%s LeadMonomialsEnv(k=2), %d envs x %d fused steps per launch, PMLP(128) sampling on "
                                    "device, auto-reset (BASELINE configs[3])" % (DIST, N, T),
-                       "envs_per_gpu": N, "horizon": T, "l2": "256 MiB flush write between timed launches"},
+                       "envs_per_gpu": N, "horizon": T, "l2": "160 MiB flush write (L2: 126 MB) between timed launches"},
             "gpu_launches": args.steps, "clocks": clocks,   # one fused k_rollout per step
             "e2e": {"value": float(tot[1]) / (float(t[1]) / 1000.0), "unit": UNIT,
                     "h2d_bytes_per_step": sum(x.numel() * 4 for x in w_host),

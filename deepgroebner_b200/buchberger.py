@@ -295,7 +295,7 @@ class BuchbergerEngine:
     def prepare_episodes(self, episodes=None, seed_base=0, seeds=None):
         """The preparation half of the NEXT run_episodes call (bb_prepare) on the current stream -- call it under
         `torch.cuda.stream(side)` to overlap it with a runner at work on another stream.  `seeds`: None for
-        seed_base + e, an int32 cuda tensor, or an int32 HOST tensor (pinned: copied asynchronously into one of two
+        seed_base + e, an int32 cuda tensor, or an int32 HOST tensor (pinned: copied asynchronously into one of three
         device buffers of the engine, on the current stream).  Returns the device seeds tensor (or None): pass THAT
         object as `seeds` to the run_episodes call this preparation is for."""
         episodes = self.num_envs if episodes is None else int(episodes)
@@ -305,10 +305,10 @@ class BuchbergerEngine:
                 if not seeds.is_cuda:
                     ring = getattr(self, "_seed_ring", None)
                     if ring is None or ring[0].numel() != episodes:
-                        ring = self._seed_ring = [torch.empty(episodes, dtype=torch.int32, device=self.device) for _ in range(2)]
+                        ring = self._seed_ring = [torch.empty(episodes, dtype=torch.int32, device=self.device) for _ in range(3)]
                         self._seed_turn = 0
                     dev = ring[self._seed_turn]
-                    self._seed_turn ^= 1
+                    self._seed_turn = (self._seed_turn + 1) % 3
                     dev.copy_(seeds, non_blocking=True)
                     seeds = dev
             self._ck(self.lib.bb_prepare(self.h, episodes, int(seed_base), _ptr(seeds), _stream()), "bb_prepare")
@@ -328,18 +328,22 @@ class BuchbergerEngine:
         return float(a.value), float(b.value)
 
     def run_episodes(self, strategy="degree", episodes=None, seed_base=0, seeds=None, max_steps=0, gamma=0.99,
-                     compute_gb=False, trace_episodes=0, trace_cap=0, to_host=True, selection_seed=0, out_host=None):
+                     compute_gb=False, trace_episodes=0, trace_cap=0, to_host=True, selection_seed=0, out_host=None,
+                     out=None):
         """Runs `episodes` episodes to completion with on-device selection (bb_run).  Returns (stats, trace):
         stats is a structured array of bb_episode_stats (numpy if to_host else a uint8 cuda tensor), trace an
         int32 [trace_episodes, trace_cap, 4] array of (i, j, additions, |P| after), -1 padded.
         seeds: per-episode ideal-stream seeds, a numpy array or an int32 torch tensor (pinned host memory is copied
         asynchronously); out_host: a pinned uint8 host tensor of episodes * 72 bytes that receives the records (the
-        returned array is a view of it)."""
+        returned array is a view of it); out: a uint8 cuda tensor of episodes * 72 bytes for the records instead of the
+        engine's own buffer (calls in flight on different streams need different ones)."""
         episodes = self.num_envs if episodes is None else int(episodes)
         with torch.cuda.device(self.device):
             nbytes = max(episodes, 1) * C.sizeof(_lib.BBEpisodeStats)
-            buf = getattr(self, "_run_buf", None)
-            if buf is None or buf.numel() < nbytes:
+            buf = out if out is not None else getattr(self, "_run_buf", None)
+            if out is not None:
+                assert out.is_cuda and out.dtype == torch.uint8 and out.numel() >= nbytes
+            elif buf is None or buf.numel() < nbytes:
                 buf = self._run_buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
             trace = None
             if trace_episodes > 0 and trace_cap > 0:

@@ -83,7 +83,8 @@ struct BBKernelTable {
   cudaError_t (*step)(const BBParams&, const int* actions, double* reward, uint8_t* done, const int* active, int nwarps,
                       cudaStream_t);
   cudaError_t (*step_obs)(const BBParams&, const int* actions, int action0, double* reward, uint8_t* done, int32_t* obs,
-                          int32_t* lengths, int pmax, int pad, int do_step, const int* active, int nwarps, cudaStream_t);
+                          int32_t* lengths, int pmax, int pad, int do_step, const int* active, unsigned* ready, unsigned ticket,
+                          int nwarps, cudaStream_t);
   cudaError_t (*select)(const BBParams&, int strategy, int* actions, int nwarps, cudaStream_t);
   cudaError_t (*observe)(const BBParams&, int32_t* obs, int32_t* lengths, int pmax, int nwarps, cudaStream_t);
   cudaError_t (*final_gb)(const BBParams&, int slot, int* ok_out, cudaStream_t);
@@ -208,7 +209,8 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_step_obs(const __
                                                                        double* __restrict__ reward, uint8_t* __restrict__ done,
                                                                        int32_t* __restrict__ obs, int32_t* __restrict__ lengths,
                                                                        int pmax, int pad, int do_step,
-                                                                       const int* __restrict__ active) {
+                                                                       const int* __restrict__ active,
+                                                                       unsigned* __restrict__ ready, unsigned ticket) {
   __shared__ unsigned long long sh[BB_WARPS][CT_COUNT];
   hot_init(P);
   unsigned long long* row = counters_row(sh);
@@ -240,7 +242,14 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_step_obs(const __
     if (lengths && bb_lane() == 0) lengths[slot] = e.nP;
     ct.spill(row);
   }
+  // single-CTA launches of bb_step_host: the results sit in mapped host memory; the host waits for this word instead of a
+  // stream synchronisation (every thread's writes are made visible system-wide before thread 0 publishes the ticket)
+  if (ready) __threadfence_system();
   counters_flush(P, sh);
+  if (ready) {
+    __syncthreads();
+    if (threadIdx.x == 0) { *reinterpret_cast<volatile unsigned*>(ready) = ticket; __threadfence_system(); }
+  }
 }
 
 template <int NV>
@@ -320,9 +329,14 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_prepare(const __g
 // L_i, no j < i has L_j == L_i, and no j with L_j == L_i is coprime to f.
 #define BB_PREP_S 16
 #define BB_PREP_P (BB_PREP_S * (BB_PREP_S - 1) / 2)
-#define BB_PREP_THREADS 64
+#ifndef BB_PREP_THREADS
+#define BB_PREP_THREADS 32
+#endif
+#ifndef BB_PREP_MIN_BLOCKS
+#define BB_PREP_MIN_BLOCKS 1
+#endif
 template <int NV>
-__global__ void __launch_bounds__(BB_PREP_THREADS) k_prepare_lanes(const __grid_constant__ BBParams S,
+__global__ void __launch_bounds__(BB_PREP_THREADS, BB_PREP_MIN_BLOCKS) k_prepare_lanes(const __grid_constant__ BBParams S,
                                                                     const __grid_constant__ BBRunArgs A) {
   typedef KL<NV> K;
   __shared__ unsigned long long sh_up[2];
@@ -882,9 +896,10 @@ struct BBLaunch {
     return cudaGetLastError();
   }
   static cudaError_t step_obs(const BBParams& P, const int* actions, int action0, double* reward, uint8_t* done, int32_t* obs,
-                              int32_t* lengths, int pmax, int pad, int do_step, const int* active, int nwarps, cudaStream_t s) {
+                              int32_t* lengths, int pmax, int pad, int do_step, const int* active, unsigned* ready,
+                              unsigned ticket, int nwarps, cudaStream_t s) {
     k_step_obs<NV><<<grid_for_warps(nwarps), BB_THREADS, 0, s>>>(P, actions, action0, reward, done, obs, lengths, pmax, pad, do_step,
-                                                                active);
+                                                                active, ready, ticket);
     return cudaGetLastError();
   }
   static cudaError_t select(const BBParams& P, int strategy, int* actions, int nwarps, cudaStream_t s) {
@@ -899,7 +914,22 @@ struct BBLaunch {
     k_final_gb<NV><<<1, 32, 0, s>>>(P, slot, ok_out);
     return cudaGetLastError();
   }
+  // The runner of batch i and the preparation of batch i + 1 are meant to share the SMs (bb_prepare on a side stream).  An SM
+  // runs CTAs of two kernels side by side only when both ask for the same shared-memory / L1 split, and by default the
+  // driver picks the split per kernel from its own shared-memory use (measured, profiles/README.md r2: the preparation sat
+  // in the queue until the runner's CTAs left).  Every kernel of the pipeline therefore states the same preference.
+  static void same_carveout() {
+    static bool done = false;
+    if (done) return;
+    done = true;
+    const int pct = 7;   // -> the 16 KB split: three runner CTAs use ~6.5 KB of it
+    cudaFuncSetAttribute(k_run<NV>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_prepare<NV>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_prepare_lanes<NV>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+    cudaFuncSetAttribute(k_order<NV>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+  }
   static cudaError_t prepare(const BBParams& S, const BBRunArgs& A, cudaStream_t s) {
+    same_carveout();
     // binomial distributions with few generators: one thread per episode; everything else: one warp per episode
     if (S.dist.enabled && S.dist.kind == 0 && S.dist.s <= BB_PREP_S && !A.prepare_by_warp)
       k_prepare_lanes<NV><<<(A.episodes + BB_PREP_THREADS - 1) / BB_PREP_THREADS, BB_PREP_THREADS, 0, s>>>(S, A);
@@ -909,6 +939,7 @@ struct BBLaunch {
     return cudaGetLastError();
   }
   static cudaError_t run(const BBParams& P, const BBParams& S, const BBRunArgs& A, int nwarps, cudaStream_t s) {
+    same_carveout();
     k_run<NV><<<grid_for_warps(nwarps), BB_THREADS, 0, s>>>(P, S, A);
     return cudaGetLastError();
   }

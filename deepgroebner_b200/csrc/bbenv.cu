@@ -135,6 +135,7 @@ const BBKernelTable* bb_kernel_table(int nvars) {
 }
 
 // ------------------------------------------------------------------------------------------------ host side
+#define BB_STAGE_SETS 3
 struct bb_handle {
   bb_config cfg;
   BBParams P;
@@ -145,10 +146,11 @@ struct bb_handle {
   std::string err;
   int* d_queue;             // bb_value's task counter
   int* d_ok;
-  // Staging of bb_run, TWO sets (double buffering): one compact slot per episode of a batch, holding the state right
-  // after reset(), plus the batch's queue words and longest-predicted-first order.  While the runner works through
-  // set b, the next batch is prepared into set b ^ 1 on another stream (bb_prepare, or bb_run's own side stream when a
-  // call spans several batches).
+  // Staging of bb_run, a ring of THREE sets: one compact slot per episode of a batch, holding the state right after
+  // reset(), plus the batch's queue words and longest-predicted-first order.  While the runner works through one set
+  // the next batches are prepared into the others on another stream (bb_prepare, or bb_run's own side stream when a
+  // call spans several batches); three sets let the preparation run TWO batches ahead, which is what a pipeline
+  // needs whose runners overlap (batch i + 1 starts in the tail of batch i, bb_run on alternating streams).
   struct Stage {
     int cap;                        // episodes it can hold (0 = not allocated yet)
     std::vector<void*> allocs;
@@ -160,8 +162,11 @@ struct bb_handle {
     cudaEvent_t consumed;           // recorded after the k_run that read it
     // the batch a bb_prepare call left here, waiting for its bb_run (episodes == 0: none)
     int episodes, seed_base; const int32_t* seeds;
-  } stage[2];
-  int stage_next;                   // set the next batch goes to
+    unsigned long long serial;      // order of the bb_prepare calls (the oldest matching batch is run first)
+  } stage[BB_STAGE_SETS];
+  unsigned long long stage_serial;
+  int bank_turn;
+  int stage_next;                   // ring cursor: the set the next batch is prepared into (skipping waiting ones)
   cudaStream_t side;                // bb_run's own prepare stream (calls that span several batches)
   cudaEvent_t ev_entry;
   // bb_set_timing: events around the preparation and the runner of the LAST bb_run call (first batch)
@@ -177,8 +182,19 @@ struct bb_handle {
   int episode_offset;    // bb_run: global index of episode 0 of a call (bb_set_episode_offset: shards of one job)
   int nstaged;           // fixed ideals: environments 0 .. nstaged - 1 hold a staged ideal (bb_set_ideals)
   int* d_seeds; int* h_seeds; cudaEvent_t ev_seeds;   // bb_seed: device / pinned staging of explicit seeds
+  // Environment arenas of bb_run: bank 0 is the handle's own (P: the environments of the step API); bank 1, a second
+  // full set of slots, is allocated the first time a bb_run call finds bank 0 still in use by a runner on another stream.
+  // With two banks the runners of two batches overlap: the CTAs of batch i + 1 move in while batch i drains.
+  struct Bank {
+    bool ready;
+    unsigned char* arena; BBEnvState* st;
+    uint64_t* gkey; uint32_t* gcoef; int* glen; int* gcount; uint64_t* grlm; uint32_t* gridx; uint32_t* gflag;
+    cudaEvent_t done;   // recorded after the last runner that used the bank
+    cudaStream_t stream; // ... and the stream it ran on (calls on the same stream are ordered anyway)
+  } bank[2];
   int* d_active;         // [num_envs + 1] slots of the RUNNING environments in ascending order, count in front (k_compact)
   int compaction;        // bb_set_compaction
+  unsigned ticket;       // bb_step_host: sequence number the single-CTA kernel publishes in mapped host memory
   int prepare_by_warp;   // bb_run: 1 = episode preparation by one warp per episode even where the thread-per-episode kernel applies
   int wide_mode;   // bb_run: reduce() by streams: -1 = when the capacities ask for long polynomials, 0 = never, 1 = always, 2 / 3 = always, small tables
   // host mirrors of the distribution tables
@@ -259,11 +275,12 @@ void bb_destroy(bb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
   for (void* p : h->allocs) cudaFree(p);
-  for (int b = 0; b < 2; b++) {
+  for (int b = 0; b < BB_STAGE_SETS; b++) {
     for (void* p : h->stage[b].allocs) cudaFree(p);
     if (h->stage[b].prepared) cudaEventDestroy(h->stage[b].prepared);
     if (h->stage[b].consumed) cudaEventDestroy(h->stage[b].consumed);
   }
+  for (int b = 0; b < 2; b++) if (h->bank[b].done) cudaEventDestroy(h->bank[b].done);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->ev_entry) cudaEventDestroy(h->ev_entry);
   if (h->ev_seeds) cudaEventDestroy(h->ev_seeds);
@@ -298,16 +315,17 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
   h = new bb_handle();
   h->cfg = *cfg;
   h->d_queue = nullptr; h->d_ok = nullptr;
-  for (int b = 0; b < 2; b++) {
+  for (int b = 0; b < BB_STAGE_SETS; b++) {
     bb_handle::Stage& T = h->stage[b];
     T.cap = 0; T.arena = nullptr; T.st = nullptr; T.in_key = nullptr; T.in_coef = nullptr; T.in_off = nullptr; T.in_np = nullptr;
     T.order = nullptr; T.cost_key = nullptr; T.queue = nullptr; T.prepared = nullptr; T.consumed = nullptr;
-    T.episodes = 0; T.seed_base = 0; T.seeds = nullptr;
+    T.episodes = 0; T.seed_base = 0; T.seeds = nullptr; T.serial = 0;
   }
-  h->stage_next = 0; h->side = nullptr; h->ev_entry = nullptr; h->timing = 0;
+  for (int b = 0; b < 2; b++) { h->bank[b].ready = false; h->bank[b].done = nullptr; h->bank[b].stream = nullptr; }
+  h->stage_next = 0; h->stage_serial = 0; h->bank_turn = 0; h->side = nullptr; h->ev_entry = nullptr; h->timing = 0;
   h->ev_t[0] = h->ev_t[1] = h->ev_t[2] = nullptr;
   h->episode_offset = 0; h->nstaged = 0; h->d_seeds = nullptr; h->h_seeds = nullptr; h->ev_seeds = nullptr;
-  h->d_active = nullptr; h->compaction = 1;
+  h->d_active = nullptr; h->compaction = 1; h->ticket = 0u;
   h->fork_cap = 0; h->fork_arena = nullptr; h->fork_st = nullptr;
   h->wide_mode = -1;
   h->prepare_by_warp = 0;
@@ -364,11 +382,15 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
   CKC(dev_alloc(h, &h->d_ok, (size_t)4));
   CKC(dev_alloc(h, &h->d_seeds, N));
   CKC(dev_alloc(h, &h->d_active, std::max(N + 1, (size_t)16)));
+  for (int b = 0; b < 2; b++) CKC(cudaEventCreateWithFlags(&h->bank[b].done, cudaEventDisableTiming));
+  h->bank[0].ready = true;
+  h->bank[0].arena = P.arena; h->bank[0].st = P.st; h->bank[0].gkey = P.gkey; h->bank[0].gcoef = P.gcoef; h->bank[0].glen = P.glen;
+  h->bank[0].gcount = P.gcount; h->bank[0].grlm = P.grlm; h->bank[0].gridx = P.gridx; h->bank[0].gflag = P.gflag;
   CKC(cudaHostAlloc((void**)&h->h_seeds, sizeof(int) * N, cudaHostAllocDefault));
   CKC(cudaEventCreateWithFlags(&h->ev_seeds, cudaEventDisableTiming));
   CKC(cudaEventCreateWithFlags(&h->ev_entry, cudaEventDisableTiming));
   CKC(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
-  for (int b = 0; b < 2; b++) {
+  for (int b = 0; b < BB_STAGE_SETS; b++) {
     CKC(dev_alloc(h, &h->stage[b].queue, (size_t)(BB_LPT_HIST + 2 * BB_LPT_BUCKETS)));
     CKC(cudaEventCreateWithFlags(&h->stage[b].prepared, cudaEventDisableTiming));
     CKC(cudaEventCreateWithFlags(&h->stage[b].consumed, cudaEventDisableTiming));
@@ -574,9 +596,9 @@ static int host_call(bb_handle* h, int do_step, const int32_t* actions_host, dou
   const size_t N = (size_t)P.num_envs;
   if (pmax < 0 || (obs_host && pmax < 1)) return fail(h, "bb_step_host / bb_reset_host: bad pmax");
   if (do_step && !actions_host) return fail(h, "bb_step_host: null actions");
-  // staging layout: reward f64[N] | obs i32[N * pmax * cols] | lengths i32[N] | actions i32[N] | done u8[N]
+  // staging layout: reward f64[N] | obs i32[N * pmax * cols] | lengths i32[N] | actions i32[N] | done u8[N] | ticket u32
   const size_t o_rew = 0, o_obs = o_rew + 8 * N, o_len = o_obs + (obs_host ? 4 * N * (size_t)pmax * P.cols : 0);
-  const size_t o_act = o_len + 4 * N, o_done = o_act + 4 * N, bytes = (o_done + N + 15) & ~(size_t)15;
+  const size_t o_act = o_len + 4 * N, o_done = o_act + 4 * N, o_tick = (o_done + N + 15) & ~(size_t)15, bytes = o_tick + 16;
   if (bytes > h->stage_bytes) {
     CK(cudaStreamSynchronize(s));
     if (h->host_stage) cudaFreeHost(h->host_stage);
@@ -601,13 +623,28 @@ static int host_call(bb_handle* h, int do_step, const int32_t* actions_host, dou
   }
   const int* active = nullptr;
   if (do_step) { int rc = compact_for_step(h, s, &active); if (rc < 0) return rc; }
+  // one CTA writing mapped host memory: the host waits for the kernel's ticket in that memory (a few hundred nanoseconds
+  // after the kernel's last store) instead of a stream synchronisation through the driver
+  const bool poll = zero_copy && P.num_envs <= BB_WARPS && !active;
+  volatile unsigned* tick = reinterpret_cast<volatile unsigned*>(hs + o_tick);
+  const unsigned ticket = ++h->ticket ? h->ticket : ++h->ticket;   // never 0
+  if (poll) *tick = 0u;
   CK(h->K->step_obs(P, d_actions, action0, do_step ? (double*)(ds + o_rew) : nullptr, do_step ? (uint8_t*)(ds + o_done) : nullptr,
-                    obs_host ? (int32_t*)(ds + o_obs) : nullptr, (int32_t*)(ds + o_len), pmax, pad, do_step, active, P.num_envs, s));
+                    obs_host ? (int32_t*)(ds + o_obs) : nullptr, (int32_t*)(ds + o_len), pmax, pad, do_step, active,
+                    poll ? (unsigned*)(hs + o_tick) : nullptr, ticket, P.num_envs, s));
   if (!zero_copy) {
     CK(cudaMemcpyAsync(hs, ds, o_act, cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(hs + o_done, ds + o_done, N, cudaMemcpyDeviceToHost, s));
   }
-  CK(cudaStreamSynchronize(s));
+  bool seen = false;
+  if (poll) {
+    for (long spin = 0; spin < 4000000L; spin++) {   // ~ a few milliseconds, then the ordinary wait (which also reports faults)
+      if (*tick == ticket) { seen = true; break; }
+      __builtin_ia32_pause();
+    }
+  }
+  if (!seen) CK(cudaStreamSynchronize(s));
+  __atomic_thread_fence(__ATOMIC_ACQUIRE);   // the results below are read after the ticket
   const int32_t* len = (const int32_t*)(hs + o_len);
   if (lengths_host) memcpy(lengths_host, len, 4 * N);
   if (do_step && reward_host) memcpy(reward_host, hs + o_rew, 8 * N);
@@ -629,8 +666,8 @@ int bb_step_observe(bb_handle* h, const int32_t* actions_dev, double* reward_dev
   const int* active = nullptr;
   int rc = compact_for_step(h, (cudaStream_t)stream, &active);
   if (rc < 0) return rc;
-  CK(h->K->step_obs(h->P, actions_dev, 0, reward_dev, done_dev, obs_dev, lengths_dev, pmax, 1, 1, active, h->P.num_envs,
-                    (cudaStream_t)stream));
+  CK(h->K->step_obs(h->P, actions_dev, 0, reward_dev, done_dev, obs_dev, lengths_dev, pmax, 1, 1, active, nullptr, 0u,
+                    h->P.num_envs, (cudaStream_t)stream));
   return 0;
 }
 
@@ -767,19 +804,26 @@ static int check_staged(bb_handle* h, const char* who) {
   return 0;
 }
 
+// The next set of the ring that no prepared batch is waiting in (all waiting: the oldest one is given up).
+static int stage_take(bb_handle* h) {
+  int which = h->stage_next;
+  for (int t = 0; t < BB_STAGE_SETS && h->stage[which].episodes != 0; t++) which = (which + 1) % BB_STAGE_SETS;
+  h->stage[which].episodes = 0;
+  h->stage_next = (which + 1) % BB_STAGE_SETS;
+  return which;
+}
+
 int bb_prepare(bb_handle* h, int episodes, int seed_base, const int32_t* seeds_dev, void* stream) {
   if (!h) return -1;
   if (episodes < 1 || episodes > BB_RUN_BATCH) return fail(h, "bb_prepare: episodes must be in 1..65536 (one batch)");
   CK(cudaSetDevice(h->cfg.device));
   int rc = check_staged(h, "bb_prepare");
   if (rc < 0) return rc;
-  // the set the next runner would take, unless a prepared batch is already waiting there
-  const int which = h->stage[h->stage_next].episodes == 0 ? h->stage_next : h->stage_next ^ 1;
-  h->stage[which].episodes = 0;
+  const int which = stage_take(h);
   rc = enqueue_prepare(h, which, 0, episodes, seed_base, seeds_dev, (cudaStream_t)stream);
   if (rc < 0) return rc;
   bb_handle::Stage& T = h->stage[which];
-  T.episodes = episodes; T.seed_base = seed_base; T.seeds = seeds_dev;
+  T.episodes = episodes; T.seed_base = seed_base; T.seeds = seeds_dev; T.serial = ++h->stage_serial;
   return 0;
 }
 
@@ -804,18 +848,53 @@ int bb_run(bb_handle* h, int strategy, int episodes, int seed_base, const int32_
     if (wide_ctas <= 0) return fail(h, "bb_run: the CTA-per-environment stream runner does not fit this device");
   }
   const int nbatch = (episodes + BB_RUN_BATCH - 1) / BB_RUN_BATCH;
+  // the arena bank of this call: bank 0 unless a runner (of a call on another stream) may still be using it
+  int bk = 0;
+  if (h->bank[0].stream != s && cudaEventQuery(h->bank[0].done) != cudaSuccess) {
+    (void)cudaGetLastError();   // cudaErrorNotReady is not an error
+    if (!h->bank[1].ready) {
+      bb_handle::Bank& B = h->bank[1];
+      const size_t N = (size_t)h->P.num_envs;
+      const BBParams& P = h->P;
+      CK(dev_alloc(h, &B.arena, N * P.slot_stride));
+      CK(dev_alloc(h, &B.st, N));
+      CK(dev_alloc(h, &B.gkey, N * P.max_terms));
+      CK(dev_alloc(h, &B.gcoef, N * P.max_terms));
+      CK(dev_alloc(h, &B.glen, N * P.max_basis));
+      CK(dev_alloc(h, &B.gcount, N * 2));
+      CK(dev_alloc(h, &B.grlm, N * P.max_basis));
+      CK(dev_alloc(h, &B.gridx, N * P.max_basis));
+      CK(dev_alloc(h, &B.gflag, N * P.max_basis));
+      CK(cudaDeviceSynchronize());   // the allocations' memsets ran on the legacy stream
+      B.ready = true;
+    }
+    bk = 1;
+    if (h->bank[1].stream != s && cudaEventQuery(h->bank[1].done) != cudaSuccess) {   // both in use elsewhere: queue behind the older one
+      (void)cudaGetLastError();
+      bk = h->bank_turn;
+      CK(cudaStreamWaitEvent(s, h->bank[bk].done, 0));
+    }
+  }
+  h->bank_turn = bk ^ 1;
+  h->bank[bk].stream = s;
+  BBParams PB = h->P;
+  {
+    const bb_handle::Bank& B = h->bank[bk];
+    PB.arena = B.arena; PB.st = B.st; PB.gkey = B.gkey; PB.gcoef = B.gcoef; PB.glen = B.glen; PB.gcount = B.gcount;
+    PB.grlm = B.grlm; PB.gridx = B.gridx; PB.gflag = B.gflag;
+  }
   // Batch 0: already prepared by a matching bb_prepare, or prepared here on the caller's stream.  Batches 1.. of the
   // same call are prepared on the handle's side stream while the runner works through their predecessor.
-  int which = h->stage_next;
+  int which = -1;
   {
     const int count0 = std::min(BB_RUN_BATCH, episodes);
-    auto matches = [&](int b) {
+    for (int b = 0; b < BB_STAGE_SETS; b++) {   // the oldest waiting batch that is this call's
       const bb_handle::Stage& T = h->stage[b];
-      return T.episodes == count0 && nbatch == 1 && T.seed_base == seed_base && T.seeds == seeds_dev;
-    };
-    bool ready = matches(which);
-    if (!ready && matches(which ^ 1)) { which ^= 1; ready = true; }
-    if (!ready && h->stage[which].episodes != 0 && h->stage[which ^ 1].episodes == 0) which ^= 1;   // leave the waiting batch alone
+      const bool m = T.episodes == count0 && nbatch == 1 && T.seed_base == seed_base && T.seeds == seeds_dev;
+      if (m && (which < 0 || T.serial < h->stage[which].serial)) which = b;
+    }
+    const bool ready = which >= 0;
+    if (!ready) which = stage_take(h);
     bb_handle::Stage& T = h->stage[which];
     if (h->timing) CK(cudaEventRecord(h->ev_t[0], s));
     if (ready) CK(cudaStreamWaitEvent(s, T.prepared, 0));
@@ -829,11 +908,12 @@ int bb_run(bb_handle* h, int strategy, int episodes, int seed_base, const int32_
   if (nbatch > 1) CK(cudaEventRecord(h->ev_entry, s));   // seeds_dev and the ideals are valid on the side stream from here on
   for (int bi = 0; bi < nbatch; bi++) {
     const int base = bi * BB_RUN_BATCH, count = std::min(BB_RUN_BATCH, episodes - base);
-    if (bi + 1 < nbatch) {   // the next batch into the other set, concurrently with this batch's runner
+    int next = -1;
+    if (bi + 1 < nbatch) {   // the next batch into another set, concurrently with this batch's runner
       const int nbase = base + BB_RUN_BATCH;
       if (bi == 0) CK(cudaStreamWaitEvent(h->side, h->ev_entry, 0));
-      h->stage[which ^ 1].episodes = 0;
-      rc = enqueue_prepare(h, which ^ 1, nbase, std::min(BB_RUN_BATCH, episodes - nbase), seed_base, seeds_dev, h->side);
+      next = stage_take(h);
+      rc = enqueue_prepare(h, next, nbase, std::min(BB_RUN_BATCH, episodes - nbase), seed_base, seeds_dev, h->side);
       if (rc < 0) return rc;
     }
     BBParams S;
@@ -847,14 +927,14 @@ int bb_run(bb_handle* h, int strategy, int episodes, int seed_base, const int32_
     A.stream_kmax = h->wide_mode == 2 ? 6 : (h->wide_mode == 3 ? 48 : BBS_KMAX);
     if (bi > 0) CK(cudaStreamWaitEvent(s, h->stage[which].prepared, 0));
     const int workers = std::min(h->P.num_envs, count);
-    if (streams && h->wide_mode == 4) CK(h->K->run_streams(h->P, S, A, workers, s));
-    else if (streams) CK(h->K->run_wide(h->P, S, A, std::min(workers, wide_ctas), s));
-    else CK(h->K->run(h->P, S, A, workers, s));
+    if (streams && h->wide_mode == 4) CK(h->K->run_streams(PB, S, A, workers, s));
+    else if (streams) CK(h->K->run_wide(PB, S, A, std::min(workers, wide_ctas), s));
+    else CK(h->K->run(PB, S, A, workers, s));
     CK(cudaEventRecord(h->stage[which].consumed, s));
+    CK(cudaEventRecord(h->bank[bk].done, s));
     if (h->timing && bi == 0) CK(cudaEventRecord(h->ev_t[2], s));
-    which ^= 1;
+    which = next;
   }
-  h->stage_next = which;
   return 0;
 }
 

@@ -213,10 +213,15 @@ int bb_run(bb_handle* h, int strategy, int episodes, int seed_base, const int32_
            int max_steps, double gamma, int compute_gb, bb_episode_stats* stats_dev, int32_t* trace_dev,
            int trace_episodes, int trace_cap, void* stream);
 
-/* bb_prepare: the preparation half of the NEXT bb_run call (ideal generator + reset() of every episode of the batch,
+/* Pipelines.  Calls of bb_run on ONE stream run one after the other in the handle's own environments.  A call on a second
+ * stream while a runner of the first is still at work uses a second bank of environment slots (allocated on first use),
+ * so the runners of two batches overlap: the CTAs of batch i + 1 move in while batch i drains (an episode runner ends with
+ * its longest episodes on a mostly idle GPU).  Host views (bb_download_basis, bb_final_gb, bb_stats ...) read the first bank.
+ *
+ * bb_prepare: the preparation half of the NEXT bb_run call (ideal generator + reset() of every episode of the batch,
  * buchberger.cpp:299-315) enqueued on `stream`, which may be a different stream than the one the runner uses: the handle
- * keeps two staging sets, so the batch of call i + 1 is prepared while the runner of call i is still at work.  A later
- * bb_run with the same (episodes, seed_base, seeds_dev) waits for it instead of preparing; any other bb_run ignores it.
+ * keeps a ring of three staging sets, so batches can be prepared up to two calls ahead of the runner.  A later bb_run
+ * with the same (episodes, seed_base, seeds_dev) takes the oldest such batch instead of preparing; any other bb_run ignores it.
  * episodes <= 65536 (one batch).  Results are those of bb_run alone. */
 int bb_prepare(bb_handle* h, int episodes, int seed_base, const int32_t* seeds_dev, void* stream);
 

@@ -8,7 +8,7 @@
  *
  * Parity status: PINNED.  tests/test_oracle_*.py check this file (a) against every known answer the
  * reference's own tests hold for this path (tests/test_polynomials.cpp, tests/test_buchberger.cpp,
- * tests/test_ideals.cpp, tests/test_buchberger.py -- restated in tests/golden/reference_known_answers.json),
+ * tests/test_ideals.cpp, tests/test_buchberger.py -- restated one by one in tests/test_oracle_known_answers.py),
  * (b) against golden traces generated from the UNMODIFIED reference sources compiled here
  * (oracle/_ref/libdgref.so via oracle/ref_shim.cpp; generator script tests/golden/make_golden.py), and
  * (c) function-by-function against oracle/_ref on random inputs whenever that library is present.

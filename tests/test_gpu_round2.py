@@ -417,3 +417,37 @@ def test_discount_kernel_equals_the_host_restatement(torch_cuda):
     a = compute_advantages(rewards, values, done, 0.99, 0.97)
     b = compute_advantages(rewards.cuda(), values.cuda(), done.cuda(), 0.99, 0.97, eng)
     assert torch.equal(a, b.cpu())
+
+
+def test_runners_of_two_batches_overlap_on_two_streams(torch_cuda):
+    """bb_run on alternating streams: the CTAs of batch i + 1 move in while batch i drains (the call on the second stream
+    runs in a second bank of environment slots), the preparation runs two batches ahead on a third stream (ring of three
+    staging sets).  Every record of every batch equals the reference's."""
+    torch = torch_cuda
+    from deepgroebner_b200 import _lib
+    from deepgroebner_b200.buchberger import BuchbergerEngine, resident_envs
+    orc = ref_oracle()
+    E = 6000
+    eng = BuchbergerEngine("3-20-10-weighted", num_envs=min(resident_envs(0, 3), E))
+    bases = [0, 7000, 14000, 0, 7000, 14000, 0]
+    want = {b: orc.run_records("3-20-10-weighted", "degree", E, seed0=b, compute_gb=True) for b in set(bases)}
+    main, alt, side = torch.cuda.current_stream(), torch.cuda.Stream(), torch.cuda.Stream()
+    outs = [torch.empty(E * 72, dtype=torch.uint8, device="cuda") for _ in bases]
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        eng.prepare_episodes(E, seed_base=bases[0])
+        eng.prepare_episodes(E, seed_base=bases[1])
+    for i, b in enumerate(bases):
+        with torch.cuda.stream(main if i % 2 == 0 else alt):
+            eng.run_episodes("degree", episodes=E, seed_base=b, compute_gb=True, to_host=False, out=outs[i])
+        if i + 2 < len(bases):
+            with torch.cuda.stream(side):
+                eng.prepare_episodes(E, seed_base=bases[i + 2])
+    torch.cuda.synchronize()
+    for i, b in enumerate(bases):
+        assert_records_equal(outs[i].cpu().numpy().view(np.dtype(_lib.STATS_DTYPE)), want[b], "batch %d (seed base %d)" % (i, b))
+    c = eng.counters()
+    assert c["episodes"] == E * len(bases)
+    # a plain run afterwards works and is exact
+    stats, _ = eng.run_episodes("degree", episodes=E, seed_base=7000, compute_gb=True)
+    assert_records_equal(stats, want[7000], "plain run after the pipeline")
