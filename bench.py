@@ -407,34 +407,61 @@ def extra_dropin_n1(seconds=2.0):
 
 
 def extra_cyclic6(torch, local, orc, kind):
-    """BASELINE configs[4] beside the headline: cyclic-6, seeded Random selection, one launch of 1024 and one of 8192
-    episodes (the launch lasts at least as long as its longest episode, so the larger batch is the steady-state figure);
-    the first 256 records of the 1024-episode launch are checked against the reference."""
+    """BASELINE configs[4] beside the headline: cyclic-6, seeded Random selection.  A launch lasts at least as long as its
+    longest episode (697 000 dependent additions in the longest of 1024), so three figures: one launch of 1024 episodes
+    alone; a pipeline of six such launches on alternating streams (the CTAs of the next batch move in while the longest
+    episodes of the current one finish: the steady state of a job of many batches, as in the headline); one launch of
+    8192 episodes.  The first 256 records of the 1024-episode launch are checked against the reference."""
     import numpy as np
     from deepgroebner_b200 import _lib
     from deepgroebner_b200.buchberger import BuchbergerEngine
     eng = BuchbergerEngine("cyclic-6", num_envs=1024, device="cuda:%d" % local)
     out = {"what": "cyclic-6 over GF(32003), seeded Random selection (episode e: minstd_rand0 seeded %d + e), k_run_wide "
                    "(one CTA per environment, dividend as streams)" % SEL_SEED}
+    dt = np.dtype(_lib.STATS_DTYPE)
+    main, alt = torch.cuda.current_stream(), torch.cuda.Stream()
+    bufs = [torch.empty(1024 * 72, dtype=torch.uint8, device="cuda:%d" % local) for _ in range(2)]
     eng.run_episodes("random", episodes=64, selection_seed=SEL_SEED)
+    with torch.cuda.stream(alt):   # first use of the second stream allocates the second bank of environment slots
+        eng.run_episodes("random", episodes=64, selection_seed=SEL_SEED, to_host=False, out=bufs[1])
+    torch.cuda.synchronize()
+
+    def figures(ms, st, launches=1):
+        adds, steps = int(st["additions"].sum()) * launches, int(st["steps"].sum()) * launches
+        return {"ms": ms, "additions_per_sec": adds / (ms / 1e3), "env_steps_per_sec": steps / (ms / 1e3),
+                "additions": adds, "env_steps": steps}
+
     for n in (1024, 8192):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         buf, _ = eng.run_episodes("random", episodes=n, selection_seed=SEL_SEED, to_host=False)
         b.record()
         torch.cuda.synchronize()
-        st = buf.cpu().numpy().view(np.dtype(_lib.STATS_DTYPE))[:n]
+        st = buf.cpu().numpy().view(dt)[:n].copy()
         assert (st["status"] == 2).all()
-        ms = a.elapsed_time(b)
-        out["episodes_%d" % n] = {"ms": ms, "additions_per_sec": float(st["additions"].sum()) / (ms / 1e3),
-                                  "env_steps_per_sec": float(st["steps"].sum()) / (ms / 1e3),
-                                  "additions": int(st["additions"].sum()), "env_steps": int(st["steps"].sum())}
-        if n == 1024 and kind == "reference":
-            want = orc.run_records("cyclic-6", "random", 256, sel_seed0=SEL_SEED, gamma=0.99, compute_gb=False)
-            bad = sum(int((st[f][:256] != want[f]).sum()) for f in RECORD_FIELDS)
-            if bad:
-                raise SystemExit("bench.py: PARITY FAILURE on cyclic-6 (%d field mismatches)" % bad)
-            out["parity"] = {"episodes_checked": 256, "mismatches": 0}
+        out["episodes_%d" % n] = figures(a.elapsed_time(b), st)
+        if n == 1024:
+            st1024 = st
+            if kind == "reference":
+                want = orc.run_records("cyclic-6", "random", 256, sel_seed0=SEL_SEED, gamma=0.99, compute_gb=False)
+                bad = sum(int((st[f][:256] != want[f]).sum()) for f in RECORD_FIELDS)
+                if bad:
+                    raise SystemExit("bench.py: PARITY FAILURE on cyclic-6 (%d field mismatches)" % bad)
+                out["parity"] = {"episodes_checked": 256, "mismatches": 0}
+    L = 6
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record(main)
+    alt.wait_event(t0)
+    for i in range(L):
+        with torch.cuda.stream(main if i % 2 == 0 else alt):
+            eng.run_episodes("random", episodes=1024, selection_seed=SEL_SEED, to_host=False, out=bufs[i % 2])
+    main.wait_stream(alt)
+    t1.record(main)
+    torch.cuda.synchronize()
+    for bf in bufs:   # every batch of the pipeline produced the records of the single launch
+        assert np.array_equal(bf.cpu().numpy().view(dt)[:1024][list(RECORD_FIELDS)], st1024[list(RECORD_FIELDS)])
+    out["episodes_1024_pipelined"] = dict(figures(t0.elapsed_time(t1), st1024, L), launches=L,
+                                          what="six launches of 1024 episodes on alternating streams, span / 6")
     return out
 
 
