@@ -389,8 +389,12 @@ def extra_dropin_n1(seconds=2.0):
     drive(env, 0.3)
     ours, eps = drive(env, seconds)
     out = {"value": ours, "unit": UNIT, "episodes": eps,
-           "what": "LeadMonomialsEnv(k=2, num_envs=1): one kernel launch + one stream synchronisation per reset()/step(), "
-                   "state matrix returned as a numpy array (bb_reset_host / bb_step_host)"}
+           "what": "LeadMonomialsEnv(k=2, num_envs=1): reset()/step() answered by the handle's resident warp through a mailbox in "
+                   "mapped host memory (bb_set_serve), state matrix returned as a numpy array (bb_reset_host / bb_step_host)"}
+    env.engine.set_serve(False)
+    drive(env, 0.2)
+    out["launch_per_call"] = {"value": drive(env, seconds / 2)[0], "unit": UNIT,
+                              "what": "the same with one kernel launch + a ticket in mapped host memory per call"}
     try:
         sys.path.insert(0, os.path.join(ROOT, "oracle", "_ref"))
         from deepgroebner_ref.wrapped import CLeadMonomialsEnv
@@ -409,7 +413,7 @@ def extra_dropin_n1(seconds=2.0):
 def extra_cyclic6(torch, local, orc, kind):
     """BASELINE configs[4] beside the headline: cyclic-6, seeded Random selection.  A launch lasts at least as long as its
     longest episode (697 000 dependent additions in the longest of 1024), so three figures: one launch of 1024 episodes
-    alone; a pipeline of six such launches on alternating streams (the CTAs of the next batch move in while the longest
+    alone; a pipeline of nine such launches on three alternating streams (the CTAs of the next batches move in while the longest
     episodes of the current one finish: the steady state of a job of many batches, as in the headline); one launch of
     8192 episodes.  The first 256 records of the 1024-episode launch are checked against the reference."""
     import numpy as np
@@ -419,11 +423,12 @@ def extra_cyclic6(torch, local, orc, kind):
     out = {"what": "cyclic-6 over GF(32003), seeded Random selection (episode e: minstd_rand0 seeded %d + e), k_run_wide "
                    "(one CTA per environment, dividend as streams)" % SEL_SEED}
     dt = np.dtype(_lib.STATS_DTYPE)
-    main, alt = torch.cuda.current_stream(), torch.cuda.Stream()
-    bufs = [torch.empty(1024 * 72, dtype=torch.uint8, device="cuda:%d" % local) for _ in range(2)]
+    streams = [torch.cuda.current_stream(), torch.cuda.Stream(), torch.cuda.Stream()]
+    bufs = [torch.empty(1024 * 72, dtype=torch.uint8, device="cuda:%d" % local) for _ in streams]
     eng.run_episodes("random", episodes=64, selection_seed=SEL_SEED)
-    with torch.cuda.stream(alt):   # first use of the second stream allocates the second bank of environment slots
-        eng.run_episodes("random", episodes=64, selection_seed=SEL_SEED, to_host=False, out=bufs[1])
+    for i in (1, 2):   # a stream's first call while the others are busy allocates its bank of environment slots
+        with torch.cuda.stream(streams[i]):
+            eng.run_episodes("random", episodes=64, selection_seed=SEL_SEED, to_host=False, out=bufs[i])
     torch.cuda.synchronize()
 
     def figures(ms, st, launches=1):
@@ -448,20 +453,24 @@ def extra_cyclic6(torch, local, orc, kind):
                 if bad:
                     raise SystemExit("bench.py: PARITY FAILURE on cyclic-6 (%d field mismatches)" % bad)
                 out["parity"] = {"episodes_checked": 256, "mismatches": 0}
-    L = 6
+    L = 9
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t0.record(main)
-    alt.wait_event(t0)
+    t0.record(streams[0])
+    for x in streams[1:]:
+        x.wait_event(t0)
     for i in range(L):
-        with torch.cuda.stream(main if i % 2 == 0 else alt):
-            eng.run_episodes("random", episodes=1024, selection_seed=SEL_SEED, to_host=False, out=bufs[i % 2])
-    main.wait_stream(alt)
-    t1.record(main)
+        with torch.cuda.stream(streams[i % 3]):
+            eng.run_episodes("random", episodes=1024, selection_seed=SEL_SEED, to_host=False, out=bufs[i % 3])
+    for x in streams[1:]:
+        streams[0].wait_stream(x)
+    t1.record(streams[0])
     torch.cuda.synchronize()
     for bf in bufs:   # every batch of the pipeline produced the records of the single launch
-        assert np.array_equal(bf.cpu().numpy().view(dt)[:1024][list(RECORD_FIELDS)], st1024[list(RECORD_FIELDS)])
+        got = bf.cpu().numpy().view(dt)[:1024]
+        assert all(np.array_equal(got[f], st1024[f]) for f in RECORD_FIELDS)
     out["episodes_1024_pipelined"] = dict(figures(t0.elapsed_time(t1), st1024, L), launches=L,
-                                          what="six launches of 1024 episodes on alternating streams, span / 6")
+                                          what="nine launches of 1024 episodes on three alternating streams (three banks of "
+                                               "environment slots), whole span")
     return out
 
 
@@ -692,7 +701,7 @@ def gpu_arm(args):
             # per step: k_prepare(_lanes) + k_order + the runner (one batch) -- the L2 flush fill and the queue memset are not ours
             "gpu_launches": 3 * args.steps * ((ep_local + 65535) // 65536),
             "wall_s_timed_region": wall,
-            "step_ms": [round(a.elapsed_time(b), 4) for a, b in ev[:8]],
+            "step_ms": [round(a.elapsed_time(b), 4) for a, b in ev],
             "clocks": clocks,
             "parity": parity,
             "e2e": {"value": total_steps * args.steps / (e2e_ms_max / 1000.0), "unit": UNIT,

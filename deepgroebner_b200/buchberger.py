@@ -269,6 +269,11 @@ class BuchbergerEngine:
             self._ck(self.lib.bb_compact(self.h, _ptr(out), _stream()), "bb_compact")
         return out
 
+    def set_serve(self, on=True):
+        """One-environment engines answer step_host / reset_host / observe_host through a resident warp polling a mailbox in
+        mapped host memory (bb_set_serve; the default for num_envs == 1); off: one kernel launch per call."""
+        self._ck(self.lib.bb_set_serve(self.h, int(bool(on))), "bb_set_serve")
+
     def set_compaction(self, on=True):
         self._ck(self.lib.bb_set_compaction(self.h, int(bool(on))), "bb_set_compaction")
 

@@ -77,6 +77,27 @@ struct BBRolloutArgs {
   int32_t* obs; int pmax;         // optional [N, T, pmax, cols] state matrices BEFORE each step, padded with -1
 };
 
+// Mailbox of the single-environment server (k_serve), in mapped pinned host memory.  The host writes a command and bumps
+// cmd_seq; the resident warp polls cmd_seq over PCIe, executes, writes the results (the state matrix behind the header) and
+// publishes done_seq = cmd_seq.  alive: 1 while an instance of the kernel polls.
+enum { BB_CMD_STEP = 1, BB_CMD_RESET = 2, BB_CMD_OBSERVE = 3, BB_CMD_STOP = 4 };
+struct BBMailbox {
+  // one 16-byte word, read by the device with ONE load (one PCIe round trip per poll, and the command comes with it)
+  volatile unsigned cmd_seq;
+  unsigned cmd;
+  int arg;            // STEP: the action
+  int rows;           // (rows of the state matrix to write, 0: none) << 1 | pad (rows beyond |P| are -1)
+  unsigned pad0[12];
+  volatile unsigned done_seq;   // second 64-byte line: written by the device
+  volatile unsigned alive;
+  int length;         // |P| after the command
+  unsigned done;
+  double reward;
+  unsigned pad1[10];
+  // int32 obs[pmax * cols] follows
+};
+static_assert(sizeof(BBMailbox) == 128, "mailbox header is two 64-byte lines");
+
 struct BBKernelTable {
   int nvars, w, dw, dshift, eshift;
   cudaError_t (*reset)(const BBParams&, const uint8_t* mask, int nwarps, cudaStream_t);
@@ -85,6 +106,7 @@ struct BBKernelTable {
   cudaError_t (*step_obs)(const BBParams&, const int* actions, int action0, double* reward, uint8_t* done, int32_t* obs,
                           int32_t* lengths, int pmax, int pad, int do_step, const int* active, unsigned* ready, unsigned ticket,
                           int nwarps, cudaStream_t);
+  cudaError_t (*serve)(const BBParams&, BBMailbox* mb, unsigned long long idle_ns, cudaStream_t);
   cudaError_t (*select)(const BBParams&, int strategy, int* actions, int nwarps, cudaStream_t);
   cudaError_t (*observe)(const BBParams&, int32_t* obs, int32_t* lengths, int pmax, int nwarps, cudaStream_t);
   cudaError_t (*final_gb)(const BBParams&, int slot, int* ok_out, cudaStream_t);
@@ -250,6 +272,78 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_step_obs(const __
     __syncthreads();
     if (threadIdx.x == 0) { *reinterpret_cast<volatile unsigned*>(ready) = ticket; __threadfence_system(); }
   }
+}
+
+// The single-environment server: ONE resident warp that executes reset() / step() / observe() of environment 0 on command,
+// so that a host call of the reference's binding (wrapped.pyx:18-26: one environment, one action, the state matrix back)
+// costs a PCIe round trip instead of a kernel launch and a stream synchronisation.  Same code as k_step_obs / k_reset.
+// The warp leaves after idle_ns without a command (the host starts a new instance on demand), on BB_CMD_STOP, or with its
+// environment's parameters changed (every other entry point of the library stops it first).
+__device__ __forceinline__ unsigned long long bb_globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+template <int NV>
+__global__ void __launch_bounds__(32) k_serve(const __grid_constant__ BBParams P, BBMailbox* mb, unsigned long long idle_ns) {
+  __shared__ unsigned long long sh[1][CT_COUNT];
+  hot_init(P);
+  const int lane = bb_lane();
+  if (lane < CT_COUNT) sh[0][lane] = 0ull;
+  __syncwarp();
+  unsigned long long* row = sh[0];
+  int32_t* obs = reinterpret_cast<int32_t*>(mb + 1);
+  unsigned seen = mb->done_seq;
+  unsigned long long t_idle = bb_globaltimer();
+  for (;;) {
+    uint4 c = make_uint4(0u, 0u, 0u, 0u);
+    if (lane == 0)   // the host writes the 16 bytes with one aligned store: sequence number and command arrive together
+      asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(c.x), "=r"(c.y), "=r"(c.z), "=r"(c.w) : "l"(mb));
+    const unsigned s = __shfl_sync(BB_FULL, c.x, 0);
+    if (s == seen) {
+      if (bb_globaltimer() - t_idle > idle_ns) break;
+      continue;
+    }
+    const unsigned cmd = __shfl_sync(BB_FULL, c.y, 0);
+    const int arg = (int)__shfl_sync(BB_FULL, c.z, 0);
+    const int rowsw = (int)__shfl_sync(BB_FULL, c.w, 0);
+    const int pmax = rowsw >> 1, pad = rowsw & 1;
+    if (cmd != BB_CMD_STOP) {
+      Ctr ct; ct.clear();
+      double r = 0.0;
+      if (cmd == BB_CMD_RESET) warp_reset_slot<NV>(P, 0, 0, (uint32_t)P.st[0].rng, row);
+      Env e; env_load(P, 0, e);
+      if (cmd == BB_CMD_STEP) {
+        if (e.status == BB_STATUS_RUNNING) {
+          r = step_and_account<NV>(P, 0, e, arg, ct, row);
+          env_store(P, 0, e);
+        }
+        if (lane == 0) { mb->reward = r; mb->done = (e.status != BB_STATUS_RUNNING) ? 1u : 0u; }
+        if (P.auto_reset && e.status != BB_STATUS_RUNNING) {
+          __syncwarp();
+          warp_reset_slot<NV>(P, 0, 0, (uint32_t)P.st[0].rng, row);
+          env_load(P, 0, e);
+        }
+      }
+      if (pmax > 0) {
+        const int rows = e.nP < pmax ? e.nP : pmax;
+        warp_observe<NV>(P, e, obs, pad ? pmax : rows, ct);
+      }
+      if (lane == 0) mb->length = e.nP;
+      ct.spill(row);
+    }
+    __threadfence_system();   // every lane's results before the sequence number
+    __syncwarp();
+    if (lane == 0) mb->done_seq = s;
+    seen = s;
+    if (cmd == BB_CMD_STOP) break;
+    t_idle = bb_globaltimer();
+  }
+  __syncwarp();
+  if (lane < CT_COUNT && sh[0][lane]) atomicAdd(&P.counters[lane], sh[0][lane]);
+  __threadfence_system();
+  __syncwarp();
+  if (lane == 0) { mb->alive = 0u; __threadfence_system(); }
 }
 
 template <int NV>
@@ -902,6 +996,10 @@ struct BBLaunch {
                                                                 active, ready, ticket);
     return cudaGetLastError();
   }
+  static cudaError_t serve(const BBParams& P, BBMailbox* mb, unsigned long long idle_ns, cudaStream_t s) {
+    k_serve<NV><<<1, 32, 0, s>>>(P, mb, idle_ns);
+    return cudaGetLastError();
+  }
   static cudaError_t select(const BBParams& P, int strategy, int* actions, int nwarps, cudaStream_t s) {
     k_select<NV><<<grid_for_warps(nwarps), BB_THREADS, 0, s>>>(P, strategy, actions);
     return cudaGetLastError();
@@ -1026,7 +1124,7 @@ struct BBLaunch {
   }
   static const BBKernelTable* table() {
     static const BBKernelTable t = {NV, KL<NV>::w, KL<NV>::dw, KL<NV>::dshift, KL<NV>::eshift,
-                                    &reset, &step, &step_obs, &select, &observe, &final_gb, &prepare, &run, &run_streams, &streams_warps_per_sm, &run_wide, &wide_ctas_per_sm, &value, &policy,
+                                    &reset, &step, &step_obs, &serve, &select, &observe, &final_gb, &prepare, &run, &run_streams, &streams_warps_per_sm, &run_wide, &wide_ctas_per_sm, &value, &policy,
                                     &rollout,
                                     &run_blocks_per_sm};
     return &t;

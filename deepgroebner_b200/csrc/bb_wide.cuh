@@ -101,12 +101,16 @@ __device__ __forceinline__ void wide_round(WideShared& sh, int& half, StreamStat
     const uint32_t c = st.coef[i];
     if (k < mk) { mk = k; ms = c; } else if (k == mk) ms += c;
   }
-  // (c) warp: 64-bit minimum through two 32-bit reductions, the coefficient sum at it, the first divisor
+  // (c) warp: the first divisor of the warp's slices, then the 64-bit minimum through two 32-bit reductions and the
+  // coefficient sum at it.  The divisor's basis index is fetched here (one uniform load per warp, in flight during the
+  // three reductions) and travels with its position in one word, position on top: the fold's minimum still picks the first
+  // divisor and the block knows its head record's address one dependent load earlier.
   {
+    best = __reduce_min_sync(BB_FULL, best);
+    if (best != BBS_NONE) best = (best << 16) | ridx[best];   // positions and basis indices are below 2^16 (max_basis <= 65535)
     const uint32_t hi = __reduce_min_sync(BB_FULL, (uint32_t)(mk >> 32));
     const uint32_t lo = __reduce_min_sync(BB_FULL, (uint32_t)(mk >> 32) == hi ? (uint32_t)mk : 0xffffffffu);
     const uint32_t wsum = __reduce_add_sync(BB_FULL, ((uint32_t)(mk >> 32) == hi && (uint32_t)mk == lo) ? ms : 0u);
-    best = __reduce_min_sync(BB_FULL, best);
     if (lane == 0) sh.wrec[half][tid >> 5] = make_uint4(lo, hi, wsum, best);
   }
   __syncthreads();
@@ -121,8 +125,8 @@ __device__ __forceinline__ void wide_round(WideShared& sh, int& half, StreamStat
     M2 = ((uint64_t)hi << 32) | lo; S2 = bbf_reduce(F, gs);
   }
   half ^= 1;
-  found = best == BBS_NONE ? -1 : (int)best;
-  fidx = best == BBS_NONE ? 0u : ridx[best];
+  found = best == BBS_NONE ? -1 : (int)(best >> 16);
+  fidx = best == BBS_NONE ? 0u : (best & 0xffffu);
 }
 
 // Opens stream ws.K (owner: thread K % BBW_THREADS); as stream_open.

@@ -1,6 +1,7 @@
 // bbenv.cu -- the extern "C" ABI (include/bbenv.h) of libbbenv.so: handle, arenas, host views, and dispatch to the
 // per-NV kernel tables (bb_kernels.cuh, compiled in bb_nv.cu once per number of variables).  sm_100a only.
 #include <cuda_runtime.h>
+#include <emmintrin.h>
 
 #include <algorithm>
 #include <cmath>
@@ -135,7 +136,12 @@ const BBKernelTable* bb_kernel_table(int nvars) {
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-#define BB_STAGE_SETS 3
+#ifndef BB_STAGE_SETS
+#define BB_STAGE_SETS 3   // 4 (preparation three batches ahead) was measured: two preparations at once crowd out the next runner's CTAs
+#endif
+#ifndef BB_BANKS
+#define BB_BANKS 3
+#endif
 struct bb_handle {
   bb_config cfg;
   BBParams P;
@@ -165,7 +171,6 @@ struct bb_handle {
     unsigned long long serial;      // order of the bb_prepare calls (the oldest matching batch is run first)
   } stage[BB_STAGE_SETS];
   unsigned long long stage_serial;
-  int bank_turn;
   int stage_next;                   // ring cursor: the set the next batch is prepared into (skipping waiting ones)
   cudaStream_t side;                // bb_run's own prepare stream (calls that span several batches)
   cudaEvent_t ev_entry;
@@ -182,19 +187,29 @@ struct bb_handle {
   int episode_offset;    // bb_run: global index of episode 0 of a call (bb_set_episode_offset: shards of one job)
   int nstaged;           // fixed ideals: environments 0 .. nstaged - 1 hold a staged ideal (bb_set_ideals)
   int* d_seeds; int* h_seeds; cudaEvent_t ev_seeds;   // bb_seed: device / pinned staging of explicit seeds
-  // Environment arenas of bb_run: bank 0 is the handle's own (P: the environments of the step API); bank 1, a second
-  // full set of slots, is allocated the first time a bb_run call finds bank 0 still in use by a runner on another stream.
-  // With two banks the runners of two batches overlap: the CTAs of batch i + 1 move in while batch i drains.
+  // Environment arenas of bb_run: bank 0 is the handle's own (P: the environments of the step API); further banks, each a
+  // full set of slots, are allocated the first time a bb_run call finds the earlier ones still in use by runners on other
+  // streams.  With several banks the runners of consecutive batches overlap: the CTAs of batch i + 1 move in while batch i
+  // drains (two streams fill the tail of a binomial batch; cyclic-6, whose launches last as long as their longest episode,
+  // gains from a third).
   struct Bank {
     bool ready;
     unsigned char* arena; BBEnvState* st;
     uint64_t* gkey; uint32_t* gcoef; int* glen; int* gcount; uint64_t* grlm; uint32_t* gridx; uint32_t* gflag;
     cudaEvent_t done;   // recorded after the last runner that used the bank
     cudaStream_t stream; // ... and the stream it ran on (calls on the same stream are ordered anyway)
-  } bank[2];
+    unsigned long long serial;   // order of use (all busy: queue behind the least recently taken)
+  } bank[BB_BANKS];
   int* d_active;         // [num_envs + 1] slots of the RUNNING environments in ascending order, count in front (k_compact)
   int compaction;        // bb_set_compaction
   unsigned ticket;       // bb_step_host: sequence number the single-CTA kernel publishes in mapped host memory
+  // single-environment server (k_serve): bb_step_host / bb_reset_host / bb_observe_host of a one-environment handle talk to a
+  // resident warp through a mailbox in mapped pinned memory instead of launching a kernel per call
+  int serve_on;          // bb_set_serve (default: on when num_envs == 1)
+  bool serving;          // an instance was launched and not yet joined
+  BBMailbox* mb; size_t mb_bytes;
+  unsigned serve_seq;
+  cudaStream_t serve_stream; cudaEvent_t ev_serve;
   int prepare_by_warp;   // bb_run: 1 = episode preparation by one warp per episode even where the thread-per-episode kernel applies
   int wide_mode;   // bb_run: reduce() by streams: -1 = when the capacities ask for long polynomials, 0 = never, 1 = always, 2 / 3 = always, small tables
   // host mirrors of the distribution tables
@@ -250,6 +265,96 @@ static bool layout_arena(BBParams& P) {
 
 static inline int grid_for_warps_host(int nwarps) { return (nwarps + BB_WARPS - 1) / BB_WARPS; }
 
+// ------------------------------------------------------------------------------------------------ single-environment server
+#define BB_SERVE_IDLE_NS 10000000ull   // the resident warp leaves after 10 ms without a command
+
+static inline void serve_post(bb_handle* h, unsigned cmd, int arg, int pmax, int pad) {
+  // the whole command in one aligned 16-byte store (the device reads it with one 16-byte load)
+  const unsigned seq = ++h->serve_seq;
+  const __m128i w = _mm_set_epi32((int)(((unsigned)pmax << 1) | (pad ? 1u : 0u)), arg, (int)cmd, (int)seq);
+  __atomic_thread_fence(__ATOMIC_RELEASE);
+  _mm_store_si128(reinterpret_cast<__m128i*>(h->mb), w);
+}
+
+// Joins the server: asks a live instance to leave, waits for the kernel.  Every entry point that touches the environments
+// or the handle's parameters by other means calls this first (ENTER).
+static int serve_stop(bb_handle* h) {
+  if (!h->serving) return 0;
+  if (h->mb->alive) {
+    serve_post(h, BB_CMD_STOP, 0, 0, 0);
+    for (long spin = 0; spin < 200000000L && h->mb->alive && h->mb->done_seq != h->serve_seq; spin++) __builtin_ia32_pause();
+  }
+  CK(cudaStreamSynchronize(h->serve_stream));
+  h->serving = false;
+  return 0;
+}
+
+static int serve_launch(bb_handle* h, cudaStream_t s) {
+  // after everything the caller enqueued on its stream (a seed, a reset of other state ...)
+  CK(cudaEventRecord(h->ev_serve, s));
+  CK(cudaStreamWaitEvent(h->serve_stream, h->ev_serve, 0));
+  h->mb->alive = 1u;
+  __atomic_thread_fence(__ATOMIC_RELEASE);
+  CK(h->K->serve(h->P, h->mb, BB_SERVE_IDLE_NS, h->serve_stream));
+  h->serving = true;
+  return 0;
+}
+
+// One command through the mailbox: posts it, (re)starts the resident warp if none is polling, waits for the answer.
+static int serve_call(bb_handle* h, unsigned cmd, int action, double* reward_host, uint8_t* done_host, int32_t* obs_host,
+                      int32_t* lengths_host, int pmax, int pad, cudaStream_t s) {
+  const BBParams& P = h->P;
+  const int rows = obs_host ? pmax : 0;
+  const size_t need = sizeof(BBMailbox) + 4 * (size_t)rows * P.cols + 64;
+  if (need > h->mb_bytes) {
+    int rc = serve_stop(h);
+    if (rc < 0) return rc;
+    if (h->mb) cudaFreeHost(h->mb);
+    h->mb = nullptr; h->mb_bytes = 0;
+    CK(cudaHostAlloc((void**)&h->mb, need, cudaHostAllocMapped));
+    memset(h->mb, 0, need);
+    h->mb_bytes = need;
+    h->serve_seq = 0u;
+  }
+  BBMailbox* mb = h->mb;
+  if (!h->serving || !mb->alive) { int rc = serve_launch(h, s); if (rc < 0) return rc; }
+  serve_post(h, cmd, action, rows, pad);
+  const unsigned seq = h->serve_seq;
+  bool ok = false;
+  for (int attempt = 0; attempt < 64 && !ok; attempt++) {
+    for (long spin = 0; spin < 4000000L; spin++) {
+      if (mb->done_seq == seq) { ok = true; break; }
+      if ((spin & 1023) == 1023 && !mb->alive) break;   // the instance left (idle) before it saw the command
+      __builtin_ia32_pause();
+    }
+    if (ok || mb->done_seq == seq) { ok = true; break; }
+    if (!mb->alive) { int rc = serve_launch(h, s); if (rc < 0) return rc; }   // a new instance takes the pending command
+    else if (cudaStreamQuery(h->serve_stream) != cudaErrorNotReady) {      // the kernel is gone without an answer: a fault
+      CK(cudaStreamSynchronize(h->serve_stream));
+      return fail(h, "bb_step_host: the environment server stopped without answering");
+    }
+  }
+  if (!ok) return fail(h, "bb_step_host: the environment server did not answer");
+  __atomic_thread_fence(__ATOMIC_ACQUIRE);
+  const int len = mb->length;
+  if (lengths_host) lengths_host[0] = len;
+  if (cmd == BB_CMD_STEP) {
+    if (reward_host) reward_host[0] = mb->reward;
+    if (done_host) done_host[0] = (uint8_t)mb->done;
+  }
+  if (obs_host) {
+    const size_t rowb = 4 * (size_t)P.cols;
+    memcpy(obs_host, reinterpret_cast<const unsigned char*>(mb + 1), (size_t)(pad ? pmax : std::min(len, pmax)) * rowb);
+  }
+  return 0;
+}
+
+#define ENTER(h)                                                                                      \
+  do {                                                                                                \
+    CK(cudaSetDevice((h)->cfg.device));                                                               \
+    if ((h)->serving) { int _rc = serve_stop(h); if (_rc < 0) return _rc; }                           \
+  } while (0)
+
 extern "C" {
 
 int bb_abi_version(void) { return BB_ABI_VERSION; }
@@ -274,13 +379,17 @@ int bb_resident_envs(int device, int nvars) {
 void bb_destroy(bb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->cfg.device);
+  serve_stop(h);
+  if (h->mb) cudaFreeHost(h->mb);
+  if (h->serve_stream) cudaStreamDestroy(h->serve_stream);
+  if (h->ev_serve) cudaEventDestroy(h->ev_serve);
   for (void* p : h->allocs) cudaFree(p);
   for (int b = 0; b < BB_STAGE_SETS; b++) {
     for (void* p : h->stage[b].allocs) cudaFree(p);
     if (h->stage[b].prepared) cudaEventDestroy(h->stage[b].prepared);
     if (h->stage[b].consumed) cudaEventDestroy(h->stage[b].consumed);
   }
-  for (int b = 0; b < 2; b++) if (h->bank[b].done) cudaEventDestroy(h->bank[b].done);
+  for (int b = 0; b < BB_BANKS; b++) if (h->bank[b].done) cudaEventDestroy(h->bank[b].done);
   if (h->side) cudaStreamDestroy(h->side);
   if (h->ev_entry) cudaEventDestroy(h->ev_entry);
   if (h->ev_seeds) cudaEventDestroy(h->ev_seeds);
@@ -321,11 +430,13 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
     T.order = nullptr; T.cost_key = nullptr; T.queue = nullptr; T.prepared = nullptr; T.consumed = nullptr;
     T.episodes = 0; T.seed_base = 0; T.seeds = nullptr; T.serial = 0;
   }
-  for (int b = 0; b < 2; b++) { h->bank[b].ready = false; h->bank[b].done = nullptr; h->bank[b].stream = nullptr; }
-  h->stage_next = 0; h->stage_serial = 0; h->bank_turn = 0; h->side = nullptr; h->ev_entry = nullptr; h->timing = 0;
+  for (int b = 0; b < BB_BANKS; b++) { h->bank[b].ready = false; h->bank[b].done = nullptr; h->bank[b].stream = nullptr; h->bank[b].serial = 0; }
+  h->stage_next = 0; h->stage_serial = 0; h->side = nullptr; h->ev_entry = nullptr; h->timing = 0;
   h->ev_t[0] = h->ev_t[1] = h->ev_t[2] = nullptr;
   h->episode_offset = 0; h->nstaged = 0; h->d_seeds = nullptr; h->h_seeds = nullptr; h->ev_seeds = nullptr;
   h->d_active = nullptr; h->compaction = 1; h->ticket = 0u;
+  h->serve_on = cfg->num_envs == 1 ? 1 : 0; h->serving = false; h->mb = nullptr; h->mb_bytes = 0; h->serve_seq = 0u;
+  h->serve_stream = nullptr; h->ev_serve = nullptr;
   h->fork_cap = 0; h->fork_arena = nullptr; h->fork_st = nullptr;
   h->wide_mode = -1;
   h->prepare_by_warp = 0;
@@ -382,7 +493,7 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
   CKC(dev_alloc(h, &h->d_ok, (size_t)4));
   CKC(dev_alloc(h, &h->d_seeds, N));
   CKC(dev_alloc(h, &h->d_active, std::max(N + 1, (size_t)16)));
-  for (int b = 0; b < 2; b++) CKC(cudaEventCreateWithFlags(&h->bank[b].done, cudaEventDisableTiming));
+  for (int b = 0; b < BB_BANKS; b++) CKC(cudaEventCreateWithFlags(&h->bank[b].done, cudaEventDisableTiming));
   h->bank[0].ready = true;
   h->bank[0].arena = P.arena; h->bank[0].st = P.st; h->bank[0].gkey = P.gkey; h->bank[0].gcoef = P.gcoef; h->bank[0].glen = P.glen;
   h->bank[0].gcount = P.gcount; h->bank[0].grlm = P.grlm; h->bank[0].gridx = P.gridx; h->bank[0].gflag = P.gflag;
@@ -390,6 +501,8 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
   CKC(cudaEventCreateWithFlags(&h->ev_seeds, cudaEventDisableTiming));
   CKC(cudaEventCreateWithFlags(&h->ev_entry, cudaEventDisableTiming));
   CKC(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+  CKC(cudaStreamCreateWithFlags(&h->serve_stream, cudaStreamNonBlocking));
+  CKC(cudaEventCreateWithFlags(&h->ev_serve, cudaEventDisableTiming));
   for (int b = 0; b < BB_STAGE_SETS; b++) {
     CKC(dev_alloc(h, &h->stage[b].queue, (size_t)(BB_LPT_HIST + 2 * BB_LPT_BUCKETS)));
     CKC(cudaEventCreateWithFlags(&h->stage[b].prepared, cudaEventDisableTiming));
@@ -430,7 +543,7 @@ static int set_distribution_impl(bb_handle* h, int kind, int d, int s, double la
                    "which is not restated on device)");
   if ((unsigned)dist > 2u) return fail(h, "bb_set_distribution: bad dist");
   if ((unsigned)d > h->L.emax || (unsigned)d > h->L.dmax) return fail(h, "bb_set_distribution: degree does not fit the packed layout");
-  CK(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   const int n = h->L.n;
   // degree_distribution counts (ideals.cpp:75-100)
   std::vector<double> prob;
@@ -481,7 +594,7 @@ int bb_set_distribution_poly(bb_handle* h, int d, int s, double lam, int dist, i
 // synchronisation; a second call waits for the first one's copy only if it is still in flight).
 static int seed_impl(bb_handle* h, const int32_t* seeds, int base, int selection, cudaStream_t s) {
   if (!h) return -1;
-  CK(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   const int* d_seeds = nullptr;
   if (seeds) {
     CK(cudaEventSynchronize(h->ev_seeds));
@@ -505,7 +618,7 @@ int bb_set_ideals(bb_handle* h, const int32_t* env_ids, int count, const int32_t
   if (!h) return -1;
   BBParams& P = h->P;
   if (count < 0 || !ideal_offsets || !poly_offsets || !exps || !coefs) return fail(h, "bb_set_ideals: null argument");
-  CK(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   const int n = h->L.n;
   const BBLayout& L = h->L;
   std::vector<uint64_t> keys((size_t)P.max_gen_terms);
@@ -560,7 +673,7 @@ int bb_set_ideals(bb_handle* h, const int32_t* env_ids, int count, const int32_t
 
 int bb_reset(bb_handle* h, const uint8_t* mask_dev, void* stream) {
   if (!h) return -1;
-  CK(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   CK(h->K->reset(h->P, mask_dev, h->P.num_envs, (cudaStream_t)stream));
   return 0;
 }
@@ -580,7 +693,7 @@ static int compact_for_step(bb_handle* h, cudaStream_t s, const int** active) {
 int bb_step(bb_handle* h, const int32_t* actions_dev, double* reward_dev, uint8_t* done_dev, void* stream) {
   if (!h) return -1;
   if (!actions_dev) return fail(h, "bb_step: null actions");
-  CK(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   const int* active = nullptr;
   int rc = compact_for_step(h, (cudaStream_t)stream, &active);
   if (rc < 0) return rc;
@@ -595,7 +708,12 @@ static int host_call(bb_handle* h, int do_step, const int32_t* actions_host, dou
   const BBParams& P = h->P;
   const size_t N = (size_t)P.num_envs;
   if (pmax < 0 || (obs_host && pmax < 1)) return fail(h, "bb_step_host / bb_reset_host: bad pmax");
-  if (do_step && !actions_host) return fail(h, "bb_step_host: null actions");
+  if (do_step == 1 && !actions_host) return fail(h, "bb_step_host: null actions");
+  if (h->serve_on && P.num_envs == 1)   // one environment: a command to the resident warp instead of a launch
+    return serve_call(h, do_step == 1 ? BB_CMD_STEP : (do_step == 2 ? BB_CMD_RESET : BB_CMD_OBSERVE), do_step == 1 ? actions_host[0] : 0,
+                      reward_host, done_host, obs_host, lengths_host, pmax, pad, s);
+  if (h->serving) { int rc = serve_stop(h); if (rc < 0) return rc; }
+  if (do_step == 2) { CK(h->K->reset(P, nullptr, P.num_envs, s)); do_step = 0; }
   // staging layout: reward f64[N] | obs i32[N * pmax * cols] | lengths i32[N] | actions i32[N] | done u8[N] | ticket u32
   const size_t o_rew = 0, o_obs = o_rew + 8 * N, o_len = o_obs + (obs_host ? 4 * N * (size_t)pmax * P.cols : 0);
   const size_t o_act = o_len + 4 * N, o_done = o_act + 4 * N, o_tick = (o_done + N + 15) & ~(size_t)15, bytes = o_tick + 16;
@@ -662,7 +780,7 @@ int bb_step_observe(bb_handle* h, const int32_t* actions_dev, double* reward_dev
                     int32_t* lengths_dev, int pmax, void* stream) {
   if (!h) return -1;
   if (!actions_dev || pmax < 0 || (obs_dev && pmax < 1)) return fail(h, "bb_step_observe: bad argument");
-  CK(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   const int* active = nullptr;
   int rc = compact_for_step(h, (cudaStream_t)stream, &active);
   if (rc < 0) return rc;
@@ -681,8 +799,7 @@ int bb_step_host(bb_handle* h, const int32_t* actions_host, double* reward_host,
 int bb_reset_host(bb_handle* h, int32_t* obs_host, int32_t* lengths_host, int pmax, int pad, void* stream) {
   if (!h) return -1;
   CK(cudaSetDevice(h->cfg.device));
-  CK(h->K->reset(h->P, nullptr, h->P.num_envs, (cudaStream_t)stream));
-  return host_call(h, 0, nullptr, nullptr, nullptr, obs_host, lengths_host, pmax, pad, (cudaStream_t)stream);
+  return host_call(h, 2, nullptr, nullptr, nullptr, obs_host, lengths_host, pmax, pad, (cudaStream_t)stream);
 }
 
 int bb_observe_host(bb_handle* h, int32_t* obs_host, int32_t* lengths_host, int pmax, int pad, void* stream) {
@@ -694,7 +811,7 @@ int bb_observe_host(bb_handle* h, int32_t* obs_host, int32_t* lengths_host, int 
 int bb_select(bb_handle* h, int strategy, int32_t* actions_dev, void* stream) {
   if (!h) return -1;
   if ((unsigned)strategy > 8u || !actions_dev) return fail(h, "bb_select: bad argument");
-  CK(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   CK(h->K->select(h->P, strategy, actions_dev, h->P.num_envs, (cudaStream_t)stream));
   return 0;
 }
@@ -702,7 +819,7 @@ int bb_select(bb_handle* h, int strategy, int32_t* actions_dev, void* stream) {
 int bb_observe(bb_handle* h, int32_t* obs_dev, int32_t* lengths_dev, int pmax, void* stream) {
   if (!h) return -1;
   if (pmax < 0 || (obs_dev && pmax == 0)) return fail(h, "bb_observe: bad pmax");
-  CK(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   CK(h->K->observe(h->P, obs_dev, lengths_dev, pmax, h->P.num_envs, (cudaStream_t)stream));
   return 0;
 }
@@ -710,7 +827,7 @@ int bb_observe(bb_handle* h, int32_t* obs_dev, int32_t* lengths_dev, int pmax, v
 int bb_pairs(bb_handle* h, int32_t* pairs_dev, int32_t* lengths_dev, int pmax, void* stream) {
   if (!h) return -1;
   if (!pairs_dev || pmax < 1) return fail(h, "bb_pairs: bad argument");
-  CK(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   k_pairs<<<grid_for_warps_host(h->P.num_envs), BB_THREADS, 0, (cudaStream_t)stream>>>(h->P, pairs_dev, lengths_dev, pmax);
   CK(cudaGetLastError());
   return 0;
@@ -718,7 +835,7 @@ int bb_pairs(bb_handle* h, int32_t* pairs_dev, int32_t* lengths_dev, int pmax, v
 
 int bb_status(bb_handle* h, int32_t* status_dev, void* stream) {
   if (!h) return -1;
-  CK(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   k_status<<<(h->P.num_envs + BB_THREADS - 1) / BB_THREADS, BB_THREADS, 0, (cudaStream_t)stream>>>(h->P, status_dev, nullptr);
   CK(cudaGetLastError());
   return 0;
@@ -726,7 +843,7 @@ int bb_status(bb_handle* h, int32_t* status_dev, void* stream) {
 
 int bb_stats(bb_handle* h, bb_episode_stats* stats_dev, void* stream) {
   if (!h) return -1;
-  CK(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   k_status<<<(h->P.num_envs + BB_THREADS - 1) / BB_THREADS, BB_THREADS, 0, (cudaStream_t)stream>>>(h->P, nullptr, stats_dev);
   CK(cudaGetLastError());
   return 0;
@@ -816,7 +933,7 @@ static int stage_take(bb_handle* h) {
 int bb_prepare(bb_handle* h, int episodes, int seed_base, const int32_t* seeds_dev, void* stream) {
   if (!h) return -1;
   if (episodes < 1 || episodes > BB_RUN_BATCH) return fail(h, "bb_prepare: episodes must be in 1..65536 (one batch)");
-  CK(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   int rc = check_staged(h, "bb_prepare");
   if (rc < 0) return rc;
   const int which = stage_take(h);
@@ -832,7 +949,7 @@ int bb_run(bb_handle* h, int strategy, int episodes, int seed_base, const int32_
            int trace_episodes, int trace_cap, void* stream) {
   if (!h) return -1;
   if ((unsigned)strategy > 8u || episodes < 0 || !stats_dev) return fail(h, "bb_run: bad argument");
-  CK(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   cudaStream_t s = (cudaStream_t)stream;
   if (episodes == 0) return 0;
   int rc = check_staged(h, "bb_run");
@@ -848,35 +965,43 @@ int bb_run(bb_handle* h, int strategy, int episodes, int seed_base, const int32_
     if (wide_ctas <= 0) return fail(h, "bb_run: the CTA-per-environment stream runner does not fit this device");
   }
   const int nbatch = (episodes + BB_RUN_BATCH - 1) / BB_RUN_BATCH;
-  // the arena bank of this call: bank 0 unless a runner (of a call on another stream) may still be using it
-  int bk = 0;
-  if (h->bank[0].stream != s && cudaEventQuery(h->bank[0].done) != cudaSuccess) {
-    (void)cudaGetLastError();   // cudaErrorNotReady is not an error
-    if (!h->bank[1].ready) {
-      bb_handle::Bank& B = h->bank[1];
-      const size_t N = (size_t)h->P.num_envs;
-      const BBParams& P = h->P;
-      CK(dev_alloc(h, &B.arena, N * P.slot_stride));
-      CK(dev_alloc(h, &B.st, N));
-      CK(dev_alloc(h, &B.gkey, N * P.max_terms));
-      CK(dev_alloc(h, &B.gcoef, N * P.max_terms));
-      CK(dev_alloc(h, &B.glen, N * P.max_basis));
-      CK(dev_alloc(h, &B.gcount, N * 2));
-      CK(dev_alloc(h, &B.grlm, N * P.max_basis));
-      CK(dev_alloc(h, &B.gridx, N * P.max_basis));
-      CK(dev_alloc(h, &B.gflag, N * P.max_basis));
-      CK(cudaDeviceSynchronize());   // the allocations' memsets ran on the legacy stream
-      B.ready = true;
+  // the arena bank of this call: the one this stream used last (calls on a stream are ordered anyway), else the first bank
+  // no runner on another stream may still be using (allocated on first use), else the least recently taken one
+  int bk = -1;
+  for (int b = 0; b < BB_BANKS && bk < 0; b++)
+    if (h->bank[b].ready && h->bank[b].stream == s) bk = b;
+  if (bk < 0) {
+    for (int b = 0; b < BB_BANKS && bk < 0; b++) {
+      bb_handle::Bank& B = h->bank[b];
+      if (!B.ready) {
+        const size_t N = (size_t)h->P.num_envs;
+        const BBParams& P = h->P;
+        CK(dev_alloc(h, &B.arena, N * P.slot_stride));
+        CK(dev_alloc(h, &B.st, N));
+        CK(dev_alloc(h, &B.gkey, N * P.max_terms));
+        CK(dev_alloc(h, &B.gcoef, N * P.max_terms));
+        CK(dev_alloc(h, &B.glen, N * P.max_basis));
+        CK(dev_alloc(h, &B.gcount, N * 2));
+        CK(dev_alloc(h, &B.grlm, N * P.max_basis));
+        CK(dev_alloc(h, &B.gridx, N * P.max_basis));
+        CK(dev_alloc(h, &B.gflag, N * P.max_basis));
+        CK(cudaDeviceSynchronize());   // the allocations' memsets ran on the legacy stream
+        B.ready = true;
+        bk = b;
+      } else if (cudaEventQuery(B.done) == cudaSuccess) {
+        bk = b;
+      } else {
+        (void)cudaGetLastError();   // cudaErrorNotReady is not an error
+      }
     }
-    bk = 1;
-    if (h->bank[1].stream != s && cudaEventQuery(h->bank[1].done) != cudaSuccess) {   // both in use elsewhere: queue behind the older one
-      (void)cudaGetLastError();
-      bk = h->bank_turn;
+    if (bk < 0) {   // every bank is in use elsewhere: queue behind the least recently taken
+      bk = 0;
+      for (int b = 1; b < BB_BANKS; b++) if (h->bank[b].serial < h->bank[bk].serial) bk = b;
       CK(cudaStreamWaitEvent(s, h->bank[bk].done, 0));
     }
   }
-  h->bank_turn = bk ^ 1;
   h->bank[bk].stream = s;
+  h->bank[bk].serial = ++h->stage_serial;
   BBParams PB = h->P;
   {
     const bb_handle::Bank& B = h->bank[bk];
@@ -947,7 +1072,7 @@ int bb_set_timing(bb_handle* h, int on) {
 int bb_last_run_ms(bb_handle* h, float* prepare_ms, float* run_ms) {
   if (!h) return -1;
   if (!h->timing) return fail(h, "bb_last_run_ms: timing is off (bb_set_timing)");
-  CK(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   CK(cudaEventSynchronize(h->ev_t[2]));
   float a = 0.f, b = 0.f;
   CK(cudaEventElapsedTime(&a, h->ev_t[0], h->ev_t[1]));
@@ -992,7 +1117,7 @@ int bb_value(bb_handle* h, int strategy, double gamma, int rollouts, int sel_see
   if (strategy == BB_VALUE_SAMPLE) rollouts = rollouts > 0 ? rollouts : 101;  // 1 Degree + 100 Random (buchberger.cpp:333-341)
   else if ((unsigned)strategy > 8u) return fail(h, "bb_value: bad strategy");
   else if (strategy != BB_SELECT_RANDOM || rollouts < 1) rollouts = 1;
-  CK(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   cudaStream_t s = (cudaStream_t)stream;
   const int N = h->P.num_envs;
   const long long ntasks = (long long)N * rollouts;
@@ -1030,6 +1155,8 @@ int bb_copy_env(bb_handle* dst, int dst_env, bb_handle* src, int src_env, void* 
     return fail(h, "bb_copy_env: handles differ in device, field, variables or capacities");
   if (dst == src && dst_env == src_env) return 0;
   CK(cudaSetDevice(a.device));
+  if (dst->serving) { int rc = serve_stop(dst); if (rc < 0) return rc; }
+  if (src->serving && serve_stop(src) < 0) return fail(h, "bb_copy_env: " + src->err);
   cudaStream_t s = (cudaStream_t)stream;
   const BBParams &D = dst->P, &S = src->P;
   CK(cudaMemcpyAsync(D.arena + (size_t)dst_env * D.slot_stride, S.arena + (size_t)src_env * S.slot_stride, S.slot_stride,
@@ -1050,9 +1177,16 @@ int bb_discount(bb_handle* h, int N, int T, const double* x_dev, const uint8_t* 
   if (!h) return -1;
   if (N < 0 || T < 0 || !x_dev || !done_dev || !out_dev) return fail(h, "bb_discount: bad argument");
   if (N == 0 || T == 0) return 0;
-  CK(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   k_discount<<<(N + BB_THREADS - 1) / BB_THREADS, BB_THREADS, 0, (cudaStream_t)stream>>>(N, T, x_dev, done_dev, gam, out_dev);
   CK(cudaGetLastError());
+  return 0;
+}
+
+int bb_set_serve(bb_handle* h, int on) {
+  if (!h) return -1;
+  ENTER(h);
+  h->serve_on = on ? 1 : 0;
   return 0;
 }
 
@@ -1064,7 +1198,7 @@ int bb_set_compaction(bb_handle* h, int on) {
 
 int bb_compact(bb_handle* h, int32_t* active_dev, void* stream) {
   if (!h) return -1;
-  CK(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   cudaStream_t s = (cudaStream_t)stream;
   k_compact<<<1, 1024, 0, s>>>(h->P, active_dev ? active_dev : h->d_active);
   CK(cudaGetLastError());
@@ -1073,7 +1207,7 @@ int bb_compact(bb_handle* h, int32_t* active_dev, void* stream) {
 
 int bb_status_summary(bb_handle* h, int32_t* counts_host, void* stream) {
   if (!h || !counts_host) return -1;
-  CK(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   cudaStream_t s = (cudaStream_t)stream;
   int* hist = h->d_active;   // the list is rebuilt by every call that uses it
   CK(cudaMemsetAsync(hist, 0, sizeof(int) * BB_STATUS_COUNT, s));
@@ -1087,6 +1221,7 @@ int bb_status_summary(bb_handle* h, int32_t* counts_host, void* stream) {
 int bb_set_max_episode_length(bb_handle* h, int max_steps) {
   if (!h) return -1;
   if (max_steps < 0) return fail(h, "bb_set_max_episode_length: negative length");
+  ENTER(h);
   h->P.max_episode_length = max_steps;
   return 0;
 }
@@ -1094,6 +1229,7 @@ int bb_set_max_episode_length(bb_handle* h, int max_steps) {
 int bb_set_obs_nvars(bb_handle* h, int n_obs) {
   if (!h) return -1;
   if (n_obs < 1 || n_obs > h->cfg.nvars) return fail(h, "bb_set_obs_nvars: must be in 1..nvars");
+  ENTER(h);
   h->P.obs_nv = n_obs;
   h->P.cols = 2 * n_obs * h->P.k;
   return 0;
@@ -1120,6 +1256,7 @@ int bb_set_selection_seed_stride(bb_handle* h, int stride) {
 
 int bb_set_auto_reset(bb_handle* h, int on) {
   if (!h) return -1;
+  ENTER(h);
   h->P.auto_reset = on ? 1 : 0;
   return 0;
 }
@@ -1139,7 +1276,7 @@ int bb_policy_pmlp(bb_handle* h, int hidden, const float* W1_dev, const float* b
   int rc = check_policy(h, hidden, W1_dev, b1_dev, w2_dev, b2_dev);
   if (rc < 0) return rc;
   if (!actions_dev || (logprobs_all_dev && pmax < 1)) return fail(h, "bb_policy_pmlp: bad argument");
-  CK(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   BBPolicy W;
   W.hidden = hidden; W.W1 = W1_dev; W.b1 = b1_dev; W.w2 = w2_dev; W.b2 = b2_dev; W.seed = seed; W.greedy = greedy ? 1 : 0;
   CK(h->K->policy(h->P, W, counter, actions_dev, logprob_dev, logprobs_all_dev, pmax, h->P.num_envs, (cudaStream_t)stream));
@@ -1153,7 +1290,7 @@ int bb_rollout(bb_handle* h, int hidden, const float* W1_dev, const float* b1_de
   int rc = check_policy(h, hidden, W1_dev, b1_dev, w2_dev, b2_dev);
   if (rc < 0) return rc;
   if (T < 1 || (obs_dev && pmax < 1)) return fail(h, "bb_rollout: bad argument");
-  CK(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   BBRolloutArgs A;
   A.W.hidden = hidden; A.W.W1 = W1_dev; A.W.b1 = b1_dev; A.W.w2 = w2_dev; A.W.b2 = b2_dev; A.W.seed = seed;
   A.W.greedy = greedy ? 1 : 0;
@@ -1184,7 +1321,7 @@ int bb_download_basis(bb_handle* h, int env, int32_t* lens, int cap_polys, int32
   if (!h) return -1;
   BBParams& P = h->P;
   if (env < 0 || env >= P.num_envs) return fail(h, "bb_download_basis: environment index out of range");
-  CK(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   CK(cudaDeviceSynchronize());
   BBEnvState S;
   CK(cudaMemcpy(&S, P.st + env, sizeof S, cudaMemcpyDeviceToHost));
@@ -1208,7 +1345,7 @@ int bb_final_gb(bb_handle* h, int env, int32_t* lens, int cap_polys, int32_t* ex
   if (!h) return -1;
   BBParams& P = h->P;
   if (env < 0 || env >= P.num_envs) return fail(h, "bb_final_gb: environment index out of range");
-  CK(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   CK(h->K->final_gb(P, env, h->d_ok, (cudaStream_t)0));
   CK(cudaDeviceSynchronize());
   int ok = 0, cnt[2] = {0, 0};
@@ -1228,7 +1365,7 @@ int bb_final_gb(bb_handle* h, int env, int32_t* lens, int cap_polys, int32_t* ex
 
 int bb_counters_read(bb_handle* h, bb_counters* out, int reset) {
   if (!h || !out) return -1;
-  CK(cudaSetDevice(h->cfg.device));
+  ENTER(h);
   CK(cudaDeviceSynchronize());
   unsigned long long v[CT_COUNT];
   CK(cudaMemcpy(v, h->P.counters, sizeof v, cudaMemcpyDeviceToHost));

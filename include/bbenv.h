@@ -187,6 +187,14 @@ int bb_step_observe(bb_handle* h, const int32_t* actions_dev, double* reward_dev
 int bb_step_host(bb_handle* h, const int32_t* actions_host, double* reward_host, uint8_t* done_host, int32_t* obs_host,
                  int32_t* lengths_host, int pmax, int pad, void* stream);
 int bb_reset_host(bb_handle* h, int32_t* obs_host, int32_t* lengths_host, int pmax, int pad, void* stream);
+/* bb_set_serve: a handle of ONE environment answers bb_step_host / bb_reset_host / bb_observe_host through a resident warp
+ * (the "environment server") that polls a mailbox in mapped pinned host memory: the host writes the action, the warp runs
+ * the step and writes reward, done, |P| and the state matrix back -- a PCIe round trip per call instead of a kernel launch
+ * and a synchronisation (the reference's binding is called once per environment step, wrapped.pyx:23-26).  The warp is
+ * started on demand (ordered after the work already enqueued on `stream`), leaves after 10 ms without a command, and is
+ * joined by every other entry point before it touches the handle.  on = 0: one kernel launch per call.  Default: on when
+ * num_envs == 1. */
+int bb_set_serve(bb_handle* h, int on);
 int bb_observe_host(bb_handle* h, int32_t* obs_host, int32_t* lengths_host, int pmax, int pad, void* stream);
 /* bb_select: built-in pair selection (buchberger.cpp:160-241, any BB_SELECT_*): actions_dev int32[N]. */
 int bb_select(bb_handle* h, int strategy, int32_t* actions_dev, void* stream);
@@ -214,9 +222,10 @@ int bb_run(bb_handle* h, int strategy, int episodes, int seed_base, const int32_
            int trace_episodes, int trace_cap, void* stream);
 
 /* Pipelines.  Calls of bb_run on ONE stream run one after the other in the handle's own environments.  A call on a second
- * stream while a runner of the first is still at work uses a second bank of environment slots (allocated on first use),
- * so the runners of two batches overlap: the CTAs of batch i + 1 move in while batch i drains (an episode runner ends with
- * its longest episodes on a mostly idle GPU).  Host views (bb_download_basis, bb_final_gb, bb_stats ...) read the first bank.
+ * stream while a runner of the first is still at work uses another bank of environment slots (up to three banks, each
+ * allocated on first use; a fourth concurrent call queues behind the least recently started one), so the runners of
+ * consecutive batches overlap: the CTAs of batch i + 1 move in while batch i drains (an episode runner ends with its longest
+ * episodes on a mostly idle GPU).  Host views (bb_download_basis, bb_final_gb, bb_stats ...) read the first bank.
  *
  * bb_prepare: the preparation half of the NEXT bb_run call (ideal generator + reset() of every episode of the batch,
  * buchberger.cpp:299-315) enqueued on `stream`, which may be a different stream than the one the runner uses: the handle

@@ -451,3 +451,59 @@ def test_runners_of_two_batches_overlap_on_two_streams(torch_cuda):
     # a plain run afterwards works and is exact
     stats, _ = eng.run_episodes("degree", episodes=E, seed_base=7000, compute_gb=True)
     assert_records_equal(stats, want[7000], "plain run after the pipeline")
+
+
+def test_single_environment_server_equals_launch_per_call(torch_cuda):
+    """bb_set_serve: a one-environment handle answers reset() / step() through a resident warp and a mailbox in mapped host
+    memory.  Same states, rewards and done flags as one kernel launch per call and as the reference, across re-seeding,
+    value() and copy() in between (they join the server), an idle period longer than the warp's patience (it leaves and a
+    new instance picks the pending command up), a larger state matrix, auto-reset and truncation."""
+    import time
+    torch = torch_cuda
+    from deepgroebner_b200 import LeadMonomialsEnv
+    orc = best_oracle()
+    served = LeadMonomialsEnv("3-20-10-weighted", k=2, pmax=64)
+    plain = LeadMonomialsEnv("3-20-10-weighted", k=2, pmax=64)
+    plain.engine.set_serve(False)
+    ref = orc.lm_env("3-20-10-weighted", k=2)
+    rng = np.random.default_rng(12)
+    steps = 0
+    for ep, seed in enumerate((5, 6, 7, 5, 8, 9)):
+        for env in (served, plain, ref):
+            env.seed(seed)
+        s, p, r = served.reset(), plain.reset(), ref.reset()
+        done = False
+        while not done:
+            assert np.array_equal(s, r) and np.array_equal(p, r)
+            a = int(rng.integers(len(r)))
+            if steps % 17 == 5:
+                assert served.value("degree") == plain.value("degree") == ref.value("degree")
+            if steps % 23 == 7:
+                time.sleep(0.03)   # longer than the resident warp waits for a command
+            if steps % 29 == 11:
+                twin = served.copy()
+                t_s, t_r, t_d, _ = twin.step(a)
+            s, rs, ds, _ = served.step(a)
+            p, rp, dp, _ = plain.step(a)
+            r, rr, done, _ = ref.step(a)
+            if steps % 29 == 11:
+                assert np.array_equal(t_s, s) and t_r == rs and t_d == ds
+            assert rs == rp == rr and ds == dp == done
+            steps += 1
+    assert steps > 200
+    cs, cp = served.engine.counters(), plain.engine.counters()
+    for k in ("env_steps", "additions", "episodes", "lms_scanned", "obs_rows"):
+        assert cs[k] == cp[k], k
+    # a state matrix with more rows than the mailbox was sized for; auto-reset and truncation through the server
+    wide = LeadMonomialsEnv("3-20-10-weighted", k=2, pmax=16, max_episode_length=4)
+    wide.engine.set_auto_reset(True)
+    wide.seed(3)
+    s = wide.reset()
+    wide.pmax = 512
+    dones = 0
+    for t in range(40):
+        s, rew, done, _ = wide.step(0)
+        dones += done
+        assert len(s) > 0   # auto-reset: the state after a finished episode is the next episode's first state
+    assert dones >= 8       # cut after max + 1 = 5 steps (or finished earlier)
+    assert wide.engine.status_summary()["running"] == 1
