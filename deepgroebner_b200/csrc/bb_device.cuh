@@ -940,24 +940,40 @@ __device__ __forceinline__ void warp_observe(const BBParams& P, const Env& e, in
   typedef KL<NV> K;
   const int lane = bb_lane();
   const int nv = P.obs_nv;   // == NV except under bb_set_obs_nvars (the C++ FixedIdealGenerator::nvars quirk, ideals.cpp:146-154)
-  const int cols = P.cols, half = nv * P.k;
+  const int k = P.k, cols = P.cols, half = nv * k;
   const int rows = e.nP < pmax ? e.nP : pmax;
-  const int live = rows * cols, total = pmax * cols;
   const uint32_t* pairs = ENV_PTR(uint32_t, e, P, o_pairs);
   const GHeadMem* gh = ENV_PTR(GHeadMem, e, P, o_ghead);
   const uint64_t* tk = ENV_PTR(uint64_t, e, P, o_tkey);
-  for (int x = lane; x < live; x += 32) {
-    const int row = x / cols, c = x - row * cols;
-    const uint32_t pr = pairs[row];
-    const int side = c >= half;
-    const int cc = c - side * half;
-    const int t = cc / nv, v = cc - t * nv;
-    const GHeadMem* g = gh + (side ? (pr >> 16) : (pr & 0xffffu));
-    int32_t val = 0;
-    if (t < (int)g->len) val = (int32_t)K::exp(t == 0 ? g->lm : (t == 1 ? g->k1 : tk[g->off + t]), v);
-    obs[x] = val;
+  // one lane per (row, side): 16 rows per pass; the lane loads its polynomial's head record once and writes the k * nv
+  // exponents of that half row, so consecutive lanes write consecutive half rows (no division per element, two
+  // dependent loads per half row instead of three per element)
+  const int side = lane & 1;
+#pragma unroll 1
+  for (int r0 = 0; r0 < rows; r0 += 16) {
+    const int row = r0 + (lane >> 1);
+    if (row < rows) {
+      const uint32_t pr = pairs[row];
+      const GHead g = load_head(gh + (side ? (pr >> 16) : (pr & 0xffffu)));
+      int32_t* o = obs + (size_t)row * cols + side * half;
+#pragma unroll 1
+      for (int t = 0; t < k; t++) {
+        const bool have = t < (int)g.len;
+        const uint64_t key = t == 0 ? g.lm : (t == 1 ? g.k1 : (have ? tk[g.off + t] : 0ull));
+        for (int v = 0; v < nv; v++) o[t * nv + v] = have ? (int32_t)K::exp(key, v) : 0;
+      }
+    }
   }
-  for (int x = live + lane; x < total; x += 32) obs[x] = -1;
+  // rows [|P|, pmax) are -1: 16-byte stores where the row pitch allows it
+  const int live = rows * cols, total = pmax * cols;
+  if (((cols & 3) == 0) && ((reinterpret_cast<uintptr_t>(obs) & 15) == 0)) {
+    int4* o4 = reinterpret_cast<int4*>(obs + live);
+    const int n4 = (total - live) >> 2;
+    const int4 m1 = make_int4(-1, -1, -1, -1);
+    for (int x = lane; x < n4; x += 32) o4[x] = m1;
+  } else {
+    for (int x = live + lane; x < total; x += 32) obs[x] = -1;
+  }
   ct.obs += (unsigned)rows;
 }
 
