@@ -59,7 +59,7 @@ EXPORTS = [
     "bb_status", "bb_stats", "bb_run", "bb_download_basis", "bb_final_gb", "bb_counters_read", "bb_hash_item",
     "bb_seed_selection", "bb_value", "bb_copy_env", "bb_set_auto_reset", "bb_step_observe", "bb_step_host", "bb_reset_host", "bb_observe_host", "bb_set_wide", "bb_set_prepare_mode", "bb_set_selection_seed_stride", "bb_policy_pmlp", "bb_rollout",
     "bb_seed_on", "bb_prepare", "bb_set_episode_offset", "bb_set_timing", "bb_last_run_ms", "bb_set_max_episode_length",
-    "bb_set_compaction", "bb_compact", "bb_status_summary", "bb_set_obs_nvars", "bb_discount", "bb_set_serve",
+    "bb_set_compaction", "bb_compact", "bb_status_summary", "bb_set_obs_nvars", "bb_discount", "bb_set_serve", "bb_set_prefetch",
 ]
 
 _lib = None
@@ -142,7 +142,7 @@ def load():
     lib.bb_prepare.restype = i
     lib.bb_prepare.argtypes = [vp, i, i, vp, vp]
     for n in ("bb_set_episode_offset", "bb_set_timing", "bb_set_max_episode_length", "bb_set_compaction", "bb_set_obs_nvars",
-              "bb_set_serve"):
+              "bb_set_serve", "bb_set_prefetch"):
         getattr(lib, n).restype = i
         getattr(lib, n).argtypes = [vp, i]
     lib.bb_last_run_ms.restype = i

@@ -269,6 +269,11 @@ class BuchbergerEngine:
             self._ck(self.lib.bb_compact(self.h, _ptr(out), _stream()), "bb_compact")
         return out
 
+    def set_prefetch(self, depth=8):
+        """Queues of prepared next episodes per environment for reset() / auto-reset (bb_set_prefetch); 0 = off.  The default
+        is 8 for engines of at least 64 environments.  What an environment draws does not change."""
+        self._ck(self.lib.bb_set_prefetch(self.h, int(depth)), "bb_set_prefetch")
+
     def set_serve(self, on=True):
         """One-environment engines answer step_host / reset_host / observe_host through a resident warp polling a mailbox in
         mapped host memory (bb_set_serve; the default for num_envs == 1); off: one kernel launch per call."""

@@ -68,6 +68,8 @@ struct BBDist {           // RandomBinomialIdealGenerator / RandomIdealGenerator
   const int* basis_off;   // [d+2]
 };
 
+struct BBPre;   // prefetch queues of the step API (bb_kernels.cuh)
+
 struct BBParams {
   BBField F;
   int nvars;
@@ -103,6 +105,7 @@ struct BBParams {
   int* gcount;                          // [num_envs][2] = (npolys, nterms)
   uint64_t* grlm; uint32_t* gridx; uint32_t* gflag;  // [num_envs][max_basis] scratch of warp_final_gb
   BBDist dist;
+  const BBPre* pre;                     // per-environment queues of prepared next episodes (NULL: none), see warp_next_episode
   const uint16_t* invtab;               // [p] multiplicative inverses in GF(p) (invtab[0] = 0)
   unsigned long long* counters;         // bb_counters as 12 x u64
 };

@@ -51,6 +51,21 @@ struct BBRunArgs {
 #define BB_LPT_BUCKETS 256
 #define BB_LPT_HIST 4
 
+// Prefetch queues of the step API.  reset() inside a step kernel (auto-reset) is a cold detour of one warp through the ideal
+// generator and s update() calls: 38 us, while the other warps of the launch wait for it at the kernel's end.  Instead every
+// environment keeps a short queue of its NEXT episodes' initial states, prepared in bulk by k_prefill (one thread per
+// environment, k_prepare_lanes' code) from the environment's own ideal stream, in stream order; a reset takes the head of the
+// queue with a copy.  st.rng stays the stream position after the CURRENT episode's draw (= before the head of the queue), so
+// dropping a queue (seed(), copy()) never changes what an environment draws next.  Lives in device memory; P.pre points at it.
+#define BB_PREP_S 16   // most generators the thread-per-episode preparation handles
+struct BBPre {
+  BBParams S;        // staging-layout parameters of the queue slots: slot (e * depth + j)
+  int depth;
+  int* count;        // [num_envs] episodes waiting
+  int* head;         // [num_envs] position of the first one
+  unsigned* rng;     // [num_envs] stream state after the LAST prepared episode (where k_prefill goes on)
+};
+
 struct BBEpisodeAcc {
   unsigned long long th;
   double ret, disc;
@@ -107,6 +122,7 @@ struct BBKernelTable {
                           int32_t* lengths, int pmax, int pad, int do_step, const int* active, unsigned* ready, unsigned ticket,
                           int nwarps, cudaStream_t);
   cudaError_t (*serve)(const BBParams&, BBMailbox* mb, unsigned long long idle_ns, cudaStream_t);
+  cudaError_t (*prefill)(const BBParams&, const BBParams& stage, cudaStream_t);
   cudaError_t (*select)(const BBParams&, int strategy, int* actions, int nwarps, cudaStream_t);
   cudaError_t (*observe)(const BBParams&, int32_t* obs, int32_t* lengths, int pmax, int nwarps, cudaStream_t);
   cudaError_t (*final_gb)(const BBParams&, int slot, int* ok_out, cudaStream_t);
@@ -146,13 +162,17 @@ __device__ __forceinline__ unsigned long long* counters_row(unsigned long long (
   return row;
 }
 
+// reset() of one environment of the step API: the head of its prefetch queue, else the generator (defined below)
+template <int NV>
+__device__ __noinline__ void warp_next_episode(const BBParams& P, int slot, unsigned long long* row);
+
 template <int NV>
 __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_reset(const __grid_constant__ BBParams P, const uint8_t* mask) {
   __shared__ unsigned long long sh[BB_WARPS][CT_COUNT];
   hot_init(P);
   unsigned long long* row = counters_row(sh);
   const int slot = (blockIdx.x * BB_THREADS + threadIdx.x) >> 5;
-  if (slot < P.num_envs && (!mask || mask[slot])) warp_reset_slot<NV>(P, slot, slot, (uint32_t)P.st[slot].rng, row);
+  if (slot < P.num_envs && (!mask || mask[slot])) warp_next_episode<NV>(P, slot, row);
   counters_flush(P, sh);
 }
 
@@ -214,7 +234,7 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_step(const __grid
     ct.spill(row);
     if (P.auto_reset && e.status != BB_STATUS_RUNNING) {  // the caller sees done = 1 and the NEXT episode's first state
       __syncwarp();
-      warp_reset_slot<NV>(P, slot, slot, (uint32_t)P.st[slot].rng, row);
+      warp_next_episode<NV>(P, slot, row);
     }
   }
   counters_flush(P, sh);
@@ -253,7 +273,7 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_step_obs(const __
       }
       if (P.auto_reset && e.status != BB_STATUS_RUNNING) {
         __syncwarp();
-        warp_reset_slot<NV>(P, slot, slot, (uint32_t)P.st[slot].rng, row);
+        warp_next_episode<NV>(P, slot, row);
         env_load(P, slot, e);
       }
     }
@@ -311,7 +331,7 @@ __global__ void __launch_bounds__(32) k_serve(const __grid_constant__ BBParams P
     if (cmd != BB_CMD_STOP) {
       Ctr ct; ct.clear();
       double r = 0.0;
-      if (cmd == BB_CMD_RESET) warp_reset_slot<NV>(P, 0, 0, (uint32_t)P.st[0].rng, row);
+      if (cmd == BB_CMD_RESET) warp_next_episode<NV>(P, 0, row);
       Env e; env_load(P, 0, e);
       if (cmd == BB_CMD_STEP) {
         if (e.status == BB_STATUS_RUNNING) {
@@ -321,7 +341,7 @@ __global__ void __launch_bounds__(32) k_serve(const __grid_constant__ BBParams P
         if (lane == 0) { mb->reward = r; mb->done = (e.status != BB_STATUS_RUNNING) ? 1u : 0u; }
         if (P.auto_reset && e.status != BB_STATUS_RUNNING) {
           __syncwarp();
-          warp_reset_slot<NV>(P, 0, 0, (uint32_t)P.st[0].rng, row);
+          warp_next_episode<NV>(P, 0, row);
           env_load(P, 0, e);
         }
       }
@@ -421,7 +441,6 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_prepare(const __g
 // out of thread-local arrays and writes each finished state to its staging slot.  Same results, same counters.
 // update() in closed form (see warp_add_basis): with L_i = lcm(LM_i, LM f), (i, m) is emitted iff no L_j strictly divides
 // L_i, no j < i has L_j == L_i, and no j with L_j == L_i is coprime to f.
-#define BB_PREP_S 16
 #define BB_PREP_P (BB_PREP_S * (BB_PREP_S - 1) / 2)
 #ifndef BB_PREP_THREADS
 #define BB_PREP_THREADS 32
@@ -429,128 +448,137 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_prepare(const __g
 #ifndef BB_PREP_MIN_BLOCKS
 #define BB_PREP_MIN_BLOCKS 1
 #endif
+// One episode prepared by ONE thread: the ideal drawn from the stream state x (advanced), BuchbergerEnv::reset on it (re-rolls
+// included), the finished state written to slot b of the staging arena S.  Returns the summed degree of the generators' lead
+// monomials (the episode's predicted cost); upb / upp accumulate the update() traffic counters.
+template <int NV>
+__device__ __forceinline__ uint32_t prepare_lane_episode(const BBParams& S, int b, uint32_t& x, unsigned& upb, unsigned& upp) {
+  typedef KL<NV> K;
+  const BBDist& D = S.dist;
+  const BBField F = S.F;
+  const int s = D.s;
+  uint64_t gk0[BB_PREP_S], gk1[BB_PREP_S];          // generators: lead / second monomial, second coefficient (lead coefficient 1)
+  uint32_t gc1[BB_PREP_S];
+  uint64_t L[BB_PREP_S];                             // update(): key of lcm(LM_i, LM f)
+  uint64_t rl[BB_PREP_S]; uint32_t ri[BB_PREP_S];    // reducer list G_
+  uint32_t prs[BB_PREP_P]; uint64_t plc[BB_PREP_P];  // pair list P with cached lcm keys
+  int nG = 0, nP = 0, status = BB_STATUS_EMPTY, rerolls = 0;
+  for (;;) {
+    bool ok = true;
+    for (int i = 0; i < s && ok; i++) {   // RandomBinomialIdealGenerator::next, as gen_binomial_ideal
+      const uint32_t c = D.pure ? (F.p - 1u) : (uint32_t)rng_uniform(x, 1, (int)F.p - 1);
+      int d1, d2;
+      if (D.homogeneous) d1 = d2 = rng_degree(D, x);
+      else { d1 = rng_degree(D, x); d2 = rng_degree(D, x); }
+      const int o1 = D.basis_off[d1], n1 = D.basis_off[d1 + 1] - o1, o2 = D.basis_off[d2], n2 = D.basis_off[d2 + 1] - o2;
+      ok = false;
+      for (int trials = 0; trials < 1000 && !ok; trials++) {
+        const uint64_t m1 = D.basis[o1 + rng_uniform(x, 0, n1 - 1)];
+        const uint64_t m2 = D.basis[o2 + rng_uniform(x, 0, n2 - 1)];
+        if (m1 != m2) { gk0[i] = m1 < m2 ? m1 : m2; gk1[i] = m1 < m2 ? m2 : m1; gc1[i] = c; ok = true; }
+      }
+    }
+    if (!ok) { nG = nP = 0; status = BB_STATUS_EMPTY; break; }   // the reference throws (ideals.cpp:196-197)
+    if (S.sort_input) {   // ascending lead monomial == descending key, stable (buchberger.cpp:301-302; see warp_load_ideal)
+      for (int i = 1; i < s; i++) {
+        const uint64_t a0 = gk0[i], a1 = gk1[i]; const uint32_t ac = gc1[i];
+        int j = i;
+        while (j > 0 && gk0[j - 1] < a0) { gk0[j] = gk0[j - 1]; gk1[j] = gk1[j - 1]; gc1[j] = gc1[j - 1]; j--; }
+        gk0[j] = a0; gk1[j] = a1; gc1[j] = ac;
+      }
+    }
+    nG = 0; nP = 0; status = BB_STATUS_RUNNING;
+    for (int m = 0; m < s; m++) {   // update(G, P, f) + insertion into G_, generator by generator
+      const uint64_t fk = gk0[m], fe = fk & K::ex_mask;
+      upb += (unsigned)m; upp += (unsigned)nP;
+      int kept = nP;   // old pairs that survive
+      if (S.elimination == BB_ELIM_GEBAUERMOELLER) {
+        bool ovf = false;
+        uint32_t cop = 0u;
+        for (int i = 0; i < m; i++) {
+          const uint64_t le = K::lcm_exps(gk0[i], fk);
+          const uint32_t dg = K::sum_fields(le);
+          ovf |= dg > K::dmax;
+          L[i] = le | ((uint64_t)(K::dmax - dg) << K::dshift);
+          cop |= K::coprime(gk0[i], fk) ? (1u << i) : 0u;
+        }
+        if (ovf) { status = BB_STATUS_OVERFLOW_EXPONENT; break; }
+        int w = 0;
+        for (int q = 0; q < nP; q++) {
+          const uint32_t pr = prs[q]; const uint64_t pl = plc[q];
+          const uint64_t l = pl & K::ex_mask;
+          const bool drop = K::divides(fe, l) && l != (L[pr & 0xffffu] & K::ex_mask) && l != (L[pr >> 16] & K::ex_mask);
+          if (!drop) { prs[w] = pr; plc[w] = pl; w++; }
+        }
+        nP = w; kept = w;
+        for (int i = 0; i < m; i++) {
+          const uint64_t li = L[i] & K::ex_mask;
+          bool emit = true;
+          for (int j = 0; j < m && emit; j++) {   // a third of this kernel's instructions were spent here without the early exit
+            const uint64_t lj = L[j] & K::ex_mask;
+            if (lj == li) emit = emit && !(j < i) && !((cop >> j) & 1u);
+            else emit = emit && !((((li | K::ge_mask) - lj) & K::ge_mask) == K::ge_mask);
+          }
+          if (emit) { prs[nP] = ((uint32_t)m << 16) | (uint32_t)i; plc[nP] = L[i]; nP++; }
+        }
+      } else {
+        for (int i = 0; i < m; i++) {
+          if (S.elimination == BB_ELIM_LCM && K::coprime(gk0[i], fk)) continue;
+          prs[nP] = ((uint32_t)m << 16) | (uint32_t)i; plc[nP] = K::key_from_exps(K::lcm_exps(gk0[i], fk)); nP++;
+        }
+      }
+      upp += (unsigned)(nP - kept);   // emitted pairs, counted as warp_load_ideal counts them
+      int pos = m;
+      if (S.sort_reducers) {   // after every element whose lead monomial is <= the new one (key >= new key)
+        pos = 0;
+        while (pos < m && rl[pos] >= fk) pos++;
+        for (int r = m; r > pos; r--) { rl[r] = rl[r - 1]; ri[r] = ri[r - 1]; }
+      }
+      rl[pos] = fk; ri[pos] = (uint32_t)m;
+      nG = m + 1;
+    }
+    if (status != BB_STATUS_RUNNING || nP > 0) break;
+    rerolls++;   // P came out empty: the next ideal of the same stream (buchberger.cpp:313-314)
+  }
+  if (status == BB_STATUS_RUNNING && nP == 0) status = BB_STATUS_DONE;
+  // the finished state goes to the episode's staging slot
+  unsigned char* base = S.arena + (size_t)b * S.slot_stride;
+  GHeadMem* gh = reinterpret_cast<GHeadMem*>(base + S.o_ghead);
+  uint64_t* lm = reinterpret_cast<uint64_t*>(base + S.o_lm);
+  uint64_t* rlm = reinterpret_cast<uint64_t*>(base + S.o_rlm);
+  uint32_t* ridx = reinterpret_cast<uint32_t*>(base + S.o_ridx);
+  uint32_t* pairs = reinterpret_cast<uint32_t*>(base + S.o_pairs);
+  uint64_t* plcm = reinterpret_cast<uint64_t*>(base + S.o_plcm);
+  uint64_t* tk = reinterpret_cast<uint64_t*>(base + S.o_tkey);
+  uint32_t* tc = reinterpret_cast<uint32_t*>(base + S.o_tcoef);
+  uint32_t sd = 0;
+  for (int m = 0; m < nG; m++) {
+    const uint64_t fk = gk0[m], k1 = gk1[m];
+    reinterpret_cast<uint4*>(gh + m)[0] = make_uint4((uint32_t)fk, (uint32_t)(fk >> 32), (uint32_t)k1, (uint32_t)(k1 >> 32));
+    reinterpret_cast<uint4*>(gh + m)[1] = make_uint4(1u | (gc1[m] << 16), K::deg(fk), (uint32_t)(2 * m), 2u);   // 1 / LC = 1
+    lm[m] = fk; rlm[m] = rl[m]; ridx[m] = ri[m];
+    tk[2 * m] = fk; tk[2 * m + 1] = k1; tc[2 * m] = 1u; tc[2 * m + 1] = gc1[m];
+    sd += K::deg(fk);
+  }
+  for (int q = 0; q < nP; q++) { pairs[q] = prs[q]; plcm[q] = plc[q]; }
+  *reinterpret_cast<int4*>(&S.st[b]) = make_int4(nG, nP, 2 * nG, status);
+  S.st[b].rng = x; S.st[b].rerolls = rerolls;
+  return sd;
+}
+
 template <int NV>
 __global__ void __launch_bounds__(BB_PREP_THREADS, BB_PREP_MIN_BLOCKS) k_prepare_lanes(const __grid_constant__ BBParams S,
                                                                     const __grid_constant__ BBRunArgs A) {
-  typedef KL<NV> K;
   __shared__ unsigned long long sh_up[2];
   if (threadIdx.x < 2) sh_up[threadIdx.x] = 0ull;
   __syncthreads();
   const int b = blockIdx.x * BB_PREP_THREADS + threadIdx.x;
   unsigned upb = 0u, upp = 0u;
   if (b < A.episodes) {
-    const BBDist& D = S.dist;
-    const BBField F = S.F;
     const int ep = A.ep_base + b;
-    const int s = D.s;
     uint32_t x = rng_seed(A.seeds ? A.seeds[ep] : A.seed_base + ep);
-    uint64_t gk0[BB_PREP_S], gk1[BB_PREP_S];          // generators: lead / second monomial, second coefficient (lead coefficient 1)
-    uint32_t gc1[BB_PREP_S];
-    uint64_t L[BB_PREP_S];                             // update(): key of lcm(LM_i, LM f)
-    uint64_t rl[BB_PREP_S]; uint32_t ri[BB_PREP_S];    // reducer list G_
-    uint32_t prs[BB_PREP_P]; uint64_t plc[BB_PREP_P];  // pair list P with cached lcm keys
-    int nG = 0, nP = 0, status = BB_STATUS_EMPTY, rerolls = 0;
-    for (;;) {
-      bool ok = true;
-      for (int i = 0; i < s && ok; i++) {   // RandomBinomialIdealGenerator::next, as gen_binomial_ideal
-        const uint32_t c = D.pure ? (F.p - 1u) : (uint32_t)rng_uniform(x, 1, (int)F.p - 1);
-        int d1, d2;
-        if (D.homogeneous) d1 = d2 = rng_degree(D, x);
-        else { d1 = rng_degree(D, x); d2 = rng_degree(D, x); }
-        const int o1 = D.basis_off[d1], n1 = D.basis_off[d1 + 1] - o1, o2 = D.basis_off[d2], n2 = D.basis_off[d2 + 1] - o2;
-        ok = false;
-        for (int trials = 0; trials < 1000 && !ok; trials++) {
-          const uint64_t m1 = D.basis[o1 + rng_uniform(x, 0, n1 - 1)];
-          const uint64_t m2 = D.basis[o2 + rng_uniform(x, 0, n2 - 1)];
-          if (m1 != m2) { gk0[i] = m1 < m2 ? m1 : m2; gk1[i] = m1 < m2 ? m2 : m1; gc1[i] = c; ok = true; }
-        }
-      }
-      if (!ok) { nG = nP = 0; status = BB_STATUS_EMPTY; break; }   // the reference throws (ideals.cpp:196-197)
-      if (S.sort_input) {   // ascending lead monomial == descending key, stable (buchberger.cpp:301-302; see warp_load_ideal)
-        for (int i = 1; i < s; i++) {
-          const uint64_t a0 = gk0[i], a1 = gk1[i]; const uint32_t ac = gc1[i];
-          int j = i;
-          while (j > 0 && gk0[j - 1] < a0) { gk0[j] = gk0[j - 1]; gk1[j] = gk1[j - 1]; gc1[j] = gc1[j - 1]; j--; }
-          gk0[j] = a0; gk1[j] = a1; gc1[j] = ac;
-        }
-      }
-      nG = 0; nP = 0; status = BB_STATUS_RUNNING;
-      for (int m = 0; m < s; m++) {   // update(G, P, f) + insertion into G_, generator by generator
-        const uint64_t fk = gk0[m], fe = fk & K::ex_mask;
-        upb += (unsigned)m; upp += (unsigned)nP;
-        int kept = nP;   // old pairs that survive
-        if (S.elimination == BB_ELIM_GEBAUERMOELLER) {
-          bool ovf = false;
-          uint32_t cop = 0u;
-          for (int i = 0; i < m; i++) {
-            const uint64_t le = K::lcm_exps(gk0[i], fk);
-            const uint32_t dg = K::sum_fields(le);
-            ovf |= dg > K::dmax;
-            L[i] = le | ((uint64_t)(K::dmax - dg) << K::dshift);
-            cop |= K::coprime(gk0[i], fk) ? (1u << i) : 0u;
-          }
-          if (ovf) { status = BB_STATUS_OVERFLOW_EXPONENT; break; }
-          int w = 0;
-          for (int q = 0; q < nP; q++) {
-            const uint32_t pr = prs[q]; const uint64_t pl = plc[q];
-            const uint64_t l = pl & K::ex_mask;
-            const bool drop = K::divides(fe, l) && l != (L[pr & 0xffffu] & K::ex_mask) && l != (L[pr >> 16] & K::ex_mask);
-            if (!drop) { prs[w] = pr; plc[w] = pl; w++; }
-          }
-          nP = w; kept = w;
-          for (int i = 0; i < m; i++) {
-            const uint64_t li = L[i] & K::ex_mask;
-            bool emit = true;
-            for (int j = 0; j < m && emit; j++) {   // a third of this kernel's instructions were spent here without the early exit
-              const uint64_t lj = L[j] & K::ex_mask;
-              if (lj == li) emit = emit && !(j < i) && !((cop >> j) & 1u);
-              else emit = emit && !((((li | K::ge_mask) - lj) & K::ge_mask) == K::ge_mask);
-            }
-            if (emit) { prs[nP] = ((uint32_t)m << 16) | (uint32_t)i; plc[nP] = L[i]; nP++; }
-          }
-        } else {
-          for (int i = 0; i < m; i++) {
-            if (S.elimination == BB_ELIM_LCM && K::coprime(gk0[i], fk)) continue;
-            prs[nP] = ((uint32_t)m << 16) | (uint32_t)i; plc[nP] = K::key_from_exps(K::lcm_exps(gk0[i], fk)); nP++;
-          }
-        }
-        upp += (unsigned)(nP - kept);   // emitted pairs, counted as warp_load_ideal counts them
-        int pos = m;
-        if (S.sort_reducers) {   // after every element whose lead monomial is <= the new one (key >= new key)
-          pos = 0;
-          while (pos < m && rl[pos] >= fk) pos++;
-          for (int r = m; r > pos; r--) { rl[r] = rl[r - 1]; ri[r] = ri[r - 1]; }
-        }
-        rl[pos] = fk; ri[pos] = (uint32_t)m;
-        nG = m + 1;
-      }
-      if (status != BB_STATUS_RUNNING || nP > 0) break;
-      rerolls++;   // P came out empty: the next ideal of the same stream (buchberger.cpp:313-314)
-    }
-    if (status == BB_STATUS_RUNNING && nP == 0) status = BB_STATUS_DONE;
-    // the finished state goes to the episode's staging slot
-    unsigned char* base = S.arena + (size_t)b * S.slot_stride;
-    GHeadMem* gh = reinterpret_cast<GHeadMem*>(base + S.o_ghead);
-    uint64_t* lm = reinterpret_cast<uint64_t*>(base + S.o_lm);
-    uint64_t* rlm = reinterpret_cast<uint64_t*>(base + S.o_rlm);
-    uint32_t* ridx = reinterpret_cast<uint32_t*>(base + S.o_ridx);
-    uint32_t* pairs = reinterpret_cast<uint32_t*>(base + S.o_pairs);
-    uint64_t* plcm = reinterpret_cast<uint64_t*>(base + S.o_plcm);
-    uint64_t* tk = reinterpret_cast<uint64_t*>(base + S.o_tkey);
-    uint32_t* tc = reinterpret_cast<uint32_t*>(base + S.o_tcoef);
-    uint32_t sd = 0;
-    for (int m = 0; m < nG; m++) {
-      const uint64_t fk = gk0[m], k1 = gk1[m];
-      reinterpret_cast<uint4*>(gh + m)[0] = make_uint4((uint32_t)fk, (uint32_t)(fk >> 32), (uint32_t)k1, (uint32_t)(k1 >> 32));
-      reinterpret_cast<uint4*>(gh + m)[1] = make_uint4(1u | (gc1[m] << 16), K::deg(fk), (uint32_t)(2 * m), 2u);   // 1 / LC = 1
-      lm[m] = fk; rlm[m] = rl[m]; ridx[m] = ri[m];
-      tk[2 * m] = fk; tk[2 * m + 1] = k1; tc[2 * m] = 1u; tc[2 * m + 1] = gc1[m];
-      sd += K::deg(fk);
-    }
-    for (int q = 0; q < nP; q++) { pairs[q] = prs[q]; plcm[q] = plc[q]; }
-    *reinterpret_cast<int4*>(&S.st[b]) = make_int4(nG, nP, 2 * nG, status);
-    S.st[b].rng = x; S.st[b].rerolls = rerolls;
-    uint32_t key = (sd * (BB_LPT_BUCKETS - 1)) / (uint32_t)max(1, D.s * D.d);
+    const uint32_t sd = prepare_lane_episode<NV>(S, b, x, upb, upp);
+    uint32_t key = (sd * (BB_LPT_BUCKETS - 1)) / (uint32_t)max(1, S.dist.s * S.dist.d);
     key = key < BB_LPT_BUCKETS ? key : BB_LPT_BUCKETS - 1;
     A.cost_key[b] = (uint8_t)key;
     atomicAdd(&A.queue[BB_LPT_HIST + key], 1);
@@ -602,6 +630,73 @@ __device__ __forceinline__ void warp_copy_env(const BBParams& D, unsigned char* 
   warp_copy_words((uint32_t*)(db + D.o_plcm), (const uint32_t*)(sb + S.o_plcm), e.nP * 2);
   warp_copy_words((uint32_t*)(db + D.o_tkey), (const uint32_t*)(sb + S.o_tkey), e.nT * 2);
   warp_copy_words((uint32_t*)(db + D.o_tcoef), (const uint32_t*)(sb + S.o_tcoef), e.nT);
+}
+
+template <int NV>
+__device__ __noinline__ void warp_next_episode(const BBParams& P, int slot, unsigned long long* row) {
+  const int lane = bb_lane();
+  const BBPre* Q = P.pre;
+  if (Q && P.dist.enabled) {
+    const int cnt = Q->count[slot], hd = Q->head[slot], depth = Q->depth;
+    __syncwarp();   // every lane has read the queue words before lane 0 moves them
+    if (cnt > 0) {
+      const int idx = slot * depth + hd;
+      Env se; env_load(Q->S, idx, se);
+      unsigned char* db = bb_global(P.arena + (size_t)slot * P.slot_stride);
+      warp_copy_env(P, db, Q->S, se.base, se);
+      __syncwarp();
+      if (lane == 0) {
+        BBEnvState& T = P.st[slot];
+        const BBEnvState& U = Q->S.st[idx];
+        *reinterpret_cast<int4*>(&T) = make_int4(se.nG, se.nP, se.nT, se.status);
+        T.rng = U.rng; T.rerolls = U.rerolls;
+        T.steps = 0; T.adds = 0; T.zero = 0; T.nonzero = 0; T.truncated = 0;
+        T.trace_hash = 0; T.disc_return = 0.0; T.discount = 1.0;
+        Q->head[slot] = hd + 1 == depth ? 0 : hd + 1;
+        Q->count[slot] = cnt - 1;
+      }
+      __syncwarp();
+      return;
+    }
+  }
+  warp_reset_slot<NV>(P, slot, slot, (uint32_t)P.st[slot].rng, row);
+  if (Q && P.dist.enabled && lane == 0) Q->rng[slot] = (uint32_t)P.st[slot].rng;   // empty queue: its tail is the new position
+  __syncwarp();
+}
+
+// Tops the prefetch queues up: thread e prepares the next episodes of environment e's stream until its queue is full.
+template <int NV>
+__global__ void __launch_bounds__(BB_PREP_THREADS, BB_PREP_MIN_BLOCKS) k_prefill(const __grid_constant__ BBParams P,
+                                                                               const __grid_constant__ BBParams S) {
+  __shared__ unsigned long long sh_up[2];
+  if (threadIdx.x < 2) sh_up[threadIdx.x] = 0ull;
+  __syncthreads();
+  const int e = blockIdx.x * BB_PREP_THREADS + threadIdx.x;
+  unsigned upb = 0u, upp = 0u;
+  const BBPre* Q = P.pre;
+  if (e < P.num_envs) {
+    const int depth = Q->depth;
+    int cnt = Q->count[e];
+    if (cnt < depth) {
+      uint32_t x = Q->rng[e];
+      int tail = Q->head[e] + cnt;
+      if (tail >= depth) tail -= depth;
+      while (cnt < depth) {
+        prepare_lane_episode<NV>(S, e * depth + tail, x, upb, upp);
+        tail = tail + 1 == depth ? 0 : tail + 1;
+        cnt++;
+      }
+      Q->count[e] = cnt;
+      Q->rng[e] = x;
+    }
+  }
+  upb = __reduce_add_sync(BB_FULL, upb); upp = __reduce_add_sync(BB_FULL, upp);
+  if (bb_lane() == 0) { atomicAdd(&sh_up[0], (unsigned long long)upb); atomicAdd(&sh_up[1], (unsigned long long)upp); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (sh_up[0]) atomicAdd(&P.counters[CT_UPB], sh_up[0]);
+    if (sh_up[1]) atomicAdd(&P.counters[CT_UPP], sh_up[1]);
+  }
 }
 
 // The loop of buchberger() (buchberger.cpp:243-263) on one environment: select, step, accumulate the trace checksum and
@@ -941,7 +1036,7 @@ __global__ void __launch_bounds__(BB_THREADS, BB_ROLLOUT_MIN_BLOCKS) k_rollout(c
     Env e; env_load(P, slot, e);
     Ctr ct; ct.clear();
     if (e.status != BB_STATUS_RUNNING && P.auto_reset) {  // a slot that was never reset (or finished before the call)
-      warp_reset_slot<NV>(P, slot, slot, (uint32_t)P.st[slot].rng, row);
+      warp_next_episode<NV>(P, slot, row);
       env_load(P, slot, e);
     }
 #pragma unroll 1
@@ -965,7 +1060,7 @@ __global__ void __launch_bounds__(BB_THREADS, BB_ROLLOUT_MIN_BLOCKS) k_rollout(c
       if (fin && P.auto_reset) {  // same convention as k_step: the next state is the first state of the next episode
         env_store(P, slot, e);
         __syncwarp();
-        warp_reset_slot<NV>(P, slot, slot, (uint32_t)P.st[slot].rng, row);
+        warp_next_episode<NV>(P, slot, row);
         env_load(P, slot, e);
       }
     }
@@ -998,6 +1093,10 @@ struct BBLaunch {
   }
   static cudaError_t serve(const BBParams& P, BBMailbox* mb, unsigned long long idle_ns, cudaStream_t s) {
     k_serve<NV><<<1, 32, 0, s>>>(P, mb, idle_ns);
+    return cudaGetLastError();
+  }
+  static cudaError_t prefill(const BBParams& P, const BBParams& S, cudaStream_t s) {
+    k_prefill<NV><<<(P.num_envs + BB_PREP_THREADS - 1) / BB_PREP_THREADS, BB_PREP_THREADS, 0, s>>>(P, S);
     return cudaGetLastError();
   }
   static cudaError_t select(const BBParams& P, int strategy, int* actions, int nwarps, cudaStream_t s) {
@@ -1124,7 +1223,7 @@ struct BBLaunch {
   }
   static const BBKernelTable* table() {
     static const BBKernelTable t = {NV, KL<NV>::w, KL<NV>::dw, KL<NV>::dshift, KL<NV>::eshift,
-                                    &reset, &step, &step_obs, &serve, &select, &observe, &final_gb, &prepare, &run, &run_streams, &streams_warps_per_sm, &run_wide, &wide_ctas_per_sm, &value, &policy,
+                                    &reset, &step, &step_obs, &serve, &prefill, &select, &observe, &final_gb, &prepare, &run, &run_streams, &streams_warps_per_sm, &run_wide, &wide_ctas_per_sm, &value, &policy,
                                     &rollout,
                                     &run_blocks_per_sm};
     return &t;

@@ -17,7 +17,18 @@ __global__ void __launch_bounds__(BB_THREADS) k_seed(BBParams P, const int* seed
   int e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= P.num_envs) return;
   const uint32_t x = rng_seed(seeds ? seeds[e] : base + e);
-  if (selection) P.st[e].sel_rng = x; else P.st[e].rng = x;
+  if (selection) P.st[e].sel_rng = x;
+  else {
+    P.st[e].rng = x;
+    if (P.pre) { P.pre->count[e] = 0; P.pre->head[e] = 0; P.pre->rng[e] = x; }   // episodes prepared from the old stream are dropped
+  }
+}
+
+// (re)starts the prefetch queues from every environment's current stream position / drops the queue of one environment
+__global__ void __launch_bounds__(BB_THREADS) k_pre_flush(BBParams P, int only_env) {
+  int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= P.num_envs || (only_env >= 0 && e != only_env)) return;
+  P.pre->count[e] = 0; P.pre->head[e] = 0; P.pre->rng[e] = (uint32_t)P.st[e].rng;
 }
 
 __global__ void __launch_bounds__(BB_THREADS) k_fill_double(double* p, int n, double v) {
@@ -203,6 +214,11 @@ struct bb_handle {
   int* d_active;         // [num_envs + 1] slots of the RUNNING environments in ascending order, count in front (k_compact)
   int compaction;        // bb_set_compaction
   unsigned ticket;       // bb_step_host: sequence number the single-CTA kernel publishes in mapped host memory
+  // prefetch queues of the step API (BBPre, bb_kernels.cuh): allocated on first use when the ideals are binomial draws
+  int pre_depth;         // bb_set_prefetch: queue depth (0: off)
+  bool pre_ready;
+  int pre_calls;         // step calls since the last k_prefill
+  BBPre* d_pre; BBParams preS; std::vector<void*> pre_allocs;
   // single-environment server (k_serve): bb_step_host / bb_reset_host / bb_observe_host of a one-environment handle talk to a
   // resident warp through a mailbox in mapped pinned memory instead of launching a kernel per call
   int serve_on;          // bb_set_serve (default: on when num_envs == 1)
@@ -349,6 +365,69 @@ static int serve_call(bb_handle* h, unsigned cmd, int action, double* reward_hos
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------ prefetch queues
+#define BB_PRE_DEPTH 8        // episodes prepared ahead per environment; the queues are topped up every 4 * depth step calls
+#define BB_PRE_MIN_ENVS 64    // below this a reset inside a step is not worth a queue (and a one-environment handle is served)
+static bool layout_arena(BBParams& P);
+
+static void pre_drop(bb_handle* h) {
+  for (void* p : h->pre_allocs) cudaFree(p);
+  h->pre_allocs.clear();
+  h->pre_ready = false; h->d_pre = nullptr; h->P.pre = nullptr; h->pre_calls = 0;
+}
+
+// Allocates the queues on first use (binomial draws with at most BB_PREP_S generators: what k_prefill's code prepares).
+static int pre_setup(bb_handle* h, cudaStream_t s) {
+  const BBParams& P = h->P;
+  const bool want = h->pre_depth > 0 && P.dist.enabled && P.dist.kind == 0 && P.dist.s <= BB_PREP_S;
+  if (!want) { if (h->pre_ready) { CK(cudaDeviceSynchronize()); pre_drop(h); } return 0; }
+  if (h->pre_ready) return 0;
+  BBParams S = P;
+  S.pre = nullptr;
+  S.max_basis = P.max_gens;
+  S.max_pairs = std::max(1, P.max_gens * (P.max_gens - 1) / 2);
+  S.max_terms = P.max_gen_terms;
+  S.max_poly_terms = 1;
+  if (!layout_arena(S)) return fail(h, "prefetch: staging slot too large");
+  const size_t n = (size_t)P.num_envs * h->pre_depth, N = (size_t)P.num_envs;
+  auto alloc = [&](void** out, size_t bytes) {
+    cudaError_t e = cudaMalloc(out, bytes + 16);
+    if (e == cudaSuccess) { h->pre_allocs.push_back(*out); e = cudaMemset(*out, 0, bytes + 16); }
+    return e;
+  };
+  BBPre Q;
+  CK(alloc((void**)&S.arena, n * S.slot_stride));
+  CK(alloc((void**)&S.st, n * sizeof(BBEnvState)));
+  S.num_envs = (int)n;
+  S.in_key = nullptr; S.in_coef = nullptr; S.in_off = nullptr; S.in_np = nullptr;   // the lane code keeps the ideal in registers
+  CK(alloc((void**)&Q.count, N * sizeof(int)));
+  CK(alloc((void**)&Q.head, N * sizeof(int)));
+  CK(alloc((void**)&Q.rng, N * sizeof(unsigned)));
+  CK(alloc((void**)&h->d_pre, sizeof(BBPre)));
+  Q.S = S; Q.depth = h->pre_depth;
+  CK(cudaMemcpy(h->d_pre, &Q, sizeof Q, cudaMemcpyHostToDevice));
+  CK(cudaDeviceSynchronize());
+  h->preS = S;
+  h->P.pre = h->d_pre;
+  h->pre_ready = true;
+  k_pre_flush<<<(P.num_envs + BB_THREADS - 1) / BB_THREADS, BB_THREADS, 0, s>>>(h->P, -1);
+  CK(cudaGetLastError());
+  h->pre_calls = 4 * h->pre_depth;   // fill at once
+  return 0;
+}
+
+// Before a call that may reset environments: the queues exist and are topped up every pre_depth calls (`now`: at once).
+static int pre_refill(bb_handle* h, cudaStream_t s, bool now) {
+  int rc = pre_setup(h, s);
+  if (rc < 0 || !h->pre_ready) return rc;
+  // an environment takes at most one episode per step call, and on the binomial distributions an episode lasts tens of steps:
+  // a queue of `depth` outlasts 4 * depth calls except for runs of very short episodes (which then reset through the generator)
+  if (!now && ++h->pre_calls < 4 * h->pre_depth) return 0;
+  h->pre_calls = 0;
+  CK(h->K->prefill(h->P, h->preS, s));
+  return 0;
+}
+
 #define ENTER(h)                                                                                      \
   do {                                                                                                \
     CK(cudaSetDevice((h)->cfg.device));                                                               \
@@ -396,6 +475,7 @@ void bb_destroy(bb_handle* h) {
   for (int t = 0; t < 3; t++) if (h->ev_t[t]) cudaEventDestroy(h->ev_t[t]);
   if (h->h_seeds) cudaFreeHost(h->h_seeds);
   for (void* p : h->fork_allocs) cudaFree(p);
+  for (void* p : h->pre_allocs) cudaFree(p);
   if (h->host_stage) cudaFreeHost(h->host_stage);
   if (h->dev_stage) cudaFree(h->dev_stage);
   delete h;
@@ -435,6 +515,7 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
   h->ev_t[0] = h->ev_t[1] = h->ev_t[2] = nullptr;
   h->episode_offset = 0; h->nstaged = 0; h->d_seeds = nullptr; h->h_seeds = nullptr; h->ev_seeds = nullptr;
   h->d_active = nullptr; h->compaction = 1; h->ticket = 0u;
+  h->pre_depth = cfg->num_envs >= BB_PRE_MIN_ENVS ? BB_PRE_DEPTH : 0; h->pre_ready = false; h->pre_calls = 0; h->d_pre = nullptr;
   h->serve_on = cfg->num_envs == 1 ? 1 : 0; h->serving = false; h->mb = nullptr; h->mb_bytes = 0; h->serve_seq = 0u;
   h->serve_stream = nullptr; h->ev_serve = nullptr;
   h->fork_cap = 0; h->fork_arena = nullptr; h->fork_st = nullptr;
@@ -577,6 +658,7 @@ static int set_distribution_impl(bb_handle* h, int kind, int d, int s, double la
   if (!cp.empty()) CK(cudaMemcpy(d_cp, cp.data(), cp.size() * sizeof(double), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_basis, basis.data(), basis.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
   CK(cudaMemcpy(d_off, off.data(), off.size() * sizeof(int), cudaMemcpyHostToDevice));
+  if (h->pre_ready) { CK(cudaDeviceSynchronize()); pre_drop(h); }
   P.dist.enabled = 1; P.dist.d = d; P.dist.s = s; P.dist.homogeneous = homogeneous ? 1 : 0; P.dist.pure = pure ? 1 : 0;
   P.dist.ncp = (int)cp.size(); P.dist.cp = d_cp; P.dist.basis = d_basis; P.dist.basis_off = d_off;
   P.dist.kind = kind; P.dist.lm_thr = kind == 1 ? std::exp(-lam) : 0.0;
@@ -665,6 +747,7 @@ int bb_set_ideals(bb_handle* h, const int32_t* env_ids, int count, const int32_t
     h->staged[(size_t)env] = 1;
   }
   P.dist.enabled = 0;
+  if (h->pre_ready) { CK(cudaDeviceSynchronize()); pre_drop(h); }
   // bb_run replays staged ideal (e mod nstaged): the staged environments must be a prefix 0 .. nstaged - 1
   h->nstaged = 0;
   while (h->nstaged < P.num_envs && !h->staged.empty() && h->staged[(size_t)h->nstaged]) h->nstaged++;
@@ -674,6 +757,7 @@ int bb_set_ideals(bb_handle* h, const int32_t* env_ids, int count, const int32_t
 int bb_reset(bb_handle* h, const uint8_t* mask_dev, void* stream) {
   if (!h) return -1;
   ENTER(h);
+  { int rc = pre_refill(h, (cudaStream_t)stream, true); if (rc < 0) return rc; }
   CK(h->K->reset(h->P, mask_dev, h->P.num_envs, (cudaStream_t)stream));
   return 0;
 }
@@ -695,7 +779,9 @@ int bb_step(bb_handle* h, const int32_t* actions_dev, double* reward_dev, uint8_
   if (!actions_dev) return fail(h, "bb_step: null actions");
   ENTER(h);
   const int* active = nullptr;
-  int rc = compact_for_step(h, (cudaStream_t)stream, &active);
+  int rc = h->P.auto_reset ? pre_refill(h, (cudaStream_t)stream, false) : 0;
+  if (rc < 0) return rc;
+  rc = compact_for_step(h, (cudaStream_t)stream, &active);
   if (rc < 0) return rc;
   CK(h->K->step(h->P, actions_dev, reward_dev, done_dev, active, h->P.num_envs, (cudaStream_t)stream));
   return 0;
@@ -713,7 +799,8 @@ static int host_call(bb_handle* h, int do_step, const int32_t* actions_host, dou
     return serve_call(h, do_step == 1 ? BB_CMD_STEP : (do_step == 2 ? BB_CMD_RESET : BB_CMD_OBSERVE), do_step == 1 ? actions_host[0] : 0,
                       reward_host, done_host, obs_host, lengths_host, pmax, pad, s);
   if (h->serving) { int rc = serve_stop(h); if (rc < 0) return rc; }
-  if (do_step == 2) { CK(h->K->reset(P, nullptr, P.num_envs, s)); do_step = 0; }
+  if (do_step == 2 || (do_step == 1 && P.auto_reset)) { int rc = pre_refill(h, s, do_step == 2); if (rc < 0) return rc; }
+  if (do_step == 2) { CK(h->K->reset(h->P, nullptr, P.num_envs, s)); do_step = 0; }
   // staging layout: reward f64[N] | obs i32[N * pmax * cols] | lengths i32[N] | actions i32[N] | done u8[N] | ticket u32
   const size_t o_rew = 0, o_obs = o_rew + 8 * N, o_len = o_obs + (obs_host ? 4 * N * (size_t)pmax * P.cols : 0);
   const size_t o_act = o_len + 4 * N, o_done = o_act + 4 * N, o_tick = (o_done + N + 15) & ~(size_t)15, bytes = o_tick + 16;
@@ -782,7 +869,9 @@ int bb_step_observe(bb_handle* h, const int32_t* actions_dev, double* reward_dev
   if (!actions_dev || pmax < 0 || (obs_dev && pmax < 1)) return fail(h, "bb_step_observe: bad argument");
   ENTER(h);
   const int* active = nullptr;
-  int rc = compact_for_step(h, (cudaStream_t)stream, &active);
+  int rc = h->P.auto_reset ? pre_refill(h, (cudaStream_t)stream, false) : 0;
+  if (rc < 0) return rc;
+  rc = compact_for_step(h, (cudaStream_t)stream, &active);
   if (rc < 0) return rc;
   CK(h->K->step_obs(h->P, actions_dev, 0, reward_dev, done_dev, obs_dev, lengths_dev, pmax, 1, 1, active, nullptr, 0u,
                     h->P.num_envs, (cudaStream_t)stream));
@@ -856,6 +945,7 @@ static int stage_params(bb_handle* h, int which, int batch, BBParams& S) {
   const BBParams& P = h->P;
   bb_handle::Stage& T = h->stage[which];
   S = P;
+  S.pre = nullptr;
   S.max_basis = P.max_gens;
   S.max_pairs = std::max(1, P.max_gens * (P.max_gens - 1) / 2);
   S.max_terms = P.max_gen_terms;
@@ -1169,6 +1259,10 @@ int bb_copy_env(bb_handle* dst, int dst_env, bb_handle* src, int src_env, void* 
   CK(cudaMemcpyAsync(D.in_off + (size_t)dst_env * (D.max_gens + 1), S.in_off + (size_t)src_env * (S.max_gens + 1),
                      sizeof(int) * (S.max_gens + 1), cudaMemcpyDeviceToDevice, s));
   CK(cudaMemcpyAsync(D.in_np + dst_env, S.in_np + src_env, sizeof(int), cudaMemcpyDeviceToDevice, s));
+  if (dst->pre_ready) {   // the destination's prepared episodes belonged to its old stream
+    k_pre_flush<<<(D.num_envs + BB_THREADS - 1) / BB_THREADS, BB_THREADS, 0, s>>>(D, dst_env);
+    CK(cudaGetLastError());
+  }
   return 0;
 }
 
@@ -1180,6 +1274,15 @@ int bb_discount(bb_handle* h, int N, int T, const double* x_dev, const uint8_t* 
   ENTER(h);
   k_discount<<<(N + BB_THREADS - 1) / BB_THREADS, BB_THREADS, 0, (cudaStream_t)stream>>>(N, T, x_dev, done_dev, gam, out_dev);
   CK(cudaGetLastError());
+  return 0;
+}
+
+int bb_set_prefetch(bb_handle* h, int depth) {
+  if (!h) return -1;
+  if (depth < 0 || depth > 64) return fail(h, "bb_set_prefetch: depth must be in 0..64");
+  ENTER(h);
+  if (h->pre_ready) { CK(cudaDeviceSynchronize()); pre_drop(h); }
+  h->pre_depth = depth;
   return 0;
 }
 
@@ -1296,6 +1399,7 @@ int bb_rollout(bb_handle* h, int hidden, const float* W1_dev, const float* b1_de
   A.W.greedy = greedy ? 1 : 0;
   A.T = T; A.counter0 = counter0; A.actions = actions_dev; A.logp = logprob_dev; A.reward = reward_dev; A.done = done_dev;
   A.lengths = lengths_dev; A.obs = obs_dev; A.pmax = pmax;
+  if (h->P.auto_reset) { rc = pre_refill(h, (cudaStream_t)stream, true); if (rc < 0) return rc; }
   CK(h->K->rollout(h->P, A, h->P.num_envs, (cudaStream_t)stream));
   return 0;
 }

@@ -289,6 +289,15 @@ int bb_copy_env(bb_handle* dst, int dst_env, bb_handle* src, int src_env, void* 
  * round trip, and no idle slots. */
 int bb_set_auto_reset(bb_handle* h, int on);
 
+/* bb_set_prefetch: a reset inside a step kernel (auto-reset) is one warp's detour through the ideal generator and s update()
+ * calls -- 38 us during which the rest of the launch waits for that warp.  With prefetch every environment keeps a queue of
+ * `depth` initial states of its NEXT episodes, prepared in bulk from the environment's own ideal stream (in stream order: what
+ * an environment draws is unchanged) by one thread per environment; bb_reset / auto-reset then take the head of the queue with
+ * a copy, and bb_step / bb_step_observe top the queues up every 4 * depth calls, bb_reset and bb_rollout at every call.  Applies
+ * to binomial distributions with at most 16 generators.  depth 0 turns it off; default 8 for handles of at least 64
+ * environments.  bb_seed, bb_copy_env and a change of the distribution drop the queues concerned. */
+int bb_set_prefetch(bb_handle* h, int depth);
+
 /* bb_set_max_episode_length: bb_step / bb_step_observe / bb_step_host / bb_rollout cut an episode once it has MORE than
  * `max_steps` steps (the loop of pg.Agent.run_episode, pg.py:470-471: `if episode_length > max_episode_length: break`;
  * train.py's default is 500): the environment goes to BB_STATUS_TRUNCATED, reports done = 1 and is reset by auto-reset

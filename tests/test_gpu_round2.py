@@ -507,3 +507,68 @@ def test_single_environment_server_equals_launch_per_call(torch_cuda):
         assert len(s) > 0   # auto-reset: the state after a finished episode is the next episode's first state
     assert dones >= 8       # cut after max + 1 = 5 steps (or finished earlier)
     assert wide.engine.status_summary()["running"] == 1
+
+
+def test_prefetched_resets_draw_the_same_episodes(torch_cuda):
+    """bb_set_prefetch: resets served from per-environment queues of prepared episodes (filled by one thread per environment
+    from the environment's own stream) give the states, rewards, done flags and records of resets through the generator --
+    across auto-reset, explicit masked resets, re-seeding of some environments mid-run, a copy into the batch and queues that
+    run empty (depth 1) -- and the reference's first states."""
+    torch = torch_cuda
+    from deepgroebner_b200 import LeadMonomialsEnv
+    orc = best_oracle()
+    N = 192
+    envs = []
+    for depth in (8, 1, 0):
+        env = LeadMonomialsEnv("3-20-10-weighted", k=2, num_envs=N, pmax=96)
+        env.engine.set_prefetch(depth)
+        env.engine.set_auto_reset(True)
+        env.seed(np.arange(70, 70 + N))
+        envs.append(env)
+    states = [env.reset() for env in envs]
+    ref = orc.lm_env("3-20-10-weighted", k=2)
+    for e in (0, 17, N - 1):
+        ref.seed(70 + e)
+        r = ref.reset()
+        assert np.array_equal(states[0][0][e, :len(r)].cpu().numpy(), r)
+    rng = np.random.default_rng(9)
+    donor = LeadMonomialsEnv("3-20-10-weighted", k=2, num_envs=N, pmax=96)
+    donor.seed(np.arange(900, 900 + N))
+    donor.reset()
+    for step in range(150):
+        for a, b in zip(states[0], states[1]):
+            assert torch.equal(a, b), step
+        for a, b in zip(states[0], states[2]):
+            assert torch.equal(a, b), step
+        lens = states[0][1].cpu().numpy()
+        acts = torch.as_tensor(np.array([0 if step % 3 else rng.integers(l) for l in lens], dtype=np.int32), device="cuda")
+        outs = []
+        for i, env in enumerate(envs):
+            if step == 40:      # new streams for a third of the environments: their prepared episodes are dropped
+                seeds = np.arange(70, 70 + N)
+                seeds[::3] += 5000
+                env.seed(seeds)
+            if step == 60:      # an explicit reset of some environments
+                mask = torch.zeros(N, dtype=torch.uint8, device="cuda")
+                mask[5:50] = 1
+                env.engine.reset(mask)
+            if step == 80:      # a foreign environment copied in: its stream comes with it
+                env.engine.copy_env(7, donor.engine, 3)
+            if step in (60, 80):
+                states[i] = env.engine.observe(96)
+            (obs, lengths), reward, done, _ = env.step(acts)
+            outs.append((reward, done))
+            states[i] = (obs, lengths)
+        if step in (60, 80):
+            continue   # the action tensor was built for the states before the reset / copy
+        for a, b in zip(outs[0], outs[1]):
+            assert torch.equal(a, b), step
+        for a, b in zip(outs[0], outs[2]):
+            assert torch.equal(a, b), step
+    sa, sb, sc = (env.engine.stats() for env in envs)
+    for f in ("steps", "additions", "status", "trace_hash", "nbasis", "rerolls"):
+        assert np.array_equal(sa[f], sb[f]) and np.array_equal(sa[f], sc[f]), f
+    ca, cc = envs[0].engine.counters(), envs[2].engine.counters()
+    for k in ("env_steps", "additions", "episodes", "lms_scanned"):
+        assert ca[k] == cc[k], k
+    assert ca["episodes"] > N   # plenty of auto-resets happened
