@@ -359,9 +359,10 @@ def extra_step_api(torch, dev, local, flush):
     c = eng.counters(reset=True)
     assert c["env_steps"] == N * G * 10, (c["env_steps"], N * G * 10)
     return {"value": N * G * 10 / (tot / 1e3), "unit": UNIT, "eager_launches": eager, "environments": N, "pmax": PMAX,
-            "calls_per_graph": G, "kernels_per_call": 2, "obs_bytes_per_call": int(obs.numel() * 4),
-            "what": "bb_select(degree) + bb_step_observe (step + auto-reset + state matrix + |P| + reward + done) per call, "
-                    "device-timed, L2 flushed between graph replays"}
+            "calls_per_graph": G, "kernels_per_call": 3, "obs_bytes_per_call": int(obs.numel() * 4),
+            "what": "bb_select(degree) + bb_step_observe (k_prefill: the environments' queues of prepared next episodes, topped up "
+                    "every 32nd call; k_step_obs: step + auto-reset + state matrix + |P| + reward + done) per call, device-timed, "
+                    "L2 flushed between graph replays"}
 
 
 def extra_dropin_n1(seconds=2.0):

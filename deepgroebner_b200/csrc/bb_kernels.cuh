@@ -64,6 +64,8 @@ struct BBPre {
   int* count;        // [num_envs] episodes waiting
   int* head;         // [num_envs] position of the first one
   unsigned* rng;     // [num_envs] stream state after the LAST prepared episode (where k_prefill goes on)
+  int* calls;        // [1] step calls so far (ticked by k_step / k_step_obs): k_prefill, launched with every call, works every
+                     // `period`-th one only -- the decision is taken on the device so that it survives CUDA-graph replay
 };
 
 struct BBEpisodeAcc {
@@ -122,7 +124,7 @@ struct BBKernelTable {
                           int32_t* lengths, int pmax, int pad, int do_step, const int* active, unsigned* ready, unsigned ticket,
                           int nwarps, cudaStream_t);
   cudaError_t (*serve)(const BBParams&, BBMailbox* mb, unsigned long long idle_ns, cudaStream_t);
-  cudaError_t (*prefill)(const BBParams&, const BBParams& stage, cudaStream_t);
+  cudaError_t (*prefill)(const BBParams&, const BBParams& stage, int period, cudaStream_t);
   cudaError_t (*select)(const BBParams&, int strategy, int* actions, int nwarps, cudaStream_t);
   cudaError_t (*observe)(const BBParams&, int32_t* obs, int32_t* lengths, int pmax, int nwarps, cudaStream_t);
   cudaError_t (*final_gb)(const BBParams&, int slot, int* ok_out, cudaStream_t);
@@ -237,6 +239,7 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_step(const __grid
       warp_next_episode<NV>(P, slot, row);
     }
   }
+  if (P.pre && blockIdx.x == 0 && threadIdx.x == 0) (*P.pre->calls)++;   // one step call more (see BBPre::calls)
   counters_flush(P, sh);
 }
 
@@ -284,6 +287,7 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_step_obs(const __
     if (lengths && bb_lane() == 0) lengths[slot] = e.nP;
     ct.spill(row);
   }
+  if (do_step && P.pre && blockIdx.x == 0 && threadIdx.x == 0) (*P.pre->calls)++;   // one step call more (see BBPre::calls)
   // single-CTA launches of bb_step_host: the results sit in mapped host memory; the host waits for this word instead of a
   // stream synchronisation (every thread's writes are made visible system-wide before thread 0 publishes the ticket)
   if (ready) __threadfence_system();
@@ -667,7 +671,8 @@ __device__ __noinline__ void warp_next_episode(const BBParams& P, int slot, unsi
 // Tops the prefetch queues up: thread e prepares the next episodes of environment e's stream until its queue is full.
 template <int NV>
 __global__ void __launch_bounds__(BB_PREP_THREADS, BB_PREP_MIN_BLOCKS) k_prefill(const __grid_constant__ BBParams P,
-                                                                               const __grid_constant__ BBParams S) {
+                                                                               const __grid_constant__ BBParams S, int period) {
+  if (period > 0 && (*P.pre->calls % period) != 0) return;   // nobody writes the counter while this kernel runs
   __shared__ unsigned long long sh_up[2];
   if (threadIdx.x < 2) sh_up[threadIdx.x] = 0ull;
   __syncthreads();
@@ -1095,8 +1100,8 @@ struct BBLaunch {
     k_serve<NV><<<1, 32, 0, s>>>(P, mb, idle_ns);
     return cudaGetLastError();
   }
-  static cudaError_t prefill(const BBParams& P, const BBParams& S, cudaStream_t s) {
-    k_prefill<NV><<<(P.num_envs + BB_PREP_THREADS - 1) / BB_PREP_THREADS, BB_PREP_THREADS, 0, s>>>(P, S);
+  static cudaError_t prefill(const BBParams& P, const BBParams& S, int period, cudaStream_t s) {
+    k_prefill<NV><<<(P.num_envs + BB_PREP_THREADS - 1) / BB_PREP_THREADS, BB_PREP_THREADS, 0, s>>>(P, S, period);
     return cudaGetLastError();
   }
   static cudaError_t select(const BBParams& P, int strategy, int* actions, int nwarps, cudaStream_t s) {

@@ -217,7 +217,6 @@ struct bb_handle {
   // prefetch queues of the step API (BBPre, bb_kernels.cuh): allocated on first use when the ideals are binomial draws
   int pre_depth;         // bb_set_prefetch: queue depth (0: off)
   bool pre_ready;
-  int pre_calls;         // step calls since the last k_prefill
   BBPre* d_pre; BBParams preS; std::vector<void*> pre_allocs;
   // single-environment server (k_serve): bb_step_host / bb_reset_host / bb_observe_host of a one-environment handle talk to a
   // resident warp through a mailbox in mapped pinned memory instead of launching a kernel per call
@@ -373,7 +372,7 @@ static bool layout_arena(BBParams& P);
 static void pre_drop(bb_handle* h) {
   for (void* p : h->pre_allocs) cudaFree(p);
   h->pre_allocs.clear();
-  h->pre_ready = false; h->d_pre = nullptr; h->P.pre = nullptr; h->pre_calls = 0;
+  h->pre_ready = false; h->d_pre = nullptr; h->P.pre = nullptr;
 }
 
 // Allocates the queues on first use (binomial draws with at most BB_PREP_S generators: what k_prefill's code prepares).
@@ -403,6 +402,7 @@ static int pre_setup(bb_handle* h, cudaStream_t s) {
   CK(alloc((void**)&Q.count, N * sizeof(int)));
   CK(alloc((void**)&Q.head, N * sizeof(int)));
   CK(alloc((void**)&Q.rng, N * sizeof(unsigned)));
+  CK(alloc((void**)&Q.calls, sizeof(int)));
   CK(alloc((void**)&h->d_pre, sizeof(BBPre)));
   Q.S = S; Q.depth = h->pre_depth;
   CK(cudaMemcpy(h->d_pre, &Q, sizeof Q, cudaMemcpyHostToDevice));
@@ -412,19 +412,17 @@ static int pre_setup(bb_handle* h, cudaStream_t s) {
   h->pre_ready = true;
   k_pre_flush<<<(P.num_envs + BB_THREADS - 1) / BB_THREADS, BB_THREADS, 0, s>>>(h->P, -1);
   CK(cudaGetLastError());
-  h->pre_calls = 4 * h->pre_depth;   // fill at once
   return 0;
 }
 
-// Before a call that may reset environments: the queues exist and are topped up every pre_depth calls (`now`: at once).
+// Before a call that may reset environments: the queues exist, and k_prefill goes with the call.  `now`: it tops the queues
+// up; else it does so on every (4 * depth)-th step call by the device's own count (an environment takes at most one episode
+// per step call, and on the binomial distributions an episode lasts tens of steps: a queue of `depth` outlasts 4 * depth
+// calls except for runs of very short episodes, which then reset through the generator).
 static int pre_refill(bb_handle* h, cudaStream_t s, bool now) {
   int rc = pre_setup(h, s);
   if (rc < 0 || !h->pre_ready) return rc;
-  // an environment takes at most one episode per step call, and on the binomial distributions an episode lasts tens of steps:
-  // a queue of `depth` outlasts 4 * depth calls except for runs of very short episodes (which then reset through the generator)
-  if (!now && ++h->pre_calls < 4 * h->pre_depth) return 0;
-  h->pre_calls = 0;
-  CK(h->K->prefill(h->P, h->preS, s));
+  CK(h->K->prefill(h->P, h->preS, now ? 0 : 4 * h->pre_depth, s));
   return 0;
 }
 
@@ -515,7 +513,7 @@ int bb_create(const bb_config* cfg, bb_handle** out) {
   h->ev_t[0] = h->ev_t[1] = h->ev_t[2] = nullptr;
   h->episode_offset = 0; h->nstaged = 0; h->d_seeds = nullptr; h->h_seeds = nullptr; h->ev_seeds = nullptr;
   h->d_active = nullptr; h->compaction = 1; h->ticket = 0u;
-  h->pre_depth = cfg->num_envs >= BB_PRE_MIN_ENVS ? BB_PRE_DEPTH : 0; h->pre_ready = false; h->pre_calls = 0; h->d_pre = nullptr;
+  h->pre_depth = cfg->num_envs >= BB_PRE_MIN_ENVS ? BB_PRE_DEPTH : 0; h->pre_ready = false; h->d_pre = nullptr;
   h->serve_on = cfg->num_envs == 1 ? 1 : 0; h->serving = false; h->mb = nullptr; h->mb_bytes = 0; h->serve_seq = 0u;
   h->serve_stream = nullptr; h->ev_serve = nullptr;
   h->fork_cap = 0; h->fork_arena = nullptr; h->fork_st = nullptr;
