@@ -14,6 +14,7 @@
 #include "bb_policy.cuh"
 #include "bb_streams.cuh"
 #include "bb_wide.cuh"
+#include "bb_rstreams.cuh"
 
 #ifndef BB_WARPS
 #define BB_WARPS 8
@@ -43,7 +44,8 @@ struct BBRunArgs {
   int32_t* trace;
   int trace_eps, trace_cap;
   int prepare_by_warp;  // 1: k_prepare (one warp per episode) even where k_prepare_lanes applies (tests compare the two)
-  int stream_kmax;   // k_run_streams: streams per step kept in shared memory (BBS_KMAX; less under bb_set_wide(2 / 3))
+  int stream_kmax;   // stream slots a step's reduction may use (BBS_KMAX; less under bb_set_wide(2 / 3 / 5 / 6)), see bb_streams.cuh
+  int stream_regs;   // k_run_wide: how many of them are register slots (BBW_THREADS; 8 under bb_set_wide(7))
   int* queue;        // [0]: next queue position; [BB_LPT_HIST .. +BB_LPT_BUCKETS): histogram of the cost keys of the batch, then as many cursors
   int* order;        // [episodes] queue position -> episode of the batch, longest predicted first (k_order)
   uint8_t* cost_key; // [episodes] predicted-cost bucket of each episode of the batch (k_prepare)
@@ -710,13 +712,13 @@ __global__ void __launch_bounds__(BB_PREP_THREADS, BB_PREP_MIN_BLOCKS) k_prefill
 template <int NV, bool STREAMS>
 __device__ __forceinline__ void run_episode(const BBParams& P, Env& e, int strategy, int max_steps, double gamma,
                                             BBEpisodeAcc& acc, Ctr& ct, int& steps, int& adds, int4* trace, int trace_cap,
-                                            StreamState* ws, WarpStreams* st) {
+                                            RegStreams* ws) {
   const int lane = bb_lane();
   while (e.status == BB_STATUS_RUNNING && (max_steps == 0 || steps < max_steps)) {
     const int prow = warp_select<NV>(P, e, strategy, &acc.sel_rng);
     uint32_t pr;
     int a;
-    if (STREAMS) a = warp_step_streams<NV>(P, e, *ws, *st, prow, pr, ct);
+    if (STREAMS) a = warp_step_rstreams<NV>(P, e, *ws, prow, pr, ct);
     else a = warp_step<NV>(P, e, prow, pr, ct);
     if (lane == 0) {
       const int pi = pr & 0xffffu, pj = pr >> 16;
@@ -734,7 +736,7 @@ __device__ __forceinline__ void run_episode(const BBParams& P, Env& e, int strat
 // prepared initial state from the staging arena, select/step until P is empty (or max_steps), write the episode
 // record, repeat.  WARPS = warps per CTA.
 template <int NV, bool STREAMS, int WARPS>
-__device__ __forceinline__ void run_worker(const BBParams& P, const BBParams& S, const BBRunArgs& A, WarpStreams* st) {
+__device__ __forceinline__ void run_worker(const BBParams& P, const BBParams& S, const BBRunArgs& A) {
   __shared__ unsigned long long sh[WARPS][CT_COUNT];
   __shared__ BBEpisodeAcc acc_sh[WARPS];  // per-episode accumulators only lane 0 touches: kept out of registers
   hot_init(P);
@@ -744,8 +746,8 @@ __device__ __forceinline__ void run_worker(const BBParams& P, const BBParams& S,
   BBEpisodeAcc& acc = acc_sh[threadIdx.x >> 5];
   const int slot = (blockIdx.x * (WARPS * 32) + threadIdx.x) >> 5;
   const int lane = bb_lane();
-  StreamState ws;
-  ws.clear(); ws.kmax = A.stream_kmax; ws.cz = 0;
+  RegStreams ws;
+  ws.clear(); ws.kmax = A.stream_kmax < BBR_ROWS * 32 ? A.stream_kmax : BBR_ROWS * 32; ws.cz = 0;
   if (slot < P.num_envs) {
     Ctr ct; ct.clear();
     for (;;) {
@@ -767,7 +769,7 @@ __device__ __forceinline__ void run_worker(const BBParams& P, const BBParams& S,
       __syncwarp();
       run_episode<NV, STREAMS>(P, e, A.strategy, A.max_steps, A.gamma, acc, ct, steps, adds,
                                (A.trace && ep < A.trace_eps) ? reinterpret_cast<int4*>(A.trace) + (size_t)ep * A.trace_cap : nullptr,
-                               A.trace_cap, &ws, st);
+                               A.trace_cap, &ws);
       const int nonzero = e.nG - g_start, zero = steps - nonzero;
       env_store(P, slot, e);
       __syncwarp();
@@ -817,7 +819,7 @@ template <int NV>
 __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_run(const __grid_constant__ BBParams P,
                                                                   const __grid_constant__ BBParams S,
                                                                   const __grid_constant__ BBRunArgs A) {
-  run_worker<NV, false, BB_WARPS>(P, S, A, nullptr);
+  run_worker<NV, false, BB_WARPS>(P, S, A);
 }
 
 // The same runner for long polynomials: reduce() by streams, the warp's stream table in dynamic shared memory.
@@ -831,8 +833,7 @@ template <int NV>
 __global__ void __launch_bounds__(BBS_WARPS * 32, BBS_MIN_CTAS) k_run_streams(const __grid_constant__ BBParams P,
                                                                              const __grid_constant__ BBParams S,
                                                                              const __grid_constant__ BBRunArgs A) {
-  extern __shared__ __align__(16) unsigned char streams_smem[];
-  run_worker<NV, true, BBS_WARPS>(P, S, A, reinterpret_cast<WarpStreams*>(streams_smem) + (threadIdx.x >> 5));
+  run_worker<NV, true, BBS_WARPS>(P, S, A);
 }
 
 // block-strided copy of n 32-bit words
@@ -860,8 +861,10 @@ __global__ void __launch_bounds__(BBW_THREADS, BBW_MIN_CTAS) k_run_wide(const __
   __syncthreads();
   unsigned long long* row = sh[0];
   Ctr ct; ct.clear();
-  StreamState ws;
-  ws.clear(); ws.kmax = A.stream_kmax < BBS_KMAX ? A.stream_kmax : BBW_KMAX; ws.cz = 0;
+  WideState ws;
+  ws.clear(); ws.cz = 0;
+  ws.regs = A.stream_regs < BBW_THREADS ? (A.stream_regs < 2 ? 2 : A.stream_regs) : BBW_THREADS;
+  ws.tcap = A.stream_kmax - ws.regs < 0 ? 0 : (A.stream_kmax - ws.regs < BBW_KMAX - BBW_THREADS ? A.stream_kmax - ws.regs : BBW_KMAX - BBW_THREADS);
   int half = 0;
   for (;;) {
     if (tid == 0) { int q = atomicAdd(A.queue, 1); next_b = q < A.episodes ? A.order[q] : -1; }
@@ -991,7 +994,7 @@ __global__ void __launch_bounds__(BB_THREADS, BB_MIN_BLOCKS) k_value(const __gri
         if (lane == 0) { acc.th = 0ull; acc.ret = 0.0; acc.disc = 1.0; acc.sel_rng = rng_seed(seed); }
         __syncwarp();
         int steps = 0, adds = 0;
-        run_episode<NV, false>(F, e, strategy, A.max_steps, A.gamma, acc, ct, steps, adds, nullptr, 0, nullptr, nullptr);
+        run_episode<NV, false>(F, e, strategy, A.max_steps, A.gamma, acc, ct, steps, adds, nullptr, 0, nullptr);
         __syncwarp();
         ret = acc.ret;
         if (e.status != BB_STATUS_DONE && !(A.max_steps && steps >= A.max_steps)) ret = __longlong_as_double(0x7ff8000000000000LL);  // fault: NaN
@@ -1145,7 +1148,7 @@ struct BBLaunch {
     k_run<NV><<<grid_for_warps(nwarps), BB_THREADS, 0, s>>>(P, S, A);
     return cudaGetLastError();
   }
-  static size_t streams_smem() { return sizeof(WarpStreams) * (size_t)BBS_WARPS; }
+  static size_t streams_smem() { return 0; }   // every stream lives in registers (bb_rstreams.cuh)
   static int streams_warps_per_sm() {
     const size_t sm = streams_smem();
     if (cudaFuncSetAttribute(k_run_streams<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm) != cudaSuccess) return 0;

@@ -1,14 +1,22 @@
-// bb_wide.cuh -- the stream reducer of bb_streams.cuh run by a whole CTA (BBW_WARPS warps) on ONE environment, sm_100a.
+// bb_wide.cuh -- the stream reducer (bb_streams.cuh) run by a whole CTA (BBW_WARPS warps) on ONE environment, sm_100a.
 //
-// Why both: a cyclic-6 launch is as long as its longest episode (697 000 dependent additions in the longest of 1024
-// seeded-Random episodes), so what decides it is the latency of one ROUND (one lead term of the dividend: divisor search
-// + advance of the streams at it + next lead term, see bb_streams.cuh).  A single warp runs a round as ~380 dependent
-// instructions; a CTA splits the divisor search and the streams over its warps -- thread t owns stream t in REGISTERS
-// (streams beyond BBW_THREADS live in shared memory), one slice of the reducer lead monomials per thread -- and pays one
-// block barrier per round: every warp reduces its part (three REDUX for the 64-bit minimum head key and the coefficient
-// sum at it, one for the first divisor), writes a 16-byte record, and after the barrier every warp folds the records
-// with the same four reductions (one record per lane).  Same algorithm, same results (the tests compare both with the
-// materialising runner), shorter chain; the warp version is the one to use when there are many more episodes than SMs.
+// A cyclic-6 launch is as long as its longest episode (697 000 dependent additions in the longest of 1024 seeded-Random
+// episodes), so what decides it is the latency of one ROUND (one lead term of the dividend: divisor search + advance of
+// the streams at it + next lead term).  A CTA splits the divisor search and the streams over its threads -- thread t owns
+// the stream in REGISTER slot t and reducer lead monomial t of G_ (also in a register, with its basis index) -- and pays
+// one block barrier per round: every warp reduces its part (three REDUX for the 64-bit minimum head key and the
+// coefficient sum at it, one for the first divisor, one ballot for its first free slot), writes a 16-byte record, and
+// after the barrier every warp folds the records with the same reductions (one record per lane).  Measured per dependent
+// operation on B200 (tools/ub/lat.cu): REDUX.MIN 22 cycles, REDUX.ADD 47, the three-REDUX fold 108, STS + BAR + LDS 58.
+//
+// A new stream takes the first free register slot of the block (the fold reports it), so the register slots hold the LIVE
+// streams; only when all BBW_THREADS are live does a stream go to the shared-memory table behind them (append only;
+// scanned by its owner thread each round), and only when that is full too is h consolidated (bb_streams.cuh).
+// bb_set_wide(2 / 3): 6 / 48 register slots and no table (consolidations every few additions); bb_set_wide(7): 8 register
+// slots and the whole table (the shared-memory path on every step).
+//
+// Every routine that touches the per-thread state is inlined: a call would take the state's address and move it from
+// registers to local memory (LDL / STL on the chain of every round: 1.35 -> 1.06 us per addition when that was removed).
 #pragma once
 #include "bb_streams.cuh"
 
@@ -20,12 +28,14 @@
 #define BBW_MIN_CTAS 2
 #endif
 #ifndef BBW_KMAX
-#define BBW_KMAX 1024           // streams of one step: BBW_THREADS in registers, the rest in shared memory
+#define BBW_KMAX 1024           // stream slots of one step: BBW_THREADS in registers, the rest in shared memory
 #endif
 static_assert(BBW_KMAX % BBW_THREADS == 0 && BBW_KMAX > BBW_THREADS, "whole rows of streams");
 static_assert(BBW_WARPS <= 32, "one record per lane in the fold");
+static_assert(BBW_KMAX / BBW_THREADS <= 8, "per-thread coefficient sums of a round stay below 2^19, a warp's below 2^24");
+#define BBW_NOFREE 0x3fu
 
-struct WideStreams {             // dynamic shared memory: streams BBW_THREADS .. BBW_KMAX - 1 (entry i at index i - BBW_THREADS)
+struct WideStreams {             // dynamic shared memory: the table behind the register slots (entry i belongs to thread i % BBW_THREADS)
   uint64_t key[BBW_KMAX - BBW_THREADS];
   uint64_t adj[BBW_KMAX - BBW_THREADS];
   uint64_t pkey[BBW_KMAX - BBW_THREADS];
@@ -37,34 +47,62 @@ struct WideStreams {             // dynamic shared memory: streams BBW_THREADS .
 };
 
 struct WideShared {
-  __align__(16) uint4 wrec[2][BBW_WARPS];   // per-warp round results, double-buffered: (min head key lo, hi, coefficient sum, first divisor position)
+  // per-warp round results, double-buffered: (min head key lo, hi, coefficient sum | first free lane << 24,
+  // first divisor: position in G_ << 16 | basis index)
+  __align__(16) uint4 wrec[2][BBW_WARPS];
   int row;                  // the pair row warp 0 selected
   long long upd;            // result of warp_add_basis
 };
 
-// One round by the block; contract as streams_round.  `half` = which half of sh.wrec this round writes.
+// Block-uniform state of a step's reduction plus per-thread registers; every member is a scalar so that the whole record
+// lives in registers.
+struct WideState {
+  int T;                    // entries of the shared-memory table in use (append only until a consolidation)
+  int tcap;                 // entries of the table that may be used
+  int regs;                 // register slots that may be used (threads 0 .. regs - 1)
+  int cz;                   // scratch half the next consolidation writes
+  // per thread: the stream in this thread's register slot.  k0 all ones: free.
+  uint64_t k0, adj0, pk0; uint32_t c0, nc0, pc0, p0, e0;
+  // per thread: reducer `tid` of G_: lead monomial (all ones: absent) and (position << 16) | basis index (BBS_NONE: absent)
+  uint64_t rl0; uint32_t rc0;
+  // per thread: the raw term behind the head of table entry pend_i, loaded but not yet stored to st.pkey / st.pcoef
+  int pend_i; uint64_t pend_k; uint32_t pend_c;
+  uint32_t bad;             // per thread: a produced key overflowed its exponent fields
+  __device__ __forceinline__ void clear() {
+    T = 0; k0 = ~0ull; adj0 = pk0 = 0ull; c0 = nc0 = pc0 = p0 = e0 = 0u; pend_i = -1; pend_k = 0ull; pend_c = 0u; bad = 0u;
+  }
+};
+
+// One round by the block: the streams whose head is M advance (M all ones: nothing to consume) and the next lead term of h
+// comes back as (M2, S2): M2 all ones when h is exhausted, S2 in [0, p) (0: the monomial cancelled).  search: also M's
+// first divisor in G_, best = (position << 16) | basis index or BBS_NONE.  freet: the first thread whose register slot is
+// free after the advance, -1 if none.  `half` = which half of sh.wrec this round writes.
 template <int NV>
-__device__ __forceinline__ void wide_round(WideShared& sh, int& half, StreamState& ws, WideStreams& st, const BBField F,
-                                           const uint64_t M, const bool consume, const bool search, const uint64_t* rlm,
-                                           const uint32_t* ridx, const int nR, const bool sorted, const uint64_t* tk,
-                                           const uint32_t* tc, uint64_t& M2, uint32_t& S2, int& found, uint32_t& fidx) {
+__device__ __forceinline__ void wide_round(WideShared& sh, int& half, WideState& ws, WideStreams& st, const BBField F,
+                                           const uint64_t M, const bool search, const uint64_t* rlm, const uint32_t* ridx,
+                                           const int nR, const bool sorted, const uint64_t* tk, const uint32_t* tc,
+                                           uint64_t& M2, uint32_t& S2, uint32_t& best, int& freet) {
   typedef KL<NV> K;
   const int tid = threadIdx.x, lane = bb_lane();
-  // (a) this thread's slice of the reducer lead monomials; sorted: stop at the first whose lead monomial exceeds M
-  uint32_t best = BBS_NONE;
+  // (a) this thread's slice of G_: reducer tid from its register, reducers tid + BBW_THREADS, ... from memory (sorted: G_
+  // ascends in lead monomial, so nothing at or after the first key below M's can divide)
+  uint32_t cand = BBS_NONE;
   if (search) {
-    const uint64_t stop = sorted ? M : 0ull;
     const uint64_t mg = (M & K::ex_mask) | K::ge_mask;
+    if (((mg - (ws.rl0 & K::ex_mask)) & K::ge_mask) == K::ge_mask) cand = ws.rc0;   // absent: rc0 = BBS_NONE
+    else if (nR > BBW_THREADS) {
+      const uint64_t stop = sorted ? M : 0ull;
 #pragma unroll 1
-    for (int r = tid; r < nR; r += BBW_THREADS) {
-      const uint64_t l = rlm[r];
-      if (l < stop) break;
-      if (((mg - (l & K::ex_mask)) & K::ge_mask) == K::ge_mask) { best = (uint32_t)r; break; }
+      for (int r = tid + BBW_THREADS; r < nR && ws.rl0 >= stop; r += BBW_THREADS) {
+        const uint64_t l = rlm[r];
+        if (l < stop) break;
+        if (((mg - (l & K::ex_mask)) & K::ge_mask) == K::ge_mask) { cand = ((uint32_t)r << 16) | ridx[r]; break; }
+      }
     }
   }
-  // (b) this thread's streams: stream tid in registers, streams tid + BBW_THREADS, ... in shared memory
+  // (b) this thread's streams: its register slot, then its entries of the table
   uint64_t mk = ws.k0;
-  if (consume && mk == M) {
+  if (mk == M) {
     if (ws.p0 < ws.e0) {
       mk = ws.pk0 + ws.adj0;
       ws.c0 = bbf_mulmod(F, ws.pc0, ws.nc0);
@@ -77,85 +115,91 @@ __device__ __forceinline__ void wide_round(WideShared& sh, int& half, StreamStat
     ws.k0 = mk;
   }
   uint32_t ms = ws.c0;
+  if (ws.T > 0) {
 #pragma unroll 1
-  for (int i = tid; i < ws.K - BBW_THREADS; i += BBW_THREADS) {
-    uint64_t k = st.key[i];
-    if (consume && k == M) {
-      const uint32_t p = st.ptr[i];
-      if (p < st.end[i]) {
-        uint64_t kr; uint32_t cr;
-        if (ws.pend_i == i) { kr = ws.pend_k; cr = ws.pend_c; ws.pend_i = -1; }
-        else { kr = st.pkey[i]; cr = st.pcoef[i]; }
-        k = kr + st.adj[i];
-        const uint32_t c = bbf_mulmod(F, cr, st.nc[i]);
-        if (k & K::g_all) ws.bad = 1u;
-        st.key[i] = k; st.coef[i] = c; st.ptr[i] = p + 1u;
-        if (p + 1u < st.end[i]) {
-          if (ws.pend_i >= 0) { st.pkey[ws.pend_i] = ws.pend_k; st.pcoef[ws.pend_i] = ws.pend_c; }
-          ws.pend_i = i; ws.pend_k = tk[p + 1u]; ws.pend_c = tc[p + 1u];
+    for (int i = tid; i < ws.T; i += BBW_THREADS) {
+      uint64_t k = st.key[i];
+      if (k == M && k != ~0ull) {
+        const uint32_t p = st.ptr[i];
+        if (p < st.end[i]) {
+          uint64_t kr; uint32_t cr;
+          if (ws.pend_i == i) { kr = ws.pend_k; cr = ws.pend_c; ws.pend_i = -1; }
+          else { kr = st.pkey[i]; cr = st.pcoef[i]; }
+          k = kr + st.adj[i];
+          const uint32_t c = bbf_mulmod(F, cr, st.nc[i]);
+          if (k & K::g_all) ws.bad = 1u;
+          st.key[i] = k; st.coef[i] = c; st.ptr[i] = p + 1u;
+          if (p + 1u < st.end[i]) {
+            if (ws.pend_i >= 0) { st.pkey[ws.pend_i] = ws.pend_k; st.pcoef[ws.pend_i] = ws.pend_c; }
+            ws.pend_i = i; ws.pend_k = tk[p + 1u]; ws.pend_c = tc[p + 1u];
+          }
+        } else {
+          k = ~0ull; st.key[i] = k;
         }
-      } else {
-        k = ~0ull; st.key[i] = k;
       }
+      const uint32_t c = st.coef[i];
+      if (k < mk) { mk = k; ms = c; } else if (k == mk) ms += c;
     }
-    const uint32_t c = st.coef[i];
-    if (k < mk) { mk = k; ms = c; } else if (k == mk) ms += c;
   }
-  // (c) warp: the first divisor of the warp's slices, then the 64-bit minimum through two 32-bit reductions and the
-  // coefficient sum at it.  The divisor's basis index is fetched here (one uniform load per warp, in flight during the
-  // three reductions) and travels with its position in one word, position on top: the fold's minimum still picks the first
-  // divisor and the block knows its head record's address one dependent load earlier.
+  // (c) warp: the first divisor of the warp's slices, its first free register slot, the 64-bit minimum through two 32-bit
+  // reductions and the coefficient sum at it
   {
-    best = __reduce_min_sync(BB_FULL, best);
-    if (best != BBS_NONE) best = (best << 16) | ridx[best];   // positions and basis indices are below 2^16 (max_basis <= 65535)
+    const uint32_t wb = __reduce_min_sync(BB_FULL, cand);
+    const uint32_t fm = __ballot_sync(BB_FULL, ws.k0 == ~0ull && tid < ws.regs);
     const uint32_t hi = __reduce_min_sync(BB_FULL, (uint32_t)(mk >> 32));
     const uint32_t lo = __reduce_min_sync(BB_FULL, (uint32_t)(mk >> 32) == hi ? (uint32_t)mk : 0xffffffffu);
     const uint32_t wsum = __reduce_add_sync(BB_FULL, ((uint32_t)(mk >> 32) == hi && (uint32_t)mk == lo) ? ms : 0u);
-    if (lane == 0) sh.wrec[half][tid >> 5] = make_uint4(lo, hi, wsum, best);
+    const uint32_t fl = fm ? (uint32_t)(__ffs((int)fm) - 1) : BBW_NOFREE;
+    if (lane == 0) sh.wrec[half][tid >> 5] = make_uint4(lo, hi, wsum | (fl << 24), wb);
   }
   __syncthreads();
   // (d) every warp folds the warps' records, one per lane, with the same reductions
   {
-    uint4 v = make_uint4(0xffffffffu, 0xffffffffu, 0u, BBS_NONE);
+    uint4 v = make_uint4(0xffffffffu, 0xffffffffu, BBW_NOFREE << 24, BBS_NONE);
     if (lane < BBW_WARPS) v = sh.wrec[half][lane];
     const uint32_t hi = __reduce_min_sync(BB_FULL, v.y);
     const uint32_t lo = __reduce_min_sync(BB_FULL, v.y == hi ? v.x : 0xffffffffu);
-    const uint32_t gs = __reduce_add_sync(BB_FULL, (v.y == hi && v.x == lo) ? v.z : 0u);   // < BBW_KMAX values below 2^16
+    const uint32_t gs = __reduce_add_sync(BB_FULL, (v.y == hi && v.x == lo) ? (v.z & 0xffffffu) : 0u);   // < 2^27
     best = __reduce_min_sync(BB_FULL, v.w);
+    const uint32_t fr = __reduce_min_sync(BB_FULL, (v.z >> 24) != BBW_NOFREE ? ((uint32_t)lane << 5) | (v.z >> 24) : BBS_NONE);
     M2 = ((uint64_t)hi << 32) | lo; S2 = bbf_reduce(F, gs);
+    freet = fr == BBS_NONE ? -1 : (int)fr;
   }
   half ^= 1;
-  found = best == BBS_NONE ? -1 : (int)(best >> 16);
-  fidx = best == BBS_NONE ? 0u : (best & 0xffffu);
 }
 
-// Opens stream ws.K (owner: thread K % BBW_THREADS); as stream_open.
-__device__ __forceinline__ void wide_open(StreamState& ws, WideStreams& st, uint64_t hk, uint32_t hc, uint64_t adj, uint32_t nc,
-                                          uint32_t next, uint32_t end, const uint64_t* tk, const uint32_t* tc) {
-  const int i = ws.K;
-  if ((int)threadIdx.x == (i & (BBW_THREADS - 1))) {
-    if (i < BBW_THREADS) {
+// Opens a stream in register slot `target` (>= 0), else as the next entry of the table (the caller has checked the room):
+// head (hk, hc) already scaled, multiplier (adj, nc), the terms behind the head at [next, end).
+__device__ __forceinline__ void wide_open(WideState& ws, WideStreams& st, int target, uint64_t hk, uint32_t hc, uint64_t adj,
+                                          uint32_t nc, uint32_t next, uint32_t end, const uint64_t* tk, const uint32_t* tc) {
+  if (target >= 0) {
+    if ((int)threadIdx.x == target) {
       ws.k0 = hk; ws.c0 = hc; ws.adj0 = adj; ws.nc0 = nc; ws.p0 = next; ws.e0 = end;
       if (next < end) { ws.pk0 = tk[next]; ws.pc0 = tc[next]; }
-    } else {
-      const int j = i - BBW_THREADS;
+    }
+  } else {
+    const int j = ws.T;
+    if ((int)threadIdx.x == (j & (BBW_THREADS - 1))) {
       st.key[j] = hk; st.coef[j] = hc; st.adj[j] = adj; st.nc[j] = nc; st.ptr[j] = next; st.end[j] = end;
       if (next < end) {
         if (ws.pend_i >= 0) { st.pkey[ws.pend_i] = ws.pend_k; st.pcoef[ws.pend_i] = ws.pend_c; }
         ws.pend_i = j; ws.pend_k = tk[next]; ws.pend_c = tc[next];
       }
     }
+    ws.T = j + 1;
   }
-  ws.K = i + 1;
 }
 
-// Consolidation, as streams_consolidate: h from (M, S) on goes to scratch half ws.cz in order, one stream over it remains.
+// Consolidation (bb_streams.cuh): h from (M, S) on goes to scratch half ws.cz in order, one stream over it (register slot
+// 0) remains and (M, S) becomes its head, M all ones if nothing is left.  Returns the number of terms, -1 if they do not
+// fit `cap`.
 template <int NV>
-__device__ __noinline__ int wide_consolidate(WideShared& sh, int& half, StreamState& ws, WideStreams& st, const BBField F,
-                                             uint64_t& M, uint32_t& S, uint64_t* tk, uint32_t* tc, uint32_t sbase, int cap) {
+__device__ __forceinline__ int wide_consolidate(WideShared& sh, int& half, WideState& ws, WideStreams& st, const BBField F,
+                                                uint64_t& M, uint32_t& S, uint64_t* tk, uint32_t* tc, uint32_t sbase, int cap) {
   const uint32_t base = sbase + (uint32_t)(ws.cz * cap);
   int t = 0;
   uint64_t m = M, fm = ~0ull; uint32_t s = S, fs = 0u;
+#pragma unroll 1
   while (m != ~0ull) {
     if (s != 0u) {
       if (t >= cap) return -1;
@@ -163,22 +207,23 @@ __device__ __noinline__ int wide_consolidate(WideShared& sh, int& half, StreamSt
       if (threadIdx.x == 0) { tk[base + t] = m; tc[base + t] = s; }
       t++;
     }
-    int found; uint32_t fidx;
-    wide_round<NV>(sh, half, ws, st, F, m, true, false, nullptr, nullptr, 0, false, tk, tc, m, s, found, fidx);
+    uint32_t best; int freet;
+    wide_round<NV>(sh, half, ws, st, F, m, false, nullptr, nullptr, 0, false, tk, tc, m, s, best, freet);
   }
-  ws.pend_i = -1;
-  ws.K = 0;
-  ws.k0 = ~0ull;
+  ws.pend_i = -1;   // every stream is exhausted: every slot is free
+  ws.T = 0;
   ws.cz ^= 1;
   M = fm; S = fs;
-  __syncthreads();   // thread 0's list before thread 0 (the owner of stream 0) reads it back
-  if (t > 0) wide_open(ws, st, fm, fs, 0ull, 1u, base + 1u, base + (uint32_t)t, tk, tc);
+  __syncthreads();   // thread 0's list before thread 0 (the owner of slot 0) reads it back
+  if (t > 0) wide_open(ws, st, 0, fm, fs, 0ull, 1u, base + 1u, base + (uint32_t)t, tk, tc);
   return t;
 }
 
-// reduce(spoly(G[i], G[j]), G_) by the block; contract as warp_reduce_streams.
+// reduce(spoly(G[i], G[j]), G_) (buchberger.cpp:18-49) by the block for the pair heads (hf, hg) and gamma = the key of the
+// pair's lcm.  The remainder goes to (rk, rc) [cap rcap]; returns its length or a negative BB_STATUS_* on a fault; `steps`
+// = reductions, `sug` = the sugar of the result (polynomials.cpp:150, 198).
 template <int NV>
-__device__ __forceinline__ int block_reduce_streams(const BBParams& P, const Env& e, WideShared& sh, int& half, StreamState& ws,
+__device__ __forceinline__ int block_reduce_streams(const BBParams& P, const Env& e, WideShared& sh, int& half, WideState& ws,
                                                     WideStreams& st, const GHead hf, const GHead hg, const uint64_t gam, int& sug,
                                                     int& steps, uint64_t* rk, uint32_t* rc, int rcap, Ctr& ct) {
   typedef KL<NV> K;
@@ -190,57 +235,62 @@ __device__ __forceinline__ int block_reduce_streams(const BBParams& P, const Env
   const uint32_t* ridx = ENV_PTR(uint32_t, e, P, o_ridx);
   const int nR = e.nG;
   const bool sorted = P.sort_reducers != 0;
+  const int tid = threadIdx.x;
   int rlen = 0;
   steps = 0;
   ws.clear();
+  ws.rl0 = tid < nR ? rlm[tid] : ~0ull;                                   // G_ changes only between reductions
+  ws.rc0 = tid < nR ? (((uint32_t)tid << 16) | ridx[tid]) : BBS_NONE;     // positions and basis indices are below 2^16
+  // s = (gamma / LT f) tail(f) - (gamma / LT g) tail(g): the lead terms cancel exactly (buchberger.cpp:18-21); two streams
+  // whose heads come from the head records, in register slots 0 and 1 (ws.regs >= 2)
+  int opened = 0;
   if (hf.len > 1u) {
     const uint64_t adj = gam - hf.lm, k = hf.k1 + adj;
     if (k & K::g_all) return -BB_STATUS_OVERFLOW_EXPONENT;
-    wide_open(ws, st, k, bbf_mulmod(F, hf.c1, hf.invlc), adj, hf.invlc, hf.off + 2u, hf.off + hf.len, tk, tc);
+    wide_open(ws, st, opened++, k, bbf_mulmod(F, hf.c1, hf.invlc), adj, hf.invlc, hf.off + 2u, hf.off + hf.len, tk, tc);
   }
   if (hg.len > 1u) {
     const uint64_t adj = gam - hg.lm, k = hg.k1 + adj;
     const uint32_t nc = F.p - hg.invlc;
     if (k & K::g_all) return -BB_STATUS_OVERFLOW_EXPONENT;
-    wide_open(ws, st, k, bbf_mulmod(F, hg.c1, nc), adj, nc, hg.off + 2u, hg.off + hg.len, tk, tc);
+    wide_open(ws, st, opened++, k, bbf_mulmod(F, hg.c1, nc), adj, nc, hg.off + 2u, hg.off + hg.len, tk, tc);
   }
-  uint64_t M; uint32_t S, fidx; int found;
-  wide_round<NV>(sh, half, ws, st, F, ~0ull, false, false, rlm, ridx, nR, sorted, tk, tc, M, S, found, fidx);
+  uint64_t M = ~0ull; uint32_t S = 0u;   // pseudo lead term: consumes nothing, is no term of h
 #pragma unroll 1
-  while (M != ~0ull) {
-    uint64_t M2; uint32_t S2;
-    if (S == 0u) {   // the monomial cancelled: it is not a term of h
-      wide_round<NV>(sh, half, ws, st, F, M, true, false, rlm, ridx, nR, sorted, tk, tc, M2, S2, found, fidx);
-      M = M2; S = S2;
-      continue;
-    }
-    wide_round<NV>(sh, half, ws, st, F, M, true, true, rlm, ridx, nR, sorted, tk, tc, M2, S2, found, fidx);
-    ct.lms += (found >= 0) ? (unsigned)(found + 1) : (unsigned)nR;
-    if (found >= 0) {   // h <- h - (LT h / LT f) f: the lead terms cancel, f's tail becomes a stream
-      const GHead f = load_head(gh + fidx);
-      const uint32_t c = bbf_mulmod(F, S, f.invlc);
-      const uint32_t nc = F.p - c;              // c != 0
-      const uint64_t adj = M - f.lm;            // key(LM h / LM f) - bias
-      const int sf = (int)f.sug + (int)(uint32_t)(f.lm >> K::dshift) - (int)(uint32_t)(M >> K::dshift);
-      sug = sf > sug ? sf : sug;
-      ct.tread += f.len;
-      steps++;
-      if (f.len > 1u) {
-        if (ws.K >= ws.kmax && wide_consolidate<NV>(sh, half, ws, st, F, M2, S2, tk, tc, (uint32_t)P.max_terms, P.max_poly_terms) < 0)
-          return -BB_STATUS_OVERFLOW_SCRATCH;
-        const uint64_t k = f.k1 + adj;
-        const uint32_t ck = bbf_mulmod(F, f.c1, nc);
-        if (k & K::g_all) return -BB_STATUS_OVERFLOW_EXPONENT;
-        wide_open(ws, st, k, ck, adj, nc, f.off + 2u, f.off + f.len, tk, tc);
-        if (k < M2) { M2 = k; S2 = ck; } else if (k == M2) S2 = bbf_addmod(F, S2, ck);
+  do {
+    uint64_t M2; uint32_t S2, best; int freet;
+    wide_round<NV>(sh, half, ws, st, F, M, S != 0u, rlm, ridx, nR, sorted, tk, tc, M2, S2, best, freet);
+    if (S != 0u) {   // S == 0: the monomial cancelled, it is not a term of h
+      ct.lms += (best != BBS_NONE) ? (best >> 16) + 1u : (unsigned)nR;
+      if (best != BBS_NONE) {   // h <- h - (LT h / LT f) f: the lead terms cancel, f's tail becomes a stream
+        const GHead f = load_head(gh + (best & 0xffffu));
+        const uint32_t c = bbf_mulmod(F, S, f.invlc);
+        const uint32_t nc = F.p - c;              // c != 0
+        const uint64_t adj = M - f.lm;            // key(LM h / LM f) - bias
+        const int sf = (int)f.sug + (int)(uint32_t)(f.lm >> K::dshift) - (int)(uint32_t)(M >> K::dshift);
+        sug = sf > sug ? sf : sug;
+        ct.tread += f.len;
+        steps++;
+        if (f.len > 1u) {
+          if (freet < 0 && ws.T >= ws.tcap) {   // no register slot, no room in the table
+            const int t = wide_consolidate<NV>(sh, half, ws, st, F, M2, S2, tk, tc, (uint32_t)P.max_terms, P.max_poly_terms);
+            if (t < 0) return -BB_STATUS_OVERFLOW_SCRATCH;
+            freet = t > 0 ? 1 : 0;
+          }
+          const uint64_t k = f.k1 + adj;
+          const uint32_t ck = bbf_mulmod(F, f.c1, nc);
+          if (k & K::g_all) return -BB_STATUS_OVERFLOW_EXPONENT;
+          wide_open(ws, st, freet, k, ck, adj, nc, f.off + 2u, f.off + f.len, tk, tc);
+          if (k < M2) { M2 = k; S2 = ck; } else if (k == M2) S2 = bbf_addmod(F, S2, ck);
+        }
+      } else {            // no divisor: the lead term moves to the remainder
+        if (rlen >= rcap) return -BB_STATUS_OVERFLOW_TERMS;
+        if (tid == 0) { rk[rlen] = M; rc[rlen] = S; }
+        rlen++; ct.moves++;
       }
-    } else {            // no divisor: the lead term moves to the remainder
-      if (rlen >= rcap) return -BB_STATUS_OVERFLOW_TERMS;
-      if (threadIdx.x == 0) { rk[rlen] = M; rc[rlen] = S; }
-      rlen++; ct.moves++;
     }
     M = M2; S = S2;
-  }
+  } while (M != ~0ull);
   if (__syncthreads_or(ws.bad != 0u)) return -BB_STATUS_OVERFLOW_EXPONENT;   // also: thread 0's remainder before warp 0 reads it
   return rlen;
 }
@@ -267,7 +317,7 @@ __device__ __forceinline__ void block_take_pair(const BBParams& P, const Env& e,
 // `strategy`).  e and every scalar below are block-uniform.  Pair selection and update() (Gebauer-Moeller) are the warp
 // routines of bb_device.cuh run by warp 0.  Returns the number of polynomial additions; `pair` receives (j << 16) | i.
 template <int NV>
-__device__ __forceinline__ int block_step(const BBParams& P, Env& e, WideShared& sh, int& half, StreamState& ws, WideStreams& st,
+__device__ __forceinline__ int block_step(const BBParams& P, Env& e, WideShared& sh, int& half, WideState& ws, WideStreams& st,
                                           int strategy, uint32_t* sel_rng, uint32_t& pair, Ctr& ct) {
   typedef KL<NV> K;
   const int tid = threadIdx.x;

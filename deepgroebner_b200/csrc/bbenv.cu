@@ -1046,7 +1046,7 @@ int bb_run(bb_handle* h, int strategy, int episodes, int seed_base, const int32_
   // environment (bb_wide.cuh: the shortest chain of additions); mode 4: one warp per environment
   const bool streams = h->wide_mode != 0 && (h->wide_mode >= 1 || h->P.max_poly_terms >= 256);
   int wide_ctas = 0;
-  if (streams && h->wide_mode == 4) {
+  if (streams && h->wide_mode >= 4 && h->wide_mode <= 6) {
     if (h->K->streams_warps_per_sm() <= 0) return fail(h, "bb_run: the stream runner does not fit this device");
   } else if (streams) {
     wide_ctas = h->K->wide_ctas_per_sm() * h->sm_count;
@@ -1137,10 +1137,11 @@ int bb_run(bb_handle* h, int strategy, int episodes, int seed_base, const int32_
     A.strategy = strategy; A.sel_seed_base = sel_seed_base; A.sel_seed_stride = h->sel_seed_stride;
     A.max_steps = max_steps; A.gamma = gamma; A.compute_gb = compute_gb; A.out = stats_dev;
     A.trace = trace_dev; A.trace_eps = trace_dev ? trace_episodes : 0; A.trace_cap = trace_cap;
-    A.stream_kmax = h->wide_mode == 2 ? 6 : (h->wide_mode == 3 ? 48 : BBS_KMAX);
+    A.stream_kmax = (h->wide_mode == 2 || h->wide_mode == 5) ? 6 : ((h->wide_mode == 3 || h->wide_mode == 6) ? 48 : BBS_KMAX);
+    A.stream_regs = h->wide_mode == 7 ? 8 : A.stream_kmax;
     if (bi > 0) CK(cudaStreamWaitEvent(s, h->stage[which].prepared, 0));
     const int workers = std::min(h->P.num_envs, count);
-    if (streams && h->wide_mode == 4) CK(h->K->run_streams(PB, S, A, workers, s));
+    if (streams && h->wide_mode >= 4 && h->wide_mode <= 6) CK(h->K->run_streams(PB, S, A, workers, s));
     else if (streams) CK(h->K->run_wide(PB, S, A, std::min(workers, wide_ctas), s));
     else CK(h->K->run(PB, S, A, workers, s));
     CK(cudaEventRecord(h->stage[which].consumed, s));
@@ -1338,7 +1339,7 @@ int bb_set_obs_nvars(bb_handle* h, int n_obs) {
 
 int bb_set_wide(bb_handle* h, int mode) {
   if (!h) return -1;
-  if (mode < -1 || mode > 4) return fail(h, "bb_set_wide: mode must be -1 (auto), 0 (off), 1 (on), 2 or 3 (on, small stream tables), 4 (on, one warp per environment)");
+  if (mode < -1 || mode > 7) return fail(h, "bb_set_wide: mode must be -1 (auto), 0 (off), 1 (on), 2 or 3 (on, 6 / 48 stream slots), 4 (on, one warp per environment), 5 or 6 (as 4, 6 / 48 stream slots), 7 (as 1, 8 register slots + the shared-memory table)");
   h->wide_mode = mode;
   return 0;
 }

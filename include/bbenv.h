@@ -260,11 +260,13 @@ int bb_set_prepare_mode(bb_handle* h, int by_warp);
 /* bb_set_wide: how bb_run's episode runner reduces.  0: the dividend is materialised (warp-cooperative merges, built
  * for the 2-term polynomials of binomial ideals); 1: the dividend is a set of streams into the term arena, one round per
  * lead term and O(1) work per addition (built for long polynomials, e.g. cyclic-n), run by one CTA per environment
- * (shortest chain of additions: a cyclic-6 launch lasts as long as its longest episode); 4: the same by one warp per
- * environment (more environments in flight); -1 (default): 1 when the capacities are sized for long polynomials
- * (max_poly_terms >= 256), else 0; 2 / 3: as 1 with the stream table capped at 6 / 48 entries so that tests reach the
- * consolidation of the dividend into a scratch list.  Every mode produces bit-identical episodes; this is a performance
- * switch.  Of the bb_counters, terms_read / terms_written count |h| per addition only where h is materialised (mode 0). */
+ * (shortest chain of additions: a cyclic-6 launch lasts as long as its longest episode; 256 streams in registers, 768
+ * more in shared memory); 4: the same by one warp per environment with 128 streams in registers; -1 (default): 1 when
+ * the capacities are sized for long polynomials (max_poly_terms >= 256), else 0.  Test modes: 2 / 3 as 1 and 5 / 6 as 4
+ * with 6 / 48 stream slots (consolidation of the dividend into a scratch list every few additions); 7 as 1 with 8
+ * register slots (the shared-memory table on every step).  Every mode produces bit-identical episodes; this is a
+ * performance switch.  Of the bb_counters, terms_read / terms_written count |h| per addition only where h is
+ * materialised (mode 0). */
 int bb_set_wide(bb_handle* h, int mode);
 
 /* bb_value: BuchbergerEnv::value(strategy, gamma) (buchberger.cpp:332-351) for every environment at once:

@@ -497,16 +497,17 @@ def test_sharded_blocks_equal_one_run(torch_cuda):
 def test_cta_per_environment_runner_equals_warp_runner(torch_cuda, name, strategy):
     """bb_set_wide: reduce() by streams (bb_streams.cuh: the dividend is never materialised, one round per lead term) and
     the materialising runner (warp_merge / warp_reduce) produce bit-identical episode records -- pair sequence checksum,
-    additions, final basis, reduced Groebner basis, discounted return -- and traffic counters.  Modes 2 / 3 cap the stream
-    table at 6 / 48 entries: consolidation of the dividend into a scratch list every few additions.  Modes 1-3 run the
-    streams with one CTA per environment (bb_wide.cuh), mode 4 with one warp per environment (bb_streams.cuh, whose
-    garbage collection of exhausted streams runs at every 32nd stream).  terms_read / terms_written (|h| per addition)
-    exist only where h is materialised."""
+    additions, final basis, reduced Groebner basis, discounted return -- and traffic counters.  Modes 1-3 and 7 run the
+    streams with one CTA per environment (bb_wide.cuh): 1 = 256 register slots + the shared-memory table, 2 / 3 = 6 / 48
+    slots (consolidation of the dividend into a scratch list every few additions), 7 = 8 register slots + the table (the
+    shared-memory path on every step).  Modes 4-6 run one warp per environment with every stream in registers
+    (bb_rstreams.cuh): 128 / 6 / 48 slots.  terms_read / terms_written (|h| per addition) exist only where h is
+    materialised."""
     from deepgroebner_b200.buchberger import BuchbergerEngine
     episodes = 12
     eng = BuchbergerEngine(name, num_envs=episodes, **({} if name.startswith("cyclic") else dict(max_poly_terms=256)))
     out = {}
-    for mode in (0, 1, 2, 3, 4):
+    for mode in (0, 1, 2, 3, 4, 5, 6, 7):
         eng.set_wide(mode)
         eng.counters(reset=True)
         stats, trace = eng.run_episodes(strategy, episodes=episodes, seed_base=7, compute_gb=True, selection_seed=99,
@@ -514,7 +515,7 @@ def test_cta_per_environment_runner_equals_warp_runner(torch_cuda, name, strateg
         out[mode] = (stats, trace, eng.counters(reset=True))
     s0, t0, c0 = out[0]
     assert (s0["status"] == 2).all()
-    for mode in (1, 2, 3, 4):
+    for mode in (1, 2, 3, 4, 5, 6, 7):
         s1, t1, c1 = out[mode]
         for f in s0.dtype.names:
             assert np.array_equal(s0[f], s1[f]), (mode, f)
