@@ -47,7 +47,7 @@ struct WideStreams {             // dynamic shared memory: the table behind the 
 };
 
 struct WideShared {
-  // per-warp round results, double-buffered: (min head key lo, hi, coefficient sum | first free lane << 24,
+  // per-warp round results, double-buffered: (min head key lo, hi, coefficient sum of the consumed monomial | first free lane << 24,
   // first divisor: position in G_ << 16 | basis index)
   __align__(16) uint4 wrec[2][BBW_WARPS];
   int row;                  // the pair row warp 0 selected
@@ -73,15 +73,17 @@ struct WideState {
   }
 };
 
-// One round by the block: the streams whose head is M advance (M all ones: nothing to consume) and the next lead term of h
-// comes back as (M2, S2): M2 all ones when h is exhausted, S2 in [0, p) (0: the monomial cancelled).  search: also M's
-// first divisor in G_, best = (position << 16) | basis index or BBS_NONE.  freet: the first thread whose register slot is
-// free after the advance, -1 if none.  `half` = which half of sh.wrec this round writes.
+// One round by the block for the lead monomial M of h: S = the sum of the coefficients of the heads that carry M, in
+// [0, p) (0: the monomial cancelled; taken HERE, when M is consumed, so that the sum's reduction is off the chain of the
+// 64-bit minimum: REDUX.ADD costs as much as both REDUX.MIN), those streams advance, and M2 = the next lead monomial, all
+// ones when h is exhausted.  M all ones (the pseudo lead monomial a reduction starts from): nothing is consumed, S is
+// meaningless.  search: also M's first divisor in G_, best = (position << 16) | basis index or BBS_NONE.  freet: the
+// first thread whose register slot is free after the advance, -1 if none.  `half` = which half of sh.wrec this round writes.
 template <int NV>
 __device__ __forceinline__ void wide_round(WideShared& sh, int& half, WideState& ws, WideStreams& st, const BBField F,
                                            const uint64_t M, const bool search, const uint64_t* rlm, const uint32_t* ridx,
                                            const int nR, const bool sorted, const uint64_t* tk, const uint32_t* tc,
-                                           uint64_t& M2, uint32_t& S2, uint32_t& best, int& freet) {
+                                           uint32_t& S, uint64_t& M2, uint32_t& best, int& freet) {
   typedef KL<NV> K;
   const int tid = threadIdx.x, lane = bb_lane();
   // (a) this thread's slice of G_: reducer tid from its register, reducers tid + BBW_THREADS, ... from memory (sorted: G_
@@ -102,7 +104,9 @@ __device__ __forceinline__ void wide_round(WideShared& sh, int& half, WideState&
   }
   // (b) this thread's streams: its register slot, then its entries of the table
   uint64_t mk = ws.k0;
+  uint32_t sc = 0u;        // this thread's part of M's coefficient: at most BBW_KMAX / BBW_THREADS values below 2^16
   if (mk == M) {
+    sc = ws.c0;
     if (ws.p0 < ws.e0) {
       mk = ws.pk0 + ws.adj0;
       ws.c0 = bbf_mulmod(F, ws.pc0, ws.nc0);
@@ -114,12 +118,12 @@ __device__ __forceinline__ void wide_round(WideShared& sh, int& half, WideState&
     }
     ws.k0 = mk;
   }
-  uint32_t ms = ws.c0;
   if (ws.T > 0) {
 #pragma unroll 1
     for (int i = tid; i < ws.T; i += BBW_THREADS) {
       uint64_t k = st.key[i];
       if (k == M && k != ~0ull) {
+        sc += st.coef[i];
         const uint32_t p = st.ptr[i];
         if (p < st.end[i]) {
           uint64_t kr; uint32_t cr;
@@ -137,8 +141,7 @@ __device__ __forceinline__ void wide_round(WideShared& sh, int& half, WideState&
           k = ~0ull; st.key[i] = k;
         }
       }
-      const uint32_t c = st.coef[i];
-      if (k < mk) { mk = k; ms = c; } else if (k == mk) ms += c;
+      mk = k < mk ? k : mk;
     }
   }
   // (c) warp: the first divisor of the warp's slices, its first free register slot, the 64-bit minimum through two 32-bit
@@ -146,9 +149,9 @@ __device__ __forceinline__ void wide_round(WideShared& sh, int& half, WideState&
   {
     const uint32_t wb = __reduce_min_sync(BB_FULL, cand);
     const uint32_t fm = __ballot_sync(BB_FULL, ws.k0 == ~0ull && tid < ws.regs);
+    const uint32_t wsum = __reduce_add_sync(BB_FULL, sc);   // < 2^24
     const uint32_t hi = __reduce_min_sync(BB_FULL, (uint32_t)(mk >> 32));
     const uint32_t lo = __reduce_min_sync(BB_FULL, (uint32_t)(mk >> 32) == hi ? (uint32_t)mk : 0xffffffffu);
-    const uint32_t wsum = __reduce_add_sync(BB_FULL, ((uint32_t)(mk >> 32) == hi && (uint32_t)mk == lo) ? ms : 0u);
     const uint32_t fl = fm ? (uint32_t)(__ffs((int)fm) - 1) : BBW_NOFREE;
     if (lane == 0) sh.wrec[half][tid >> 5] = make_uint4(lo, hi, wsum | (fl << 24), wb);
   }
@@ -157,12 +160,12 @@ __device__ __forceinline__ void wide_round(WideShared& sh, int& half, WideState&
   {
     uint4 v = make_uint4(0xffffffffu, 0xffffffffu, BBW_NOFREE << 24, BBS_NONE);
     if (lane < BBW_WARPS) v = sh.wrec[half][lane];
+    const uint32_t gs = __reduce_add_sync(BB_FULL, v.z & 0xffffffu);   // < 2^27
     const uint32_t hi = __reduce_min_sync(BB_FULL, v.y);
     const uint32_t lo = __reduce_min_sync(BB_FULL, v.y == hi ? v.x : 0xffffffffu);
-    const uint32_t gs = __reduce_add_sync(BB_FULL, (v.y == hi && v.x == lo) ? (v.z & 0xffffffu) : 0u);   // < 2^27
     best = __reduce_min_sync(BB_FULL, v.w);
     const uint32_t fr = __reduce_min_sync(BB_FULL, (v.z >> 24) != BBW_NOFREE ? ((uint32_t)lane << 5) | (v.z >> 24) : BBS_NONE);
-    M2 = ((uint64_t)hi << 32) | lo; S2 = bbf_reduce(F, gs);
+    M2 = ((uint64_t)hi << 32) | lo; S = bbf_reduce(F, gs);
     freet = fr == BBS_NONE ? -1 : (int)fr;
   }
   half ^= 1;
@@ -190,30 +193,31 @@ __device__ __forceinline__ void wide_open(WideState& ws, WideStreams& st, int ta
   }
 }
 
-// Consolidation (bb_streams.cuh): h from (M, S) on goes to scratch half ws.cz in order, one stream over it (register slot
-// 0) remains and (M, S) becomes its head, M all ones if nothing is left.  Returns the number of terms, -1 if they do not
-// fit `cap`.
+// Consolidation (bb_streams.cuh): h from its lead monomial M on goes to scratch half ws.cz in order, one stream over it
+// (register slot 0) remains and M becomes its head monomial, all ones if nothing is left.  Returns the number of terms, -1
+// if they do not fit `cap`.
 template <int NV>
 __device__ __forceinline__ int wide_consolidate(WideShared& sh, int& half, WideState& ws, WideStreams& st, const BBField F,
-                                                uint64_t& M, uint32_t& S, uint64_t* tk, uint32_t* tc, uint32_t sbase, int cap) {
+                                                uint64_t& M, uint64_t* tk, uint32_t* tc, uint32_t sbase, int cap) {
   const uint32_t base = sbase + (uint32_t)(ws.cz * cap);
   int t = 0;
-  uint64_t m = M, fm = ~0ull; uint32_t s = S, fs = 0u;
+  uint64_t m = M, fm = ~0ull; uint32_t fs = 0u;
 #pragma unroll 1
   while (m != ~0ull) {
+    uint64_t m2; uint32_t s, best; int freet;
+    wide_round<NV>(sh, half, ws, st, F, m, false, nullptr, nullptr, 0, false, tk, tc, s, m2, best, freet);
     if (s != 0u) {
       if (t >= cap) return -1;
       if (t == 0) { fm = m; fs = s; }
       if (threadIdx.x == 0) { tk[base + t] = m; tc[base + t] = s; }
       t++;
     }
-    uint32_t best; int freet;
-    wide_round<NV>(sh, half, ws, st, F, m, false, nullptr, nullptr, 0, false, tk, tc, m, s, best, freet);
+    m = m2;
   }
   ws.pend_i = -1;   // every stream is exhausted: every slot is free
   ws.T = 0;
   ws.cz ^= 1;
-  M = fm; S = fs;
+  M = fm;
   __syncthreads();   // thread 0's list before thread 0 (the owner of slot 0) reads it back
   if (t > 0) wide_open(ws, st, 0, fm, fs, 0ull, 1u, base + 1u, base + (uint32_t)t, tk, tc);
   return t;
@@ -255,12 +259,12 @@ __device__ __forceinline__ int block_reduce_streams(const BBParams& P, const Env
     if (k & K::g_all) return -BB_STATUS_OVERFLOW_EXPONENT;
     wide_open(ws, st, opened++, k, bbf_mulmod(F, hg.c1, nc), adj, nc, hg.off + 2u, hg.off + hg.len, tk, tc);
   }
-  uint64_t M = ~0ull; uint32_t S = 0u;   // pseudo lead term: consumes nothing, is no term of h
+  uint64_t M = ~0ull;   // pseudo lead monomial: consumes nothing, is no term of h
 #pragma unroll 1
   do {
-    uint64_t M2; uint32_t S2, best; int freet;
-    wide_round<NV>(sh, half, ws, st, F, M, S != 0u, rlm, ridx, nR, sorted, tk, tc, M2, S2, best, freet);
-    if (S != 0u) {   // S == 0: the monomial cancelled, it is not a term of h
+    uint64_t M2; uint32_t S, best; int freet;
+    wide_round<NV>(sh, half, ws, st, F, M, true, rlm, ridx, nR, sorted, tk, tc, S, M2, best, freet);
+    if (M != ~0ull && S != 0u) {   // S == 0: the monomial cancelled, it is not a term of h
       ct.lms += (best != BBS_NONE) ? (best >> 16) + 1u : (unsigned)nR;
       if (best != BBS_NONE) {   // h <- h - (LT h / LT f) f: the lead terms cancel, f's tail becomes a stream
         const GHead f = load_head(gh + (best & 0xffffu));
@@ -273,15 +277,14 @@ __device__ __forceinline__ int block_reduce_streams(const BBParams& P, const Env
         steps++;
         if (f.len > 1u) {
           if (freet < 0 && ws.T >= ws.tcap) {   // no register slot, no room in the table
-            const int t = wide_consolidate<NV>(sh, half, ws, st, F, M2, S2, tk, tc, (uint32_t)P.max_terms, P.max_poly_terms);
+            const int t = wide_consolidate<NV>(sh, half, ws, st, F, M2, tk, tc, (uint32_t)P.max_terms, P.max_poly_terms);
             if (t < 0) return -BB_STATUS_OVERFLOW_SCRATCH;
             freet = t > 0 ? 1 : 0;
           }
           const uint64_t k = f.k1 + adj;
-          const uint32_t ck = bbf_mulmod(F, f.c1, nc);
           if (k & K::g_all) return -BB_STATUS_OVERFLOW_EXPONENT;
-          wide_open(ws, st, freet, k, ck, adj, nc, f.off + 2u, f.off + f.len, tk, tc);
-          if (k < M2) { M2 = k; S2 = ck; } else if (k == M2) S2 = bbf_addmod(F, S2, ck);
+          wide_open(ws, st, freet, k, bbf_mulmod(F, f.c1, nc), adj, nc, f.off + 2u, f.off + f.len, tk, tc);
+          M2 = k < M2 ? k : M2;
         }
       } else {            // no divisor: the lead term moves to the remainder
         if (rlen >= rcap) return -BB_STATUS_OVERFLOW_TERMS;
@@ -289,7 +292,7 @@ __device__ __forceinline__ int block_reduce_streams(const BBParams& P, const Env
         rlen++; ct.moves++;
       }
     }
-    M = M2; S = S2;
+    M = M2;
   } while (M != ~0ull);
   if (__syncthreads_or(ws.bad != 0u)) return -BB_STATUS_OVERFLOW_EXPONENT;   // also: thread 0's remainder before warp 0 reads it
   return rlen;
