@@ -863,7 +863,7 @@ __global__ void __launch_bounds__(BBW_THREADS, BBW_MIN_CTAS) k_run_wide(const __
   Ctr ct; ct.clear();
   WideState ws;
   ws.clear(); ws.cz = 0;
-  ws.regs = A.stream_regs < BBW_THREADS ? (A.stream_regs < 2 ? 2 : A.stream_regs) : BBW_THREADS;
+  ws.regs = A.stream_regs < BBW_SLOTS ? (A.stream_regs < 2 ? 2 : A.stream_regs) : BBW_SLOTS;
   ws.tcap = A.stream_kmax - ws.regs < 0 ? 0 : (A.stream_kmax - ws.regs < BBW_KMAX - BBW_THREADS ? A.stream_kmax - ws.regs : BBW_KMAX - BBW_THREADS);
   int half = 0;
   for (;;) {

@@ -46,10 +46,17 @@ struct WideStreams {             // dynamic shared memory: the table behind the 
   uint32_t end[BBW_KMAX - BBW_THREADS];
 };
 
+#define BBW_SLOTS ((BBW_WARPS - 1) * 32)   // register slots = stream threads: the last warp of the block is the CONTROL warp
+
 struct WideShared {
-  // per-warp round results, double-buffered: (min head key lo, hi, coefficient sum of the consumed monomial | first free lane << 24,
-  // first divisor: position in G_ << 16 | basis index)
+  // per-warp round results of the stream warps, double-buffered: (min head key lo, hi, coefficient sum of the consumed
+  // monomial | first free lane << 24, -)
   __align__(16) uint4 wrec[2][BBW_WARPS];
+  // what the control warp found for the round's lead monomial M, double-buffered: [0] = (key of the new stream's head
+  // f.k1 + M - f.lm lo, hi, key(M / LM f) - bias lo, hi), [1] = (f.invlc | f.c1 << 16, first term behind the head, end,
+  // flags: 1 a divisor exists, 2 the head key overflowed its exponent fields), [2] = (lead monomials scanned: the
+  // counter's increment, the sugar f would give the result, -, -)
+  __align__(16) uint4 desc[2][3];
   int row;                  // the pair row warp 0 selected
   long long upd;            // result of warp_add_basis
 };
@@ -59,13 +66,14 @@ struct WideShared {
 struct WideState {
   int T;                    // entries of the shared-memory table in use (append only until a consolidation)
   int tcap;                 // entries of the table that may be used
-  int regs;                 // register slots that may be used (threads 0 .. regs - 1)
+  int regs;                 // register slots that may be used (threads 0 .. regs - 1), at most BBW_SLOTS
   int cz;                   // scratch half the next consolidation writes
-  // per thread: the stream in this thread's register slot.  k0 all ones: free.
+  // stream threads: the stream in this thread's register slot.  k0 all ones: free.
   uint64_t k0, adj0, pk0; uint32_t c0, nc0, pc0, p0, e0;
-  // per thread: reducer `tid` of G_: lead monomial (all ones: absent) and (position << 16) | basis index (BBS_NONE: absent)
-  uint64_t rl0; uint32_t rc0;
-  // per thread: the raw term behind the head of table entry pend_i, loaded but not yet stored to st.pkey / st.pcoef
+  // control warp: reducers lane, lane + 32, ... lane + 224 of G_: lead monomial (all ones: absent) and (position << 16) |
+  // basis index (BBS_NONE: absent)
+  uint64_t rl[8]; uint32_t rc[8];
+  // stream threads: the raw term behind the head of table entry pend_i, loaded but not yet stored to st.pkey / st.pcoef
   int pend_i; uint64_t pend_k; uint32_t pend_c;
   uint32_t bad;             // per thread: a produced key overflowed its exponent fields
   __device__ __forceinline__ void clear() {
@@ -73,97 +81,121 @@ struct WideState {
   }
 };
 
-// One round by the block for the lead monomial M of h: S = the sum of the coefficients of the heads that carry M, in
-// [0, p) (0: the monomial cancelled; taken HERE, when M is consumed, so that the sum's reduction is off the chain of the
-// 64-bit minimum: REDUX.ADD costs as much as both REDUX.MIN), those streams advance, and M2 = the next lead monomial, all
-// ones when h is exhausted.  M all ones (the pseudo lead monomial a reduction starts from): nothing is consumed, S is
-// meaningless.  search: also M's first divisor in G_, best = (position << 16) | basis index or BBS_NONE.  freet: the
-// first thread whose register slot is free after the advance, -1 if none.  `half` = which half of sh.wrec this round writes.
+// One round by the block for the lead monomial M of h (M all ones, the pseudo lead monomial a reduction starts from:
+// nothing is consumed, S is meaningless).
+//   stream warps: S = the sum of the coefficients of the heads that carry M (taken HERE, when M is consumed, so that the
+//     sum's reduction is off the chain of the 64-bit minimum), those streams advance, M2 = the minimum head key after that
+//     (all ones: h is exhausted), freet = the first thread whose register slot is free (-1: none);
+//   control warp, concurrently (search): M's first divisor f in G_ (buchberger.cpp:27-32), f's head record, and everything
+//     about the stream f would open that does not depend on S, as the round's descriptor (dA, dB; see WideShared).
+// One barrier; behind it every warp folds the stream warps' records and reads the descriptor.  `half` = which half of the
+// double buffers this round uses.
 template <int NV>
 __device__ __forceinline__ void wide_round(WideShared& sh, int& half, WideState& ws, WideStreams& st, const BBField F,
-                                           const uint64_t M, const bool search, const uint64_t* rlm, const uint32_t* ridx,
-                                           const int nR, const bool sorted, const uint64_t* tk, const uint32_t* tc,
-                                           uint32_t& S, uint64_t& M2, uint32_t& best, int& freet) {
+                                           const uint64_t M, const bool search, const GHeadMem* gh, const uint64_t* rlm,
+                                           const uint32_t* ridx, const int nR, const bool sorted, const uint64_t* tk,
+                                           const uint32_t* tc, uint32_t& S, uint64_t& M2, uint4& dA, uint4& dB, uint4& dC, int& freet) {
   typedef KL<NV> K;
   const int tid = threadIdx.x, lane = bb_lane();
-  // (a) this thread's slice of G_: reducer tid from its register, reducers tid + BBW_THREADS, ... from memory (sorted: G_
-  // ascends in lead monomial, so nothing at or after the first key below M's can divide)
-  uint32_t cand = BBS_NONE;
-  if (search) {
-    const uint64_t mg = (M & K::ex_mask) | K::ge_mask;
-    if (((mg - (ws.rl0 & K::ex_mask)) & K::ge_mask) == K::ge_mask) cand = ws.rc0;   // absent: rc0 = BBS_NONE
-    else if (nR > BBW_THREADS) {
-      const uint64_t stop = sorted ? M : 0ull;
+  if (tid >= BBW_SLOTS) {
+    // ---- control warp: the divisor search and the head record of the divisor
+    if (search && M != ~0ull) {
+      const uint64_t mg = (M & K::ex_mask) | K::ge_mask;
+      uint32_t cand = BBS_NONE;
+#pragma unroll
+      for (int q = 7; q >= 0; q--)
+        if (((mg - (ws.rl[q] & K::ex_mask)) & K::ge_mask) == K::ge_mask) cand = ws.rc[q];   // absent: rc = BBS_NONE
+      uint32_t best = __reduce_min_sync(BB_FULL, cand);
+      if (best == BBS_NONE && nR > 256) {   // the rest of G_ from memory, 128 per pass
+        // sorted: G_ ascends in lead monomial (keys descend): a reducer whose key is below M's cannot divide, nor any after it
+        const uint64_t stop = sorted ? M : 0ull;
+        bool over = __any_sync(BB_FULL, ws.rl[7] < stop);   // lane 31's is the last of the register part
 #pragma unroll 1
-      for (int r = tid + BBW_THREADS; r < nR && ws.rl0 >= stop; r += BBW_THREADS) {
-        const uint64_t l = rlm[r];
-        if (l < stop) break;
-        if (((mg - (l & K::ex_mask)) & K::ge_mask) == K::ge_mask) { cand = ((uint32_t)r << 16) | ridx[r]; break; }
-      }
-    }
-  }
-  // (b) this thread's streams: its register slot, then its entries of the table
-  uint64_t mk = ws.k0;
-  uint32_t sc = 0u;        // this thread's part of M's coefficient: at most BBW_KMAX / BBW_THREADS values below 2^16
-  if (mk == M) {
-    sc = ws.c0;
-    if (ws.p0 < ws.e0) {
-      mk = ws.pk0 + ws.adj0;
-      ws.c0 = bbf_mulmod(F, ws.pc0, ws.nc0);
-      if (mk & K::g_all) ws.bad = 1u;
-      ws.p0++;
-      if (ws.p0 < ws.e0) { ws.pk0 = tk[ws.p0]; ws.pc0 = tc[ws.p0]; }   // the term behind the new head, needed a round later at the earliest
-    } else {
-      mk = ~0ull;
-    }
-    ws.k0 = mk;
-  }
-  if (ws.T > 0) {
-#pragma unroll 1
-    for (int i = tid; i < ws.T; i += BBW_THREADS) {
-      uint64_t k = st.key[i];
-      if (k == M && k != ~0ull) {
-        sc += st.coef[i];
-        const uint32_t p = st.ptr[i];
-        if (p < st.end[i]) {
-          uint64_t kr; uint32_t cr;
-          if (ws.pend_i == i) { kr = ws.pend_k; cr = ws.pend_c; ws.pend_i = -1; }
-          else { kr = st.pkey[i]; cr = st.pcoef[i]; }
-          k = kr + st.adj[i];
-          const uint32_t c = bbf_mulmod(F, cr, st.nc[i]);
-          if (k & K::g_all) ws.bad = 1u;
-          st.key[i] = k; st.coef[i] = c; st.ptr[i] = p + 1u;
-          if (p + 1u < st.end[i]) {
-            if (ws.pend_i >= 0) { st.pkey[ws.pend_i] = ws.pend_k; st.pcoef[ws.pend_i] = ws.pend_c; }
-            ws.pend_i = i; ws.pend_k = tk[p + 1u]; ws.pend_c = tc[p + 1u];
-          }
-        } else {
-          k = ~0ull; st.key[i] = k;
+        for (int base = 256; base < nR && !over; base += 128) {
+          const int r0 = base + lane, r1 = r0 + 32, r2 = r0 + 64, r3 = r0 + 96;
+          const bool v0 = r0 < nR, v1 = r1 < nR, v2 = r2 < nR, v3 = r3 < nR;
+          const uint64_t l0 = v0 ? rlm[r0] : ~0ull, l1 = v1 ? rlm[r1] : ~0ull, l2 = v2 ? rlm[r2] : ~0ull, l3 = v3 ? rlm[r3] : ~0ull;
+          const bool h0 = v0 && ((mg - (l0 & K::ex_mask)) & K::ge_mask) == K::ge_mask, h1 = v1 && ((mg - (l1 & K::ex_mask)) & K::ge_mask) == K::ge_mask;
+          const bool h2 = v2 && ((mg - (l2 & K::ex_mask)) & K::ge_mask) == K::ge_mask, h3 = v3 && ((mg - (l3 & K::ex_mask)) & K::ge_mask) == K::ge_mask;
+          const uint32_t c2 = h0 ? (uint32_t)r0 : (h1 ? (uint32_t)r1 : (h2 ? (uint32_t)r2 : (h3 ? (uint32_t)r3 : BBS_NONE)));
+          const uint32_t b2 = __reduce_min_sync(BB_FULL, c2);
+          if (b2 != BBS_NONE) { best = (b2 << 16) | ridx[b2]; break; }
+          over = __any_sync(BB_FULL, l0 < stop || l1 < stop || l2 < stop || l3 < stop);
         }
       }
-      mk = k < mk ? k : mk;
+      uint4 a = make_uint4(0u, 0u, 0u, 0u), b = make_uint4(0u, 0u, 0u, 0u), c = make_uint4((uint32_t)nR, 0u, 0u, 0u);
+      if (best != BBS_NONE) {
+        const GHead f = load_head(gh + (best & 0xffffu));
+        const uint64_t adj = M - f.lm;            // key(LM h / LM f) - bias
+        const uint64_t k = f.k1 + adj;
+        const uint32_t sf = f.sug + (uint32_t)(f.lm >> K::dshift) - (uint32_t)(M >> K::dshift);   // >= 0: LM f divides M
+        a = make_uint4((uint32_t)k, (uint32_t)(k >> 32), (uint32_t)adj, (uint32_t)(adj >> 32));
+        b = make_uint4(f.invlc | (f.c1 << 16), f.off + 2u, f.off + f.len, 1u | ((f.len > 1u && (k & K::g_all)) ? 2u : 0u));
+        c = make_uint4((best >> 16) + 1u, sf, 0u, 0u);
+      }
+      if (lane == 0) { sh.desc[half][0] = a; sh.desc[half][1] = b; sh.desc[half][2] = c; }
     }
-  }
-  // (c) warp: the first divisor of the warp's slices, its first free register slot, the 64-bit minimum through two 32-bit
-  // reductions and the coefficient sum at it
-  {
-    const uint32_t wb = __reduce_min_sync(BB_FULL, cand);
+  } else {
+    // ---- stream warps: this thread's streams: its register slot, then its entries of the table
+    uint64_t mk = ws.k0;
+    uint32_t sc = 0u;        // this thread's part of M's coefficient: at most 1 + 768 / BBW_SLOTS values below 2^16
+    if (mk == M) {
+      sc = ws.c0;
+      if (ws.p0 < ws.e0) {
+        mk = ws.pk0 + ws.adj0;
+        ws.c0 = bbf_mulmod(F, ws.pc0, ws.nc0);
+        if (mk & K::g_all) ws.bad = 1u;
+        ws.p0++;
+        if (ws.p0 < ws.e0) { ws.pk0 = tk[ws.p0]; ws.pc0 = tc[ws.p0]; }   // the term behind the new head, needed a round later at the earliest
+      } else {
+        mk = ~0ull;
+      }
+      ws.k0 = mk;
+    }
+    if (ws.T > 0) {
+#pragma unroll 1
+      for (int i = tid; i < ws.T; i += BBW_SLOTS) {
+        uint64_t k = st.key[i];
+        if (k == M && k != ~0ull) {
+          sc += st.coef[i];
+          const uint32_t p = st.ptr[i];
+          if (p < st.end[i]) {
+            uint64_t kr; uint32_t cr;
+            if (ws.pend_i == i) { kr = ws.pend_k; cr = ws.pend_c; ws.pend_i = -1; }
+            else { kr = st.pkey[i]; cr = st.pcoef[i]; }
+            k = kr + st.adj[i];
+            const uint32_t c = bbf_mulmod(F, cr, st.nc[i]);
+            if (k & K::g_all) ws.bad = 1u;
+            st.key[i] = k; st.coef[i] = c; st.ptr[i] = p + 1u;
+            if (p + 1u < st.end[i]) {
+              if (ws.pend_i >= 0) { st.pkey[ws.pend_i] = ws.pend_k; st.pcoef[ws.pend_i] = ws.pend_c; }
+              ws.pend_i = i; ws.pend_k = tk[p + 1u]; ws.pend_c = tc[p + 1u];
+            }
+          } else {
+            k = ~0ull; st.key[i] = k;
+          }
+        }
+        mk = k < mk ? k : mk;
+      }
+    }
+    // the warp's first free register slot, the consumed monomial's coefficient sum, the 64-bit minimum through two 32-bit
+    // reductions
     const uint32_t fm = __ballot_sync(BB_FULL, ws.k0 == ~0ull && tid < ws.regs);
     const uint32_t wsum = __reduce_add_sync(BB_FULL, sc);   // < 2^24
     const uint32_t hi = __reduce_min_sync(BB_FULL, (uint32_t)(mk >> 32));
     const uint32_t lo = __reduce_min_sync(BB_FULL, (uint32_t)(mk >> 32) == hi ? (uint32_t)mk : 0xffffffffu);
     const uint32_t fl = fm ? (uint32_t)(__ffs((int)fm) - 1) : BBW_NOFREE;
-    if (lane == 0) sh.wrec[half][tid >> 5] = make_uint4(lo, hi, wsum | (fl << 24), wb);
+    if (lane == 0) sh.wrec[half][tid >> 5] = make_uint4(lo, hi, wsum | (fl << 24), 0u);
   }
   __syncthreads();
-  // (d) every warp folds the warps' records, one per lane, with the same reductions
+  // every warp folds the stream warps' records, one per lane, and reads the descriptor
   {
-    uint4 v = make_uint4(0xffffffffu, 0xffffffffu, BBW_NOFREE << 24, BBS_NONE);
-    if (lane < BBW_WARPS) v = sh.wrec[half][lane];
+    uint4 v = make_uint4(0xffffffffu, 0xffffffffu, BBW_NOFREE << 24, 0u);
+    if (lane < BBW_WARPS - 1) v = sh.wrec[half][lane];
+    dA = sh.desc[half][0]; dB = sh.desc[half][1]; dC = sh.desc[half][2];
     const uint32_t gs = __reduce_add_sync(BB_FULL, v.z & 0xffffffu);   // < 2^27
     const uint32_t hi = __reduce_min_sync(BB_FULL, v.y);
     const uint32_t lo = __reduce_min_sync(BB_FULL, v.y == hi ? v.x : 0xffffffffu);
-    best = __reduce_min_sync(BB_FULL, v.w);
     const uint32_t fr = __reduce_min_sync(BB_FULL, (v.z >> 24) != BBW_NOFREE ? ((uint32_t)lane << 5) | (v.z >> 24) : BBS_NONE);
     M2 = ((uint64_t)hi << 32) | lo; S = bbf_reduce(F, gs);
     freet = fr == BBS_NONE ? -1 : (int)fr;
@@ -172,25 +204,28 @@ __device__ __forceinline__ void wide_round(WideShared& sh, int& half, WideState&
 }
 
 // Opens a stream in register slot `target` (>= 0), else as the next entry of the table (the caller has checked the room):
-// head (hk, hc) already scaled, multiplier (adj, nc), the terms behind the head at [next, end).
-__device__ __forceinline__ void wide_open(WideState& ws, WideStreams& st, int target, uint64_t hk, uint32_t hc, uint64_t adj,
-                                          uint32_t nc, uint32_t next, uint32_t end, const uint64_t* tk, const uint32_t* tc) {
-  if (target >= 0) {
-    if ((int)threadIdx.x == target) {
+// head key hk, the terms behind the head at [next, end), multiplier monomial adj; multiplier coefficient nc = -(S * invlc)
+// and head coefficient c1 * nc are worked out by the one thread that owns the slot (icc = invlc | c1 << 16); S = 0 with
+// icc = 1 | c << 16 opens a stream over a list as it is (multiplier 1).
+__device__ __forceinline__ void wide_open(WideState& ws, WideStreams& st, const BBField F, int target, uint64_t hk, uint64_t adj,
+                                          uint32_t S, uint32_t icc, uint32_t next, uint32_t end, const uint64_t* tk, const uint32_t* tc) {
+  const int j = ws.T;
+  const int owner = target >= 0 ? target : j % BBW_SLOTS;
+  if ((int)threadIdx.x == owner) {
+    const uint32_t nc = S ? F.p - bbf_mulmod(F, S, icc & 0xffffu) : 1u;   // S * invlc != 0
+    const uint32_t hc = bbf_mulmod(F, icc >> 16, nc);
+    if (target >= 0) {
       ws.k0 = hk; ws.c0 = hc; ws.adj0 = adj; ws.nc0 = nc; ws.p0 = next; ws.e0 = end;
       if (next < end) { ws.pk0 = tk[next]; ws.pc0 = tc[next]; }
-    }
-  } else {
-    const int j = ws.T;
-    if ((int)threadIdx.x == (j & (BBW_THREADS - 1))) {
+    } else {
       st.key[j] = hk; st.coef[j] = hc; st.adj[j] = adj; st.nc[j] = nc; st.ptr[j] = next; st.end[j] = end;
       if (next < end) {
         if (ws.pend_i >= 0) { st.pkey[ws.pend_i] = ws.pend_k; st.pcoef[ws.pend_i] = ws.pend_c; }
         ws.pend_i = j; ws.pend_k = tk[next]; ws.pend_c = tc[next];
       }
     }
-    ws.T = j + 1;
   }
+  if (target < 0) ws.T = j + 1;
 }
 
 // Consolidation (bb_streams.cuh): h from its lead monomial M on goes to scratch half ws.cz in order, one stream over it
@@ -204,8 +239,8 @@ __device__ __forceinline__ int wide_consolidate(WideShared& sh, int& half, WideS
   uint64_t m = M, fm = ~0ull; uint32_t fs = 0u;
 #pragma unroll 1
   while (m != ~0ull) {
-    uint64_t m2; uint32_t s, best; int freet;
-    wide_round<NV>(sh, half, ws, st, F, m, false, nullptr, nullptr, 0, false, tk, tc, s, m2, best, freet);
+    uint64_t m2; uint32_t s; uint4 dA, dB, dC; int freet;
+    wide_round<NV>(sh, half, ws, st, F, m, false, nullptr, nullptr, nullptr, 0, false, tk, tc, s, m2, dA, dB, dC, freet);
     if (s != 0u) {
       if (t >= cap) return -1;
       if (t == 0) { fm = m; fs = s; }
@@ -219,7 +254,7 @@ __device__ __forceinline__ int wide_consolidate(WideShared& sh, int& half, WideS
   ws.cz ^= 1;
   M = fm;
   __syncthreads();   // thread 0's list before thread 0 (the owner of slot 0) reads it back
-  if (t > 0) wide_open(ws, st, 0, fm, fs, 0ull, 1u, base + 1u, base + (uint32_t)t, tk, tc);
+  if (t > 0) wide_open(ws, st, F, 0, fm, 0ull, 0u, 1u | (fs << 16), base + 1u, base + (uint32_t)t, tk, tc);
   return t;
 }
 
@@ -243,47 +278,48 @@ __device__ __forceinline__ int block_reduce_streams(const BBParams& P, const Env
   int rlen = 0;
   steps = 0;
   ws.clear();
-  ws.rl0 = tid < nR ? rlm[tid] : ~0ull;                                   // G_ changes only between reductions
-  ws.rc0 = tid < nR ? (((uint32_t)tid << 16) | ridx[tid]) : BBS_NONE;     // positions and basis indices are below 2^16
+  if (tid >= BBW_SLOTS) {   // the control warp's part of G_ (G_ changes only between reductions)
+#pragma unroll
+    for (int q = 0; q < 8; q++) {
+      const int r = (tid - BBW_SLOTS) + 32 * q;
+      ws.rl[q] = r < nR ? rlm[r] : ~0ull;
+      ws.rc[q] = r < nR ? (((uint32_t)r << 16) | ridx[r]) : BBS_NONE;   // positions and basis indices are below 2^16
+    }
+  }
   // s = (gamma / LT f) tail(f) - (gamma / LT g) tail(g): the lead terms cancel exactly (buchberger.cpp:18-21); two streams
   // whose heads come from the head records, in register slots 0 and 1 (ws.regs >= 2)
   int opened = 0;
   if (hf.len > 1u) {
     const uint64_t adj = gam - hf.lm, k = hf.k1 + adj;
     if (k & K::g_all) return -BB_STATUS_OVERFLOW_EXPONENT;
-    wide_open(ws, st, opened++, k, bbf_mulmod(F, hf.c1, hf.invlc), adj, hf.invlc, hf.off + 2u, hf.off + hf.len, tk, tc);
+    wide_open(ws, st, F, opened++, k, adj, F.p - 1u, hf.invlc | (hf.c1 << 16), hf.off + 2u, hf.off + hf.len, tk, tc);   // S = -1: nc = +invlc
   }
   if (hg.len > 1u) {
     const uint64_t adj = gam - hg.lm, k = hg.k1 + adj;
-    const uint32_t nc = F.p - hg.invlc;
     if (k & K::g_all) return -BB_STATUS_OVERFLOW_EXPONENT;
-    wide_open(ws, st, opened++, k, bbf_mulmod(F, hg.c1, nc), adj, nc, hg.off + 2u, hg.off + hg.len, tk, tc);
+    wide_open(ws, st, F, opened++, k, adj, 1u, hg.invlc | (hg.c1 << 16), hg.off + 2u, hg.off + hg.len, tk, tc);          // S = +1: nc = -invlc
   }
   uint64_t M = ~0ull;   // pseudo lead monomial: consumes nothing, is no term of h
 #pragma unroll 1
   do {
-    uint64_t M2; uint32_t S, best; int freet;
-    wide_round<NV>(sh, half, ws, st, F, M, true, rlm, ridx, nR, sorted, tk, tc, S, M2, best, freet);
+    uint64_t M2; uint32_t S; uint4 dA, dB, dC; int freet;
+    wide_round<NV>(sh, half, ws, st, F, M, true, gh, rlm, ridx, nR, sorted, tk, tc, S, M2, dA, dB, dC, freet);
     if (M != ~0ull && S != 0u) {   // S == 0: the monomial cancelled, it is not a term of h
-      ct.lms += (best != BBS_NONE) ? (best >> 16) + 1u : (unsigned)nR;
-      if (best != BBS_NONE) {   // h <- h - (LT h / LT f) f: the lead terms cancel, f's tail becomes a stream
-        const GHead f = load_head(gh + (best & 0xffffu));
-        const uint32_t c = bbf_mulmod(F, S, f.invlc);
-        const uint32_t nc = F.p - c;              // c != 0
-        const uint64_t adj = M - f.lm;            // key(LM h / LM f) - bias
-        const int sf = (int)f.sug + (int)(uint32_t)(f.lm >> K::dshift) - (int)(uint32_t)(M >> K::dshift);
+      ct.lms += dC.x;
+      if (dB.w & 1u) {   // h <- h - (LT h / LT f) f: the lead terms cancel, f's tail becomes a stream
+        const int sf = (int)dC.y;
         sug = sf > sug ? sf : sug;
-        ct.tread += f.len;
+        ct.tread += dB.z - dB.y + 2u;   // |f|
         steps++;
-        if (f.len > 1u) {
+        if (dB.z + 1u > dB.y) {         // |f| > 1
+          if (dB.w & 2u) return -BB_STATUS_OVERFLOW_EXPONENT;
           if (freet < 0 && ws.T >= ws.tcap) {   // no register slot, no room in the table
             const int t = wide_consolidate<NV>(sh, half, ws, st, F, M2, tk, tc, (uint32_t)P.max_terms, P.max_poly_terms);
             if (t < 0) return -BB_STATUS_OVERFLOW_SCRATCH;
             freet = t > 0 ? 1 : 0;
           }
-          const uint64_t k = f.k1 + adj;
-          if (k & K::g_all) return -BB_STATUS_OVERFLOW_EXPONENT;
-          wide_open(ws, st, freet, k, bbf_mulmod(F, f.c1, nc), adj, nc, f.off + 2u, f.off + f.len, tk, tc);
+          const uint64_t k = ((uint64_t)dA.y << 32) | dA.x;
+          wide_open(ws, st, F, freet, k, ((uint64_t)dA.w << 32) | dA.z, S, dB.x, dB.y, dB.z, tk, tc);
           M2 = k < M2 ? k : M2;
         }
       } else {            // no divisor: the lead term moves to the remainder
