@@ -13,6 +13,9 @@
 #include "bb_device.cuh"
 #include "bb_policy.cuh"
 #include "bb_streams.cuh"
+#ifdef BBW_CLOCK
+#include <cstdio>
+#endif
 #include "bb_wide.cuh"
 #include "bb_rstreams.cuh"
 
@@ -863,6 +866,9 @@ __global__ void __launch_bounds__(BBW_THREADS, BBW_MIN_CTAS) k_run_wide(const __
   Ctr ct; ct.clear();
   WideState ws;
   ws.clear(); ws.cz = 0;
+#ifdef BBW_CLOCK
+  ws.cw = ws.cb = ws.cp = ws.co = 0; ws.tl = clock64();
+#endif
   ws.regs = A.stream_regs < BBW_SLOTS ? (A.stream_regs < 2 ? 2 : A.stream_regs) : BBW_SLOTS;
   ws.tcap = A.stream_kmax - ws.regs < 0 ? 0 : (A.stream_kmax - ws.regs < BBW_KMAX - BBW_THREADS ? A.stream_kmax - ws.regs : BBW_KMAX - BBW_THREADS);
   int half = 0;
@@ -944,6 +950,9 @@ __global__ void __launch_bounds__(BBW_THREADS, BBW_MIN_CTAS) k_run_wide(const __
     }
     __syncthreads();
   }
+#ifdef BBW_CLOCK
+  if ((tid & 31) == 0) printf("warp %d: before the barrier %lld, barrier + fold %lld, post-processing %lld, outside the rounds %lld cycles\n", tid >> 5, ws.cw, ws.cb, ws.cp, ws.co);
+#endif
   __syncthreads();
   if (tid < CT_COUNT && sh[0][tid]) atomicAdd(&P.counters[tid], sh[0][tid]);
 }

@@ -48,6 +48,14 @@ struct WideStreams {             // dynamic shared memory: the table behind the 
 
 #define BBW_SLOTS ((BBW_WARPS - 1) * 32)   // register slots = stream threads: the last warp of the block is the CONTROL warp
 
+#ifdef BBW_CLOCK
+__device__ __forceinline__ long long bbw_clock(uint32_t dep) {   // the clock, read once `dep` has been computed
+  long long t;
+  asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "r"(dep) : "memory");
+  return t;
+}
+#endif
+
 struct WideShared {
   // per-warp round results of the stream warps, double-buffered: (min head key lo, hi, coefficient sum of the consumed
   // monomial | first free lane << 24, -)
@@ -57,6 +65,9 @@ struct WideShared {
   // flags: 1 a divisor exists, 2 the head key overflowed its exponent fields), [2] = (lead monomials scanned: the
   // counter's increment, the sugar f would give the result, -, -)
   __align__(16) uint4 desc[2][3];
+  // what the book-keeping warp kept count of during a reduction, published at its end: (remainder length or -BB_STATUS_*,
+  // reductions, sugar of the result, -), (lead monomials scanned, reducer terms read, terms moved to the remainder, -)
+  __align__(16) uint4 fin[2];
   int row;                  // the pair row warp 0 selected
   long long upd;            // result of warp_add_basis
 };
@@ -76,6 +87,9 @@ struct WideState {
   // stream threads: the raw term behind the head of table entry pend_i, loaded but not yet stored to st.pkey / st.pcoef
   int pend_i; uint64_t pend_k; uint32_t pend_c;
   uint32_t bad;             // per thread: a produced key overflowed its exponent fields
+#ifdef BBW_CLOCK
+  long long cw, cb, cp, co, tl; // diagnostic: cycles before the round's barrier, barrier + fold, post-processing, outside; end of the last post-processing
+#endif
   __device__ __forceinline__ void clear() {
     T = 0; k0 = ~0ull; adj0 = pk0 = 0ull; c0 = nc0 = pc0 = p0 = e0 = 0u; pend_i = -1; pend_k = 0ull; pend_c = 0u; bad = 0u;
   }
@@ -97,6 +111,10 @@ __device__ __forceinline__ void wide_round(WideShared& sh, int& half, WideState&
                                            const uint32_t* tc, uint32_t& S, uint64_t& M2, uint4& dA, uint4& dB, uint4& dC, int& freet) {
   typedef KL<NV> K;
   const int tid = threadIdx.x, lane = bb_lane();
+#ifdef BBW_CLOCK
+  const long long t0 = bbw_clock((uint32_t)M);
+  ws.co += t0 - ws.tl;
+#endif
   if (tid >= BBW_SLOTS) {
     // ---- control warp: the divisor search and the head record of the divisor
     if (search && M != ~0ull) {
@@ -187,7 +205,13 @@ __device__ __forceinline__ void wide_round(WideShared& sh, int& half, WideState&
     const uint32_t fl = fm ? (uint32_t)(__ffs((int)fm) - 1) : BBW_NOFREE;
     if (lane == 0) sh.wrec[half][tid >> 5] = make_uint4(lo, hi, wsum | (fl << 24), 0u);
   }
+#ifdef BBW_CLOCK
+  const long long t1 = bbw_clock(0u);
   __syncthreads();
+  ws.cw += t1 - t0;
+#else
+  __syncthreads();
+#endif
   // every warp folds the stream warps' records, one per lane, and reads the descriptor
   {
     uint4 v = make_uint4(0xffffffffu, 0xffffffffu, BBW_NOFREE << 24, 0u);
@@ -200,6 +224,10 @@ __device__ __forceinline__ void wide_round(WideShared& sh, int& half, WideState&
     M2 = ((uint64_t)hi << 32) | lo; S = bbf_reduce(F, gs);
     freet = fr == BBS_NONE ? -1 : (int)fr;
   }
+#ifdef BBW_CLOCK
+  ws.tl = bbw_clock(S ^ (uint32_t)M2 ^ (uint32_t)freet ^ dA.x ^ dB.w ^ dC.x);   // behind the fold's results
+  ws.cb += ws.tl - t1;
+#endif
   half ^= 1;
 }
 
@@ -210,7 +238,8 @@ __device__ __forceinline__ void wide_round(WideShared& sh, int& half, WideState&
 __device__ __forceinline__ void wide_open(WideState& ws, WideStreams& st, const BBField F, int target, uint64_t hk, uint64_t adj,
                                           uint32_t S, uint32_t icc, uint32_t next, uint32_t end, const uint64_t* tk, const uint32_t* tc) {
   const int j = ws.T;
-  const int owner = target >= 0 ? target : j % BBW_SLOTS;
+  int owner = target;
+  if (target < 0) owner = j % BBW_SLOTS;
   if ((int)threadIdx.x == owner) {
     const uint32_t nc = S ? F.p - bbf_mulmod(F, S, icc & 0xffffu) : 1u;   // S * invlc != 0
     const uint32_t hc = bbf_mulmod(F, icc >> 16, nc);
@@ -299,39 +328,59 @@ __device__ __forceinline__ int block_reduce_streams(const BBParams& P, const Env
     if (k & K::g_all) return -BB_STATUS_OVERFLOW_EXPONENT;
     wide_open(ws, st, F, opened++, k, adj, 1u, hg.invlc | (hg.c1 << 16), hg.off + 2u, hg.off + hg.len, tk, tc);          // S = +1: nc = -invlc
   }
+  // The block's threads agree on the lead monomial sequence, the streams and the faults; the reduction's bookkeeping
+  // (remainder, counters, sugar) is left to ONE warp and published at the end: the last stream warp, whose slots fill last
+  // (the control warp's round is the longest of the block, the first stream warps' come next).
+  const int tbook = BBW_SLOTS - 32;
+  const bool ctl = (tid >> 5) == BBW_WARPS - 2;
+  int err = 0;
+  uint32_t n_lms = 0u, n_tread = 0u;
   uint64_t M = ~0ull;   // pseudo lead monomial: consumes nothing, is no term of h
 #pragma unroll 1
   do {
     uint64_t M2; uint32_t S; uint4 dA, dB, dC; int freet;
     wide_round<NV>(sh, half, ws, st, F, M, true, gh, rlm, ridx, nR, sorted, tk, tc, S, M2, dA, dB, dC, freet);
     if (M != ~0ull && S != 0u) {   // S == 0: the monomial cancelled, it is not a term of h
-      ct.lms += dC.x;
-      if (dB.w & 1u) {   // h <- h - (LT h / LT f) f: the lead terms cancel, f's tail becomes a stream
-        const int sf = (int)dC.y;
-        sug = sf > sug ? sf : sug;
-        ct.tread += dB.z - dB.y + 2u;   // |f|
-        steps++;
-        if (dB.z + 1u > dB.y) {         // |f| > 1
-          if (dB.w & 2u) return -BB_STATUS_OVERFLOW_EXPONENT;
-          if (freet < 0 && ws.T >= ws.tcap) {   // no register slot, no room in the table
-            const int t = wide_consolidate<NV>(sh, half, ws, st, F, M2, tk, tc, (uint32_t)P.max_terms, P.max_poly_terms);
-            if (t < 0) return -BB_STATUS_OVERFLOW_SCRATCH;
-            freet = t > 0 ? 1 : 0;
-          }
-          const uint64_t k = ((uint64_t)dA.y << 32) | dA.x;
-          wide_open(ws, st, F, freet, k, ((uint64_t)dA.w << 32) | dA.z, S, dB.x, dB.y, dB.z, tk, tc);
-          M2 = k < M2 ? k : M2;
+      if (ctl) {
+        n_lms += dC.x;
+        if (dB.w & 1u) {
+          const int sf = (int)dC.y;
+          sug = sf > sug ? sf : sug;
+          n_tread += dB.z - dB.y + 2u;   // |f|
+          steps++;
+        } else {          // no divisor: the lead term moves to the remainder (beyond its capacity: counted, not written)
+          if (rlen < rcap && tid == tbook) { rk[rlen] = M; rc[rlen] = S; }
+          rlen++;
         }
-      } else {            // no divisor: the lead term moves to the remainder
-        if (rlen >= rcap) return -BB_STATUS_OVERFLOW_TERMS;
-        if (tid == 0) { rk[rlen] = M; rc[rlen] = S; }
-        rlen++; ct.moves++;
+      }
+      if ((dB.w & 1u) && dB.z + 1u > dB.y) {   // h <- h - (LT h / LT f) f, |f| > 1: the lead terms cancel, f's tail becomes a stream
+        if (dB.w & 2u) { err = -BB_STATUS_OVERFLOW_EXPONENT; break; }
+        if (freet < 0 && ws.T >= ws.tcap) {   // no register slot, no room in the table
+          const int t = wide_consolidate<NV>(sh, half, ws, st, F, M2, tk, tc, (uint32_t)P.max_terms, P.max_poly_terms);
+          if (t < 0) { err = -BB_STATUS_OVERFLOW_SCRATCH; break; }
+          freet = t > 0 ? 1 : 0;
+        }
+        const uint64_t k = ((uint64_t)dA.y << 32) | dA.x;
+        wide_open(ws, st, F, freet, k, ((uint64_t)dA.w << 32) | dA.z, S, dB.x, dB.y, dB.z, tk, tc);
+        M2 = k < M2 ? k : M2;
       }
     }
     M = M2;
+#ifdef BBW_CLOCK
+    { const long long t3 = bbw_clock((uint32_t)M ^ ws.c0 ^ (uint32_t)ws.k0); ws.cp += t3 - ws.tl; ws.tl = t3; }
+#endif
   } while (M != ~0ull);
-  if (__syncthreads_or(ws.bad != 0u)) return -BB_STATUS_OVERFLOW_EXPONENT;   // also: thread 0's remainder before warp 0 reads it
-  return rlen;
+  if (tid == tbook) {
+    sh.fin[0] = make_uint4((uint32_t)(err ? err : (rlen > rcap ? -BB_STATUS_OVERFLOW_TERMS : rlen)), (uint32_t)steps, (uint32_t)sug, 0u);
+    sh.fin[1] = make_uint4(n_lms, n_tread, (uint32_t)(rlen < rcap ? rlen : rcap), 0u);
+  }
+  const int bad = __syncthreads_or(ws.bad != 0u);   // also: the book-keeping warp's remainder and counts before the others read them
+  const uint4 f0 = sh.fin[0], f1 = sh.fin[1];
+  steps = (int)f0.y; sug = (int)f0.z;
+  ct.lms += f1.x; ct.tread += f1.y; ct.moves += f1.z;
+  if ((int)f0.x < 0) return (int)f0.x;
+  if (bad) return -BB_STATUS_OVERFLOW_EXPONENT;
+  return (int)f0.x;
 }
 
 // Removes row `row` from the pair list keeping order (buchberger.cpp:319), by the whole block: chunk by chunk, read, barrier,
