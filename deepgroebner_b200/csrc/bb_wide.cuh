@@ -1,16 +1,26 @@
 // bb_wide.cuh -- the stream reducer (bb_streams.cuh) run by a whole CTA (BBW_WARPS warps) on ONE environment, sm_100a.
 //
 // A cyclic-6 launch is as long as its longest episode (697 000 dependent additions in the longest of 1024 seeded-Random
-// episodes), so what decides it is the latency of one ROUND (one lead term of the dividend: divisor search + advance of
-// the streams at it + next lead term).  A CTA splits the divisor search and the streams over its threads -- thread t owns
-// the stream in REGISTER slot t and reducer lead monomial t of G_ (also in a register, with its basis index) -- and pays
-// one block barrier per round: every warp reduces its part (three REDUX for the 64-bit minimum head key and the
-// coefficient sum at it, one for the first divisor, one ballot for its first free slot), writes a 16-byte record, and
-// after the barrier every warp folds the records with the same reductions (one record per lane).  Measured per dependent
-// operation on B200 (tools/ub/lat.cu): REDUX.MIN 22 cycles, REDUX.ADD 47, the three-REDUX fold 108, STS + BAR + LDS 58.
+// episodes), so what decides it is the latency of one ROUND (one lead monomial of the dividend: its coefficient, its
+// divisor, the advance of the streams that carry it, the next lead monomial).  A round is a dependent chain of
+// instructions, issued one per ~4 cycles, plus fixed latencies (measured on B200, tools/ub/lat.cu: REDUX.MIN 22 cycles,
+// REDUX.ADD 47 -- a warp's REDUX operations do not overlap --, STS + BAR + LDS 58), so the CTA is WARP-SPECIALISED to keep
+// every warp's chain short:
+//   * the first BBW_WARPS - 1 warps are STREAM warps: thread t owns the stream in REGISTER slot t; in a round it adds its
+//     head's coefficient to the round's sum and advances if its head is the lead monomial, and the warp folds its minimum
+//     head key (two REDUX), coefficient sum (one) and first free slot (a ballot) into a 16-byte record;
+//   * the last warp is the CONTROL warp: 256 reducer lead monomials of G_ (and their basis indices) in its registers; in a
+//     round it finds the lead monomial's first divisor, loads the divisor's head record and writes everything about the
+//     stream this divisor opens that does not depend on the coefficient -- head key, multiplier monomial, term range,
+//     counter increments -- as a 48-byte descriptor to shared memory;
+//   * ONE block barrier per round; behind it every warp folds the stream warps' records (one per lane) and reads the
+//     descriptor; the thread that owns the new stream's slot alone works out the multiplier and head coefficients; one
+//     warp keeps the reduction's books (remainder, counters, sugar) and publishes them at the end.
+// Longest episode: 0.79 us per addition (1.37 rounds); clock probes (-DBBW_CLOCK) give per round ~480 cycles before the
+// barrier for the control warp (330 - 450 for the stream warps), ~300 for barrier + fold, ~230 - 300 behind it.
 //
 // A new stream takes the first free register slot of the block (the fold reports it), so the register slots hold the LIVE
-// streams; only when all BBW_THREADS are live does a stream go to the shared-memory table behind them (append only;
+// streams; only when all BBW_SLOTS are live does a stream go to the shared-memory table behind them (append only;
 // scanned by its owner thread each round), and only when that is full too is h consolidated (bb_streams.cuh).
 // bb_set_wide(2 / 3): 6 / 48 register slots and no table (consolidations every few additions); bb_set_wide(7): 8 register
 // slots and the whole table (the shared-memory path on every step).
@@ -28,7 +38,7 @@
 #define BBW_MIN_CTAS 2
 #endif
 #ifndef BBW_KMAX
-#define BBW_KMAX 1024           // stream slots of one step: BBW_THREADS in registers, the rest in shared memory
+#define BBW_KMAX 1024           // BBW_KMAX - BBW_THREADS entries in the shared-memory table behind the register slots
 #endif
 static_assert(BBW_KMAX % BBW_THREADS == 0 && BBW_KMAX > BBW_THREADS, "whole rows of streams");
 static_assert(BBW_WARPS <= 32, "one record per lane in the fold");
