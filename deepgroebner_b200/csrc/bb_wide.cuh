@@ -91,8 +91,8 @@ struct WideState {
   int cz;                   // scratch half the next consolidation writes
   // stream threads: the stream in this thread's register slot.  k0 all ones: free.
   uint64_t k0, adj0, pk0; uint32_t c0, nc0, pc0, p0, e0;
-  // control warp: reducers lane, lane + 32, ... lane + 224 of G_: lead monomial (all ones: absent) and (position << 16) |
-  // basis index (BBS_NONE: absent)
+  // control warp: reducers lane, lane + 32, ... lane + 224 of G_: the exponent fields of the lead monomial and
+  // (position << 16) | basis index (BBS_NONE: absent)
   uint64_t rl[8]; uint32_t rc[8];
   // stream threads: the raw term behind the head of table entry pend_i, loaded but not yet stored to st.pkey / st.pcoef
   int pend_i; uint64_t pend_k; uint32_t pend_c;
@@ -132,12 +132,12 @@ __device__ __forceinline__ void wide_round(WideShared& sh, int& half, WideState&
       uint32_t cand = BBS_NONE;
 #pragma unroll
       for (int q = 7; q >= 0; q--)
-        if (((mg - (ws.rl[q] & K::ex_mask)) & K::ge_mask) == K::ge_mask) cand = ws.rc[q];   // absent: rc = BBS_NONE
+        if (((mg - ws.rl[q]) & K::ge_mask) == K::ge_mask) cand = ws.rc[q];   // rl: exponent fields only; absent: rc = BBS_NONE
       uint32_t best = __reduce_min_sync(BB_FULL, cand);
       if (best == BBS_NONE && nR > 256) {   // the rest of G_ from memory, 128 per pass
         // sorted: G_ ascends in lead monomial (keys descend): a reducer whose key is below M's cannot divide, nor any after it
         const uint64_t stop = sorted ? M : 0ull;
-        bool over = __any_sync(BB_FULL, ws.rl[7] < stop);   // lane 31's is the last of the register part
+        bool over = rlm[255] < stop;                        // the last reducer of the register part
 #pragma unroll 1
         for (int base = 256; base < nR && !over; base += 128) {
           const int r0 = base + lane, r1 = r0 + 32, r2 = r0 + 64, r3 = r0 + 96;
@@ -321,7 +321,7 @@ __device__ __forceinline__ int block_reduce_streams(const BBParams& P, const Env
 #pragma unroll
     for (int q = 0; q < 8; q++) {
       const int r = (tid - BBW_SLOTS) + 32 * q;
-      ws.rl[q] = r < nR ? rlm[r] : ~0ull;
+      ws.rl[q] = r < nR ? (rlm[r] & K::ex_mask) : K::ex_mask;
       ws.rc[q] = r < nR ? (((uint32_t)r << 16) | ridx[r]) : BBS_NONE;   // positions and basis indices are below 2^16
     }
   }
