@@ -48,7 +48,8 @@ struct BBRunArgs {
   int trace_eps, trace_cap;
   int prepare_by_warp;  // 1: k_prepare (one warp per episode) even where k_prepare_lanes applies (tests compare the two)
   int stream_kmax;   // stream slots a step's reduction may use (BBS_KMAX; less under bb_set_wide(2 / 3 / 5 / 6)), see bb_streams.cuh
-  int stream_regs;   // k_run_wide: how many of them are register slots (BBW_THREADS; 8 under bb_set_wide(7))
+  int stream_regs;   // k_run_wide: how many of them are register slots (BBW_SLOTS; 8 under bb_set_wide(7))
+  int ctl_reducers;  // k_run_wide: reducers of G_ in the control warp's registers (256; 32 under bb_set_wide(8))
   int* queue;        // [0]: next queue position; [BB_LPT_HIST .. +BB_LPT_BUCKETS): histogram of the cost keys of the batch, then as many cursors
   int* order;        // [episodes] queue position -> episode of the batch, longest predicted first (k_order)
   uint8_t* cost_key; // [episodes] predicted-cost bucket of each episode of the batch (k_prepare)
@@ -870,6 +871,7 @@ __global__ void __launch_bounds__(BBW_THREADS, BBW_MIN_CTAS) k_run_wide(const __
   ws.cw = ws.cb = ws.cp = ws.co = 0; ws.tl = clock64();
 #endif
   ws.regs = A.stream_regs < BBW_SLOTS ? (A.stream_regs < 2 ? 2 : A.stream_regs) : BBW_SLOTS;
+  ws.cbase = A.ctl_reducers >= 32 && A.ctl_reducers < 256 ? (A.ctl_reducers & ~31) : 256;
   ws.tcap = A.stream_kmax - ws.regs < 0 ? 0 : (A.stream_kmax - ws.regs < BBW_KMAX - BBW_THREADS ? A.stream_kmax - ws.regs : BBW_KMAX - BBW_THREADS);
   int half = 0;
   for (;;) {

@@ -23,7 +23,8 @@
 // streams; only when all BBW_SLOTS are live does a stream go to the shared-memory table behind them (append only;
 // scanned by its owner thread each round), and only when that is full too is h consolidated (bb_streams.cuh).
 // bb_set_wide(2 / 3): 6 / 48 register slots and no table (consolidations every few additions); bb_set_wide(7): 8 register
-// slots and the whole table (the shared-memory path on every step).
+// slots and the whole table (the shared-memory path on every step); bb_set_wide(8): the control warp keeps 32 reducers in
+// registers instead of 256 (its scan of the rest of G_ in memory on most rounds).
 //
 // Every routine that touches the per-thread state is inlined: a call would take the state's address and move it from
 // registers to local memory (LDL / STL on the chain of every round: 1.35 -> 1.06 us per addition when that was removed).
@@ -88,6 +89,7 @@ struct WideState {
   int T;                    // entries of the shared-memory table in use (append only until a consolidation)
   int tcap;                 // entries of the table that may be used
   int regs;                 // register slots that may be used (threads 0 .. regs - 1), at most BBW_SLOTS
+  int cbase;                // reducers of G_ the control warp keeps in registers (256; 32 under bb_set_wide(8)): the rest is scanned in memory
   int cz;                   // scratch half the next consolidation writes
   // stream threads: the stream in this thread's register slot.  k0 all ones: free.
   uint64_t k0, adj0, pk0; uint32_t c0, nc0, pc0, p0, e0;
@@ -134,12 +136,12 @@ __device__ __forceinline__ void wide_round(WideShared& sh, int& half, WideState&
       for (int q = 7; q >= 0; q--)
         if (((mg - ws.rl[q]) & K::ge_mask) == K::ge_mask) cand = ws.rc[q];   // rl: exponent fields only; absent: rc = BBS_NONE
       uint32_t best = __reduce_min_sync(BB_FULL, cand);
-      if (best == BBS_NONE && nR > 256) {   // the rest of G_ from memory, 128 per pass
+      if (best == BBS_NONE && nR > ws.cbase) {   // the rest of G_ from memory, 128 per pass
         // sorted: G_ ascends in lead monomial (keys descend): a reducer whose key is below M's cannot divide, nor any after it
         const uint64_t stop = sorted ? M : 0ull;
-        bool over = rlm[255] < stop;                        // the last reducer of the register part
+        bool over = rlm[ws.cbase - 1] < stop;               // the last reducer of the register part
 #pragma unroll 1
-        for (int base = 256; base < nR && !over; base += 128) {
+        for (int base = ws.cbase; base < nR && !over; base += 128) {
           const int r0 = base + lane, r1 = r0 + 32, r2 = r0 + 64, r3 = r0 + 96;
           const bool v0 = r0 < nR, v1 = r1 < nR, v2 = r2 < nR, v3 = r3 < nR;
           const uint64_t l0 = v0 ? rlm[r0] : ~0ull, l1 = v1 ? rlm[r1] : ~0ull, l2 = v2 ? rlm[r2] : ~0ull, l3 = v3 ? rlm[r3] : ~0ull;
@@ -321,8 +323,9 @@ __device__ __forceinline__ int block_reduce_streams(const BBParams& P, const Env
 #pragma unroll
     for (int q = 0; q < 8; q++) {
       const int r = (tid - BBW_SLOTS) + 32 * q;
-      ws.rl[q] = r < nR ? (rlm[r] & K::ex_mask) : K::ex_mask;
-      ws.rc[q] = r < nR ? (((uint32_t)r << 16) | ridx[r]) : BBS_NONE;   // positions and basis indices are below 2^16
+      const bool in = r < nR && r < ws.cbase;
+      ws.rl[q] = in ? (rlm[r] & K::ex_mask) : K::ex_mask;
+      ws.rc[q] = in ? (((uint32_t)r << 16) | ridx[r]) : BBS_NONE;   // positions and basis indices are below 2^16
     }
   }
   // s = (gamma / LT f) tail(f) - (gamma / LT g) tail(g): the lead terms cancel exactly (buchberger.cpp:18-21); two streams

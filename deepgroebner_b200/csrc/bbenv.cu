@@ -1139,6 +1139,7 @@ int bb_run(bb_handle* h, int strategy, int episodes, int seed_base, const int32_
     A.trace = trace_dev; A.trace_eps = trace_dev ? trace_episodes : 0; A.trace_cap = trace_cap;
     A.stream_kmax = (h->wide_mode == 2 || h->wide_mode == 5) ? 6 : ((h->wide_mode == 3 || h->wide_mode == 6) ? 48 : BBS_KMAX);
     A.stream_regs = h->wide_mode == 7 ? 8 : A.stream_kmax;
+    A.ctl_reducers = h->wide_mode == 8 ? 32 : 256;
     if (bi > 0) CK(cudaStreamWaitEvent(s, h->stage[which].prepared, 0));
     const int workers = std::min(h->P.num_envs, count);
     if (streams && h->wide_mode >= 4 && h->wide_mode <= 6) CK(h->K->run_streams(PB, S, A, workers, s));
@@ -1339,7 +1340,7 @@ int bb_set_obs_nvars(bb_handle* h, int n_obs) {
 
 int bb_set_wide(bb_handle* h, int mode) {
   if (!h) return -1;
-  if (mode < -1 || mode > 7) return fail(h, "bb_set_wide: mode must be -1 (auto), 0 (off), 1 (on), 2 or 3 (on, 6 / 48 stream slots), 4 (on, one warp per environment), 5 or 6 (as 4, 6 / 48 stream slots), 7 (as 1, 8 register slots + the shared-memory table)");
+  if (mode < -1 || mode > 8) return fail(h, "bb_set_wide: mode must be -1 (auto), 0 (off), 1 (on), 2 or 3 (on, 6 / 48 stream slots), 4 (on, one warp per environment), 5 or 6 (as 4, 6 / 48 stream slots), 7 (as 1, 8 register slots + the shared-memory table), 8 (as 1, 32 reducers in the control warp's registers)");
   h->wide_mode = mode;
   return 0;
 }

@@ -264,7 +264,8 @@ int bb_set_prepare_mode(bb_handle* h, int by_warp);
  * more in shared memory); 4: the same by one warp per environment with 128 streams in registers; -1 (default): 1 when
  * the capacities are sized for long polynomials (max_poly_terms >= 256), else 0.  Test modes: 2 / 3 as 1 and 5 / 6 as 4
  * with 6 / 48 stream slots (consolidation of the dividend into a scratch list every few additions); 7 as 1 with 8
- * register slots (the shared-memory table on every step).  Every mode produces bit-identical episodes; this is a
+ * register slots (the shared-memory table on every step); 8 as 1 with 32 instead of 256 reducers in the control warp's
+ * registers (the rest of the reducer list scanned in memory).  Every mode produces bit-identical episodes; this is a
  * performance switch.  Of the bb_counters, terms_read / terms_written count |h| per addition only where h is
  * materialised (mode 0). */
 int bb_set_wide(bb_handle* h, int mode);

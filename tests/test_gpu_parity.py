@@ -500,14 +500,15 @@ def test_cta_per_environment_runner_equals_warp_runner(torch_cuda, name, strateg
     additions, final basis, reduced Groebner basis, discounted return -- and traffic counters.  Modes 1-3 and 7 run the
     streams with one CTA per environment (bb_wide.cuh): 1 = 256 register slots + the shared-memory table, 2 / 3 = 6 / 48
     slots (consolidation of the dividend into a scratch list every few additions), 7 = 8 register slots + the table (the
-    shared-memory path on every step).  Modes 4-6 run one warp per environment with every stream in registers
+    shared-memory path on every step), 8 = 32 instead of 256 reducers in the control warp's registers (the scan of the
+    rest of the reducer list in memory).  Modes 4-6 run one warp per environment with every stream in registers
     (bb_rstreams.cuh): 128 / 6 / 48 slots.  terms_read / terms_written (|h| per addition) exist only where h is
     materialised."""
     from deepgroebner_b200.buchberger import BuchbergerEngine
     episodes = 12
     eng = BuchbergerEngine(name, num_envs=episodes, **({} if name.startswith("cyclic") else dict(max_poly_terms=256)))
     out = {}
-    for mode in (0, 1, 2, 3, 4, 5, 6, 7):
+    for mode in (0, 1, 2, 3, 4, 5, 6, 7, 8):
         eng.set_wide(mode)
         eng.counters(reset=True)
         stats, trace = eng.run_episodes(strategy, episodes=episodes, seed_base=7, compute_gb=True, selection_seed=99,
@@ -515,7 +516,7 @@ def test_cta_per_environment_runner_equals_warp_runner(torch_cuda, name, strateg
         out[mode] = (stats, trace, eng.counters(reset=True))
     s0, t0, c0 = out[0]
     assert (s0["status"] == 2).all()
-    for mode in (1, 2, 3, 4, 5, 6, 7):
+    for mode in (1, 2, 3, 4, 5, 6, 7, 8):
         s1, t1, c1 = out[mode]
         for f in s0.dtype.names:
             assert np.array_equal(s0[f], s1[f]), (mode, f)
