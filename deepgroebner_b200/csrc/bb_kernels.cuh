@@ -13,7 +13,7 @@
 #include "bb_device.cuh"
 #include "bb_policy.cuh"
 #include "bb_streams.cuh"
-#ifdef BBW_CLOCK
+#if defined(BBW_CLOCK) || defined(BBW_INSTR)
 #include <cstdio>
 #endif
 #include "bb_wide.cuh"
@@ -867,6 +867,9 @@ __global__ void __launch_bounds__(BBW_THREADS, BBW_MIN_CTAS) k_run_wide(const __
   Ctr ct; ct.clear();
   WideState ws;
   ws.clear(); ws.cz = 0;
+#ifdef BBW_INSTR
+  ws.n_rounds = ws.n_trounds = ws.sum_T = ws.n_consol = ws.n_crounds = ws.n_topen = 0;
+#endif
 #ifdef BBW_CLOCK
   ws.cw = ws.cb = ws.cp = ws.co = 0; ws.tl = clock64();
 #endif
@@ -952,6 +955,9 @@ __global__ void __launch_bounds__(BBW_THREADS, BBW_MIN_CTAS) k_run_wide(const __
     }
     __syncthreads();
   }
+#ifdef BBW_INSTR
+  if (tid == 0) printf("rounds %lld, with table entries %lld (sum of the table lengths %lld), consolidations %lld (their rounds %lld), streams opened in the table %lld\n", ws.n_rounds, ws.n_trounds, ws.sum_T, ws.n_consol, ws.n_crounds, ws.n_topen);
+#endif
 #ifdef BBW_CLOCK
   if ((tid & 31) == 0) printf("warp %d: before the barrier %lld, barrier + fold %lld, post-processing %lld, outside the rounds %lld cycles\n", tid >> 5, ws.cw, ws.cb, ws.cp, ws.co);
 #endif

@@ -99,6 +99,9 @@ struct WideState {
   // stream threads: the raw term behind the head of table entry pend_i, loaded but not yet stored to st.pkey / st.pcoef
   int pend_i; uint64_t pend_k; uint32_t pend_c;
   uint32_t bad;             // per thread: a produced key overflowed its exponent fields
+#ifdef BBW_INSTR
+  long long n_rounds, n_trounds, sum_T, n_consol, n_crounds, n_topen;   // diagnostic counts (block-uniform)
+#endif
 #ifdef BBW_CLOCK
   long long cw, cb, cp, co, tl; // diagnostic: cycles before the round's barrier, barrier + fold, post-processing, outside; end of the last post-processing
 #endif
@@ -123,6 +126,9 @@ __device__ __forceinline__ void wide_round(WideShared& sh, int& half, WideState&
                                            const uint32_t* tc, uint32_t& S, uint64_t& M2, uint4& dA, uint4& dB, uint4& dC, int& freet) {
   typedef KL<NV> K;
   const int tid = threadIdx.x, lane = bb_lane();
+#ifdef BBW_INSTR
+  ws.n_rounds++; if (ws.T > 0) { ws.n_trounds++; ws.sum_T += ws.T; } if (!search) ws.n_crounds++;
+#endif
 #ifdef BBW_CLOCK
   const long long t0 = bbw_clock((uint32_t)M);
   ws.co += t0 - ws.tl;
@@ -267,6 +273,9 @@ __device__ __forceinline__ void wide_open(WideState& ws, WideStreams& st, const 
     }
   }
   if (target < 0) ws.T = j + 1;
+#ifdef BBW_INSTR
+  if (target < 0) ws.n_topen++;
+#endif
 }
 
 // Consolidation (bb_streams.cuh): h from its lead monomial M on goes to scratch half ws.cz in order, one stream over it
@@ -369,6 +378,9 @@ __device__ __forceinline__ int block_reduce_streams(const BBParams& P, const Env
       if ((dB.w & 1u) && dB.z + 1u > dB.y) {   // h <- h - (LT h / LT f) f, |f| > 1: the lead terms cancel, f's tail becomes a stream
         if (dB.w & 2u) { err = -BB_STATUS_OVERFLOW_EXPONENT; break; }
         if (freet < 0 && ws.T >= ws.tcap) {   // no register slot, no room in the table
+#ifdef BBW_INSTR
+          ws.n_consol++;
+#endif
           const int t = wide_consolidate<NV>(sh, half, ws, st, F, M2, tk, tc, (uint32_t)P.max_terms, P.max_poly_terms);
           if (t < 0) { err = -BB_STATUS_OVERFLOW_SCRATCH; break; }
           freet = t > 0 ? 1 : 0;
