@@ -871,7 +871,7 @@ __global__ void __launch_bounds__(BBW_THREADS, BBW_MIN_CTAS) k_run_wide(const __
   ws.n_rounds = ws.n_trounds = ws.sum_T = ws.n_consol = ws.n_crounds = ws.n_topen = 0;
 #endif
 #ifdef BBW_CLOCK
-  ws.cw = ws.cb = ws.cp = ws.co = 0; ws.tl = clock64();
+  ws.cw = ws.cb = ws.cp = ws.co = ws.s_sel = ws.s_take = ws.s_red = ws.s_upd = 0; ws.tl = clock64();
 #endif
   ws.regs = A.stream_regs < BBW_SLOTS ? (A.stream_regs < 2 ? 2 : A.stream_regs) : BBW_SLOTS;
   ws.cbase = A.ctl_reducers >= 32 && A.ctl_reducers < 256 ? (A.ctl_reducers & ~31) : 256;
@@ -959,7 +959,7 @@ __global__ void __launch_bounds__(BBW_THREADS, BBW_MIN_CTAS) k_run_wide(const __
   if (tid == 0) printf("rounds %lld, with table entries %lld (sum of the table lengths %lld), consolidations %lld (their rounds %lld), streams opened in the table %lld\n", ws.n_rounds, ws.n_trounds, ws.sum_T, ws.n_consol, ws.n_crounds, ws.n_topen);
 #endif
 #ifdef BBW_CLOCK
-  if ((tid & 31) == 0) printf("warp %d: before the barrier %lld, barrier + fold %lld, post-processing %lld, outside the rounds %lld cycles\n", tid >> 5, ws.cw, ws.cb, ws.cp, ws.co);
+  if ((tid & 31) == 0) printf("warp %d: before the barrier %lld, barrier + fold %lld, post-processing %lld, outside the rounds %lld cycles; steps: select %lld, pair removal %lld, reduction %lld, update %lld\n", tid >> 5, ws.cw, ws.cb, ws.cp, ws.co, ws.s_sel, ws.s_take, ws.s_red, ws.s_upd);
 #endif
   __syncthreads();
   if (tid < CT_COUNT && sh[0][tid]) atomicAdd(&P.counters[tid], sh[0][tid]);

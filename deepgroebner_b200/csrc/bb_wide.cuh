@@ -103,6 +103,7 @@ struct WideState {
   long long n_rounds, n_trounds, sum_T, n_consol, n_crounds, n_topen;   // diagnostic counts (block-uniform)
 #endif
 #ifdef BBW_CLOCK
+  long long s_sel, s_take, s_red, s_upd;   // diagnostic: cycles of a step's parts (select, pair removal, reduction, update)
   long long cw, cb, cp, co, tl; // diagnostic: cycles before the round's barrier, barrier + fold, post-processing, outside; end of the last post-processing
 #endif
   __device__ __forceinline__ void clear() {
@@ -434,15 +435,25 @@ __device__ __forceinline__ int block_step(const BBParams& P, Env& e, WideShared&
                                           int strategy, uint32_t* sel_rng, uint32_t& pair, Ctr& ct) {
   typedef KL<NV> K;
   const int tid = threadIdx.x;
+#ifdef BBW_CLOCK
+  const long long c0 = bbw_clock(0u);
+#endif
   if (tid < 32) {   // warp 0: select the pair
     const int row = warp_select<NV>(P, e, strategy, sel_rng);
     if (tid == 0) sh.row = row;
   }
   __syncthreads();
+#ifdef BBW_CLOCK
+  const long long c1 = bbw_clock((uint32_t)sh.row);
+#endif
   uint32_t pr; uint64_t gam;
   block_take_pair(P, e, sh.row, pr, gam);
   e.nP--;
   pair = pr;
+#ifdef BBW_CLOCK
+  const long long c2 = bbw_clock(pr ^ (uint32_t)gam);
+  ws.s_sel += c1 - c0; ws.s_take += c2 - c1;
+#endif
   const GHeadMem* gh = ENV_PTR(GHeadMem, e, P, o_ghead);
   const GHead hf = load_head(gh + (pr & 0xffffu)), hg = load_head(gh + (pr >> 16));
   e.guard |= gam;
@@ -457,6 +468,10 @@ __device__ __forceinline__ int block_step(const BBParams& P, Env& e, WideShared&
   int steps = 0;
   const int rlen = block_reduce_streams<NV>(P, e, sh, half, ws, st, hf, hg, gam, sug, steps, ENV_PTR(uint64_t, e, P, o_tkey) + e.nT,
                                             ENV_PTR(uint32_t, e, P, o_tcoef) + e.nT, P.max_terms - e.nT, ct);
+#ifdef BBW_CLOCK
+  const long long c3 = bbw_clock((uint32_t)rlen);
+  ws.s_red += c3 - c2;
+#endif
   if (rlen < 0) { e.status = -rlen; return 1 + steps; }
   if (rlen > 0) {
     ct.upb += (unsigned)e.nG; ct.upp += (unsigned)e.nP;
@@ -473,6 +488,9 @@ __device__ __forceinline__ int block_step(const BBParams& P, Env& e, WideShared&
     e.nP = (int)(r & 0xffffffffll);
     ct.upp += (unsigned)(r >> 32);
     e.nG++; e.nT += rlen;
+#ifdef BBW_CLOCK
+    ws.s_upd += bbw_clock((uint32_t)e.nP) - c3;
+#endif
   }
   if (e.nP == 0) e.status = BB_STATUS_DONE;
   return 1 + steps;
