@@ -42,7 +42,7 @@
 #define BBW_KMAX 1024           // BBW_KMAX - BBW_THREADS entries in the shared-memory table behind the register slots
 #endif
 static_assert(BBW_KMAX % BBW_THREADS == 0 && BBW_KMAX > BBW_THREADS, "whole rows of streams");
-static_assert(BBW_WARPS <= 32, "one record per lane in the fold");
+static_assert(BBW_WARPS <= 32 && (BBW_WARPS & (BBW_WARPS - 1)) == 0, "one record per lane in the folds; a power of two (block_add_basis)");
 static_assert(BBW_KMAX / BBW_THREADS <= 8, "per-thread coefficient sums of a round stay below 2^19, a warp's below 2^24");
 #define BBW_NOFREE 0x3fu
 
@@ -81,6 +81,9 @@ struct WideShared {
   __align__(16) uint4 fin[2];
   int row;                  // the pair row warp 0 selected
   long long upd;            // result of warp_add_basis
+  // block_add_basis: per-warp results of one sweep of the peeling loop, double-buffered: (largest undecided key lo, hi,
+  // its lowest index, a member of the current kept lcm's group is coprime to the new element)
+  __align__(16) uint4 prec[2][BBW_WARPS];
 };
 
 // Block-uniform state of a step's reduction plus per-thread registers; every member is a scalar so that the whole record
@@ -427,6 +430,188 @@ __device__ __forceinline__ void block_take_pair(const BBParams& P, const Env& e,
   }
 }
 
+// update() (buchberger.cpp:52-99) + reducer-list insertion by the BLOCK for Gebauer-Moeller elimination and more than 64
+// basis elements; result as warp_add_basis (bb_device.cuh), to every thread.  On cyclic-6 the basis has ~600 (up to ~1200)
+// elements when one is added, and warp_add_basis's peeling loop -- one sweep of all L_i = lcm(LM_i, LM f) per kept lcm, ~16
+// of them -- took 66 K cycles per update with seven warps waiting: 7 % of an episode (clock probes, profiles/README.md).
+// Here warp 0 prepares (the L_i into the slot's scratch array, the old-pair filter, :63-70), the sweep of a kept lcm is
+// split over the warps (warp w takes chunks w, w + BBW_WARPS, ...; one barrier and one fold of BBW_WARPS records per kept
+// lcm; the thread that reads an entry is the one that writes it), and warp 0 finishes (new pairs in ascending i, reducer
+// list, head record).  Statement for statement the general path of warp_add_basis otherwise; everything else goes there.
+template <int NV>
+__device__ __forceinline__ long long block_add_basis(const BBParams& P, WideShared& sh, unsigned char* base, int m, int nP,
+                                                     int off, int len, int sug) {
+  typedef KL<NV> K;
+  const auto& H = BB_HOT(P);
+  const int tid = threadIdx.x, lane = bb_lane(), warp = tid >> 5;
+  if (H.elimination != BB_ELIM_GEBAUERMOELLER || m <= 64 || m >= H.max_basis) {
+    if (tid < 32) {
+      const long long r = warp_add_basis<NV>(P, base, m, nP, off, len, sug);
+      if (tid == 0) sh.upd = r;
+    }
+    __syncthreads();
+    return sh.upd;
+  }
+  const uint32_t ltm = bb_lt_mask();
+  base = bb_global(base);
+  const uint64_t* tk = reinterpret_cast<const uint64_t*>(base + H.o_tkey) + off;
+  const uint32_t* tc = reinterpret_cast<const uint32_t*>(base + H.o_tcoef) + off;
+  const uint64_t fk = tk[0];
+  uint64_t* lm = reinterpret_cast<uint64_t*>(base + H.o_lm);
+  uint64_t* lscr = reinterpret_cast<uint64_t*>(base + H.o_lscr);
+  uint64_t* plcm = reinterpret_cast<uint64_t*>(base + H.o_plcm);
+  uint32_t* pairs = reinterpret_cast<uint32_t*>(base + H.o_pairs);
+  // ---- every thread: lscr[i] = key of L_i (the old-pair filter gathers from it)
+  bool ovf = false;  // deg(L_i) must fit the degree field: bit 63 is a tag below, never a silently wrapped degree
+#pragma unroll 1
+  for (int i = tid; i < m; i += BBW_THREADS) {
+    const uint64_t le = K::lcm_exps(lm[i], fk);
+    const uint32_t dg = K::sum_fields(le);
+    ovf |= dg > K::dmax;
+    lscr[i] = le | ((uint64_t)(K::dmax - dg) << K::dshift);
+  }
+  if (__syncthreads_or(ovf)) return -3;
+  // ---- warp 0: (1) old pairs (i, j) dropped iff LM f | lcm_ij and lcm_ij != L_i and lcm_ij != L_j (:63-70)
+  if (tid < 32) {
+    const uint64_t fe = fk & K::ex_mask;
+    int w = 0;
+#pragma unroll 1
+    for (int b0 = 0; b0 < nP; b0 += 32) {
+      const int idx = b0 + lane;
+      const bool valid = idx < nP;
+      uint32_t pr = 0u; uint64_t pl = 0ull;
+      bool keep = false;
+      if (valid) {
+        pr = pairs[idx]; pl = plcm[idx];
+        const uint64_t l = pl & K::ex_mask;
+        const bool drop = K::divides(fe, l) && l != (lscr[pr & 0xffffu] & K::ex_mask) && l != (lscr[pr >> 16] & K::ex_mask);
+        keep = !drop;
+      }
+      const uint32_t km = __ballot_sync(BB_FULL, keep);
+      if (keep) {  // w + rank <= idx: never overtakes an unread entry of a later chunk
+        const int pos = w + __popc(km & ltm);
+        pairs[pos] = pr; plcm[pos] = pl;
+      }
+      w += __popc(km);
+      __syncwarp();
+    }
+    if (tid == 0) sh.upd = w;
+  }
+  __syncthreads();   // the filter reads the keys the sweeps below start to overwrite
+  // ---- every thread: (2)-(4) by peeling.  The smallest remaining L (largest key; lowest index among equals) cannot be
+  // strictly divided by anything still alive; it kills every multiple (strict or equal), and its pair is emitted unless a
+  // member of its group is coprime to f.  lscr[i] = key while undecided, 0 once dead, key | 1 << 63 once chosen.  Entry i
+  // belongs to the thread that sweeps it: lane i % 32 of warp (i / 32) % BBW_WARPS.
+  uint64_t kk = 0ull, kkey = 0ull;   // exponents / key of the current kept lcm
+  int kidx = -1, buf = 0;
+  for (;;) {
+    uint64_t bk = 0ull; int bi = 0x7fffffff;
+    uint32_t cop_any = 0u;
+#pragma unroll 1
+    for (int b0 = warp * 32; b0 < m; b0 += BBW_THREADS) {
+      const int i = b0 + lane;
+      uint64_t x = i < m ? lscr[i] : 0ull;
+      bool und = x != 0ull && (long long)x > 0;  // undecided
+      if (kidx >= 0) {
+        const uint64_t ei = x & K::ex_mask;
+        const bool eq = x != 0ull && ei == kk;    // the kept lcm itself included
+        if (und && ((((ei | K::ge_mask) - kk) & K::ge_mask) == K::ge_mask)) { lscr[i] = 0ull; und = false; }
+        bool cop = false;
+        if (eq) cop = K::coprime(lm[i], fk);
+        cop_any |= __ballot_sync(BB_FULL, cop);
+      }
+      if (und && x > bk) { bk = x; bi = i; }  // ascending i per lane: first occurrence kept on ties
+    }
+    {   // the warp's largest undecided key, lowest index among equals
+      const uint32_t hi = __reduce_max_sync(BB_FULL, (uint32_t)(bk >> 32));
+      const bool c1 = (uint32_t)(bk >> 32) == hi;
+      const uint32_t lo = __reduce_max_sync(BB_FULL, c1 ? (uint32_t)bk : 0u);
+      const bool c2 = c1 && (uint32_t)bk == lo;
+      const uint32_t wi = __reduce_min_sync(BB_FULL, c2 ? (uint32_t)bi : 0x7fffffffu);
+      if (lane == 0) sh.prec[buf][warp] = make_uint4(lo, hi, wi, cop_any ? 1u : 0u);
+    }
+    __syncthreads();
+    uint4 v = make_uint4(0u, 0u, 0x7fffffffu, 0u);
+    if (lane < BBW_WARPS) v = sh.prec[buf][lane];
+    buf ^= 1;
+    const bool grp_cop = __any_sync(BB_FULL, v.w != 0u);
+    const uint32_t hi = __reduce_max_sync(BB_FULL, v.y);
+    const uint32_t lo = __reduce_max_sync(BB_FULL, v.y == hi ? v.x : 0u);
+    const uint32_t ni = __reduce_min_sync(BB_FULL, (v.y == hi && v.x == lo) ? v.z : 0x7fffffffu);
+    // the kept lcm whose sweep this was: chosen for emission unless its group has a coprime member (by the entry's owner)
+    if (kidx >= 0 && ((kidx >> 5) & (BBW_WARPS - 1)) == warp && (kidx & 31) == lane) lscr[kidx] = grp_cop ? 0ull : (kkey | (1ull << 63));
+    if ((hi | lo) == 0u) break;   // nothing undecided
+    kidx = (int)ni;
+    kkey = ((uint64_t)hi << 32) | lo;
+    kk = kkey & K::ex_mask;
+    // decided: out of the undecided set while it sweeps (by the entry's owner, the only thread that reads it in a sweep)
+    if (((kidx >> 5) & (BBW_WARPS - 1)) == warp && (kidx & 31) == lane) lscr[kidx] = kkey | (1ull << 63);
+  }
+  __syncthreads();   // every owner's marks before warp 0 reads them
+  nP = (int)sh.upd;
+  // ---- warp 0: (5) new pairs in ascending i (:86) behind the survivors (:91-92), the reducer list, the head record
+  if (tid < 32) {
+    long long r = 0;
+    int emitted = 0;
+#pragma unroll 1
+    for (int b0 = 0; b0 < m && r == 0; b0 += 32) {
+      const int i = b0 + lane;
+      const uint64_t x = i < m ? lscr[i] : 0ull;
+      const bool keep = (long long)x < 0;
+      const uint32_t km = __ballot_sync(BB_FULL, keep);
+      const int cnt = __popc(km);
+      if (nP + cnt > H.max_pairs) { r = -1; break; }
+      if (keep) {
+        const int pos = nP + __popc(km & ltm);
+        pairs[pos] = ((uint32_t)m << 16) | (uint32_t)i;
+        plcm[pos] = x & ~(1ull << 63);
+      }
+      nP += cnt; emitted += cnt;
+    }
+    if (r == 0) {
+      // upper_bound by lead monomial when sort_reducers (buchberger.cpp:308-311 / 323-326), else appended
+      uint64_t* rlm = reinterpret_cast<uint64_t*>(base + H.o_rlm);
+      uint32_t* ridx = reinterpret_cast<uint32_t*>(base + H.o_ridx);
+      int pos = m;
+      if (H.sort_reducers) {
+        int cnt = 0;  // reducers with LM <= new LM  <=>  key >= new key
+#pragma unroll 1
+        for (int b0 = 0; b0 < m; b0 += 32) {
+          const int q = b0 + lane;
+          cnt += __popc(__ballot_sync(BB_FULL, q < m && rlm[q] >= fk));
+        }
+        pos = cnt;
+#pragma unroll 1
+        for (int hi = m; hi > pos; hi -= 32) {
+          const int lo = hi - 32 > pos ? hi - 32 : pos;
+          const int idx = lo + lane;
+          const bool in = idx < hi;
+          uint64_t k = 0; uint32_t ix = 0;
+          if (in) { k = rlm[idx]; ix = ridx[idx]; }
+          __syncwarp();
+          if (in) { rlm[idx + 1] = k; ridx[idx + 1] = ix; }
+          __syncwarp();
+        }
+      }
+      if (lane == 0) {
+        rlm[pos] = fk; ridx[pos] = (uint32_t)m;
+        lm[m] = fk;
+        GHeadMem* g = reinterpret_cast<GHeadMem*>(base + H.o_ghead) + m;
+        const uint32_t inv = bb_global(H.invtab)[tc[0]];
+        const uint64_t k1 = len > 1 ? tk[1] : 0ull;
+        const uint32_t c1 = len > 1 ? tc[1] : 0u;
+        reinterpret_cast<uint4*>(g)[0] = make_uint4((uint32_t)fk, (uint32_t)(fk >> 32), (uint32_t)k1, (uint32_t)(k1 >> 32));
+        reinterpret_cast<uint4*>(g)[1] = make_uint4(inv | (c1 << 16), (uint32_t)sug, (uint32_t)off, (uint32_t)len);
+      }
+      __syncwarp();
+      r = ((long long)emitted << 32) | (long long)nP;
+    }
+    if (tid == 0) sh.upd = r;
+  }
+  __syncthreads();
+  return sh.upd;
+}
+
 // One environment step by the whole CTA (BuchbergerEnv::step, buchberger.cpp:318-329, with the pair chosen by
 // `strategy`).  e and every scalar below are block-uniform.  Pair selection and update() (Gebauer-Moeller) are the warp
 // routines of bb_device.cuh run by warp 0.  Returns the number of polynomial additions; `pair` receives (j << 16) | i.
@@ -475,12 +660,7 @@ __device__ __forceinline__ int block_step(const BBParams& P, Env& e, WideShared&
   if (rlen < 0) { e.status = -rlen; return 1 + steps; }
   if (rlen > 0) {
     ct.upb += (unsigned)e.nG; ct.upp += (unsigned)e.nP;
-    if (tid < 32) {
-      const long long r = warp_add_basis<NV>(P, e.base, e.nG, e.nP, e.nT, rlen, sug);
-      if (tid == 0) sh.upd = r;
-    }
-    __syncthreads();
-    const long long r = sh.upd;
+    const long long r = block_add_basis<NV>(P, sh, e.base, e.nG, e.nP, e.nT, rlen, sug);
     if (r < 0) {
       e.status = (r == -1) ? BB_STATUS_OVERFLOW_PAIRS : (r == -2 ? BB_STATUS_OVERFLOW_BASIS : BB_STATUS_OVERFLOW_EXPONENT);
       return 1 + steps;
